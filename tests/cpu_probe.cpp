@@ -1,0 +1,143 @@
+// cpu_probe.cpp — test-only host build of the product's shared host/device headers
+// (hm_rng.h, hm_bsdf.h, hm_curve.h, hm_bvh.h).  Lets the CPU test-suite check the
+// arithmetic the CUDA kernels run against the oracle without a GPU.
+#include <cstring>
+#include <vector>
+
+#include "../hairmsnn_b200/csrc/hm_bsdf.h"
+#include "../hairmsnn_b200/csrc/hm_host.h"
+#include "../hairmsnn_b200/csrc/hm_rng.h"
+
+using namespace hm;
+
+extern "C" {
+
+uint32_t probe_rng_seed(int frame_id, uint32_t px, uint32_t py, uint32_t w) { return rng_seed(frame_id, px, py, w).state; }
+void probe_rng_draws(uint32_t state, int n, uint32_t* states, float* floats) {
+    Rng r; r.state = state;
+    for (int i = 0; i < n; ++i) { floats[i] = rng_next(r); states[i] = r.state; }
+}
+
+void probe_hair_setup(float bm, float bn, float alpha, float* out) {
+    HairLobes L; L.setup(bm, bn, alpha);
+    for (int i = 0; i < 3; ++i) { out[i] = L.v[i]; out[4 + i] = L.sin2k[i]; out[7 + i] = L.cos2k[i]; }
+    out[3] = L.s;
+}
+static HairLobes make_lobes(const float* sigma_a, float bm, float bn, float alpha) {
+    HairLobes L; L.setup(bm, bn, alpha);
+    L.sigma_a = V3(sigma_a[0], sigma_a[1], sigma_a[2]);
+    for (int i = 0; i < 4; ++i) L.gain[i] = 1.f;
+    return L;
+}
+void probe_hair_eval(int n, const float* wo, const float* wi, const float* h, const float* sigma_a,
+                     float bm, float bn, float alpha, float* out_f, float* out_pdf) {
+    HairLobes L = make_lobes(sigma_a, bm, bn, alpha);
+    for (int i = 0; i < n; ++i) {
+        float pdf;
+        V3 f = hair_eval(L, V3(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]), V3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), h[i], &pdf);
+        out_f[3 * i] = f.x; out_f[3 * i + 1] = f.y; out_f[3 * i + 2] = f.z; out_pdf[i] = pdf;
+    }
+}
+void probe_hair_sample(int n, const float* wo, const float* h, const float* u, const float* sigma_a,
+                       float bm, float bn, float alpha, float* out_wi, float* out_f, float* out_pdf) {
+    HairLobes L = make_lobes(sigma_a, bm, bn, alpha);
+    for (int i = 0; i < n; ++i) {
+        V3 o(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]);
+        V3 w = hair_sample_dir(L, o, h[i], u[4 * i], u[4 * i + 1], u[4 * i + 2], u[4 * i + 3]);
+        float pdf;
+        V3 f = hair_eval(L, o, w, h[i], &pdf);
+        out_wi[3 * i] = w.x; out_wi[3 * i + 1] = w.y; out_wi[3 * i + 2] = w.z;
+        out_f[3 * i] = f.x; out_f[3 * i + 1] = f.y; out_f[3 * i + 2] = f.z; out_pdf[i] = pdf;
+    }
+}
+void probe_surf_eval(int n, const float* wo, const float* wi, const float* kd, float alpha, float* out_f, float* out_pdf) {
+    for (int i = 0; i < n; ++i) {
+        V3 o(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]), w(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]);
+        V3 f = surf_eval(o, w, V3(kd[0], kd[1], kd[2]), alpha);
+        out_f[3 * i] = f.x; out_f[3 * i + 1] = f.y; out_f[3 * i + 2] = f.z;
+        out_pdf[i] = surf_pdf(alpha, o, normalize(o + w));
+    }
+}
+void probe_surf_sample(int n, const float* wo, const float* u, float alpha, float* out_wi, float* out_pdf) {
+    for (int i = 0; i < n; ++i) {
+        float pdf;
+        V3 w = surf_sample(u[2 * i], u[2 * i + 1], alpha, V3(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]), &pdf);
+        out_wi[3 * i] = w.x; out_wi[3 * i + 1] = w.y; out_wi[3 * i + 2] = w.z; out_pdf[i] = pdf;
+    }
+}
+void probe_curve_geometry(const float* cps16, const float* org, const float* dir, float t, float u, float* out13) {
+    CubicSeg s;
+    s.from_catmull_rom(V4(cps16[0], cps16[1], cps16[2], cps16[3]), V4(cps16[4], cps16[5], cps16[6], cps16[7]),
+                       V4(cps16[8], cps16[9], cps16[10], cps16[11]), V4(cps16[12], cps16[13], cps16[14], cps16[15]));
+    V3 o(org[0], org[1], org[2]), d(dir[0], dir[1], dir[2]);
+    FibreHit h = fibre_hit_geometry(s, u, o + t * d);
+    out13[0] = h.p.x; out13[1] = h.p.y; out13[2] = h.p.z; out13[3] = h.n.x; out13[4] = h.n.y; out13[5] = h.n.z;
+    out13[6] = h.t.x; out13[7] = h.t.y; out13[8] = h.t.z; out13[9] = h.centre.x; out13[10] = h.centre.y; out13[11] = h.centre.z;
+    out13[12] = h.radius;
+}
+// single-segment intersection; returns 1 on hit
+int probe_intersect_fibre(const float* cps16, const float* org, const float* dir, float tmin, float tmax, float* t, float* u) {
+    V3 o(org[0], org[1], org[2]), d(dir[0], dir[1], dir[2]);
+    RayFrame rf = make_ray_frame(o, d);
+    SegHit sh;
+    bool ok = intersect_fibre(rf, tmin, tmax, V4(cps16[0], cps16[1], cps16[2], cps16[3]), V4(cps16[4], cps16[5], cps16[6], cps16[7]),
+                              V4(cps16[8], cps16[9], cps16[10], cps16[11]), V4(cps16[12], cps16[13], cps16[14], cps16[15]), sh);
+    if (ok) { *t = sh.t; *u = sh.u; }
+    return ok ? 1 : 0;
+}
+
+// BVH build + trace on the host
+struct ProbeScene { HostGeometry geo; HostBvh bvh; };
+void* probe_scene_create(const float* cps, int ncps, const int* seg_cp, int nseg, const float* tri_verts, int ntri, int threads) {
+    ProbeScene* s = new ProbeScene;
+    s->geo.cps.resize(ncps);
+    memcpy(s->geo.cps.data(), cps, sizeof(float) * 4 * ncps);
+    s->geo.seg_cp.assign(seg_cp, seg_cp + nseg);
+    s->geo.tri_verts.resize(3 * (size_t)ntri);
+    if (ntri) memcpy(s->geo.tri_verts.data(), tri_verts, sizeof(float) * 12 * ntri);
+    build_bvh(s->geo, s->bvh, threads);
+    return s;
+}
+void probe_scene_destroy(void* p) { delete (ProbeScene*)p; }
+int probe_scene_num_nodes(void* p) { return (int)(((ProbeScene*)p)->bvh.nodes.size() / 4); }
+void probe_scene_arrays(void* p, const float** nodes, const int** leaf_code, const int** leaf_prim) {
+    ProbeScene* s = (ProbeScene*)p;
+    *nodes = (const float*)s->bvh.nodes.data(); *leaf_code = s->bvh.leaf_code.data(); *leaf_prim = s->bvh.leaf_prim.data();
+}
+// out per ray: t, prim (as float bits int), u, v ; stats: nodes, prims
+void probe_trace(void* p, int n, const float* org, const float* dir, float tmin, float tmax, int any,
+                 float* out_t, int* out_prim, float* out_u, float* out_v, int* out_nodes, int* out_prims) {
+    ProbeScene* s = (ProbeScene*)p;
+    GeomView g = make_view(s->geo, s->bvh);
+    for (int i = 0; i < n; ++i) {
+        TraceStats st{0, 0};
+        V3 o(org[3 * i], org[3 * i + 1], org[3 * i + 2]), d(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+        Hit h = any ? trace<true>(g, o, d, tmin, tmax, &st) : trace<false>(g, o, d, tmin, tmax, &st);
+        out_t[i] = h.t; out_prim[i] = h.prim; out_u[i] = h.u; out_v[i] = h.v;
+        if (out_nodes) { out_nodes[i] = st.nodes; out_prims[i] = st.prims; }
+    }
+}
+// exhaustive reference: test every primitive, no BVH
+void probe_trace_brute(void* p, int n, const float* org, const float* dir, float tmin, float tmax,
+                       float* out_t, int* out_prim, float* out_u) {
+    ProbeScene* s = (ProbeScene*)p;
+    int ns = (int)s->geo.seg_cp.size(), nt = (int)(s->geo.tri_verts.size() / 3);
+    for (int i = 0; i < n; ++i) {
+        V3 o(org[3 * i], org[3 * i + 1], org[3 * i + 2]), d(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+        RayFrame rf = make_ray_frame(o, d);
+        float best = tmax; int bp = -1; float bu = 0;
+        for (int k = 0; k < ns; ++k) {
+            const F4* c = s->geo.cps.data() + s->geo.seg_cp[k];
+            SegHit sh;
+            if (intersect_fibre(rf, tmin, best, f4_to_v4(c[0]), f4_to_v4(c[1]), f4_to_v4(c[2]), f4_to_v4(c[3]), sh)) { best = sh.t; bp = k; bu = sh.u; }
+        }
+        for (int k = 0; k < nt; ++k) {
+            const F4* v = s->geo.tri_verts.data() + 3 * k;
+            float t, b1, b2;
+            if (intersect_triangle(o, d, tmin, best, V3(v[0].x, v[0].y, v[0].z), V3(v[1].x, v[1].y, v[1].z), V3(v[2].x, v[2].y, v[2].z), t, b1, b2)) { best = t; bp = ns + k; bu = b1; }
+        }
+        out_t[i] = best; out_prim[i] = bp; out_u[i] = bu;
+    }
+}
+
+}  // extern "C"
