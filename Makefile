@@ -1,0 +1,38 @@
+# Builds the C-ABI shared library (sm_100a only) and the three headless executables.
+NVCC ?= /usr/local/cuda/bin/nvcc
+CSRC := hairmsnn_b200/csrc
+LIB := hairmsnn_b200/lib/libhairmsnn.so
+ARCH := -gencode arch=compute_100a,code=sm_100a
+# -fmad=false: the traversal/intersection code must round like its host build (hit-id parity)
+NVFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC,-O3,-ffp-contract=off -fmad=false --expt-relaxed-constexpr -Xptxas -v
+NVFLAGS_MLP := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC,-O3 --expt-relaxed-constexpr -Xptxas -v
+CXXFLAGS := -O2 -std=c++17 -fPIC -ffp-contract=off -mfma -pthread -I/usr/local/cuda/include
+OBJ := build/hm_wavefront.o build/hm_renderer.o build/hm_mlp.o build/hm_capi.o build/hm_io.o build/hm_piz.o build/hm_scene_util.o build/hm_bvh_build.o
+HDRS := $(wildcard $(CSRC)/*.h) include/hairmsnn.h
+
+all: $(LIB) bin
+
+build/hm_wavefront.o: $(CSRC)/hm_wavefront.cu $(HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/hm_wavefront.ptxas.log || (cat build/hm_wavefront.ptxas.log; false)
+build/hm_renderer.o: $(CSRC)/hm_renderer.cu $(HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/hm_renderer.ptxas.log || (cat build/hm_renderer.ptxas.log; false)
+build/hm_mlp.o: $(CSRC)/hm_mlp.cu $(HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS_MLP) -c $< -o $@ 2> build/hm_mlp.ptxas.log || (cat build/hm_mlp.ptxas.log; false)
+build/%.o: $(CSRC)/%.cpp $(HDRS)
+	@mkdir -p build
+	g++ $(CXXFLAGS) -c $< -o $@
+
+$(LIB): $(OBJ)
+	@mkdir -p hairmsnn_b200/lib
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lz -Xlinker -rpath,/usr/local/cuda/lib64
+
+bin: hairmsnn_b200/bin/render_path_tracing hairmsnn_b200/bin/render_nrc hairmsnn_b200/bin/render_hair_msnn
+hairmsnn_b200/bin/%: $(CSRC)/main_%.cpp $(LIB)
+	@mkdir -p hairmsnn_b200/bin
+	g++ -O2 -std=c++17 -Iinclude $< -o $@ -Lhairmsnn_b200/lib -lhairmsnn -Wl,-rpath,'$$ORIGIN/../lib'
+
+clean:
+	rm -rf build $(LIB) hairmsnn_b200/bin

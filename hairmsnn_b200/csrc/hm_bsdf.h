@@ -33,7 +33,6 @@ struct HairLobes {
     float v_sample[4];  // v[0..2], s  (see header note)
     float radius_unused;
 
-#ifndef __CUDA_ARCH__
     void setup(float beta_m, float beta_n, float alpha_rad) {
         v[0] = sqr(0.726f * beta_m + 0.812f * sqr(beta_m) + 3.7f * powf(beta_m, 20.f));
         v[1] = (float)(.25 * v[0]);
@@ -48,7 +47,6 @@ struct HairLobes {
         v_sample[0] = v[0]; v_sample[1] = v[1]; v_sample[2] = v[2]; v_sample[3] = s;
         radius_unused = 0.f;
     }
-#endif
 };
 
 namespace hairdetail {

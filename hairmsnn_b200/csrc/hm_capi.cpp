@@ -1,0 +1,488 @@
+// hm_capi.cpp — extern "C" boundary (include/hairmsnn.h).  Translates exceptions into
+// status codes; owns the opaque handles.
+#include "../../include/hairmsnn.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <stdexcept>
+#include <string>
+
+#include "hm_io.h"
+#include "hm_renderer.h"
+
+using namespace hm;
+
+struct hm_scene {
+    HostScene hs;
+};
+struct hm_mlp {
+    std::unique_ptr<Mlp> owned;
+    Mlp* m = nullptr;
+    cudaStream_t stream = nullptr;
+    int device = 0;
+};
+struct hm_renderer {
+    std::unique_ptr<Renderer> r;
+    hm_mlp mlp_view;
+};
+
+static thread_local std::string g_err;
+
+namespace {
+template <typename F>
+int guarded(F&& f) {
+    try {
+        f();
+        return HM_OK;
+    } catch (const hm::IoError& e) {
+        g_err = e.what();
+        return HM_ERR_IO;
+    } catch (const std::invalid_argument& e) {
+        g_err = e.what();
+        return HM_ERR_ARG;
+    } catch (const std::logic_error& e) {
+        g_err = e.what();
+        return HM_ERR_STATE;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return strncmp(e.what(), "CUDA", 4) == 0 ? HM_ERR_CUDA : HM_ERR_ARG;
+    } catch (...) {
+        g_err = "unknown error";
+        return HM_ERR_ARG;
+    }
+}
+void need(const void* p, const char* what) {
+    if (!p) throw std::invalid_argument(std::string("null argument: ") + what);
+}
+void cuda_ok(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA: ") + cudaGetErrorString(e) + " (" + what + ")");
+}
+}  // namespace
+
+extern "C" {
+
+const char* hm_last_error(void) { return g_err.c_str(); }
+
+int hm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ---- scene --------------------------------------------------------------------------
+int hm_scene_load(const char* path, hm_scene** out) {
+    return guarded([&] {
+        need(path, "config_json_path"); need(out, "out");
+        std::unique_ptr<hm_scene> s(new hm_scene);
+        load_scene_file(path, s->hs);
+        finalize_geometry(s->hs);
+        if (s->hs.has_env) build_env_tables(s->hs);
+        build_bvh(s->hs.geo, s->hs.bvh);
+        *out = s.release();
+    });
+}
+
+int hm_scene_create(const hm_scene_desc* d, hm_scene** out) {
+    return guarded([&] {
+        need(d, "desc"); need(out, "out");
+        if (d->num_segments < 0 || d->num_triangles < 0 || (d->num_segments == 0 && d->num_triangles == 0))
+            throw std::invalid_argument("Either hair or surface must be defined");
+        if (d->num_segments > 0) { need(d->control_points, "control_points"); need(d->segment_first_cp, "segment_first_cp"); }
+        if (d->num_triangles > 0) { need(d->tri_vertices, "tri_vertices"); need(d->tri_normals, "tri_normals"); }
+        if (!d->env_rgba && d->num_dlights <= 0)
+            throw std::invalid_argument("Either directional or environment light must be defined");
+        if ((int64_t)d->width * d->height > 2048 * 2048 && false) {}
+        if (d->width <= 0 || d->height <= 0 || ((int64_t)d->width * d->height) % 128 != 0)
+            throw std::invalid_argument("width*height must be a positive multiple of 128 (scene.cpp:302-306)");
+        std::unique_ptr<hm_scene> s(new hm_scene);
+        HostScene& hs = s->hs;
+        HostGeometry& g = hs.geo;
+        g.cps.resize(d->num_control_points);
+        if (d->num_control_points) memcpy(g.cps.data(), d->control_points, sizeof(float) * 4 * (size_t)d->num_control_points);
+        g.seg_cp.assign(d->segment_first_cp, d->segment_first_cp + d->num_segments);
+        for (int i = 0; i < d->num_segments; ++i)
+            if (g.seg_cp[i] < 0 || g.seg_cp[i] + 3 >= d->num_control_points)
+                throw std::invalid_argument("segment_first_cp out of range");
+        g.num_strands = d->num_strands;
+        const size_t nv = 3 * (size_t)d->num_triangles;
+        g.tri_verts.resize(nv); g.tri_normals.resize(nv);
+        for (size_t i = 0; i < nv; ++i) {
+            g.tri_verts[i] = F4{d->tri_vertices[3 * i], d->tri_vertices[3 * i + 1], d->tri_vertices[3 * i + 2], 0.f};
+            g.tri_normals[i] = F4{d->tri_normals[3 * i], d->tri_normals[3 * i + 1], d->tri_normals[3 * i + 2], 0.f};
+        }
+        for (int k = 0; k < 3; ++k) {
+            g.hair_min[k] = d->hair_min[k]; g.hair_max[k] = d->hair_max[k]; g.kd[k] = d->surface_kd[k];
+            hs.cam_from[k] = d->cam_from[k]; hs.cam_to[k] = d->cam_to[k]; hs.cam_up[k] = d->cam_up[k];
+            hs.sigma_a[k] = d->sigma_a[k];
+        }
+        g.surf_alpha = d->surface_alpha;
+        hs.cos_fovy = d->cos_fovy;
+        hs.beta_m = d->beta_m; hs.beta_n = d->beta_n; hs.alpha = d->alpha;
+        for (int k = 0; k < 4; ++k) hs.gains[k] = d->gains[k];
+        hs.has_env = d->env_rgba != nullptr;
+        if (hs.has_env) {
+            if (d->env_w <= 0 || d->env_h <= 0) throw std::invalid_argument("bad environment size");
+            hs.env_w = d->env_w; hs.env_h = d->env_h;
+            hs.env.assign(d->env_rgba, d->env_rgba + 4 * (size_t)d->env_w * d->env_h);
+        }
+        hs.env_scale = d->env_scale; hs.env_rot = d->env_rotation;
+        for (int i = 0; i < d->num_dlights; ++i) {
+            float x = d->dl_from[3 * i], y = d->dl_from[3 * i + 1], z = d->dl_from[3 * i + 2];
+            float r = 1.f / sqrtf(x * x + y * y + z * z);
+            hs.dl_from.push_back(x * r); hs.dl_from.push_back(y * r); hs.dl_from.push_back(z * r);
+            for (int k = 0; k < 3; ++k) hs.dl_emit.push_back(d->dl_emit[3 * i + k]);
+        }
+        hs.width = d->width; hs.height = d->height; hs.spp = d->spp;
+        hs.path_v1 = d->path_v1; hs.path_v2 = d->path_v2;
+        hs.mis = d->mis != 0; hs.env_pdf = d->env_pdf != 0;
+        if (d->tcnn_config_path) hs.tcnn_config = d->tcnn_config_path;
+        finalize_geometry(hs);
+        if (hs.has_env) build_env_tables(hs);
+        build_bvh(hs.geo, hs.bvh);
+        *out = s.release();
+    });
+}
+
+void hm_scene_free(hm_scene* s) { delete s; }
+
+int hm_scene_get_info(const hm_scene* s, hm_scene_info* info) {
+    return guarded([&] {
+        need(s, "scene"); need(info, "info");
+        const HostScene& hs = s->hs;
+        memset(info, 0, sizeof(*info));
+        info->width = hs.width; info->height = hs.height; info->spp = hs.spp;
+        info->path_v1 = hs.path_v1; info->path_v2 = hs.path_v2;
+        info->num_segments = (int)hs.geo.seg_cp.size();
+        info->num_control_points = (int)hs.geo.cps.size();
+        info->num_triangles = (int)(hs.geo.tri_verts.size() / 3);
+        info->num_strands = hs.geo.num_strands;
+        info->num_bvh_nodes = (int)(hs.bvh.nodes.size() / 4);
+        info->scene_scale = hs.geo.scene_scale;
+        camera_basis(hs, hs.width, hs.height, info->cam_pos, info->cam_d00, info->cam_du, info->cam_dv);
+        info->env_w = hs.env_w; info->env_h = hs.env_h;
+        info->num_dlights = (int)(hs.dl_from.size() / 3);
+    });
+}
+
+int hm_scene_get_arrays(const hm_scene* s, const float** nodes, const int** leaf_code, const int** leaf_prim,
+                        const float** cps, const float** tri_v, const float** tri_n, const int** seg_cp) {
+    return guarded([&] {
+        need(s, "scene");
+        const HostScene& hs = s->hs;
+        if (nodes) *nodes = (const float*)hs.bvh.nodes.data();
+        if (leaf_code) *leaf_code = hs.bvh.leaf_code.data();
+        if (leaf_prim) *leaf_prim = hs.bvh.leaf_prim.data();
+        if (cps) *cps = (const float*)hs.geo.cps.data();
+        if (tri_v) *tri_v = (const float*)hs.geo.tri_verts.data();
+        if (tri_n) *tri_n = (const float*)hs.geo.tri_normals.data();
+        if (seg_cp) *seg_cp = hs.geo.seg_cp.data();
+    });
+}
+
+int hm_scene_get_env_tables(const hm_scene* s, const float** env, const float** cpdf, const float** ccdf,
+                            const float** mpdf, const float** mcdf) {
+    return guarded([&] {
+        need(s, "scene");
+        const HostScene& hs = s->hs;
+        if (!hs.has_env) throw std::logic_error("scene has no environment light");
+        if (env) *env = hs.env.data();
+        if (cpdf) *cpdf = hs.cpdf.data();
+        if (ccdf) *ccdf = hs.ccdf.data();
+        if (mpdf) *mpdf = hs.mpdf.data();
+        if (mcdf) *mcdf = hs.mcdf.data();
+    });
+}
+
+// ---- renderer -----------------------------------------------------------------------
+int hm_renderer_create(hm_scene* s, int kind, int beta_cli, int device, int rank, int world, hm_renderer** out) {
+    if (kind == HM_RENDER_NRC) {
+        g_err = "render_nrc is not built yet (SURVEY §8f row 1)";
+        return HM_ERR_UNSUPPORTED;
+    }
+    return guarded([&] {
+        need(s, "scene"); need(out, "out");
+        if (kind != HM_RENDER_PATH_TRACING && kind != HM_RENDER_HAIR_MSNN) throw std::invalid_argument("unknown renderer kind");
+        std::unique_ptr<hm_renderer> h(new hm_renderer);
+        h->r.reset(new Renderer(s->hs, kind, beta_cli, device, rank, world));
+        h->mlp_view.m = h->r->mlp();
+        h->mlp_view.stream = h->r->stream();
+        h->mlp_view.device = device;
+        *out = h.release();
+    });
+}
+void hm_renderer_destroy(hm_renderer* r) { delete r; }
+
+int hm_render_frames(hm_renderer* r, int n) {
+    return guarded([&] { need(r, "renderer"); r->r->render_frames(n); r->r->sync(); });
+}
+int hm_render_frames_async(hm_renderer* r, int n) {
+    return guarded([&] { need(r, "renderer"); r->r->render_frames(n); });
+}
+int hm_renderer_sync(hm_renderer* r) {
+    return guarded([&] { need(r, "renderer"); r->r->sync(); });
+}
+int hm_renderer_reset_accumulation(hm_renderer* r) {
+    return guarded([&] { need(r, "renderer"); r->r->reset_accumulation(); });
+}
+int hm_renderer_accum_id(const hm_renderer* r) { return r ? r->r->accum_id() : -1; }
+void* hm_renderer_stream(hm_renderer* r) { return r ? (void*)r->r->stream() : nullptr; }
+
+int hm_msnn_trace(hm_renderer* r) { return guarded([&] { need(r, "renderer"); r->r->msnn_trace(); }); }
+int hm_msnn_train_backward(hm_renderer* r) { return guarded([&] { need(r, "renderer"); r->r->msnn_train_backward(); }); }
+int hm_msnn_train_apply(hm_renderer* r) { return guarded([&] { need(r, "renderer"); r->r->msnn_train_apply(); }); }
+int hm_msnn_finish(hm_renderer* r) { return guarded([&] { need(r, "renderer"); r->r->msnn_finish(); }); }
+int hm_msnn_pretrain(hm_renderer* r, int n) {
+    return guarded([&] { need(r, "renderer"); r->r->msnn_pretrain(n); r->r->sync(); });
+}
+hm_mlp* hm_renderer_mlp(hm_renderer* r) { return (r && r->mlp_view.m) ? &r->mlp_view : nullptr; }
+
+int hm_get_device_buffer(hm_renderer* r, int which, void** dev_ptr, size_t* bytes) {
+    return guarded([&] {
+        need(r, "renderer"); need(dev_ptr, "dev_ptr"); need(bytes, "bytes");
+        void* p = r->r->device_buffer(which, bytes);
+        if (!p) throw std::logic_error("buffer not available for this renderer kind");
+        *dev_ptr = p;
+    });
+}
+
+int hm_get_buffer(hm_renderer* r, int which, void* dst, size_t bytes) {
+    return guarded([&] {
+        need(r, "renderer"); need(dst, "host_dst");
+        size_t have = 0;
+        void* p = r->r->device_buffer(which, &have);
+        if (!p) throw std::logic_error("buffer not available for this renderer kind");
+        if (bytes > have) throw std::invalid_argument("requested more bytes than the buffer holds");
+        r->r->sync();
+        cuda_ok(cudaMemcpy(dst, p, bytes, cudaMemcpyDeviceToHost), "hm_get_buffer");
+    });
+}
+
+int hm_save_png(hm_renderer* r, const char* path) {
+    return guarded([&] {
+        need(r, "renderer"); need(path, "path");
+        const int W = r->r->width(), H = r->r->height();
+        std::vector<uint32_t> fb((size_t)W * H);
+        size_t have = 0;
+        void* p = r->r->device_buffer(HM_BUF_FB8, &have);
+        r->r->sync();
+        cuda_ok(cudaMemcpy(fb.data(), p, have, cudaMemcpyDeviceToHost), "hm_save_png");
+        write_png_flipped(path, fb.data(), W, H);
+    });
+}
+
+int hm_save_exr(hm_renderer* r, int which, const char* path) {
+    return guarded([&] {
+        need(r, "renderer"); need(path, "path");
+        if (which < 0 || which > 5) throw std::invalid_argument("hm_save_exr: not a float4 image buffer");
+        const int W = r->r->width(), H = r->r->height();
+        std::vector<float> img((size_t)W * H * 4);
+        size_t have = 0;
+        void* p = r->r->device_buffer(which, &have);
+        if (!p) throw std::logic_error("buffer not available for this renderer kind");
+        r->r->sync();
+        cuda_ok(cudaMemcpy(img.data(), p, have, cudaMemcpyDeviceToHost), "hm_save_exr");
+        write_exr_flipped(path, img.data(), W, H);
+    });
+}
+
+int hm_renderer_get_stats(hm_renderer* r, hm_stats* out) {
+    return guarded([&] {
+        need(r, "renderer"); need(out, "out");
+        Stats s = r->r->stats();
+        memset(out, 0, sizeof(*out));
+        out->ms_primary = s.ms[0]; out->ms_shade = s.ms[1]; out->ms_extend = s.ms[2]; out->ms_shadow = s.ms[3];
+        out->ms_finalize = s.ms[4]; out->ms_train = s.ms[5]; out->ms_infer = s.ms[6]; out->ms_composite = s.ms[7];
+        out->ms_total = s.ms[8];
+        out->rays_primary = s.rays_primary; out->rays_extend = s.rays_extend; out->rays_shadow = s.rays_shadow;
+        out->shade_items = s.shade_items;
+        out->kernel_launches = wavefront_launch_count() + (r->r->mlp() ? r->r->mlp()->launch_count() : 0);
+        out->last_loss = s.last_loss;
+        out->frames = s.frames;
+    });
+}
+int hm_renderer_set_profiling(hm_renderer* r, int on) {
+    return guarded([&] { need(r, "renderer"); r->r->set_profiling(on != 0); });
+}
+
+int hm_write_stats(hm_renderer* r, const char* path) {
+    return guarded([&] {
+        need(r, "renderer"); need(path, "path");
+        Stats s = r->r->stats();
+        std::ofstream f(path);
+        if (!f) throw hm::IoError(std::string("cannot write ") + path);
+        const double paths = (double)s.frames * (r->r->row1() - r->r->row0()) * r->r->width();
+        const char* kinds[3] = {"render_path_tracing", "render_nrc", "render_hair_msnn"};
+        f << "{\n  \"renderer\": \"" << kinds[r->r->kind()] << "\",\n";
+        f << "  \"width\": " << r->r->width() << ", \"height\": " << r->r->height() << ", \"spp\": " << s.frames << ",\n";
+        f << "  \"paths\": " << paths << ",\n";
+        f << "  \"ms_total\": " << s.ms[8] << ",\n";
+        f << "  \"mpaths_per_s\": " << (s.ms[8] > 0 ? paths / (s.ms[8] * 1e-3) / 1e6 : 0.0) << ",\n";
+        f << "  \"ms\": {\"primary\": " << s.ms[0] << ", \"shade\": " << s.ms[1] << ", \"extend\": " << s.ms[2]
+          << ", \"shadow\": " << s.ms[3] << ", \"finalize\": " << s.ms[4] << ", \"train\": " << s.ms[5]
+          << ", \"infer\": " << s.ms[6] << ", \"composite\": " << s.ms[7] << "},\n";
+        f << "  \"rays\": {\"primary\": " << s.rays_primary << ", \"extend\": " << s.rays_extend << ", \"shadow\": "
+          << s.rays_shadow << "},\n";
+        f << "  \"training_loss\": " << s.last_loss << "\n}\n";
+    });
+}
+
+// ---- stand-alone kernels ------------------------------------------------------------
+int hm_trace_rays_device(hm_renderer* r, const float* d_org, const float* d_dir, int n, int any, float tmin, float tmax,
+                         float* d_out) {
+    return guarded([&] {
+        need(r, "renderer"); need(d_org, "d_org3"); need(d_dir, "d_dir3"); need(d_out, "d_out_hit4");
+        if (n > 0) r->r->trace_rays_device(d_org, d_dir, n, any, tmin, tmax, d_out, nullptr);
+    });
+}
+
+int hm_trace_rays(hm_renderer* r, const float* org, const float* dir, int n, int any, float tmin, float tmax,
+                  float* out_hit, int* out_stats) {
+    return guarded([&] {
+        need(r, "renderer"); need(org, "org3"); need(dir, "dir3"); need(out_hit, "out_hit4");
+        if (n <= 0) return;
+        cuda_ok(cudaSetDevice(r->r->device()), "set device");
+        float *d_o = nullptr, *d_d = nullptr, *d_h = nullptr;
+        int* d_s = nullptr;
+        cuda_ok(cudaMalloc(&d_o, (size_t)n * 12), "malloc");
+        cuda_ok(cudaMalloc(&d_d, (size_t)n * 12), "malloc");
+        cuda_ok(cudaMalloc(&d_h, (size_t)n * 16), "malloc");
+        if (out_stats) cuda_ok(cudaMalloc(&d_s, (size_t)n * 8), "malloc");
+        cuda_ok(cudaMemcpy(d_o, org, (size_t)n * 12, cudaMemcpyHostToDevice), "h2d");
+        cuda_ok(cudaMemcpy(d_d, dir, (size_t)n * 12, cudaMemcpyHostToDevice), "h2d");
+        r->r->trace_rays_device(d_o, d_d, n, any, tmin, tmax, d_h, d_s);
+        r->r->sync();
+        cuda_ok(cudaMemcpy(out_hit, d_h, (size_t)n * 16, cudaMemcpyDeviceToHost), "d2h");
+        if (out_stats) cuda_ok(cudaMemcpy(out_stats, d_s, (size_t)n * 8, cudaMemcpyDeviceToHost), "d2h");
+        cudaFree(d_o); cudaFree(d_d); cudaFree(d_h); cudaFree(d_s);
+    });
+}
+
+// ---- MLP ----------------------------------------------------------------------------
+int hm_mlp_create(const char* config_path, int in_ch, int out_ch, int device, hm_mlp** out) {
+    return guarded([&] {
+        need(out, "out");
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            throw std::runtime_error("CUDA: no usable device (this library has no CPU path)");
+        if (device < 0 || device >= ndev) throw std::runtime_error("CUDA: device index out of range");
+        cuda_ok(cudaSetDevice(device), "set device");
+        MlpConfig cfg = config_path ? mlp_config_from_json(config_path, in_ch, out_ch) : MlpConfig();
+        cfg.in_ch = in_ch; cfg.out_ch = out_ch;
+        std::unique_ptr<hm_mlp> h(new hm_mlp);
+        cuda_ok(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "stream");
+        h->owned.reset(new Mlp(cfg, h->stream));
+        h->m = h->owned.get();
+        h->device = device;
+        *out = h.release();
+    });
+}
+void hm_mlp_destroy(hm_mlp* m) {
+    if (!m || !m->owned) return;   // renderer-owned views are not freed here
+    cudaSetDevice(m->device);
+    m->owned.reset();
+    cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+static void check_batch(int n) {
+    if (n <= 0 || n % 128 != 0) throw std::invalid_argument("batch size must be a positive multiple of 128 (tcnn common.h:280)");
+}
+
+int hm_mlp_inference(hm_mlp* m, const float* d_in, float* d_out, int n) {
+    return guarded([&] { need(m, "mlp"); need(d_in, "d_in"); need(d_out, "d_out"); check_batch(n); m->m->inference(d_in, d_out, n); });
+}
+int hm_mlp_inference_host(hm_mlp* m, const float* in, float* out, int n) {
+    return guarded([&] {
+        need(m, "mlp"); need(in, "in"); need(out, "out"); check_batch(n);
+        cuda_ok(cudaSetDevice(m->device), "set device");
+        const int ic = m->m->config().in_ch, oc = m->m->config().out_ch;
+        float *d_i = nullptr, *d_o = nullptr;
+        cuda_ok(cudaMalloc(&d_i, (size_t)n * ic * 4), "malloc");
+        cuda_ok(cudaMalloc(&d_o, (size_t)n * oc * 4), "malloc");
+        cuda_ok(cudaMemcpyAsync(d_i, in, (size_t)n * ic * 4, cudaMemcpyHostToDevice, m->stream), "h2d");
+        m->m->inference(d_i, d_o, n);
+        cuda_ok(cudaMemcpyAsync(out, d_o, (size_t)n * oc * 4, cudaMemcpyDeviceToHost, m->stream), "d2h");
+        cuda_ok(cudaStreamSynchronize(m->stream), "sync");
+        cudaFree(d_i); cudaFree(d_o);
+    });
+}
+int hm_mlp_forward_backward(hm_mlp* m, const float* d_in, const float* d_target, int n, int n_total) {
+    return guarded([&] {
+        need(m, "mlp"); need(d_in, "d_in"); need(d_target, "d_target"); check_batch(n);
+        m->m->forward_backward(d_in, d_target, n, n_total > 0 ? n_total : n);
+    });
+}
+int hm_mlp_gradients(hm_mlp* m, float** d_grads, size_t* count) {
+    return guarded([&] { need(m, "mlp"); need(d_grads, "d_grads"); need(count, "count"); *d_grads = m->m->gradients(); *count = m->m->n_params(); });
+}
+int hm_mlp_optimizer_step(hm_mlp* m) { return guarded([&] { need(m, "mlp"); m->m->optimizer_step(); }); }
+int hm_mlp_loss(hm_mlp* m, float* loss) { return guarded([&] { need(m, "mlp"); need(loss, "loss"); *loss = m->m->loss(); }); }
+int hm_mlp_train_step(hm_mlp* m, const float* d_in, const float* d_target, int n, float* loss) {
+    return guarded([&] {
+        need(m, "mlp"); need(d_in, "d_in"); need(d_target, "d_target"); check_batch(n);
+        m->m->forward_backward(d_in, d_target, n, n);
+        m->m->optimizer_step();
+        if (loss) *loss = m->m->loss();
+    });
+}
+int hm_mlp_train_step_host(hm_mlp* m, const float* in, const float* target, int n, float* loss) {
+    return guarded([&] {
+        need(m, "mlp"); need(in, "in"); need(target, "target"); check_batch(n);
+        cuda_ok(cudaSetDevice(m->device), "set device");
+        const int ic = m->m->config().in_ch, oc = m->m->config().out_ch;
+        float *d_i = nullptr, *d_t = nullptr;
+        cuda_ok(cudaMalloc(&d_i, (size_t)n * ic * 4), "malloc");
+        cuda_ok(cudaMalloc(&d_t, (size_t)n * oc * 4), "malloc");
+        cuda_ok(cudaMemcpyAsync(d_i, in, (size_t)n * ic * 4, cudaMemcpyHostToDevice, m->stream), "h2d");
+        cuda_ok(cudaMemcpyAsync(d_t, target, (size_t)n * oc * 4, cudaMemcpyHostToDevice, m->stream), "h2d");
+        m->m->forward_backward(d_i, d_t, n, n);
+        m->m->optimizer_step();
+        float l = m->m->loss();
+        if (loss) *loss = l;
+        cudaFree(d_i); cudaFree(d_t);
+    });
+}
+int hm_mlp_reset(hm_mlp* m) { return guarded([&] { need(m, "mlp"); m->m->reset_weights(); }); }
+int hm_mlp_reinitialize(hm_mlp* m) { return guarded([&] { need(m, "mlp"); m->m->reinitialize(); }); }
+size_t hm_mlp_n_params(const hm_mlp* m) { return m ? m->m->n_params() : 0; }
+int hm_mlp_get_params(hm_mlp* m, float* dst, size_t count) {
+    return guarded([&] { need(m, "mlp"); need(dst, "host_dst"); m->m->get_params(dst, count); });
+}
+int hm_mlp_set_params(hm_mlp* m, const float* src, size_t count) {
+    return guarded([&] { need(m, "mlp"); need(src, "host_src"); m->m->set_params(src, count); });
+}
+int hm_mlp_save(hm_mlp* m, const char* path) {
+    return guarded([&] {
+        need(m, "mlp"); need(path, "path");
+        std::vector<float> p(m->m->n_params());
+        m->m->get_params(p.data(), p.size());
+        std::ofstream f(path, std::ios::binary);
+        if (!f) throw hm::IoError(std::string("cannot write ") + path);
+        const char magic[8] = {'H', 'M', 'S', 'N', 'N', 'W', '1', 0};
+        uint64_t n = p.size();
+        f.write(magic, 8); f.write((const char*)&n, 8); f.write((const char*)p.data(), n * 4);
+    });
+}
+int hm_mlp_load(hm_mlp* m, const char* path) {
+    return guarded([&] {
+        need(m, "mlp"); need(path, "path");
+        std::ifstream f(path, std::ios::binary);
+        if (!f) throw hm::IoError(std::string("cannot read ") + path);
+        char magic[8]; uint64_t n = 0;
+        f.read(magic, 8); f.read((char*)&n, 8);
+        if (!f || memcmp(magic, "HMSNNW1", 7) != 0) throw std::invalid_argument("not a HairMSNN-B200 weight file");
+        if (n != m->m->n_params()) throw std::invalid_argument("weight file has a different parameter count");
+        std::vector<float> p(n);
+        f.read((char*)p.data(), n * 4);
+        if (!f) throw hm::IoError("truncated weight file");
+        m->m->set_params(p.data(), p.size());
+    });
+}
+void* hm_mlp_stream(hm_mlp* m) { return m ? (void*)m->stream : nullptr; }
+uint64_t hm_mlp_launch_count(const hm_mlp* m) { return m ? m->m->launch_count() : 0; }
+
+}  // extern "C"

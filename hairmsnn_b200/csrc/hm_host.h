@@ -36,6 +36,44 @@ struct HostBvh {
 
 void build_bvh(const HostGeometry& geo, HostBvh& out, int threads_hint = 0);
 
+// Everything parseScene produces (scene.cpp:119-339, headers/scene.h) plus the tables
+// the frame drivers derive at start-up.
+struct HostScene {
+    HostGeometry geo;
+    HostBvh bvh;
+    // camera block
+    float cam_from[3] = {0, 0, 1}, cam_to[3] = {0, 0, 0}, cam_up[3] = {0, 1, 0};
+    float cos_fovy = 0.66f;
+    // hair block (alpha already in radians: scene.cpp:207 multiplies by 3.14159f/180)
+    float sigma_a[3] = {0.06f, 0.1f, 0.2f};
+    float beta_m = 0.3f, beta_n = 0.3f, alpha = 0.f;
+    float gains[4] = {1, 1, 1, 1};
+    // lights block
+    bool has_env = false;
+    std::vector<float> env;      // RGBA32F
+    int env_w = 0, env_h = 0;
+    float env_scale = 1.f, env_rot = 0.f;
+    std::vector<float> cpdf, ccdf, mpdf, mcdf;
+    std::vector<float> dl_from;  // normalised, 3 per light
+    std::vector<float> dl_emit;
+    // integrator block
+    int width = 0, height = 0, spp = 1, path_v1 = 1, path_v2 = 40;
+    bool mis = true, env_pdf = true;
+    std::string image_output, stats_output;
+    // tcnn block
+    std::string tcnn_config, tcnn_weights;
+    bool tcnn_train = true;
+    std::string base_dir;        // directory of config.json, for relative / foreign paths
+};
+
+// scene.cpp:349-425
+void build_env_tables(HostScene& s);
+// bounds / scales as the frame drivers compute them (render_hair_msnn.cu:414-430)
+void finalize_geometry(HostScene& s);
+// cameraChanged() (render_path_tracing.cu:767-797) through the viewer's camera
+// round trip (owlViewer/Camera.cpp:94-120, Camera.h:55)
+void camera_basis(const HostScene& s, int W, int H, float pos[3], float d00[3], float du[3], float dv[3]);
+
 inline GeomView make_view(const HostGeometry& g, const HostBvh& b) {
     GeomView v;
     v.nodes = b.nodes.data();

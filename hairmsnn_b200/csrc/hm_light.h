@@ -1,0 +1,176 @@
+// hm_light.h — lat-long environment light (radiance lookup, pdf, importance sampling)
+// and directional lights.
+//
+// Behavioural contract: getEnvironmentRadiance / getEnvironmentPdf /
+// sampleEnvironmentLight (cuda_headers/optix_common.cuh:10-149) over the tables that
+// generateEnvSamplingTables builds (scene.cpp:349-425).
+//
+// The reference reads its five tables through CUDA texture objects (NEAREST/CLAMP on
+// normalised coordinates for the pdf/cdf tables, LINEAR/CLAMP for the RGBA32F map,
+// render_hair_msnn.cu:161-198).  Here they are plain arrays in HBM read with __ldg and
+// the addressing/filtering arithmetic is spelled out (CUDA C Programming Guide,
+// "Texture Fetching": i = floor(x*N) clamped; bilinear taps at x*N-0.5 with the
+// fractional weight held in 8 fractional bits).  That keeps every lookup bit-exact
+// between the sm_100a build and a host build of this same header, and the ~200 MB of
+// tables sit in B200's L2 + HBM3e without the texture path's 8-bit coordinate cache.
+#pragma once
+#include "hm_math.h"
+
+namespace hm {
+
+static constexpr int kMaxDirLights = 8;
+
+struct EnvView {
+    const float* env;   // RGBA32F, W*H*4
+    const float* cpdf;  // (W+1)*H
+    const float* ccdf;  // (W+1)*H
+    const float* mpdf;  // H+1
+    const float* mcdf;  // H+1
+    int W, H;
+    float scale, rot_phi;
+    int has_env;
+    int pdf_sampling;
+};
+
+struct LightSet {
+    EnvView env;
+    int num_dlights;
+    int num_total;
+    float dl_from[kMaxDirLights][3];   // already normalised by the scene loader (scene.cpp:263)
+    float dl_emit[kMaxDirLights][3];
+};
+
+#if defined(__CUDA_ARCH__)
+HM_D float ldf(const float* p) { return __ldg(p); }
+#else
+inline float ldf(const float* p) { return *p; }
+#endif
+
+HM_HD int clamp_idx(int v, int n) { return v < 0 ? 0 : (v > n - 1 ? n - 1 : v); }
+
+// point-sampled single-channel table, normalised coordinates, clamp addressing
+HM_HD float table_fetch(const float* t, int w, int h, float xn, float yn) {
+    int i = clamp_idx((int)floorf(xn * (float)w), w);
+    int j = clamp_idx((int)floorf(yn * (float)h), h);
+    return ldf(t + (size_t)j * w + i);
+}
+
+// bilinear RGBA fetch, normalised coordinates, clamp addressing
+HM_HD V3 env_fetch(const EnvView& e, float xn, float yn) {
+    float xb = xn * (float)e.W - 0.5f, yb = yn * (float)e.H - 0.5f;
+    float fi = floorf(xb), fj = floorf(yb);
+    int i = (int)fi, j = (int)fj;
+    float a = floorf((xb - fi) * 256.f + 0.5f) / 256.f;
+    float b = floorf((yb - fj) * 256.f + 0.5f) / 256.f;
+    int i0 = clamp_idx(i, e.W), i1 = clamp_idx(i + 1, e.W);
+    int j0 = clamp_idx(j, e.H), j1 = clamp_idx(j + 1, e.H);
+    const float* p00 = e.env + 4 * ((size_t)j0 * e.W + i0);
+    const float* p10 = e.env + 4 * ((size_t)j0 * e.W + i1);
+    const float* p01 = e.env + 4 * ((size_t)j1 * e.W + i0);
+    const float* p11 = e.env + 4 * ((size_t)j1 * e.W + i1);
+    float w00 = (1 - a) * (1 - b), w10 = a * (1 - b), w01 = (1 - a) * b, w11 = a * b;
+    V3 r;
+    r.x = w00 * ldf(p00 + 0) + w10 * ldf(p10 + 0) + w01 * ldf(p01 + 0) + w11 * ldf(p11 + 0);
+    r.y = w00 * ldf(p00 + 1) + w10 * ldf(p10 + 1) + w01 * ldf(p01 + 1) + w11 * ldf(p11 + 1);
+    r.z = w00 * ldf(p00 + 2) + w10 * ldf(p10 + 2) + w01 * ldf(p01 + 2) + w11 * ldf(p11 + 2);
+    return r;
+}
+
+HM_HD float spherical_phi(V3 v) {
+    float p = atan2f(v.y, v.x);
+    return (p < 0) ? (p + kTwoPi) : p;
+}
+HM_HD float spherical_theta(V3 v) { return acosf(v.z); }
+
+HM_HD V3 env_radiance(const EnvView& e, V3 dir) {
+    float theta = spherical_theta(dir);
+    float phi = spherical_phi(dir) + e.rot_phi;
+    if (phi > kTwoPiLoose) phi = phi - kTwoPiLoose;
+    float x = phi / kTwoPi;
+    float y = theta / kPi;
+    return e.scale * env_fetch(e, x, y);
+}
+
+HM_HD float env_pdf_from_cell(const EnvView& e, int index_u, int index_v, float sin_theta) {
+    const float width = (float)e.W, height = (float)e.H;
+    const int cw = e.W + 1, mh = e.H + 1;
+    float last_u = table_fetch(e.cpdf, cw, e.H, 1.f, index_v / height);
+    float last_v = table_fetch(e.mpdf, mh, 1, 1.f, 0.f);
+    float denom = (2.f * kPi * kPi * sin_theta) * last_u * last_v;
+    float pu = table_fetch(e.cpdf, cw, e.H, index_u / width, index_v / height);
+    float pv = table_fetch(e.mpdf, mh, 1, index_v / height, 0.f);
+    return denom ? (pu * pv) / denom : 0.f;
+}
+
+HM_HD float env_pdf(const EnvView& e, V3 wi) {
+    if (!e.pdf_sampling) return 1.f / (4.f * kPi);
+    float theta = spherical_theta(wi);
+    float phi = spherical_phi(wi) + e.rot_phi;
+    if (phi > kTwoPiLoose) phi = phi - kTwoPiLoose;
+    float u = phi / (2.f * kPi);
+    float v = theta / kPi;
+    int index_u = clampi((int)(u * e.W), 0, e.W - 1);
+    int index_v = clampi((int)(v * e.H), 0, e.H - 1);
+    return env_pdf_from_cell(e, index_u, index_v, sinf(theta));
+}
+
+// std::lower_bound over a point-sampled cdf row, as the reference spells it
+HM_HD int cdf_lower_bound(float u, const float* t, int w, int h, float yn, float size) {
+    int first = 0;
+    int count = (int)size;
+    while (count > 0) {
+        int step = count >> 1;
+        int middle = first + step;
+        if (table_fetch(t, w, h, middle / size, yn) < u) {
+            first = middle + 1;
+            count -= step + 1;
+        } else {
+            count = step;
+        }
+    }
+    return first - 1 > 0 ? first - 1 : 0;
+}
+
+HM_HD V3 uniform_sample_sphere(float u0, float u1) {
+    float z = 1 - 2 * u0;
+    float r = sqrtf(fmaxf(0.f, 1.f - z * z));
+    float phi = 2 * kPi * u1;
+    return normalize(V3(r * cosf(phi), r * sinf(phi), z));
+}
+
+// u0 = first draw (pairs with the conditional/u axis), u1 = second draw.
+// Returns radiance; wi and pdf by reference.
+HM_HD V3 env_sample(const EnvView& e, float u0, float u1, V3& wi, float& pdf) {
+    if (!e.pdf_sampling) {
+        wi = uniform_sample_sphere(u0, u1);
+        pdf = 1.f / (4.f * kPi);
+        return env_radiance(e, wi);
+    }
+    const float width = (float)e.W, height = (float)e.H;
+    const int cw = e.W + 1, mh = e.H + 1;
+
+    int index_v = cdf_lower_bound(u1, e.mcdf, mh, 1, 0.f, height);
+    float cdf_v = table_fetch(e.mcdf, mh, 1, index_v / height, 0.f);
+    float cdf_next_v = table_fetch(e.mcdf, mh, 1, (index_v + 1) / height, 0.f);
+    float dv = (cdf_next_v - u1) / (cdf_next_v - cdf_v);
+    float v = (index_v + dv) / height;
+
+    int index_u = cdf_lower_bound(u0, e.ccdf, cw, e.H, index_v / height, width);
+    float cdf_u = table_fetch(e.ccdf, cw, e.H, index_u / width, index_v / height);
+    float cdf_next_u = table_fetch(e.ccdf, cw, e.H, (index_u + 1) / width, index_v / height);
+    float du = (cdf_next_u - u0) / (cdf_next_u - cdf_u);
+    float u = (index_u + du) / width;
+
+    V3 rad = e.scale * env_fetch(e, u, v);
+
+    float theta = kPi * v;
+    float sin_theta = sinf(theta);
+    pdf = env_pdf_from_cell(e, index_u, index_v, sin_theta);
+
+    float phi = 2.f * kPi * u - e.rot_phi;
+    if (phi < 0) phi = kTwoPiLoose + phi;
+    wi = V3(sin_theta * cosf(phi), sin_theta * sinf(phi), cosf(theta));
+    return rad;
+}
+
+}  // namespace hm

@@ -1,0 +1,103 @@
+// hm_renderer.h — host frame drivers: device scene, path-state buffers, per-frame pass
+// sequencing for the three renderer kinds.
+//
+// Stands in for RenderWindowPT / RenderWindowNRC / RenderWindow_HairMSNN
+// initialize()/render()/train() (render_path_tracing.cu, render_nrc.cu,
+// render_hair_msnn.cu) minus the GLFW/ImGui shell.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "hm_host.h"
+#include "hm_mlp.h"
+#include "hm_wavefront.h"
+
+namespace hm {
+
+struct Stats {
+    double ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // primary shade extend shadow finalize train infer composite total
+    uint64_t rays_primary = 0, rays_extend = 0, rays_shadow = 0, shade_items = 0;
+    float last_loss = 0.f;
+    int frames = 0;
+};
+
+class DeviceScene {
+public:
+    explicit DeviceScene(const HostScene& hs);
+    ~DeviceScene();
+    SceneView view;
+    size_t bytes = 0;
+private:
+    std::vector<void*> allocs_;
+    template <typename T> T* upload(const T* src, size_t n);
+};
+
+class Renderer {
+public:
+    Renderer(const HostScene& hs, int kind, int beta_cli, int device, int rank, int world);
+    ~Renderer();
+
+    void render_frames(int n);          // enqueue n frames (async)
+    void sync();
+    void reset_accumulation() { accum_id_ = 0; }
+    int accum_id() const { return accum_id_; }
+    cudaStream_t stream() const { return stream_; }
+
+    // HairMSNN split frame
+    void msnn_trace();
+    void msnn_train_backward();
+    void msnn_train_apply();
+    void msnn_finish();
+    void msnn_pretrain(int steps);
+    Mlp* mlp() { return mlp_.get(); }
+
+    void* device_buffer(int which, size_t* bytes);
+    void trace_rays_device(const float* d_org, const float* d_dir, int n, int any, float tmin, float tmax,
+                           float* d_out_hit, int* d_out_stats);
+    void set_profiling(bool on) { profiling_ = on; }
+    Stats stats();
+    int width() const { return W_; }
+    int height() const { return H_; }
+    int kind() const { return kind_; }
+    int row0() const { return row0_; }
+    int row1() const { return row1_; }
+    int device() const { return device_; }
+    const HostScene& host_scene() const { return hs_; }
+
+private:
+    void frame_pt();
+    void trace_bounces(FrameParams& P, int max_vertices);
+    FrameParams base_params();
+    void shuffle_train_idxs();
+    template <typename F> void timed(int stage, F&& f);
+
+    const HostScene& hs_;
+    int kind_, beta_, device_, rank_, world_;
+    int W_, H_, row0_, row1_;
+    int accum_id_ = 0;
+    cudaStream_t stream_ = nullptr;
+    std::unique_ptr<DeviceScene> scene_;
+    Camera cam_;
+    PathBuffers paths_{};
+    Queues q_{};
+    int* h_counts_ = nullptr;      // pinned mirror of q_.counts
+    std::vector<void*> allocs_;
+    // outputs
+    float4* bufs_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // final avg/accum, pt avg/accum, nn avg/accum
+    uint32_t* fb_ = nullptr;
+    // msnn
+    std::unique_ptr<Mlp> mlp_;
+    int in_ch_ = 12, records_ = 16384, every_nth_ = 1;
+    int* d_train_idxs_ = nullptr;
+    std::vector<int> h_train_idxs_;
+    uint64_t shuffle_state_ = 0;
+    float* nn_frame_in_ = nullptr; float* nn_frame_out_ = nullptr;
+    float* nn_train_in_ = nullptr; float* nn_train_out_ = nullptr;
+    float4* gbuffer_ = nullptr;
+    bool profiling_ = false;
+    Stats stats_;
+    cudaEvent_t ev_[2] = {nullptr, nullptr};
+};
+
+}  // namespace hm

@@ -1,0 +1,410 @@
+// hm_wavefront.cu — sm_100a kernels of the wavefront path tracer.
+//
+// Replaces the reference's OptiX megakernels rayGenCam (cuda/path_tracing.cu:19-67,
+// cuda/hair_msnn.cu:187-357) and the hit/miss programs they invoke
+// (cuda_headers/optix_common.cuh:485-616).  Stages per frame:
+//
+//   primary  : pixel -> RNG stream -> camera ray -> closest hit      (coherent rays)
+//   shade    : hit -> vertex; direct-light probes (<=2 occlusion rays) + Russian
+//              roulette + BSDF continuation ray                      (ALU bound)
+//   shadow   : any-hit traversal of the occlusion queue              (L2/HBM latency)
+//   extend   : closest-hit traversal of the continuation queue       (L2/HBM latency)
+//   finalize : fold the last pending probes, write pixel / G-buffer  (HBM streaming)
+//
+// shade/shadow/extend are persistent grids (148 SMs x resident CTAs) that pull their
+// item count from device memory, so the host never synchronises inside a bounce.
+#include "hm_wavefront.h"
+
+#include <atomic>
+
+namespace hm {
+
+static std::atomic<uint64_t> g_launches{0};
+uint64_t wavefront_launch_count() { return g_launches.load(); }
+
+int wavefront_sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+namespace {
+
+constexpr int kBlock = 128;
+
+__device__ __forceinline__ float4 f4(V3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
+__device__ __forceinline__ V3 v3(float4 a) { return V3(a.x, a.y, a.z); }
+
+// Warp-aggregated append: one atomicAdd per warp, returns this lane's index (or -1).
+__device__ __forceinline__ int queue_reserve(int* counter, bool want) {
+    unsigned mask = __ballot_sync(0xffffffffu, want);
+    if (mask == 0) return -1;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(mask) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return want ? base + __popc(mask & ((1u << lane) - 1u)) : -1;
+}
+
+__device__ __forceinline__ bool is_training_pixel(const FrameParams& P, int fb_ofs, int& tr_ofs) {
+    tr_ofs = fb_ofs / P.every_nth;
+    int train_idx = __ldg(P.train_idxs + tr_ofs) % P.every_nth;
+    return fb_ofs % P.every_nth == train_idx;
+}
+
+__device__ __forceinline__ void write_nn_input(float* dst, V3 p, V3 wo, V3 t, float scene_scale) {
+    V3 point = p / scene_scale;
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    d4[0] = make_float4(point.x, point.y, point.z, wo.x);
+    d4[1] = make_float4(wo.y, wo.z, t.x, t.y);
+    d4[2] = make_float4(t.z, 0.f, 0.f, 0.f);
+}
+
+// ---------------------------------------------------------------------------------
+// primary
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_primary(const FrameParams P) {
+    const int n = (P.row1 - P.row0) * P.W;
+    const int first = P.row0 * P.W;
+    for (int base = blockIdx.x * kBlock; base < n; base += gridDim.x * kBlock) {
+        int i = base + threadIdx.x;
+        bool live = i < n;
+        bool hit_any = false;
+        int slot = first + i;
+        if (live) {
+            int px = slot % P.W, py = slot / P.W;
+            Rng rng = rng_seed(P.accum_id + 10007, (uint32_t)px, (uint32_t)py, (uint32_t)P.W);
+            float ox = rng_next(rng);
+            float oy = rng_next(rng);
+            float su = ((float)px + ox) / (float)P.W;
+            float sv = ((float)py + oy) / (float)P.H;
+            V3 o(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]);
+            V3 d = normalize(V3(P.cam.d00[0], P.cam.d00[1], P.cam.d00[2]) +
+                             su * V3(P.cam.du[0], P.cam.du[1], P.cam.du[2]) +
+                             sv * V3(P.cam.dv[0], P.cam.dv[1], P.cam.dv[2]));
+            Hit h = trace<false>(P.scene.geom, o, d, 0.f, 1e30f);
+            hit_any = h.prim >= 0;
+            P.paths.rng[slot] = rng.state;
+            P.paths.ray_o[slot] = f4(o, 0.f);
+            P.paths.ray_d[slot] = f4(d, 0.f);
+            P.paths.hit[slot] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
+            P.paths.beta[slot] = make_float4(1.f, 1.f, 1.f, __int_as_float(0));
+            P.paths.dl_light[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+            V3 c(0.f);
+            if (!hit_any && P.scene.lights.env.has_env) c = env_radiance(P.scene.lights.env, d);
+            P.paths.color[slot] = f4(c, 0.f);
+            if (P.mode == MODE_MSNN) {
+                P.paths.beta_short[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
+                P.paths.color_short[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!hit_any) {
+                    // Interaction defaults (common.cuh:46-68): p = 0, t = 0; wo = -dir
+                    write_nn_input(P.nn_frame_in + (size_t)slot * P.in_ch, V3(0.f), -1.f * d, V3(0.f), P.scene.scene_scale);
+                    int tr;
+                    if (is_training_pixel(P, slot, tr) && tr >= P.train_slot0 && tr < P.train_slot0 + P.train_slots) {
+                        write_nn_input(P.nn_train_in + (size_t)tr * P.in_ch, V3(0.f), -1.f * d, V3(0.f), P.scene.scene_scale);
+                        float* o3 = P.nn_train_out + (size_t)tr * 3;
+                        o3[0] = 0.f; o3[1] = 0.f; o3[2] = 0.f;
+                    }
+                }
+            }
+        }
+        int idx = queue_reserve(P.q.counts + 0, live && hit_any);
+        if (idx >= 0) P.q.shade[0][idx] = slot;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// shade
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void push_probe(const FrameParams& P, const Probe& pr, int slot, int bit) {
+    int idx = queue_reserve(P.q.counts + 3, pr.active);
+    if (idx >= 0) {
+        P.q.shadow[2 * (size_t)idx + 0] = make_float4(pr.o.x, pr.o.y, pr.o.z, __int_as_float(slot | (bit << 30)));
+        P.q.shadow[2 * (size_t)idx + 1] = make_float4(pr.d.x, pr.d.y, pr.d.z, 0.f);
+    }
+}
+
+__device__ __forceinline__ void fold_pending(const FrameParams& P, int slot, bool training, V3& color, V3& color_short) {
+    float4 dl = P.paths.dl_light[slot];
+    if (dl.w == 0.f) return;
+    uint32_t vis = P.paths.vis[slot];
+    V3 d = resolve_direct(v3(dl), (vis & 1u) != 0, v3(P.paths.dl_bsdf[slot]), (vis & 2u) != 0);
+    color += v3(P.paths.dl_beta[slot]) * d;
+    if (training) color_short += v3(P.paths.dl_beta_short[slot]) * d;
+}
+
+__global__ void __launch_bounds__(kBlock) k_shade(const FrameParams P, int src) {
+    const int n = P.q.counts[src];
+    const int* queue = P.q.shade[src];
+    const int rounds = (n + kBlock - 1) / kBlock;
+    for (int r = blockIdx.x; r < rounds; r += gridDim.x) {
+        int i = r * kBlock + threadIdx.x;
+        bool live = i < n;
+        int slot = live ? queue[i] : 0;
+
+        DirectSample ds;
+        ds.light.active = false; ds.bsdf.active = false;
+        bool extend = false;
+
+        if (live) {
+            Rng rng; rng.state = P.paths.rng[slot];
+            V3 ro = v3(P.paths.ray_o[slot]), rd = v3(P.paths.ray_d[slot]);
+            float4 hr = P.paths.hit[slot];
+            Hit hit; hit.t = hr.x; hit.prim = __float_as_int(hr.y); hit.u = hr.z; hit.v = hr.w;
+            float4 b4 = P.paths.beta[slot];
+            V3 beta = v3(b4);
+            int bounces = __float_as_int(b4.w);
+            V3 color = v3(P.paths.color[slot]);
+
+            int tr_ofs = 0;
+            bool training = false;
+            V3 beta_short(1.f), color_short(0.f);
+            if (P.mode == MODE_MSNN) {
+                training = is_training_pixel(P, slot, tr_ofs);
+                if (training) {
+                    beta_short = v3(P.paths.beta_short[slot]);
+                    color_short = v3(P.paths.color_short[slot]);
+                }
+            }
+
+            fold_pending(P, slot, training, color, color_short);
+
+            Vertex v = vertex_from_hit(P.scene, hit, ro, rd);
+
+            if (P.mode == MODE_MSNN && bounces == 0) {
+                write_nn_input(P.nn_frame_in + (size_t)slot * P.in_ch, v.p, v.wo, v.t, P.scene.scene_scale);
+                P.gbuffer[slot].w = __int_as_float(1 | (v.surface ? 2 : 0));
+                if (training && tr_ofs >= P.train_slot0 && tr_ofs < P.train_slot0 + P.train_slots)
+                    write_nn_input(P.nn_train_in + (size_t)tr_ofs * P.in_ch, v.p, v.wo, v.t, P.scene.scene_scale);
+            }
+
+            // direct lighting
+            const bool degenerate = P.mode == MODE_PT && P.v2_stop < P.v1_stop;   // pathTrace returns 0
+            bool do_dl = (P.mode == MODE_PT) ? (bounces >= P.v1_stop && !degenerate) : true;
+            if (do_dl) {
+                sample_direct(P.scene, v, rng, ds);
+                P.paths.dl_beta[slot] = f4(beta, 0.f);
+                if (training) P.paths.dl_beta_short[slot] = f4(beta_short, 0.f);
+                P.paths.dl_light[slot] = f4(ds.light.value, 1.f);
+                P.paths.dl_bsdf[slot] = f4(ds.bsdf.value, 0.f);
+                P.paths.vis[slot] = (ds.light.active ? 1u : 0u) | (ds.bsdf.active ? 2u : 0u);
+            } else {
+                P.paths.dl_light[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+
+            // Russian roulette (after the direct sample of every vertex but the first)
+            bool alive = !degenerate;
+            if (bounces >= 1) {
+                float q = fmaxf(0.05f, 1.f - luminance709(beta));
+                if (training) {
+                    float qs = fmaxf(0.05f, 1.f - luminance709(beta_short));
+                    float eps = rng_next(rng);
+                    if (eps < qs || bounces > P.msnn_beta) beta_short = V3(0.f);
+                    if (eps < q) alive = false;
+                    else {
+                        beta = beta / (1.f - q);
+                        if (!(beta_short == V3(0.f))) beta_short = beta_short / (1.f - qs);
+                    }
+                } else {
+                    float eps = rng_next(rng);
+                    if (eps < q) alive = false;
+                    else if (P.mode == MODE_MSNN && bounces > P.msnn_beta) alive = false;
+                    else beta = beta / (1.f - q);
+                }
+            }
+            if (alive && bounces + 1 > P.v2_stop) alive = false;
+
+            if (alive) {
+                V3 no, nd;
+                V3 mul = sample_continuation(P.scene, v, rng, no, nd);
+                beta = beta * mul;
+                if (training) beta_short = beta_short * mul;
+                P.paths.ray_o[slot] = f4(no, 0.f);
+                P.paths.ray_d[slot] = f4(nd, 0.f);
+                extend = true;
+            }
+            P.paths.rng[slot] = rng.state;
+            P.paths.beta[slot] = f4(beta, __int_as_float(bounces + 1));
+            P.paths.color[slot] = f4(color, 0.f);
+            if (training) {
+                P.paths.beta_short[slot] = f4(beta_short, 0.f);
+                P.paths.color_short[slot] = f4(color_short, 0.f);
+            }
+        }
+        push_probe(P, ds.light, slot, 0);
+        push_probe(P, ds.bsdf, slot, 1);
+        int idx = queue_reserve(P.q.counts + 2, extend);
+        if (idx >= 0) P.q.extend[idx] = slot;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// extend / shadow
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_extend(const FrameParams P, int dst) {
+    const int n = P.q.counts[2];
+    const int rounds = (n + kBlock - 1) / kBlock;
+    for (int r = blockIdx.x; r < rounds; r += gridDim.x) {
+        int i = r * kBlock + threadIdx.x;
+        bool live = i < n;
+        int slot = live ? P.q.extend[i] : 0;
+        bool hit_any = false;
+        if (live) {
+            V3 o = v3(P.paths.ray_o[slot]), d = v3(P.paths.ray_d[slot]);
+            Hit h = trace<false>(P.scene.geom, o, d, 0.f, 1e30f);
+            hit_any = h.prim >= 0;
+            if (hit_any) P.paths.hit[slot] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
+        }
+        int idx = queue_reserve(P.q.counts + dst, live && hit_any);
+        if (idx >= 0) P.q.shade[dst][idx] = slot;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_shadow(const FrameParams P) {
+    const int n = P.q.counts[3];
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+        float4 a = P.q.shadow[2 * (size_t)i + 0];
+        float4 b = P.q.shadow[2 * (size_t)i + 1];
+        int tag = __float_as_int(a.w);
+        Hit h = trace<true>(P.scene.geom, V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), 0.f, 1e30f);
+        if (h.prim >= 0) atomicAnd(P.paths.vis + (tag & 0x3fffffff), ~(1u << (tag >> 30)));
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// finalize
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_finalize(const FrameParams P) {
+    const int n = (P.row1 - P.row0) * P.W;
+    const int first = P.row0 * P.W;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int slot = first + i;
+        V3 color = v3(P.paths.color[slot]);
+        V3 color_short(0.f);
+        int tr_ofs = 0;
+        bool training = false;
+        if (P.mode == MODE_MSNN) {
+            training = is_training_pixel(P, slot, tr_ofs);
+            if (training) color_short = v3(P.paths.color_short[slot]);
+        }
+        fold_pending(P, slot, training, color, color_short);
+
+        if (P.mode == MODE_PT) {
+            // writePixel (cuda_headers/utils.cuh:13-35)
+            if (any_nan(color)) color = V3(0.f);
+            if (P.accum_id > 0) color = color + v3(P.accum[slot]);
+            P.accum[slot] = f4(color, 1.f);
+            color = (1.f / (P.accum_id + 1)) * color;
+            P.average[slot] = f4(color, 1.f);
+            P.fb[slot] = pack_rgba8(V3(linear_to_srgb(color.x), linear_to_srgb(color.y), linear_to_srgb(color.z)));
+        } else {
+            float4 hr = P.paths.hit[slot];
+            bool hit = __float_as_int(hr.y) >= 0;   // only a primary miss leaves prim < 0
+            int flags = hit ? __float_as_int(P.gbuffer[slot].w) : 0;
+            if (training) {
+                if (hit) {
+                    if (any_nan(color)) color = V3(0.f);
+                    if (any_inf(color)) color = V3(1e5f);
+                    if (any_nan(color_short)) color_short = V3(0.01f);
+                    if (any_inf(color_short)) color_short = V3(1e5f);
+                    if (tr_ofs >= P.train_slot0 && tr_ofs < P.train_slot0 + P.train_slots) {
+                        float* o3 = P.nn_train_out + (size_t)tr_ofs * 3;
+                        o3[0] = color.x - color_short.x;
+                        o3[1] = color.y - color_short.y;
+                        o3[2] = color.z - color_short.z;
+                    }
+                }
+            }
+            P.gbuffer[slot] = f4(color, __int_as_float(flags));
+        }
+    }
+}
+
+// RENDER pass of the HairMSNN program (cuda/hair_msnn.cu:314-356).
+__global__ void __launch_bounds__(256) k_msnn_composite(const MsnnComposite C) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C.count; i += gridDim.x * blockDim.x) {
+        int px = C.first + i;
+        float4 g = C.gbuffer[px];
+        int flags = __float_as_int(g.w);
+        V3 sp(g.x, g.y, g.z);
+        V3 nn(C.nn_out[3 * (size_t)px + 0], C.nn_out[3 * (size_t)px + 1], C.nn_out[3 * (size_t)px + 2]);
+        V3 color;
+        if (!(flags & 1) || (flags & 2)) { color = sp; nn = color; }
+        else color = sp + nn;
+        if (C.accum_id > 0) {
+            sp = sp + v3(C.pt_accum[px]);
+            nn = nn + v3(C.nn_accum[px]);
+            color = color + v3(C.final_accum[px]);
+        }
+        C.pt_accum[px] = f4(sp, 1.f);
+        C.nn_accum[px] = f4(nn, 1.f);
+        C.final_accum[px] = f4(color, 1.f);
+        float inv = 1.f / (C.accum_id + 1);
+        sp = inv * sp; nn = inv * nn; color = inv * color;
+        C.pt_avg[px] = f4(sp, 1.f);
+        C.nn_avg[px] = f4(nn, 1.f);
+        C.final_avg[px] = f4(color, 1.f);
+        C.fb[px] = pack_rgba8(V3(linear_to_srgb(color.x), linear_to_srgb(color.y), linear_to_srgb(color.z)));
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_trace_rays(const SceneView S, const float* org, const float* dir, int n,
+                                                        int any, float tmin, float tmax, float4* out_hit, int* out_stats) {
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+        V3 o(org[3 * i], org[3 * i + 1], org[3 * i + 2]), d(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+        TraceStats st; st.nodes = 0; st.prims = 0;
+        Hit h = any ? trace<true>(S.geom, o, d, tmin, tmax, out_stats ? &st : nullptr)
+                    : trace<false>(S.geom, o, d, tmin, tmax, out_stats ? &st : nullptr);
+        out_hit[i] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
+        if (out_stats) { out_stats[2 * i] = st.nodes; out_stats[2 * i + 1] = st.prims; }
+    }
+}
+
+int persistent_grid(int ctas_per_sm) { return wavefront_sm_count() * ctas_per_sm; }
+
+}  // namespace
+
+void launch_primary(const FrameParams& P, cudaStream_t stream) {
+    int n = (P.row1 - P.row0) * P.W;
+    int blocks = (n + kBlock - 1) / kBlock;
+    int grid = blocks < persistent_grid(16) ? blocks : persistent_grid(16);
+    if (grid < 1) grid = 1;
+    k_primary<<<grid, kBlock, 0, stream>>>(P);
+    g_launches++;
+}
+void launch_shade(const FrameParams& P, int src, cudaStream_t stream) {
+    k_shade<<<persistent_grid(8), kBlock, 0, stream>>>(P, src);
+    g_launches++;
+}
+void launch_extend(const FrameParams& P, int dst, cudaStream_t stream) {
+    k_extend<<<persistent_grid(16), kBlock, 0, stream>>>(P, dst);
+    g_launches++;
+}
+void launch_shadow(const FrameParams& P, cudaStream_t stream) {
+    k_shadow<<<persistent_grid(16), kBlock, 0, stream>>>(P);
+    g_launches++;
+}
+void launch_finalize(const FrameParams& P, cudaStream_t stream) {
+    k_finalize<<<persistent_grid(8), 256, 0, stream>>>(P);
+    g_launches++;
+}
+void launch_msnn_composite(const MsnnComposite& C, cudaStream_t stream) {
+    k_msnn_composite<<<persistent_grid(8), 256, 0, stream>>>(C);
+    g_launches++;
+}
+void launch_trace_rays(const SceneView& S, const float* org, const float* dir, int n, int any, float tmin, float tmax,
+                       float4* out_hit, int* out_stats, cudaStream_t stream) {
+    int blocks = (n + kBlock - 1) / kBlock;
+    int grid = blocks < persistent_grid(16) ? blocks : persistent_grid(16);
+    if (grid < 1) grid = 1;
+    k_trace_rays<<<grid, kBlock, 0, stream>>>(S, org, dir, n, any, tmin, tmax, out_hit, out_stats);
+    g_launches++;
+}
+
+}  // namespace hm

@@ -1,0 +1,97 @@
+// hm_wavefront.h — device-side state of the wavefront path tracer and the launch
+// entry points implemented in hm_wavefront.cu.
+//
+// One "slot" per pixel of the rank's tile rows (slot == pixel index in the FULL frame,
+// so RNG streams and training-pixel selection are independent of the partition,
+// SURVEY §8e).  Path state is SoA in HBM (float4 / u32 arrays, 128-bit accesses);
+// queues hold slot ids (extend, shade) or packed occlusion rays (shadow) and are
+// filled with warp-aggregated atomics.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hm_shade.h"
+
+namespace hm {
+
+enum PathMode { MODE_PT = 0, MODE_MSNN = 1, MODE_NRC = 2 };
+enum RendererKind { HM_KIND_PT = 0, HM_KIND_NRC = 1, HM_KIND_MSNN = 2 };
+
+struct Camera {
+    float pos[3], d00[3], du[3], dv[3];
+};
+
+struct PathBuffers {
+    uint32_t* rng;
+    float4* ray_o;
+    float4* ray_d;
+    float4* hit;         // t, prim (int bits), u, v
+    float4* beta;        // rgb, w = bounce count (int bits)
+    float4* color;       // rgb radiance so far
+    float4* dl_beta;     // throughput multiplying the pending direct sample
+    float4* dl_light;    // pending light-probe value, w = has-pending flag
+    float4* dl_bsdf;     // pending bsdf-probe value
+    uint32_t* vis;       // bit0 light probe unoccluded, bit1 bsdf probe unoccluded
+    // MSNN training paths: short-path companion
+    float4* beta_short;
+    float4* color_short;
+    float4* dl_beta_short;
+};
+
+struct Queues {
+    int* shade[2];       // double-buffered slot lists
+    int* extend;
+    float4* shadow;      // 2 x float4 per entry: (o.xyz, slot|bit<<31) (d.xyz, -)
+    int* counts;         // [0],[1] shade ; [2] extend ; [3] shadow ; [4..7] stats
+};
+
+// Everything a frame's kernels need, passed by value (fits the 4 KB param space).
+struct FrameParams {
+    SceneView scene;
+    Camera cam;
+    PathBuffers paths;
+    Queues q;
+    int W, H;            // full frame
+    int row0, row1;      // this rank's rows [row0,row1)
+    int accum_id;
+    int v1_stop, v2_stop;
+    int mode;
+    // PT outputs
+    float4* accum; float4* average; uint32_t* fb;
+    // MSNN
+    int msnn_beta;       // internal beta = CLI BETA - 1
+    int every_nth;
+    const int* train_idxs;
+    int train_slot0, train_slots;    // this rank's range of training records
+    float* nn_frame_in;  // [W*H][12]
+    float* nn_train_in;  // [records][12]
+    float* nn_train_out; // [records][3]
+    float4* gbuffer;     // rgb = short-path colour, w = flags (bit0 hit, bit1 surface)
+    int in_ch;
+};
+
+struct MsnnComposite {
+    float4* pt_accum; float4* nn_accum; float4* final_accum;
+    float4* pt_avg; float4* nn_avg; float4* final_avg;
+    uint32_t* fb;
+    const float4* gbuffer;
+    const float* nn_out;  // [W*H][3]
+    int accum_id;
+    int first, count;     // pixel range
+};
+
+// All launches are asynchronous on `stream`.
+void launch_primary(const FrameParams& P, cudaStream_t stream);
+void launch_shade(const FrameParams& P, int src_queue, cudaStream_t stream);
+void launch_extend(const FrameParams& P, int dst_queue, cudaStream_t stream);
+void launch_shadow(const FrameParams& P, cudaStream_t stream);
+void launch_finalize(const FrameParams& P, cudaStream_t stream);
+void launch_msnn_composite(const MsnnComposite& C, cudaStream_t stream);
+// test hook: closest-hit / any-hit for caller-supplied rays (device pointers)
+void launch_trace_rays(const SceneView& S, const float* org, const float* dir, int n, int any,
+                       float tmin, float tmax, float4* out_hit, int* out_stats, cudaStream_t stream);
+// test hook: vertex shading of caller-supplied hits
+int wavefront_sm_count();
+uint64_t wavefront_launch_count();
+
+}  // namespace hm

@@ -1,0 +1,226 @@
+/* hairmsnn.h — C ABI of the B200-native HairMSNN per-path rendering loop.
+ *
+ * The reference (facebookresearch/HairMSNN) has no plugin/FFI surface: the path is
+ * compiled into three executables.  This header is the boundary a maintainer would
+ * bind instead of linking OWL/OptiX + tiny-cuda-nn; each entry point cites the
+ * reference code it stands in for (paths relative to the reference root).
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success
+ * and a negative hm_status on failure; hm_last_error() gives the message of the
+ * calling thread's last failure.  No exceptions cross the boundary.  Handles are
+ * not thread-safe; independent handles may be used from different threads.
+ * There is NO CPU fallback: every compute entry point fails with HM_ERR_CUDA when
+ * no sm_100-class device is usable.
+ */
+#ifndef HAIRMSNN_H
+#define HAIRMSNN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hm_scene hm_scene;
+typedef struct hm_renderer hm_renderer;
+typedef struct hm_mlp hm_mlp;
+
+typedef enum {
+    HM_OK = 0,
+    HM_ERR_ARG = -1,      /* bad argument / malformed scene                          */
+    HM_ERR_IO = -2,       /* file missing or unreadable                               */
+    HM_ERR_CUDA = -3,     /* CUDA runtime error, or no usable device                  */
+    HM_ERR_STATE = -4,    /* call not valid for this handle (e.g. wrong renderer kind) */
+    HM_ERR_UNSUPPORTED = -5
+} hm_status;
+
+/* renderer kinds == the reference's three executables */
+enum { HM_RENDER_PATH_TRACING = 0, HM_RENDER_NRC = 1, HM_RENDER_HAIR_MSNN = 2 };
+
+/* hm_get_buffer selectors.  float4 buffers are W*H*16 bytes, FB8 is W*H*4 bytes.
+ * (viewer members accumBuffer/averageBuffer/fbPointer, OWLViewer.h:232-249;
+ *  HairMSNN's pt/nn/final triplets, render_hair_msnn.cu:139-145) */
+enum {
+    HM_BUF_FINAL_AVG = 0, HM_BUF_FINAL_ACCUM = 1,
+    HM_BUF_PT_AVG = 2, HM_BUF_PT_ACCUM = 3,
+    HM_BUF_NN_AVG = 4, HM_BUF_NN_ACCUM = 5,
+    HM_BUF_FB8 = 6,
+    HM_BUF_NN_FRAME_INPUT = 7,   /* float[W*H][in_ch]  (nnFrameInput)  */
+    HM_BUF_NN_FRAME_OUTPUT = 8,  /* float[W*H][3]      (nnFrameOutput) */
+    HM_BUF_NN_TRAIN_INPUT = 9,   /* float[records][in_ch]              */
+    HM_BUF_NN_TRAIN_OUTPUT = 10, /* float[records][3]                  */
+    HM_BUF_GBUFFER = 11,         /* float4[W*H]: rgb short-path colour, w = flags */
+    HM_BUF_TRAIN_IDXS = 12       /* int[records] (trainIdxs after this frame's shuffle) */
+};
+
+const char* hm_last_error(void);
+int hm_device_count(void);
+
+/* ---- scene -------------------------------------------------------------------- */
+
+/* parseScene(path, Scene&)  (scene.cpp:119-339): same config.json schema and
+ * defaults.  Paths inside the file that do not exist as written (the shipped scenes
+ * hold Windows absolute paths) are retried relative to the config's directory,
+ * case-insensitively. */
+int hm_scene_load(const char* config_json_path, hm_scene** out);
+
+/* A scene from arrays (synthetic benchmarks, tests).  All pointers are HOST memory
+ * and are copied.  Geometry is what Scene::extractHairData (scene.cpp:10-73) and
+ * loadOBJ (model.cpp:233-330) produce. */
+typedef struct {
+    const float* control_points;   /* [num_control_points][4] xyz + radius (phantom endpoints included) */
+    int num_control_points;
+    const int* segment_first_cp;   /* [num_segments] index of the first of 4 control points */
+    int num_segments;
+    int num_strands;
+    float hair_min[3], hair_max[3];/* bounds of the real points, grown from the origin (headers/model.h:93-94) */
+    const float* tri_vertices;     /* [num_triangles*3][3] flattened soup */
+    const float* tri_normals;      /* [num_triangles*3][3] */
+    int num_triangles;
+    float surface_kd[3];
+    float surface_alpha;
+    /* camera{} */
+    float cam_from[3], cam_to[3], cam_up[3], cos_fovy;
+    /* hair{} — alpha in RADIANS (the loader applies scene.cpp:207's degree conversion) */
+    float sigma_a[3], beta_m, beta_n, alpha, gains[4];
+    /* lights{} */
+    const float* env_rgba;         /* [env_h][env_w][4] or NULL */
+    int env_w, env_h;
+    float env_scale, env_rotation;
+    const float* dl_from;          /* [num_dlights][3], normalised here as scene.cpp:263 does */
+    const float* dl_emit;          /* [num_dlights][3] */
+    int num_dlights;
+    /* integrator{} */
+    int width, height, spp, path_v1, path_v2, mis, env_pdf;
+    /* tcnn{}: path of the tiny-cuda-nn JSON, or NULL for the shipped tcnn_hairmsnn.json values */
+    const char* tcnn_config_path;
+} hm_scene_desc;
+
+int hm_scene_create(const hm_scene_desc* desc, hm_scene** out);
+void hm_scene_free(hm_scene* scene);
+
+typedef struct {
+    int width, height, spp, path_v1, path_v2;
+    int num_segments, num_control_points, num_triangles, num_strands, num_bvh_nodes;
+    float scene_scale;
+    float cam_pos[3], cam_d00[3], cam_du[3], cam_dv[3];  /* cameraChanged(), render_path_tracing.cu:767-797 */
+    int env_w, env_h, num_dlights;
+} hm_scene_info;
+int hm_scene_get_info(const hm_scene* scene, hm_scene_info* info);
+/* host copies of the acceleration structure + geometry (test hook: lets the oracle
+ * traverse the SAME tree).  Pointers stay valid until hm_scene_free. */
+int hm_scene_get_arrays(const hm_scene* scene, const float** bvh_nodes, const int** leaf_code, const int** leaf_prim,
+                        const float** control_points, const float** tri_vertices4, const float** tri_normals4,
+                        const int** segment_first_cp);
+/* generateEnvSamplingTables (scene.cpp:349-425): cPdf/cCdf [(w+1)*h], mPdf/mCdf [h+1] */
+int hm_scene_get_env_tables(const hm_scene* scene, const float** env_rgba, const float** cpdf, const float** ccdf,
+                            const float** mpdf, const float** mcdf);
+
+/* ---- renderer ------------------------------------------------------------------ */
+
+/* RenderWindowPT / RenderWindowNRC / RenderWindow_HairMSNN ::initialize()
+ * (render_path_tracing.cu:98-402, render_nrc.cu:116-630, render_hair_msnn.cu:98-645).
+ * beta_cli is the [BETA] argument (render_hair_msnn.cu:1146-1170: internal beta = BETA-1).
+ * The frame is split into `world` contiguous row bands; this handle renders band
+ * `rank` on CUDA device `device`.  world = 1 renders everything. */
+int hm_renderer_create(hm_scene* scene, int kind, int beta_cli, int device, int rank, int world, hm_renderer** out);
+void hm_renderer_destroy(hm_renderer* r);
+
+/* n calls of RenderWindow*::render() (render_path_tracing.cu:404-423,
+ * render_hair_msnn.cu:699-771): one sample per pixel each, accumId advances. */
+int hm_render_frames(hm_renderer* r, int n_frames);
+/* same, but returns after enqueueing on the renderer's stream */
+int hm_render_frames_async(hm_renderer* r, int n_frames);
+int hm_renderer_sync(hm_renderer* r);
+/* restart accumulation (cameraChanged(): accumId = 0) */
+int hm_renderer_reset_accumulation(hm_renderer* r);
+int hm_renderer_accum_id(const hm_renderer* r);
+/* CUDA stream the renderer launches on (cudaStream_t as void*), for event timing */
+void* hm_renderer_stream(hm_renderer* r);
+
+/* HairMSNN only: the split halves of render(), for multi-GPU gradient exchange
+ * (SURVEY §8e).  trace = G_BUFFER pass; then hm_renderer_mlp() forward/backward,
+ * caller all-reduces hm_mlp_gradients(), hm_mlp_optimizer_step(); then finish =
+ * inference + RENDER pass. */
+int hm_msnn_trace(hm_renderer* r);
+int hm_msnn_train_backward(hm_renderer* r);
+int hm_msnn_train_apply(hm_renderer* r);
+int hm_msnn_finish(hm_renderer* r);
+/* deterministic stand-in for the wall-clock pre-training loop
+ * (render_hair_msnn.cu:633-641): n_steps of render-free G_BUFFER + train */
+int hm_msnn_pretrain(hm_renderer* r, int n_steps);
+hm_mlp* hm_renderer_mlp(hm_renderer* r);
+
+int hm_get_buffer(hm_renderer* r, int which, void* host_dst, size_t bytes);
+/* device pointer of the same buffers (for in-place NCCL gathers) */
+int hm_get_device_buffer(hm_renderer* r, int which, void** dev_ptr, size_t* bytes);
+
+/* OWLViewer::screenShot (OWLViewer.cpp:109-124) / saveEXR (model.cpp:366-383): rows flipped */
+int hm_save_png(hm_renderer* r, const char* path);
+int hm_save_exr(hm_renderer* r, int which, const char* path);
+/* integrator.stats_output — parsed by the reference (scene.cpp:295) but never written */
+int hm_write_stats(hm_renderer* r, const char* path);
+
+typedef struct {
+    double ms_primary, ms_shade, ms_extend, ms_shadow, ms_finalize, ms_train, ms_infer, ms_composite, ms_total;
+    uint64_t rays_primary, rays_extend, rays_shadow, shade_items;
+    uint64_t kernel_launches;
+    float last_loss;
+    int frames;
+} hm_stats;
+int hm_renderer_get_stats(hm_renderer* r, hm_stats* out);
+/* per-stage CUDA-event timing on/off (adds one event pair per stage) */
+int hm_renderer_set_profiling(hm_renderer* r, int on);
+
+/* ---- stand-alone kernels (parity tests, micro-benchmarks) ----------------------- */
+
+/* owl::traceRay (owl_device.h:153-177) for a batch of HOST rays.  any_hit = 0: closest
+ * hit (ray type 0), 1: occlusion (ray type 1).  out_hit [n][4] = t, prim (int bits),
+ * u, v; prim = segment id, or num_segments + triangle id, or -1.
+ * out_stats [n][2] = nodes visited, primitives tested (may be NULL). */
+int hm_trace_rays(hm_renderer* r, const float* org3, const float* dir3, int n, int any_hit, float tmin, float tmax,
+                  float* out_hit4, int* out_stats2);
+/* same with DEVICE pointers, asynchronous on the renderer's stream */
+int hm_trace_rays_device(hm_renderer* r, const float* d_org3, const float* d_dir3, int n, int any_hit, float tmin,
+                         float tmax, float* d_out_hit4);
+
+/* ---- MLP: TINY_MLP (cuda_headers/neural_network.cuh:33-50, cuda/neural_network.cu) ---- */
+
+/* TINY_MLP(configPath, inCh, outCh): config_path = tiny-cuda-nn JSON (NULL = the shipped
+ * tcnn_hairmsnn.json values).  Weights are initialised as tcnn does (pcg32 seeded from
+ * std::seed_seq{1337}; trainer.h:53-99). */
+int hm_mlp_create(const char* config_path, int in_ch, int out_ch, int device, hm_mlp** out);
+void hm_mlp_destroy(hm_mlp* m);
+/* TINY_MLP::inference(float* in, float* out, int n): DEVICE pointers, AoS [n][in_ch] -> [n][out_ch];
+ * n must be a multiple of 128 (tcnn batch granularity, common.h:280) */
+int hm_mlp_inference(hm_mlp* m, const float* d_in, float* d_out, int n);
+/* host-pointer convenience wrapper (copies in and out) */
+int hm_mlp_inference_host(hm_mlp* m, const float* in, float* out, int n);
+/* trainer->training_step(input, target) + trainer->loss()  (trainer.h:168-190):
+ * forward + loss + backward (+ optimizer step).  DEVICE pointers.  loss may be NULL. */
+int hm_mlp_train_step(hm_mlp* m, const float* d_in, const float* d_target, int n, float* loss);
+int hm_mlp_train_step_host(hm_mlp* m, const float* in, const float* target, int n, float* loss);
+/* split form: forward+backward with loss normalised by n_total_records (global batch), then step */
+int hm_mlp_forward_backward(hm_mlp* m, const float* d_in, const float* d_target, int n, int n_total_records);
+int hm_mlp_gradients(hm_mlp* m, float** d_grads, size_t* count);   /* fp32, loss-scaled by 128 */
+int hm_mlp_optimizer_step(hm_mlp* m);
+int hm_mlp_loss(hm_mlp* m, float* loss);
+/* TINY_MLP::reset() zeroes the weights (cuda/neural_network.cu:17-21) */
+int hm_mlp_reset(hm_mlp* m);
+int hm_mlp_reinitialize(hm_mlp* m);   /* back to the seeded initial weights + fresh optimizer */
+size_t hm_mlp_n_params(const hm_mlp* m);
+/* fp32 master parameters, tcnn order: MLP matrices first, then the hash grid
+ * (network_with_input_encoding.h:113-130) */
+int hm_mlp_get_params(hm_mlp* m, float* host_dst, size_t count);
+int hm_mlp_set_params(hm_mlp* m, const float* host_src, size_t count);
+/* Trainer::serialize / deserialize subset (trainer.h:270-310): raw little-endian blob */
+int hm_mlp_save(hm_mlp* m, const char* path);
+int hm_mlp_load(hm_mlp* m, const char* path);
+void* hm_mlp_stream(hm_mlp* m);
+uint64_t hm_mlp_launch_count(const hm_mlp* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HAIRMSNN_H */

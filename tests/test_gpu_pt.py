@@ -1,0 +1,142 @@
+"""GPU parity: the CUDA wavefront path tracer (through the C ABI) against the oracle —
+the reference's own rayGenCam / pathTrace / hit programs compiled for the host
+(oracle/_ref/libref_pt.so) traversing the SAME BVH with the SAME intersector source."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from hairmsnn_b200 import api
+from common import small_scene_kwargs, camera_rays
+from refhost import RefHost
+
+pytestmark = pytest.mark.gpu
+_fp = C.POINTER(C.c_float)
+_ip = C.POINTER(C.c_int)
+
+
+@pytest.fixture(scope="module")
+def setup():
+    kw = small_scene_kwargs(width=128, height=128, strands=1500, segs=16)
+    sc = api.Scene.from_arrays(**kw)
+    return sc, kw
+
+
+def _host_trace(probe, kw, o, d, any_hit):
+    cps = kw["control_points"]; seg = kw["segment_first_cp"]
+    tv = np.concatenate([kw["tri_vertices"], np.zeros((len(kw["tri_vertices"]), 1), np.float32)], axis=1).astype(np.float32)
+    probe.probe_scene_create.restype = C.c_void_p
+    h = C.c_void_p(probe.probe_scene_create(cps.ctypes.data_as(_fp), len(cps), seg.ctypes.data_as(_ip), len(seg),
+                                           tv.ctypes.data_as(_fp), len(tv) // 3, 0))
+    n = len(o)
+    t = np.zeros(n, np.float32); p = np.zeros(n, np.int32); u = np.zeros(n, np.float32); v = np.zeros(n, np.float32)
+    probe.probe_trace(h, n, o.ctypes.data_as(_fp), d.ctypes.data_as(_fp), C.c_float(0), C.c_float(1e30), int(any_hit),
+                      t.ctypes.data_as(_fp), p.ctypes.data_as(_ip), u.ctypes.data_as(_fp), v.ctypes.data_as(_fp), None, None)
+    probe.probe_scene_destroy(h)
+    return t, p, u, v
+
+
+def test_closest_hit_ids_bit_exact(setup, probe):
+    sc, kw = setup
+    r = api.Renderer(sc, api.PATH_TRACING)
+    o, d = camera_rays(sc.info(), 20000, seed=5)
+    g = r.trace_rays(o, d, stats=True)
+    t, p, u, v = _host_trace(probe, kw, o, d, False)
+    assert (p >= 0).mean() > 0.1
+    assert np.array_equal(g["prim"], p), "primary-hit primitive ids must be bit-exact"
+    hit = p >= 0
+    assert np.array_equal(g["t"][hit].view(np.uint32), t[hit].view(np.uint32))
+    assert np.array_equal(g["u"][hit].view(np.uint32), u[hit].view(np.uint32))
+    assert g["nodes"].max() < 5000
+
+
+def test_incoherent_and_any_hit(setup, probe):
+    sc, kw = setup
+    r = api.Renderer(sc, api.PATH_TRACING)
+    rng = np.random.default_rng(9)
+    n = 20000
+    o = rng.uniform(-40, 40, (n, 3)).astype(np.float32)
+    d = rng.standard_normal((n, 3)).astype(np.float32); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    g = r.trace_rays(o, d)
+    t, p, u, v = _host_trace(probe, kw, o, d, False)
+    assert np.array_equal(g["prim"], p)
+    ga = r.trace_rays(o, d, any_hit=True)
+    ta, pa, _, _ = _host_trace(probe, kw, o, d, True)
+    assert np.array_equal(ga["prim"] >= 0, pa >= 0), "occlusion results must agree"
+    assert np.array_equal(ga["prim"] >= 0, p >= 0), "any-hit and closest-hit must agree on hit/miss"
+
+
+def test_empty_batch_and_bad_args(setup):
+    sc, _ = setup
+    r = api.Renderer(sc, api.PATH_TRACING)
+    out = r.trace_rays(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))
+    assert out["prim"].shape == (0,)
+    with pytest.raises(api.HairMSNNError):
+        r.mlp()
+    with pytest.raises(api.HairMSNNError):
+        api.Renderer(sc, api.PATH_TRACING, device=99)
+
+
+def _compare_images(gpu, ref, frac_exact=0.97, tol=2e-3):
+    gpu = gpu[..., :3]; ref = ref[..., :3]
+    assert np.isfinite(gpu).all()
+    err = np.abs(gpu - ref).max(axis=2)
+    scale = np.maximum(np.abs(ref).max(axis=2), 1e-2)
+    close = err / scale < tol
+    # fp32 transcendental round-off differs between libdevice and glibc; a handful of
+    # paths take a different branch (lobe pick / roulette) and diverge completely
+    assert close.mean() >= frac_exact, f"only {close.mean():.4f} of pixels within {tol} rel"
+    # statistical agreement over everything
+    rel_mse = np.mean((gpu - ref) ** 2 / (ref ** 2 + 1e-2))
+    return close.mean(), rel_mse
+
+
+@pytest.mark.parametrize("mis,env_pdf", [(True, True), (False, True), (True, False)])
+def test_path_traced_frames_match_reference(mis, env_pdf):
+    kw = small_scene_kwargs(width=128, height=128, strands=1500, segs=16, mis=mis, env_pdf=env_pdf, path_v2=12)
+    sc = api.Scene.from_arrays(**kw)
+    r = api.Renderer(sc, api.PATH_TRACING)
+    ref = RefHost("pt")
+    info = ref.bind_all(sc, kw)
+    W, H = info.width, info.height
+    accum = np.zeros((H, W, 4), np.float32); avg = np.zeros((H, W, 4), np.float32)
+    for frame in range(2):
+        r.render_frames(1)
+        accum, avg, fb = ref.render_pt(frame, W, H, accum, avg)
+    g_avg = r.buffer(api.BUF_FINAL_AVG); g_acc = r.buffer(api.BUF_FINAL_ACCUM); g_fb = r.buffer(api.BUF_FB8)
+    frac, rel_mse = _compare_images(g_acc, accum)
+    assert rel_mse < 5e-3
+    # misses are pure environment lookups: bit-exact
+    o_hit = (accum[..., :3].sum(axis=2) > 0)
+    assert np.allclose(g_avg[..., 3], 1.0)
+    assert (np.abs(g_fb.view(np.uint8).astype(int) - fb.view(np.uint8).astype(int)) <= 1).mean() > 0.97
+    assert r.accum_id == 2
+
+
+def test_path_v1_skips_early_vertices():
+    kw = small_scene_kwargs(width=128, height=128, strands=800, segs=12, path_v2=6)
+    kw["path_v1"] = 3
+    sc = api.Scene.from_arrays(**kw)
+    r = api.Renderer(sc, api.PATH_TRACING)
+    ref = RefHost("pt")
+    info = ref.bind_all(sc, kw)
+    r.render_frames(1)
+    accum, avg, fb = ref.render_pt(0, info.width, info.height)
+    frac, rel_mse = _compare_images(r.buffer(api.BUF_FINAL_ACCUM), accum, frac_exact=0.95)
+    assert rel_mse < 1e-2
+
+
+def test_row_bands_reproduce_full_frame():
+    """RNG keyed by full-frame pixel index -> any partition reproduces 1-GPU streams."""
+    kw = small_scene_kwargs(width=128, height=128, strands=800, segs=12, path_v2=8)
+    sc = api.Scene.from_arrays(**kw)
+    full = api.Renderer(sc, api.PATH_TRACING)
+    full.render_frames(2)
+    ref_img = full.buffer(api.BUF_FINAL_ACCUM)
+    out = np.zeros_like(ref_img)
+    for rank in range(4):
+        r = api.Renderer(sc, api.PATH_TRACING, rank=rank, world=4)
+        r.render_frames(2)
+        img = r.buffer(api.BUF_FINAL_ACCUM)
+        out[rank * 32:(rank + 1) * 32] = img[rank * 32:(rank + 1) * 32]
+    assert np.array_equal(out.view(np.uint32), ref_img.view(np.uint32))
