@@ -141,3 +141,107 @@ void probe_trace_brute(void* p, int n, const float* org, const float* dir, float
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------
+// Host megakernel over the product's shading header (hm_shade.h): the same vertex /
+// direct-light / continuation code the CUDA shade kernel runs, driven depth-first
+// with inline traversal.  Lets the CPU suite compare the shading logic with the
+// reference host build pixel by pixel, independent of the wavefront plumbing.
+// ---------------------------------------------------------------------------------
+#include <thread>
+#include "../hairmsnn_b200/csrc/hm_shade.h"
+
+extern "C" {
+
+struct ProbeSceneDesc {
+    const float* nodes; int num_nodes; const int* leaf_code; const int* leaf_prim;
+    const float* cps; const float* tri_verts; const float* tri_normals; const int* seg_cp;
+    int num_segments, num_tris;
+    const float* env; const float* cpdf; const float* ccdf; const float* mpdf; const float* mcdf;
+    int env_w, env_h; float env_scale, env_rot; int has_env, env_pdf;
+    int num_dlights; const float* dl_from; const float* dl_emit;
+    float sigma_a[3]; float beta_m, beta_n, alpha; float gains[4];
+    float kd[3]; float surf_alpha; float scene_scale; int mis;
+    float cam_pos[3], cam_d00[3], cam_du[3], cam_dv[3];
+};
+
+static SceneView make_scene_view(const ProbeSceneDesc& d) {
+    SceneView S;
+    memset(&S, 0, sizeof(S));
+    S.geom.nodes = (const F4*)d.nodes; S.geom.num_nodes = d.num_nodes;
+    S.geom.leaf_code = d.leaf_code; S.geom.leaf_prim = d.leaf_prim;
+    S.geom.cps = (const F4*)d.cps; S.geom.tri_verts = (const F4*)d.tri_verts;
+    S.geom.num_segments = d.num_segments; S.geom.num_tris = d.num_tris;
+    S.seg_cp = d.seg_cp; S.tri_normals = (const F4*)d.tri_normals;
+    S.lights.env.env = d.env; S.lights.env.cpdf = d.cpdf; S.lights.env.ccdf = d.ccdf;
+    S.lights.env.mpdf = d.mpdf; S.lights.env.mcdf = d.mcdf;
+    S.lights.env.W = d.env_w; S.lights.env.H = d.env_h; S.lights.env.scale = d.env_scale; S.lights.env.rot_phi = d.env_rot;
+    S.lights.env.has_env = d.has_env; S.lights.env.pdf_sampling = d.env_pdf;
+    S.lights.num_dlights = d.num_dlights; S.lights.num_total = d.num_dlights + (d.has_env ? 1 : 0);
+    for (int i = 0; i < d.num_dlights; ++i)
+        for (int k = 0; k < 3; ++k) { S.lights.dl_from[i][k] = d.dl_from[3 * i + k]; S.lights.dl_emit[i][k] = d.dl_emit[3 * i + k]; }
+    S.lobes.setup(d.beta_m, d.beta_n, d.alpha);
+    S.lobes.sigma_a = V3(d.sigma_a[0], d.sigma_a[1], d.sigma_a[2]);
+    for (int i = 0; i < 4; ++i) S.lobes.gain[i] = d.gains[i];
+    for (int k = 0; k < 3; ++k) S.kd[k] = d.kd[k];
+    S.surf_alpha = d.surf_alpha; S.scene_scale = d.scene_scale; S.mis = d.mis;
+    return S;
+}
+
+static V3 probe_direct(const SceneView& S, const Vertex& v, Rng& rng) {
+    DirectSample ds;
+    sample_direct(S, v, rng, ds);
+    bool va = false, vb = false;
+    if (ds.light.active) va = trace<true>(S.geom, ds.light.o, ds.light.d, 0.f, 1e30f).prim < 0;
+    if (ds.bsdf.active) vb = trace<true>(S.geom, ds.bsdf.o, ds.bsdf.d, 0.f, 1e30f).prim < 0;
+    return resolve_direct(ds.light.value, va, ds.bsdf.value, vb);
+}
+
+// out: float[W*H*4] radiance of ONE sample per pixel (not accumulated); rows [y0,y1)
+void probe_render_pt(const ProbeSceneDesc* d, int accum_id, int W, int H, int y0, int y1, int v1_stop, int v2_stop,
+                     float* out, int threads) {
+    SceneView S = make_scene_view(*d);
+    if (threads < 1) threads = 1;
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) {
+        pool.emplace_back([=]() {
+            for (int y = y0 + t; y < y1; y += threads)
+                for (int x = 0; x < W; ++x) {
+                    Rng rng = rng_seed(accum_id + 10007, (uint32_t)x, (uint32_t)y, (uint32_t)W);
+                    float ox = rng_next(rng), oy = rng_next(rng);
+                    float su = ((float)x + ox) / (float)W, sv = ((float)y + oy) / (float)H;
+                    V3 o(d->cam_pos[0], d->cam_pos[1], d->cam_pos[2]);
+                    V3 dir = normalize(V3(d->cam_d00[0], d->cam_d00[1], d->cam_d00[2]) + su * V3(d->cam_du[0], d->cam_du[1], d->cam_du[2]) +
+                                       sv * V3(d->cam_dv[0], d->cam_dv[1], d->cam_dv[2]));
+                    Hit h = trace<false>(S.geom, o, dir, 0.f, 1e30f);
+                    V3 color(0.f);
+                    if (h.prim < 0) {
+                        if (S.lights.env.has_env) color = env_radiance(S.lights.env, dir);
+                    } else if (v2_stop >= v1_stop) {
+                        V3 beta(1.f);
+                        Vertex v = vertex_from_hit(S, h, o, dir);
+                        if (v1_stop == 0) color = probe_direct(S, v, rng);
+                        for (int b = 1; b <= v2_stop; ++b) {
+                            V3 no, nd;
+                            V3 mul = sample_continuation(S, v, rng, no, nd);
+                            beta = beta * mul;
+                            Hit nh = trace<false>(S.geom, no, nd, 0.f, 1e30f);
+                            if (nh.prim < 0) break;
+                            v = vertex_from_hit(S, nh, no, nd);
+                            if (b >= v1_stop) color += beta * probe_direct(S, v, rng);
+                            float q = fmaxf(0.05f, 1.f - luminance709(beta));
+                            float eps = rng_next(rng);
+                            if (eps < q) break;
+                            beta = beta / (1.f - q);
+                        }
+                    }
+                    if (any_nan(color)) color = V3(0.f);
+                    float* px = out + 4 * ((size_t)y * W + x);
+                    px[0] = color.x; px[1] = color.y; px[2] = color.z; px[3] = 1.f;
+                }
+        });
+    }
+    for (auto& th : pool) th.join();
+}
+
+}  // extern "C"
