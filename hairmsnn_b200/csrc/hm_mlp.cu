@@ -1,16 +1,822 @@
-// temporary stub
+// hm_mlp.cu — radiance-cache network kernels (sm_100a).
+//
+// One network configuration: Composite[HashGrid 16x2 | OneBlob 6x4 |
+// Identity] -> 64 -> 64 -> 64 -> 16(3), ReLU, no biases; RelativeL2Luminance; Adam under
+// exponential decay.  tiny-cuda-nn spreads this over ~10 kernels (encodings/grid.h:221,
+// encodings/oneblob.h:99, encodings/identity.h:46, src/fully_fused_mlp.cu:499/150,
+// losses/relative_l2_luminance.h:40, 3 CUTLASS split-K GEMMs, grid.h:395,
+// optimizers/adam.h:48); here it is
+//   k_mlp_forward<TRAIN=false> : encode + 3 layers + fp32 AoS output, one pass over HBM
+//   k_mlp_forward<TRAIN=true>  : same + saves e/h1/h2, loss value and dL/dy
+//   k_mlp_backward             : dgrad through the 3 layers + hash-grid scatter
+//   k_wgrad / k_wgrad_out      : weight gradients
+//   k_adam                     : optimizer step (+ fp16 copy, + gradient clear)
+//
+// Tiling: a CTA owns 128 rows (4 warps x 32 rows).  Activations live in shared memory as
+// fp16 [128][72] (72-half stride = conflict-free fragment loads); weights are resident
+// in shared memory for the CTA's lifetime; every warp works on its own 32 rows, so after
+// the weight load the only synchronisation is __syncwarp.  Accumulation is fp32 (the
+// reference accumulates in fp16 inside wmma — tolerance documented in tests/test_gpu_mlp.py).
 #include "hm_mlp.h"
+
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <random>
 #include <stdexcept>
+
+#include "hm_io.h"
+
 namespace hm {
-MlpConfig mlp_config_from_json(const std::string&, int in_ch, int out_ch) { MlpConfig c; c.in_ch=in_ch; c.out_ch=out_ch; return c; }
-Mlp::Mlp(const MlpConfig& cfg, cudaStream_t s) : cfg_(cfg), stream_(s) {}
-Mlp::~Mlp() {}
-void Mlp::inference(const float*, float*, int) { throw std::logic_error("mlp stub"); }
-void Mlp::forward_backward(const float*, const float*, int, int) { throw std::logic_error("mlp stub"); }
-void Mlp::optimizer_step() {}
-float Mlp::loss() { return 0.f; }
-void Mlp::reset_weights() {}
-void Mlp::reinitialize() {}
-void Mlp::get_params(float*, size_t) {}
-void Mlp::set_params(const float*, size_t) {}
+
+#define HM_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            throw std::runtime_error(std::string("CUDA: ") + cudaGetErrorString(e_) + " at " + \
+                                     __FILE__ + ":" + std::to_string(__LINE__));               \
+    } while (0)
+
+namespace {
+
+constexpr int kW = 64;          // network width
+constexpr int kOutPad = 16;     // padded output width
+constexpr int kStride = 72;     // smem row stride in halves
+constexpr int kTile = 128;      // rows per CTA
+constexpr float kLossScale = 128.f;
+
+struct NetShape {
+    GridLayout grid;
+    int in_ch;
+    int blob_dims, blob_bins, identity_dims;
+    int feats;
+    uint32_t hashed_mask;       // bit l set: level l is hashed
+};
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+
+__device__ __forceinline__ uint32_t lds32(const __half* p) { return *reinterpret_cast<const uint32_t*>(p); }
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// acc[mt][nt][4] = act(32 x 64, this warp's rows) * W^T where W is [NT*8][64] (row stride kStride)
+template <int NT>
+__device__ __forceinline__ void warp_gemm(const __half* act, const __half* W, float (&acc)[2][NT][4], int k_steps = 4) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        if (kk >= k_steps) break;
+        const int k0 = kk * 16 + t * 2;
+        uint32_t a[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const __half* r0 = act + (mt * 16 + g) * kStride + k0;
+            a[mt][0] = lds32(r0);
+            a[mt][1] = lds32(r0 + 8 * kStride);
+            a[mt][2] = lds32(r0 + 8);
+            a[mt][3] = lds32(r0 + 8 * kStride + 8);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const __half* w = W + (nt * 8 + g) * kStride + k0;
+            uint32_t b0 = lds32(w), b1 = lds32(w + 8);
+            mma16816(acc[0][nt], a[0], b0, b1);
+            mma16816(acc[1][nt], a[1], b0, b1);
+        }
+    }
+}
+
+// writes fragment values (optionally ReLU'd) back into the warp's activation rows
+template <int NT, bool RELU>
+__device__ __forceinline__ void warp_store_act(__half* act, const float (&acc)[2][NT][4]) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            float c0 = acc[mt][nt][0], c1 = acc[mt][nt][1], c2 = acc[mt][nt][2], c3 = acc[mt][nt][3];
+            if (RELU) { c0 = fmaxf(c0, 0.f); c1 = fmaxf(c1, 0.f); c2 = fmaxf(c2, 0.f); c3 = fmaxf(c3, 0.f); }
+            __half* p = act + (mt * 16 + g) * kStride + nt * 8 + t * 2;
+            *reinterpret_cast<uint32_t*>(p) = pack2(c0, c1);
+            *reinterpret_cast<uint32_t*>(p + 8 * kStride) = pack2(c2, c3);
+        }
+}
+
+// copies a [rows][64] fp16 matrix from global into shared memory with row stride kStride
+__device__ __forceinline__ void load_matrix(__half* dst, const __half* src, int rows) {
+    for (int i = threadIdx.x; i < rows * 8; i += blockDim.x) {
+        int r = i >> 3, c = i & 7;
+        *reinterpret_cast<uint4*>(dst + r * kStride + c * 8) = __ldg(reinterpret_cast<const uint4*>(src + r * kW + c * 8));
+    }
+}
+// transposed copy: dst[n][k] = src[k][n], src is [rows_k][64]; dst row stride kStride
+__device__ __forceinline__ void load_matrix_t(__half* dst, const __half* src, int rows_k) {
+    for (int i = threadIdx.x; i < rows_k * kW; i += blockDim.x) {
+        int k = i / kW, n = i % kW;
+        dst[n * kStride + k] = src[i];
+    }
+}
+
+// ---- encoding --------------------------------------------------------------------
+__device__ __forceinline__ uint32_t grid_cell_index(uint32_t x, uint32_t y, uint32_t z, uint32_t res, uint32_t size, bool hashed) {
+    uint32_t idx = hashed ? (x ^ (y * 2654435761u) ^ (z * 805459861u)) : (x + y * res + z * res * res);
+    return idx % size;
+}
+
+__device__ __forceinline__ float quartic_cdf(float x, float inv_radius) {
+    const float u = x * inv_radius;
+    const float u2 = u * u;
+    const float u4 = u2 * u2;
+    return fmaxf(0.0f, fminf(1.0f, (15.f / 16.f) * u * (1 - (2.f / 3.f) * u2 + (1.f / 5.f) * u4) + 0.5f));
+}
+
+// Encodes one input row into 64 halves at `dst` (shared memory row).
+__device__ __forceinline__ void encode_row(const NetShape& S, const __half2* __restrict__ table, const float* x, __half* dst) {
+    const int nl = S.grid.n_levels;
+    for (int l = 0; l < nl; ++l) {
+        const float scale = S.grid.scale[l];
+        const uint32_t res = S.grid.resolution[l];
+        const uint32_t size = S.grid.offset[l + 1] - S.grid.offset[l];
+        const bool hashed = (S.hashed_mask >> l) & 1u;
+        const __half2* tl = table + S.grid.offset[l];
+        float fr[3];
+        uint32_t pg[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            float pos = x[d] * scale + 0.5f;
+            float fl = floorf(pos);
+            pg[d] = (uint32_t)(int)fl;
+            fr[d] = pos - fl;
+        }
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float w = ((c & 1) ? fr[0] : 1 - fr[0]) * ((c & 2) ? fr[1] : 1 - fr[1]);
+            w *= (c & 4) ? fr[2] : 1 - fr[2];
+            uint32_t idx = grid_cell_index(pg[0] + (c & 1), pg[1] + ((c >> 1) & 1), pg[2] + ((c >> 2) & 1), res, size, hashed);
+            float2 v = __half22float2(__ldg(tl + idx));
+            acc.x += w * v.x; acc.y += w * v.y;
+        }
+        *reinterpret_cast<uint32_t*>(dst + 2 * l) = pack2(acc.x, acc.y);
+    }
+    int c0 = nl * 2;
+    const int nb = S.blob_bins;
+    const float inv_r = (float)nb;
+    for (int j = 0; j < S.blob_dims; ++j) {
+        const float xv = x[3 + j];
+        float left = quartic_cdf(-xv, inv_r) + quartic_cdf(-xv - 1.0f, inv_r) + quartic_cdf(-xv + 1.0f, inv_r);
+        for (int k = 0; k < nb; ++k) {
+            const float rb = (float)(k + 1) / (float)nb;
+            const float right = quartic_cdf(rb - xv, inv_r) + quartic_cdf(rb - xv - 1.0f, inv_r) + quartic_cdf(rb - xv + 1.0f, inv_r);
+            dst[c0 + j * nb + k] = __float2half_rn(right - left);
+            left = right;
+        }
+    }
+    c0 += S.blob_dims * nb;
+    for (int j = 0; j < S.identity_dims; ++j) dst[c0 + j] = __float2half_rn(x[3 + S.blob_dims + j]);
+    for (int c = c0 + S.identity_dims; c < kW; ++c) dst[c] = __float2half_rn(1.0f);
+}
+
+struct FwdArgs {
+    const float* in;        // [n][in_ch]
+    float* out;             // [n][3]           (inference)
+    const float* target;    // [n][3]           (training)
+    __half* e; __half* h1; __half* h2;   // [n][64] (training)
+    __half* dy;             // [n][4]           (training) loss gradient, scaled
+    float* loss;            // [1]
+    float inv_n_total;      // 1 / (records * 3)
+    int n_tiles;
+};
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(kTile) k_mlp_forward(const NetShape S, const __half* __restrict__ params, FwdArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __half* sW0 = reinterpret_cast<__half*>(smem_raw);
+    __half* sW1 = sW0 + kW * kStride;
+    __half* sWo = sW1 + kW * kStride;
+    __half* sAct = sWo + kOutPad * kStride;
+    load_matrix(sW0, params, kW);
+    load_matrix(sW1, params + kW * kW, kW);
+    load_matrix(sWo, params + 2 * kW * kW, kOutPad);
+    __syncthreads();
+    const __half2* table = reinterpret_cast<const __half2*>(params + 2 * kW * kW + kOutPad * kW);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    __half* wAct = sAct + warp * 32 * kStride;
+
+    for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+        const size_t row = (size_t)tile * kTile + threadIdx.x;
+        {
+            float x[12];
+            const float* src = A.in + row * S.in_ch;
+            if (S.in_ch == 12) {
+                const float4* s4 = reinterpret_cast<const float4*>(src);
+                float4 a = __ldg(s4), b = __ldg(s4 + 1), c = __ldg(s4 + 2);
+                x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+                x[8] = c.x; x[9] = c.y; x[10] = c.z; x[11] = c.w;
+            } else {
+                for (int i = 0; i < 12; ++i) x[i] = i < S.in_ch ? __ldg(src + i) : 0.f;
+            }
+            encode_row(S, table, x, sAct + threadIdx.x * kStride);
+        }
+        __syncwarp();
+        if (TRAIN) {
+            const uint4* s = reinterpret_cast<const uint4*>(sAct + threadIdx.x * kStride);
+            uint4* d = reinterpret_cast<uint4*>(A.e + row * kW);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d[i] = s[i];
+        }
+        float acc[2][8][4];
+        warp_gemm<8>(wAct, sW0, acc);
+        __syncwarp();
+        warp_store_act<8, true>(wAct, acc);
+        __syncwarp();
+        if (TRAIN) {
+            const uint4* s = reinterpret_cast<const uint4*>(sAct + threadIdx.x * kStride);
+            uint4* d = reinterpret_cast<uint4*>(A.h1 + row * kW);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d[i] = s[i];
+        }
+        warp_gemm<8>(wAct, sW1, acc);
+        __syncwarp();
+        warp_store_act<8, true>(wAct, acc);
+        __syncwarp();
+        if (TRAIN) {
+            const uint4* s = reinterpret_cast<const uint4*>(sAct + threadIdx.x * kStride);
+            uint4* d = reinterpret_cast<uint4*>(A.h2 + row * kW);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d[i] = s[i];
+        }
+        float o[2][1][4];
+        warp_gemm<1>(wAct, sWo, o);
+        __syncwarp();
+        // fragment: lanes t == 0 hold columns 0,1; t == 1 holds column 2 (and unused 3)
+        const size_t wrow = (size_t)tile * kTile + warp * 32;
+        float lsum = 0.f;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const size_t r = wrow + mt * 16 + hh * 8 + g;
+                // network output is held in fp16 by the reference (trim_and_cast_from)
+                float v0 = __half2float(__float2half_rn(o[mt][0][hh * 2 + 0]));
+                float v1 = __half2float(__float2half_rn(o[mt][0][hh * 2 + 1]));
+                if (!TRAIN) {
+                    if (t == 0) { A.out[r * 3 + 0] = v0; A.out[r * 3 + 1] = v1; }
+                    else if (t == 1) A.out[r * 3 + 2] = v0;
+                } else {
+                    // gather r,g,b of the row into every lane of the quad
+                    const int base = lane & ~3;
+                    float pr = __shfl_sync(0xffffffffu, v0, base), pg = __shfl_sync(0xffffffffu, v1, base);
+                    float pb = __shfl_sync(0xffffffffu, v0, base + 1);
+                    if (t < 2) {
+                        const float lum = 0.299f * pr + 0.587f * pg + 0.114f * pb;
+                        const float denom = lum * lum + 0.01f;
+                        float d0 = 0.f, d1 = 0.f;
+                        if (t == 0) {
+                            float df0 = pr - __ldg(A.target + r * 3 + 0), df1 = pg - __ldg(A.target + r * 3 + 1);
+                            lsum += df0 * df0 / denom * A.inv_n_total + df1 * df1 / denom * A.inv_n_total;
+                            d0 = kLossScale * (2 * df0 / denom) * A.inv_n_total;
+                            d1 = kLossScale * (2 * df1 / denom) * A.inv_n_total;
+                        } else {
+                            float df2 = pb - __ldg(A.target + r * 3 + 2);
+                            lsum += df2 * df2 / denom * A.inv_n_total;
+                            d0 = kLossScale * (2 * df2 / denom) * A.inv_n_total;
+                        }
+                        *reinterpret_cast<uint32_t*>(A.dy + r * 4 + t * 2) = pack2(d0, d1);
+                    }
+                }
+            }
+        if (TRAIN) {
+#pragma unroll
+            for (int ofs = 16; ofs > 0; ofs >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, ofs);
+            if (lane == 0) atomicAdd(A.loss, lsum);
+        }
+        __syncwarp();
+    }
+}
+
+// ---- backward ----------------------------------------------------------------------
+struct BwdArgs {
+    const float* in;       // [n][in_ch] (positions for the grid scatter)
+    const __half* dy;      // [n][4]
+    const __half* h1; const __half* h2;   // [n][64]
+    __half* dh1; __half* dh2;             // [n][64] out
+    float* grid_grads;     // fp32 [entries][2]
+    int n_tiles;
+};
+
+__global__ void __launch_bounds__(kTile) k_mlp_backward(const NetShape S, const __half* __restrict__ params, BwdArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __half* sW0T = reinterpret_cast<__half*>(smem_raw);       // [in 64][out 64]
+    __half* sW1T = sW0T + kW * kStride;                         // [in 64][out 64]
+    __half* sWoT = sW1T + kW * kStride;                         // [hidden 64][out 16]
+    __half* sAct = sWoT + kW * kStride;
+    load_matrix_t(sW0T, params, kW);
+    load_matrix_t(sW1T, params + kW * kW, kW);
+    load_matrix_t(sWoT, params + 2 * kW * kW, kOutPad);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    __half* wAct = sAct + warp * 32 * kStride;
+
+    for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+        const size_t wrow = (size_t)tile * kTile + warp * 32;
+        // stage dy into the activation tile: columns 0..3 from memory, 4..15 zero
+        {
+            const size_t r = wrow + lane;
+            uint2 v = __ldg(reinterpret_cast<const uint2*>(A.dy + r * 4));
+            uint32_t* d = reinterpret_cast<uint32_t*>(wAct + lane * kStride);
+            d[0] = v.x; d[1] = v.y;
+#pragma unroll
+            for (int i = 2; i < 8; ++i) d[i] = 0u;
+        }
+        __syncwarp();
+        float acc[2][8][4];
+        warp_gemm<8>(wAct, sWoT, acc, 1);    // dh2 = dy * Wout   (K = 16)
+        __syncwarp();
+        // ReLU mask from h2, store
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const size_t r = wrow + mt * 16 + hh * 8 + g;
+                    __half2 h = *reinterpret_cast<const __half2*>(A.h2 + r * kW + nt * 8 + t * 2);
+                    if (!(__low2float(h) > 0.f)) acc[mt][nt][hh * 2 + 0] = 0.f;
+                    if (!(__high2float(h) > 0.f)) acc[mt][nt][hh * 2 + 1] = 0.f;
+                }
+        warp_store_act<8, false>(wAct, acc);
+        __syncwarp();
+        {
+            const uint4* s = reinterpret_cast<const uint4*>(wAct + lane * kStride);
+            uint4* d = reinterpret_cast<uint4*>(A.dh2 + (wrow + lane) * kW);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d[i] = s[i];
+        }
+        warp_gemm<8>(wAct, sW1T, acc);       // dh1 = dh2 * W1
+        __syncwarp();
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const size_t r = wrow + mt * 16 + hh * 8 + g;
+                    __half2 h = *reinterpret_cast<const __half2*>(A.h1 + r * kW + nt * 8 + t * 2);
+                    if (!(__low2float(h) > 0.f)) acc[mt][nt][hh * 2 + 0] = 0.f;
+                    if (!(__high2float(h) > 0.f)) acc[mt][nt][hh * 2 + 1] = 0.f;
+                }
+        warp_store_act<8, false>(wAct, acc);
+        __syncwarp();
+        {
+            const uint4* s = reinterpret_cast<const uint4*>(wAct + lane * kStride);
+            uint4* d = reinterpret_cast<uint4*>(A.dh1 + (wrow + lane) * kW);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d[i] = s[i];
+        }
+        // de = dh1 * W0, only the hash-grid columns (first 2 * n_levels) are trainable inputs
+        float de[2][4][4];
+        warp_gemm<4>(wAct, sW0T, de);
+        __syncwarp();
+        // scatter: this lane holds de for rows (mt, hh) and level = nt * 4 + t (two features)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const size_t r = wrow + mt * 16 + hh * 8 + g;
+                const float* src = A.in + r * S.in_ch;
+                const float x0 = __ldg(src), x1 = __ldg(src + 1), x2 = __ldg(src + 2);
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const int l = nt * 4 + t;
+                    if (l >= S.grid.n_levels) continue;
+                    // the reference holds dL/d(encoded) in fp16 (fc_multiply output)
+                    const float g0 = __half2float(__float2half_rn(de[mt][nt][hh * 2 + 0]));
+                    const float g1 = __half2float(__float2half_rn(de[mt][nt][hh * 2 + 1]));
+                    if (g0 == 0.f && g1 == 0.f) continue;
+                    const float scale = S.grid.scale[l];
+                    const uint32_t res = S.grid.resolution[l];
+                    const uint32_t size = S.grid.offset[l + 1] - S.grid.offset[l];
+                    const bool hashed = (S.hashed_mask >> l) & 1u;
+                    float* gl = A.grid_grads + 2 * (size_t)S.grid.offset[l];
+                    float p0 = x0 * scale + 0.5f, p1 = x1 * scale + 0.5f, p2 = x2 * scale + 0.5f;
+                    float f0 = floorf(p0), f1 = floorf(p1), f2 = floorf(p2);
+                    uint32_t q0 = (uint32_t)(int)f0, q1 = (uint32_t)(int)f1, q2 = (uint32_t)(int)f2;
+                    p0 -= f0; p1 -= f1; p2 -= f2;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        float w = ((c & 1) ? p0 : 1 - p0) * ((c & 2) ? p1 : 1 - p1);
+                        w *= (c & 4) ? p2 : 1 - p2;
+                        uint32_t idx = grid_cell_index(q0 + (c & 1), q1 + ((c >> 1) & 1), q2 + ((c >> 2) & 1), res, size, hashed);
+                        // per-contribution fp16 rounding as in kernel_grid_backward's half2 atomics
+                        atomicAdd(gl + 2 * (size_t)idx + 0, __half2float(__float2half_rn(g0 * w)));
+                        atomicAdd(gl + 2 * (size_t)idx + 1, __half2float(__float2half_rn(g1 * w)));
+                    }
+                }
+            }
+        __syncwarp();
+    }
+}
+
+// dW[o][i] += sum_r D[r][o] * Aact[r][i] over a chunk of rows; D, Aact are [n][64] fp16.
+__global__ void __launch_bounds__(256) k_wgrad(const __half* __restrict__ D, const __half* __restrict__ Aact, float* __restrict__ dW,
+                                               int n, int rows_per_cta) {
+    __shared__ __align__(16) __half sD[64][kW + 8];
+    __shared__ __align__(16) __half sA[64][kW + 8];
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;   // 16 x 16 threads, 4 x 4 outputs each
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int r_begin = blockIdx.x * rows_per_cta;
+    const int r_end = min(n, r_begin + rows_per_cta);
+    for (int r0 = r_begin; r0 < r_end; r0 += 64) {
+        for (int i = threadIdx.x; i < 64 * 8; i += 256) {
+            int r = i >> 3, c = i & 7;
+            uint4 vd = make_uint4(0, 0, 0, 0), va = make_uint4(0, 0, 0, 0);
+            if (r0 + r < r_end) {
+                vd = __ldg(reinterpret_cast<const uint4*>(D + (size_t)(r0 + r) * kW + c * 8));
+                va = __ldg(reinterpret_cast<const uint4*>(Aact + (size_t)(r0 + r) * kW + c * 8));
+            }
+            *reinterpret_cast<uint4*>(&sD[r][c * 8]) = vd;
+            *reinterpret_cast<uint4*>(&sA[r][c * 8]) = va;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int r = 0; r < 64; ++r) {
+            float2 d01 = __half22float2(*reinterpret_cast<const __half2*>(&sD[r][ty * 4]));
+            float2 d23 = __half22float2(*reinterpret_cast<const __half2*>(&sD[r][ty * 4 + 2]));
+            float2 a01 = __half22float2(*reinterpret_cast<const __half2*>(&sA[r][tx * 4]));
+            float2 a23 = __half22float2(*reinterpret_cast<const __half2*>(&sA[r][tx * 4 + 2]));
+            const float d[4] = {d01.x, d01.y, d23.x, d23.y};
+            const float a[4] = {a01.x, a01.y, a23.x, a23.y};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] += d[i] * a[j];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(dW + (ty * 4 + i) * kW + tx * 4 + j, acc[i][j]);
+}
+
+// dWout[o][i] += sum_r dy[r][o] * h2[r][i], o < 4 (rows 3.. of the padded matrix get no gradient)
+__global__ void __launch_bounds__(256) k_wgrad_out(const __half* __restrict__ dy, const __half* __restrict__ h2, float* __restrict__ dW,
+                                                   int n, int rows_per_cta) {
+    const int o = threadIdx.x >> 6, i = threadIdx.x & 63;
+    const int r_begin = blockIdx.x * rows_per_cta;
+    const int r_end = min(n, r_begin + rows_per_cta);
+    float acc = 0.f;
+    for (int r = r_begin; r < r_end; ++r)
+        acc += __half2float(__ldg(dy + (size_t)r * 4 + o)) * __half2float(__ldg(h2 + (size_t)r * kW + i));
+    atomicAdd(dW + o * kW + i, acc);
+}
+
+// adam_step (optimizers/adam.h:48-120) on fp32 gradients rounded to fp16 first (tcnn's gradient
+// buffer is __half); clears the gradient for the next step.
+__global__ void __launch_bounds__(256) k_adam(size_t n, size_t n_matrix, float lr, float beta1, float beta2, float eps, float l2_reg,
+                                              float* __restrict__ master, __half* __restrict__ half_w, float* __restrict__ grads,
+                                              float* __restrict__ m1, float* __restrict__ m2, uint32_t* __restrict__ steps) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float gradient = __half2float(__float2half_rn(grads[i])) / kLossScale;
+        grads[i] = 0.f;
+        if (i >= n_matrix && gradient == 0.f) continue;
+        const float w = master[i];
+        if (i < n_matrix) gradient += l2_reg * w;
+        const float g2 = gradient * gradient;
+        const float fm = m1[i] = beta1 * m1[i] + (1 - beta1) * gradient;
+        const float sm = m2[i] = beta2 * m2[i] + (1 - beta2) * g2;
+        const uint32_t step = ++steps[i];
+        const float lr_t = lr * sqrtf(1 - powf(beta2, (float)step)) / (1 - powf(beta1, (float)step));
+        const float eff = lr_t / (sqrtf(sm) + eps);
+        const float nw = w - eff * fm;
+        master[i] = nw;
+        half_w[i] = __float2half_rn(nw);
+    }
+}
+
+__global__ void k_float_to_half(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = __float2half_rn(src[i]);
+}
+
+// pcg32 (dependencies/pcg32/pcg32.h), restated
+struct Pcg32 {
+    uint64_t state = 0, inc = 0;
+    explicit Pcg32(uint64_t initstate, uint64_t initseq = 1) {
+        state = 0; inc = (initseq << 1u) | 1u;
+        next_uint(); state += initstate; next_uint();
+    }
+    uint32_t next_uint() {
+        uint64_t old = state;
+        state = old * 0x5851f42d4c957f2dULL + inc;
+        uint32_t xs = (uint32_t)(((old >> 18u) ^ old) >> 27u);
+        uint32_t rot = (uint32_t)(old >> 59u);
+        return (xs >> rot) | (xs << ((~rot + 1u) & 31));
+    }
+    float next_float() {
+        union { uint32_t u; float f; } x;
+        x.u = (next_uint() >> 9) | 0x3f800000u;
+        return x.f - 1.0f;
+    }
+};
+
+int sm_count() {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms > 0 ? sms : 148;
+}
+
+constexpr size_t kFwdSmem = (size_t)(2 * kW + kOutPad + kTile) * kStride * sizeof(__half);
+constexpr size_t kBwdSmem = (size_t)(3 * kW + kTile) * kStride * sizeof(__half);
+
+NetShape make_shape(const MlpConfig& c, const GridLayout& g) {
+    NetShape s;
+    s.grid = g;
+    s.in_ch = c.in_ch;
+    s.blob_dims = c.blob_dims; s.blob_bins = c.blob_bins;
+    s.identity_dims = c.in_ch - c.grid_dims - c.blob_dims;
+    s.feats = c.feats;
+    s.hashed_mask = 0;
+    for (int l = 0; l < g.n_levels; ++l) {
+        // grid_index (encodings/grid.h:171-187): dense while the running stride fits the level
+        uint64_t stride = 1;
+        const uint32_t size = g.offset[l + 1] - g.offset[l];
+        for (int d = 0; d < 3 && stride <= size; ++d) stride *= g.resolution[l];
+        if (size < stride) s.hashed_mask |= 1u << l;
+    }
+    return s;
+}
+
+}  // namespace
+
+// ---- configuration -------------------------------------------------------------------
+MlpConfig mlp_config_from_json(const std::string& path, int in_ch, int out_ch) {
+    MlpConfig c;
+    c.in_ch = in_ch; c.out_ch = out_ch;
+    Json j = parse_json_file(path);
+    auto otype = [](const Json& o) { return o.has("otype") ? o.at("otype").string() : std::string(); };
+    if (const Json* loss = j.find("loss"))
+        if (otype(*loss) != "RelativeL2Luminance") throw std::invalid_argument("tcnn config: unsupported loss '" + otype(*loss) + "'");
+    if (const Json* opt = j.find("optimizer")) {
+        const Json* adam = opt;
+        if (otype(*opt) == "ExponentialDecay") {
+            if (opt->has("decay_start")) c.decay_start = (int)opt->at("decay_start").number();
+            if (opt->has("decay_interval")) c.decay_interval = (int)opt->at("decay_interval").number();
+            if (opt->has("decay_base")) c.decay_base = (float)opt->at("decay_base").number();
+            adam = &opt->at("nested");
+        } else {
+            c.decay_start = 1 << 30;
+        }
+        if (otype(*adam) != "Adam") throw std::invalid_argument("tcnn config: unsupported optimizer '" + otype(*adam) + "'");
+        if (adam->has("learning_rate")) c.lr = (float)adam->at("learning_rate").number();
+        if (adam->has("beta1")) c.beta1 = (float)adam->at("beta1").number();
+        if (adam->has("beta2")) c.beta2 = (float)adam->at("beta2").number();
+        if (adam->has("epsilon")) c.eps = (float)adam->at("epsilon").number();
+        if (adam->has("l2_reg")) c.l2_reg = (float)adam->at("l2_reg").number();
+    }
+    if (const Json* enc = j.find("encoding")) {
+        if (otype(*enc) != "Composite") throw std::invalid_argument("tcnn config: unsupported encoding '" + otype(*enc) + "'");
+        const Json& nested = enc->at("nested");
+        if (nested.arr.size() < 2) throw std::invalid_argument("tcnn config: expected HashGrid + OneBlob [+ Identity]");
+        const Json& g = nested.arr[0];
+        if (otype(g) != "HashGrid") throw std::invalid_argument("tcnn config: first nested encoding must be HashGrid");
+        if (g.has("n_dims_to_encode")) c.grid_dims = (int)g.at("n_dims_to_encode").number();
+        if (g.has("n_levels")) c.n_levels = (int)g.at("n_levels").number();
+        if (g.has("n_features_per_level")) c.feats = (int)g.at("n_features_per_level").number();
+        if (g.has("log2_hashmap_size")) c.log2_hashmap = (int)g.at("log2_hashmap_size").number();
+        if (g.has("base_resolution")) c.base_res = (int)g.at("base_resolution").number();
+        if (g.has("per_level_scale")) c.per_level_scale = (float)g.at("per_level_scale").number();
+        const Json& b = nested.arr[1];
+        if (otype(b) != "OneBlob") throw std::invalid_argument("tcnn config: second nested encoding must be OneBlob");
+        if (b.has("n_dims_to_encode")) c.blob_dims = (int)b.at("n_dims_to_encode").number();
+        if (b.has("n_bins")) c.blob_bins = (int)b.at("n_bins").number();
+        if (nested.arr.size() > 2 && otype(nested.arr[2]) != "Identity")
+            throw std::invalid_argument("tcnn config: third nested encoding must be Identity");
+    }
+    if (const Json* net = j.find("network")) {
+        if (otype(*net) != "FullyFusedMLP") throw std::invalid_argument("tcnn config: unsupported network '" + otype(*net) + "'");
+        if (net->has("n_neurons")) c.width = (int)net->at("n_neurons").number();
+        if (net->has("n_hidden_layers")) c.hidden_layers = (int)net->at("n_hidden_layers").number();
+        if (net->has("activation") && net->at("activation").string() != "ReLU") throw std::invalid_argument("tcnn config: activation must be ReLU");
+        if (net->has("output_activation") && net->at("output_activation").string() != "None")
+            throw std::invalid_argument("tcnn config: output_activation must be None");
+    }
+    return c;
+}
+
+GridLayout Mlp::grid_layout(const MlpConfig& c) {
+    GridLayout g;
+    memset(&g, 0, sizeof(g));
+    g.n_levels = c.n_levels;
+    const float log2_pls = log2f(c.per_level_scale);
+    uint32_t offset = 0;
+    for (int l = 0; l < c.n_levels; ++l) {
+        const float scale = exp2f(l * log2_pls) * c.base_res - 1.0f;          // grid_scale, grid.h:195-200
+        const uint32_t res = (uint32_t)ceilf(scale) + 1;                       // grid_resolution, grid.h:202-204
+        const uint32_t max_params = 0xffffffffu / 2;
+        uint32_t n = powf((float)res, 3.f) > (float)max_params ? max_params : res * res * res;
+        n = (n + 7u) / 8u * 8u;
+        n = std::min(n, 1u << c.log2_hashmap);
+        g.offset[l] = offset;
+        g.scale[l] = scale;
+        g.resolution[l] = res;
+        offset += n;
+    }
+    g.offset[c.n_levels] = offset;
+    return g;
+}
+
+void Mlp::initial_params(const MlpConfig& c, std::vector<float>& out, size_t& n_matrix) {
+    GridLayout g = grid_layout(c);
+    n_matrix = (size_t)kW * kW * 2 + (size_t)kOutPad * kW;
+    const size_t n_grid = (size_t)g.offset[c.n_levels] * c.feats;
+    out.assign(n_matrix + n_grid, 0.f);
+    // Trainer ctor (trainer.h:53-62)
+    std::seed_seq seq{c.seed};
+    std::vector<uint32_t> seeds(2);
+    seq.generate(seeds.begin(), seeds.end());
+    Pcg32 rng(seeds.front());
+    size_t pos = 0;
+    const int shapes[3][2] = {{kW, kW}, {kW, kW}, {kOutPad, kW}};
+    for (auto& s : shapes) {
+        const float scale = std::sqrt(6.0f / (float)(s[0] + s[1]));               // xavier uniform, gpu_matrix.h:291-305
+        for (int i = 0; i < s[0] * s[1]; ++i) out[pos++] = rng.next_float() * 2.0f * scale - scale;
+    }
+    // generate_random_kernel (random.h:66-94): thread i advances 4*i and writes elements i + T*j
+    const size_t n_thr = (n_grid + 3) / 4;
+    const size_t T = (n_thr + 127) / 128 * 128;
+    std::vector<float> stream(4 * T);
+    for (auto& f : stream) f = rng.next_float();
+    for (size_t i = 0; i < T; ++i)
+        for (size_t j = 0; j < 4; ++j) {
+            const size_t idx = i + T * j;
+            if (idx >= n_grid) break;
+            out[n_matrix + idx] = stream[4 * i + j] * (1e-4f - -1e-4f) + -1e-4f;
+        }
+}
+
+// ---- lifetime ----------------------------------------------------------------------------
+Mlp::Mlp(const MlpConfig& cfg, cudaStream_t stream) : cfg_(cfg), stream_(stream) {
+    if (cfg.width != kW || cfg.hidden_layers != 2) throw std::invalid_argument("only the 64-neuron, 2-hidden-layer network is built");
+    if (cfg.feats != 2 || cfg.grid_dims != 3 || cfg.n_levels > kMlpMaxLevels) throw std::invalid_argument("unsupported hash-grid shape");
+    if (cfg.out_ch != 3) throw std::invalid_argument("the network has 3 outputs");
+    if (cfg.in_ch > 12 || cfg.in_ch < cfg.grid_dims + cfg.blob_dims) throw std::invalid_argument("unsupported number of input channels");
+    if (2 * cfg.n_levels + cfg.blob_dims * cfg.blob_bins + (cfg.in_ch - cfg.grid_dims - cfg.blob_dims) > kW)
+        throw std::invalid_argument("encoded width exceeds 64");
+    layout_ = grid_layout(cfg);
+    std::vector<float> init;
+    initial_params(cfg, init, n_matrix_);
+    n_params_ = init.size();
+    HM_CUDA(cudaMalloc(&d_master_, n_params_ * 4));
+    HM_CUDA(cudaMalloc(&d_half_, n_params_ * 2));
+    HM_CUDA(cudaMalloc(&d_grads_, n_params_ * 4));
+    HM_CUDA(cudaMalloc(&d_m1_, n_params_ * 4));
+    HM_CUDA(cudaMalloc(&d_m2_, n_params_ * 4));
+    HM_CUDA(cudaMalloc(&d_steps_, n_params_ * 4));
+    HM_CUDA(cudaMalloc(&d_loss_, 4));
+    HM_CUDA(cudaFuncSetAttribute(k_mlp_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
+    HM_CUDA(cudaFuncSetAttribute(k_mlp_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
+    HM_CUDA(cudaFuncSetAttribute(k_mlp_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
+    reinitialize();
+}
+
+Mlp::~Mlp() {
+    cudaFree(d_master_); cudaFree(d_half_); cudaFree(d_grads_); cudaFree(d_m1_); cudaFree(d_m2_); cudaFree(d_steps_);
+    cudaFree(d_loss_); cudaFree(d_x_); cudaFree(d_h1_); cudaFree(d_h2_); cudaFree(d_dy_);
+    cudaFree(d_wpack_);
+}
+
+void Mlp::sync_half_params(bool) {
+    k_float_to_half<<<sm_count() * 4, 256, 0, stream_>>>(d_master_, (__half*)d_half_, n_params_);
+    launches_++;
+}
+
+void Mlp::reinitialize() {
+    std::vector<float> init;
+    size_t nm;
+    initial_params(cfg_, init, nm);
+    HM_CUDA(cudaMemcpyAsync(d_master_, init.data(), n_params_ * 4, cudaMemcpyHostToDevice, stream_));
+    HM_CUDA(cudaMemsetAsync(d_grads_, 0, n_params_ * 4, stream_));
+    HM_CUDA(cudaMemsetAsync(d_m1_, 0, n_params_ * 4, stream_));
+    HM_CUDA(cudaMemsetAsync(d_m2_, 0, n_params_ * 4, stream_));
+    HM_CUDA(cudaMemsetAsync(d_steps_, 0, n_params_ * 4, stream_));
+    HM_CUDA(cudaMemsetAsync(d_loss_, 0, 4, stream_));
+    sync_half_params(true);
+    HM_CUDA(cudaStreamSynchronize(stream_));
+    step_ = 0;
+    lr_factor_ = 1.f;
+}
+
+void Mlp::reset_weights() {
+    // TINY_MLP::reset (cuda/neural_network.cu:17-21): set_params(zeros) — weights only, optimizer state kept
+    HM_CUDA(cudaMemsetAsync(d_master_, 0, n_params_ * 4, stream_));
+    HM_CUDA(cudaMemsetAsync(d_half_, 0, n_params_ * 2, stream_));
+}
+
+void Mlp::get_params(float* host, size_t count) {
+    if (count > n_params_) throw std::invalid_argument("parameter count out of range");
+    HM_CUDA(cudaStreamSynchronize(stream_));
+    HM_CUDA(cudaMemcpy(host, d_master_, count * 4, cudaMemcpyDeviceToHost));
+}
+
+void Mlp::set_params(const float* host, size_t count) {
+    if (count != n_params_) throw std::invalid_argument("parameter count mismatch");
+    HM_CUDA(cudaMemcpyAsync(d_master_, host, count * 4, cudaMemcpyHostToDevice, stream_));
+    sync_half_params(true);
+    HM_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void Mlp::ensure_train_buffers(int n) {
+    if (n <= train_cap_) return;
+    cudaFree(d_x_); cudaFree(d_h1_); cudaFree(d_h2_); cudaFree(d_dy_);
+    // e, h1, h2 forward activations; dh1/dh2 reuse a second half of each allocation
+    HM_CUDA(cudaMalloc(&d_x_, (size_t)n * kW * 2));
+    HM_CUDA(cudaMalloc(&d_h1_, (size_t)n * kW * 2 * 2));
+    HM_CUDA(cudaMalloc(&d_h2_, (size_t)n * kW * 2 * 2));
+    HM_CUDA(cudaMalloc(&d_dy_, (size_t)n * 4 * 2));
+    train_cap_ = n;
+}
+
+// ---- compute -------------------------------------------------------------------------------
+void Mlp::inference(const float* d_in, float* d_out, int n) {
+    if (n % kTile != 0) throw std::invalid_argument("batch size must be a multiple of 128");
+    NetShape S = make_shape(cfg_, layout_);
+    FwdArgs A;
+    memset(&A, 0, sizeof(A));
+    A.in = d_in; A.out = d_out; A.n_tiles = n / kTile;
+    int grid = std::min(A.n_tiles, sm_count() * 4);
+    k_mlp_forward<false><<<grid, kTile, kFwdSmem, stream_>>>(S, (const __half*)d_half_, A);
+    launches_++;
+    HM_CUDA(cudaGetLastError());
+}
+
+void Mlp::forward_backward(const float* d_in, const float* d_target, int n, int n_total_records) {
+    if (n % kTile != 0) throw std::invalid_argument("batch size must be a multiple of 128");
+    ensure_train_buffers(n);
+    NetShape S = make_shape(cfg_, layout_);
+    __half* e = (__half*)d_x_;
+    __half* h1 = (__half*)d_h1_; __half* dh1 = h1 + (size_t)train_cap_ * kW;
+    __half* h2 = (__half*)d_h2_; __half* dh2 = h2 + (size_t)train_cap_ * kW;
+    HM_CUDA(cudaMemsetAsync(d_loss_, 0, 4, stream_));
+    FwdArgs A;
+    memset(&A, 0, sizeof(A));
+    A.in = d_in; A.target = d_target; A.e = e; A.h1 = h1; A.h2 = h2; A.dy = (__half*)d_dy_; A.loss = d_loss_;
+    A.inv_n_total = 1.f / (float)((size_t)n_total_records * cfg_.out_ch);
+    A.n_tiles = n / kTile;
+    int grid = std::min(A.n_tiles, sm_count() * 4);
+    k_mlp_forward<true><<<grid, kTile, kFwdSmem, stream_>>>(S, (const __half*)d_half_, A);
+    BwdArgs B;
+    B.in = d_in; B.dy = (const __half*)d_dy_; B.h1 = h1; B.h2 = h2; B.dh1 = dh1; B.dh2 = dh2;
+    B.grid_grads = d_grads_ + n_matrix_;
+    B.n_tiles = n / kTile;
+    k_mlp_backward<<<grid, kTile, kBwdSmem, stream_>>>(S, (const __half*)d_half_, B);
+    const int rows_per_cta = 256;
+    const int ctas = (n + rows_per_cta - 1) / rows_per_cta;
+    k_wgrad<<<ctas, 256, 0, stream_>>>(dh1, e, d_grads_, n, rows_per_cta);
+    k_wgrad<<<ctas, 256, 0, stream_>>>(dh2, h1, d_grads_ + kW * kW, n, rows_per_cta);
+    k_wgrad_out<<<ctas, 256, 0, stream_>>>((const __half*)d_dy_, h2, d_grads_ + 2 * kW * kW, n, rows_per_cta);
+    launches_ += 5;
+    HM_CUDA(cudaGetLastError());
+}
+
+void Mlp::optimizer_step() {
+    // ExponentialDecayOptimizer::step (optimizers/exponential_decay.h:60-71)
+    if (step_ == 0) lr_factor_ = 1.f;
+    if (step_ >= cfg_.decay_start && (step_ - cfg_.decay_start) % cfg_.decay_interval == 0) lr_factor_ *= cfg_.decay_base;
+    const float lr = cfg_.lr * lr_factor_;
+    step_++;
+    k_adam<<<sm_count() * 8, 256, 0, stream_>>>(n_params_, n_matrix_, lr, cfg_.beta1, cfg_.beta2, cfg_.eps, cfg_.l2_reg, d_master_,
+                                                  (__half*)d_half_, d_grads_, d_m1_, d_m2_, d_steps_);
+    launches_++;
+    HM_CUDA(cudaGetLastError());
+}
+
+float Mlp::loss() {
+    float v = 0.f;
+    HM_CUDA(cudaMemcpyAsync(&v, d_loss_, 4, cudaMemcpyDeviceToHost, stream_));
+    HM_CUDA(cudaStreamSynchronize(stream_));
+    return v;
+}
+
+}  // namespace hm

@@ -1,0 +1,106 @@
+"""GPU parity: render_hair_msnn's G_BUFFER pass (wavefront kernels) against the reference's own
+hair_msnn.cu compiled for the host (oracle/_ref/libref_msnn.so), and the frame loop end to end."""
+import numpy as np
+import pytest
+
+from hairmsnn_b200 import api
+from common import small_scene_kwargs
+from refhost import RefHost
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(a, b, tol=2e-3):
+    err = np.abs(a - b).max(axis=-1)
+    scale = np.maximum(np.abs(b).max(axis=-1), 1e-2)
+    return err / scale < tol
+
+
+@pytest.mark.parametrize("beta_cli", [1, 3])
+def test_gbuffer_pass_matches_reference(beta_cli):
+    W, H = 256, 128                      # 32768 pixels -> everyNth = 2
+    kw = small_scene_kwargs(width=W, height=H, strands=1500, segs=16, path_v2=10)
+    sc = api.Scene.from_arrays(**kw)
+    r = api.Renderer(sc, api.HAIR_MSNN, beta_cli=beta_cli)
+    r.msnn_trace()
+    r.sync()
+    idxs = r.buffer(api.BUF_TRAIN_IDXS)
+    assert sorted(idxs.tolist()) == list(range(16384)), "shuffle must be a permutation"
+    assert not np.array_equal(idxs, np.arange(16384))
+    ref = RefHost("msnn")
+    ref.bind_all(sc, kw)
+    nn_in, tr_in, tr_out, gb = ref.render_msnn_gbuffer(0, W, H, beta_cli - 1, 2, idxs)
+    g_in = r.buffer(api.BUF_NN_FRAME_INPUT).reshape(-1, 12)
+    g_gb = r.buffer(api.BUF_GBUFFER).reshape(-1, 4)
+    g_tr_in = r.buffer(api.BUF_NN_TRAIN_INPUT).reshape(-1, 12)
+    g_tr_out = r.buffer(api.BUF_NN_TRAIN_OUTPUT).reshape(-1, 3)
+    flags = g_gb[:, 3].copy().view(np.int32)
+    # primary-hit classification is exact (same intersector, same rays)
+    assert np.array_equal((flags & 1) != 0, gb[:, 0] != 0)
+    hit = gb[:, 0] != 0
+    assert np.array_equal(((flags & 2) != 0)[hit], (gb[:, 1] != 0)[hit])
+    assert hit.mean() > 0.15
+    # network inputs: primary vertex position / direction / tangent
+    assert np.allclose(g_in[:, :9], nn_in[:, :9], atol=2e-5)
+    assert np.all(g_in[:, 9:] == 0)
+    # short-path colour: bulk tight (see test_gpu_pt for why not all)
+    ok = _close(g_gb[:, :3], gb[:, 5:8])
+    assert ok.mean() > 0.97, ok.mean()
+    assert abs(g_gb[:, :3].mean() - gb[:, 5:8].mean()) < 0.02 * gb[:, 5:8].mean()
+    # training records
+    assert np.allclose(g_tr_in[:, :9], tr_in[:, :9], atol=2e-5)
+    okt = _close(g_tr_out, tr_out, tol=5e-3)
+    assert okt.mean() > 0.93, okt.mean()
+    assert abs(g_tr_out.mean() - tr_out.mean()) < 0.1 * abs(tr_out.mean()) + 1e-3
+
+
+def test_frame_loop_composites_and_trains():
+    W, H = 256, 128
+    kw = small_scene_kwargs(width=W, height=H, strands=1500, segs=16, path_v2=10)
+    sc = api.Scene.from_arrays(**kw)
+    r = api.Renderer(sc, api.HAIR_MSNN, beta_cli=1)
+    r.set_profiling(True)
+    r.render_frames(2)
+    r.reset_accumulation()               # cameraChanged(): accumId = 0 -> buffers restart
+    r.render_frames(1)
+    assert r.accum_id == 1
+    final, pt, nn = r.buffer(api.BUF_FINAL_AVG), r.buffer(api.BUF_PT_AVG), r.buffer(api.BUF_NN_AVG)
+    assert np.isfinite(final).all()
+    gb = r.buffer(api.BUF_GBUFFER).reshape(H, W, 4)
+    flags = gb[..., 3].copy().view(np.int32)
+    hair = ((flags & 1) != 0) & ((flags & 2) == 0)
+    # RENDER pass (cuda/hair_msnn.cu:314-356): hair pixels final = short + nn; others final = short, nn := short
+    assert np.allclose(final[hair][:, :3], pt[hair][:, :3] + nn[hair][:, :3], atol=1e-5)
+    assert np.array_equal(final[~hair][:, :3], pt[~hair][:, :3])
+    assert np.array_equal(nn[~hair][:, :3], pt[~hair][:, :3])
+    # last frame's composite against the network output buffer
+    acc = r.buffer(api.BUF_NN_ACCUM)
+    s = r.stats()
+    assert s.frames == 3 and s.kernel_launches > 20 and np.isfinite(s.last_loss) and s.last_loss > 0
+    m = r.mlp()
+    assert m.n_params == 1000448
+    p = m.get_params()
+    assert np.isfinite(p).all()
+
+
+def test_cache_learns_the_residual():
+    """With training on, nn + short-path converges towards the long-path estimate."""
+    W, H = 256, 128
+    kw = small_scene_kwargs(width=W, height=H, strands=1500, segs=16, path_v2=10)
+    sc = api.Scene.from_arrays(**kw)
+    pt = api.Renderer(sc, api.PATH_TRACING)
+    pt.render_frames(48)
+    truth = pt.buffer(api.BUF_FINAL_AVG)[..., :3]
+    r = api.Renderer(sc, api.HAIR_MSNN, beta_cli=1)
+    r.msnn_pretrain(300)
+    r.render_frames(48)
+    final = r.buffer(api.BUF_FINAL_AVG)[..., :3]
+    short = r.buffer(api.BUF_PT_AVG)[..., :3]
+    gb = r.buffer(api.BUF_GBUFFER).reshape(H, W, 4)
+    flags = gb[..., 3].copy().view(np.int32)
+    hair = ((flags & 1) != 0) & ((flags & 2) == 0)
+    e_short = np.abs(short[hair].mean(axis=0) - truth[hair].mean(axis=0)).sum()
+    e_final = np.abs(final[hair].mean(axis=0) - truth[hair].mean(axis=0)).sum()
+    print("mean |short - truth|", e_short, "mean |final - truth|", e_final)
+    assert short[hair].mean() < truth[hair].mean()          # truncated paths lose energy
+    assert e_final < 0.8 * e_short                          # the cache recovers part of it already
