@@ -64,6 +64,9 @@ class Stats(C.Structure):
         ("ms_total", C.c_double),
         ("rays_primary", C.c_uint64), ("rays_extend", C.c_uint64), ("rays_shadow", C.c_uint64), ("shade_items", C.c_uint64),
         ("kernel_launches", C.c_uint64),
+        ("stage_launches", C.c_uint64 * 8),
+        ("trav_nodes_extend", C.c_uint64), ("trav_prims_extend", C.c_uint64), ("trav_nodes_shadow", C.c_uint64),
+        ("trav_prims_shadow", C.c_uint64), ("trav_nodes_primary", C.c_uint64), ("trav_prims_primary", C.c_uint64),
         ("last_loss", C.c_float), ("frames", C.c_int),
     ]
 
@@ -344,6 +347,15 @@ class Renderer:
 
     def set_profiling(self, on):
         _check(lib.hm_renderer_set_profiling(self._h, int(on)))
+
+    def set_collect_stats(self, on):
+        _check(lib.hm_renderer_set_collect_stats(self._h, int(on)))
+
+    def reset_stats(self):
+        _check(lib.hm_renderer_reset_stats(self._h))
+
+    def set_frame_schedule(self, offset, stride):
+        _check(lib.hm_renderer_set_frame_schedule(self._h, offset, stride))
 
     def stats(self):
         s = Stats()

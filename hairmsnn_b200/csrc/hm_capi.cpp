@@ -67,6 +67,8 @@ extern "C" {
 
 const char* hm_last_error(void) { return g_err.c_str(); }
 
+int hm_frame_param_bytes(void) { return (int)sizeof(hm::FrameParams); }
+
 int hm_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -300,8 +302,25 @@ int hm_renderer_get_stats(hm_renderer* r, hm_stats* out) {
         out->rays_primary = s.rays_primary; out->rays_extend = s.rays_extend; out->rays_shadow = s.rays_shadow;
         out->shade_items = s.shade_items;
         out->kernel_launches = wavefront_launch_count() + (r->r->mlp() ? r->r->mlp()->launch_count() : 0);
+        for (int i = 0; i < 8; ++i) out->stage_launches[i] = s.launches[i];
+        out->trav_nodes_extend = s.trav[0]; out->trav_prims_extend = s.trav[1];
+        out->trav_nodes_shadow = s.trav[2]; out->trav_prims_shadow = s.trav[3];
+        out->trav_nodes_primary = s.trav[4]; out->trav_prims_primary = s.trav[5];
         out->last_loss = s.last_loss;
         out->frames = s.frames;
+    });
+}
+int hm_renderer_set_collect_stats(hm_renderer* r, int on) {
+    return guarded([&] { need(r, "renderer"); r->r->set_collect_stats(on != 0); });
+}
+int hm_renderer_reset_stats(hm_renderer* r) {
+    return guarded([&] { need(r, "renderer"); r->r->reset_stats(); });
+}
+int hm_renderer_set_frame_schedule(hm_renderer* r, int offset, int stride) {
+    return guarded([&] {
+        need(r, "renderer");
+        if (stride < 1 || offset < 0) throw std::invalid_argument("bad frame schedule");
+        r->r->set_frame_schedule(offset, stride);
     });
 }
 int hm_renderer_set_profiling(hm_renderer* r, int on) {

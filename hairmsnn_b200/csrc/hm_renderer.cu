@@ -98,8 +98,6 @@ Renderer::Renderer(const HostScene& hs, int kind, int beta_cli, int device, int 
     row0_ = (int)((int64_t)H_ * rank / world);
     row1_ = (int)((int64_t)H_ * (rank + 1) / world);
     HM_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-    HM_CUDA(cudaEventCreate(&ev_[0]));
-    HM_CUDA(cudaEventCreate(&ev_[1]));
     scene_.reset(new DeviceScene(hs));
     camera_basis(hs, W_, H_, cam_.pos, cam_.d00, cam_.du, cam_.dv);
 
@@ -131,6 +129,8 @@ Renderer::Renderer(const HostScene& hs, int kind, int beta_cli, int device, int 
     q_.extend = (int*)alloc(n * 4);
     q_.shadow = (float4*)alloc(n * 2 * 32);
     q_.counts = (int*)alloc(16 * 4);
+    d_trav_ = (unsigned long long*)alloc(8 * 8);
+    q_.trav = d_trav_;
     HM_CUDA(cudaMallocHost((void**)&h_counts_, 16 * 4));
     memset(h_counts_, 0, 16 * 4);
 
@@ -167,8 +167,8 @@ Renderer::~Renderer() {
     for (void* p : allocs_) cudaFree(p);
     if (h_counts_) cudaFreeHost(h_counts_);
     scene_.reset();
-    if (ev_[0]) cudaEventDestroy(ev_[0]);
-    if (ev_[1]) cudaEventDestroy(ev_[1]);
+    for (auto& p : pending_) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto e : event_pool_) cudaEventDestroy(e);
     if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -177,16 +177,42 @@ void Renderer::sync() {
     HM_CUDA(cudaStreamSynchronize(stream_));
 }
 
+cudaEvent_t Renderer::take_event() {
+    if (!event_pool_.empty()) { cudaEvent_t e = event_pool_.back(); event_pool_.pop_back(); return e; }
+    cudaEvent_t e;
+    HM_CUDA(cudaEventCreate(&e));
+    return e;
+}
+
+// Event pairs are recorded around each stage launch and resolved later, so profiling does
+// not add host synchronisation inside the frame.
 template <typename F>
 void Renderer::timed(int stage, F&& f) {
+    stats_.launches[stage]++;
     if (!profiling_) { f(); return; }
-    HM_CUDA(cudaEventRecord(ev_[0], stream_));
+    Pending p{stage, take_event(), take_event()};
+    HM_CUDA(cudaEventRecord(p.a, stream_));
     f();
-    HM_CUDA(cudaEventRecord(ev_[1], stream_));
-    HM_CUDA(cudaEventSynchronize(ev_[1]));
-    float ms = 0.f;
-    HM_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
-    stats_.ms[stage] += ms;
+    HM_CUDA(cudaEventRecord(p.b, stream_));
+    pending_.push_back(p);
+}
+
+void Renderer::resolve_events() {
+    if (pending_.empty()) return;
+    HM_CUDA(cudaStreamSynchronize(stream_));
+    for (auto& p : pending_) {
+        float ms = 0.f;
+        HM_CUDA(cudaEventElapsedTime(&ms, p.a, p.b));
+        stats_.ms[p.stage] += ms;
+        event_pool_.push_back(p.a); event_pool_.push_back(p.b);
+    }
+    pending_.clear();
+}
+
+void Renderer::reset_stats() {
+    resolve_events();
+    stats_ = Stats();
+    cudaMemsetAsync(d_trav_, 0, 8 * 8, stream_);
 }
 
 FrameParams Renderer::base_params() {
@@ -199,6 +225,8 @@ FrameParams Renderer::base_params() {
     P.W = W_; P.H = H_;
     P.row0 = row0_; P.row1 = row1_;
     P.accum_id = accum_id_;
+    P.frame_id = frame_offset_ + accum_id_ * frame_stride_;
+    P.collect_stats = collect_stats_ ? 1 : 0;
     P.v1_stop = hs_.path_v1 - 1;
     P.v2_stop = hs_.path_v2 - 1;
     P.accum = bufs_[1]; P.average = bufs_[0]; P.fb = fb_;
@@ -221,7 +249,7 @@ void Renderer::trace_bounces(FrameParams& P, int max_vertices) {
         const bool last = vertex + 1 >= max_vertices;
         // Long paths (PT, training paths): look at the queue sizes every few vertices so
         // the loop ends once every path died.  Short HairMSNN paths never synchronise.
-        const bool poll = profiling_ || (!last && max_vertices > 4 && (vertex & 1) == 1);
+        const bool poll = collect_stats_ || (!last && max_vertices > 4 && (vertex & 1) == 1);
         if (poll) {
             HM_CUDA(cudaMemcpyAsync(h_counts_, q_.counts, 16 * 4, cudaMemcpyDeviceToHost, stream_));
             HM_CUDA(cudaStreamSynchronize(stream_));
@@ -330,10 +358,10 @@ void Renderer::msnn_pretrain(int steps) {
 void Renderer::render_frames(int n) {
     HM_CUDA(cudaSetDevice(device_));
     for (int i = 0; i < n; ++i) {
-        cudaEvent_t t0 = nullptr, t1 = nullptr;
+        Pending whole{8, nullptr, nullptr};
         if (profiling_) {
-            HM_CUDA(cudaEventCreate(&t0)); HM_CUDA(cudaEventCreate(&t1));
-            HM_CUDA(cudaEventRecord(t0, stream_));
+            whole.a = take_event(); whole.b = take_event();
+            HM_CUDA(cudaEventRecord(whole.a, stream_));
         }
         if (kind_ == HM_KIND_PT) {
             frame_pt();
@@ -349,19 +377,20 @@ void Renderer::render_frames(int n) {
         } else {
             throw std::logic_error("render_nrc is not implemented in this build");
         }
-        if (profiling_) {
-            HM_CUDA(cudaEventRecord(t1, stream_));
-            HM_CUDA(cudaEventSynchronize(t1));
-            float ms = 0.f;
-            HM_CUDA(cudaEventElapsedTime(&ms, t0, t1));
-            stats_.ms[8] += ms;
-            cudaEventDestroy(t0); cudaEventDestroy(t1);
+        if (whole.a) {
+            HM_CUDA(cudaEventRecord(whole.b, stream_));
+            pending_.push_back(whole);
         }
     }
 }
 
 Stats Renderer::stats() {
-    if (mlp_ && profiling_) stats_.last_loss = mlp_->loss();
+    resolve_events();
+    if (mlp_) stats_.last_loss = mlp_->loss();
+    HM_CUDA(cudaStreamSynchronize(stream_));
+    unsigned long long t[8];
+    HM_CUDA(cudaMemcpy(t, d_trav_, sizeof(t), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 6; ++i) stats_.trav[i] = t[i];
     return stats_;
 }
 

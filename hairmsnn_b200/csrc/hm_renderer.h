@@ -17,7 +17,9 @@ namespace hm {
 
 struct Stats {
     double ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // primary shade extend shadow finalize train infer composite total
+    uint64_t launches[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t rays_primary = 0, rays_extend = 0, rays_shadow = 0, shade_items = 0;
+    uint64_t trav[6] = {0, 0, 0, 0, 0, 0};        // extend nodes/prims, shadow nodes/prims, primary nodes/prims
     float last_loss = 0.f;
     int frames = 0;
 };
@@ -56,6 +58,10 @@ public:
     void trace_rays_device(const float* d_org, const float* d_dir, int n, int any, float tmin, float tmax,
                            float* d_out_hit, int* d_out_stats);
     void set_profiling(bool on) { profiling_ = on; }
+    void set_collect_stats(bool on) { collect_stats_ = on; }
+    // spp sharding: RNG frame id = offset + accum_id * stride (accum_id counts this renderer's own samples)
+    void set_frame_schedule(int offset, int stride) { frame_offset_ = offset; frame_stride_ = stride; }
+    void reset_stats();
     Stats stats();
     int width() const { return W_; }
     int height() const { return H_; }
@@ -95,9 +101,15 @@ private:
     float* nn_frame_in_ = nullptr; float* nn_frame_out_ = nullptr;
     float* nn_train_in_ = nullptr; float* nn_train_out_ = nullptr;
     float4* gbuffer_ = nullptr;
-    bool profiling_ = false;
+    bool profiling_ = false, collect_stats_ = false;
+    int frame_offset_ = 0, frame_stride_ = 1;
     Stats stats_;
-    cudaEvent_t ev_[2] = {nullptr, nullptr};
+    struct Pending { int stage; cudaEvent_t a, b; };
+    std::vector<Pending> pending_;
+    std::vector<cudaEvent_t> event_pool_;
+    cudaEvent_t take_event();
+    void resolve_events();
+    unsigned long long* d_trav_ = nullptr;
 };
 
 }  // namespace hm

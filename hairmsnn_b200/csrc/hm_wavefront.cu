@@ -58,6 +58,13 @@ __device__ __forceinline__ bool is_training_pixel(const FrameParams& P, int fb_o
     return fb_ofs % P.every_nth == train_idx;
 }
 
+__device__ __forceinline__ void flush_trav(unsigned long long* dst, const TraceStats& st) {
+    unsigned n = (unsigned)st.nodes, p = (unsigned)st.prims;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { n += __shfl_xor_sync(0xffffffffu, n, o); p += __shfl_xor_sync(0xffffffffu, p, o); }
+    if ((threadIdx.x & 31) == 0 && (n | p)) { atomicAdd(dst, (unsigned long long)n); atomicAdd(dst + 1, (unsigned long long)p); }
+}
+
 __device__ __forceinline__ void write_nn_input(float* dst, V3 p, V3 wo, V3 t, float scene_scale) {
     V3 point = p / scene_scale;
     float4* d4 = reinterpret_cast<float4*>(dst);
@@ -72,6 +79,7 @@ __device__ __forceinline__ void write_nn_input(float* dst, V3 p, V3 wo, V3 t, fl
 __global__ void __launch_bounds__(kBlock) k_primary(const FrameParams P) {
     const int n = (P.row1 - P.row0) * P.W;
     const int first = P.row0 * P.W;
+    TraceStats st; st.nodes = 0; st.prims = 0;
     for (int base = blockIdx.x * kBlock; base < n; base += gridDim.x * kBlock) {
         int i = base + threadIdx.x;
         bool live = i < n;
@@ -79,7 +87,7 @@ __global__ void __launch_bounds__(kBlock) k_primary(const FrameParams P) {
         int slot = first + i;
         if (live) {
             int px = slot % P.W, py = slot / P.W;
-            Rng rng = rng_seed(P.accum_id + 10007, (uint32_t)px, (uint32_t)py, (uint32_t)P.W);
+            Rng rng = rng_seed(P.frame_id + 10007, (uint32_t)px, (uint32_t)py, (uint32_t)P.W);
             float ox = rng_next(rng);
             float oy = rng_next(rng);
             float su = ((float)px + ox) / (float)P.W;
@@ -88,7 +96,7 @@ __global__ void __launch_bounds__(kBlock) k_primary(const FrameParams P) {
             V3 d = normalize(V3(P.cam.d00[0], P.cam.d00[1], P.cam.d00[2]) +
                              su * V3(P.cam.du[0], P.cam.du[1], P.cam.du[2]) +
                              sv * V3(P.cam.dv[0], P.cam.dv[1], P.cam.dv[2]));
-            Hit h = trace<false>(P.scene.geom, o, d, 0.f, 1e30f);
+            Hit h = trace<false>(P.scene.geom, o, d, 0.f, 1e30f, P.collect_stats ? &st : nullptr);
             hit_any = h.prim >= 0;
             P.paths.rng[slot] = rng.state;
             P.paths.ray_o[slot] = f4(o, 0.f);
@@ -117,6 +125,7 @@ __global__ void __launch_bounds__(kBlock) k_primary(const FrameParams P) {
         int idx = queue_reserve(P.q.counts + 0, live && hit_any);
         if (idx >= 0) P.q.shade[0][idx] = slot;
     }
+    if (P.collect_stats) flush_trav(P.q.trav + 4, st);
 }
 
 // ---------------------------------------------------------------------------------
@@ -250,6 +259,7 @@ __global__ void __launch_bounds__(kBlock) k_shade(const FrameParams P, int src) 
 __global__ void __launch_bounds__(kBlock) k_extend(const FrameParams P, int dst) {
     const int n = P.q.counts[2];
     const int rounds = (n + kBlock - 1) / kBlock;
+    TraceStats st; st.nodes = 0; st.prims = 0;
     for (int r = blockIdx.x; r < rounds; r += gridDim.x) {
         int i = r * kBlock + threadIdx.x;
         bool live = i < n;
@@ -257,24 +267,27 @@ __global__ void __launch_bounds__(kBlock) k_extend(const FrameParams P, int dst)
         bool hit_any = false;
         if (live) {
             V3 o = v3(P.paths.ray_o[slot]), d = v3(P.paths.ray_d[slot]);
-            Hit h = trace<false>(P.scene.geom, o, d, 0.f, 1e30f);
+            Hit h = trace<false>(P.scene.geom, o, d, 0.f, 1e30f, P.collect_stats ? &st : nullptr);
             hit_any = h.prim >= 0;
             if (hit_any) P.paths.hit[slot] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
         }
         int idx = queue_reserve(P.q.counts + dst, live && hit_any);
         if (idx >= 0) P.q.shade[dst][idx] = slot;
     }
+    if (P.collect_stats) flush_trav(P.q.trav + 0, st);
 }
 
 __global__ void __launch_bounds__(kBlock) k_shadow(const FrameParams P) {
     const int n = P.q.counts[3];
+    TraceStats st; st.nodes = 0; st.prims = 0;
     for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
         float4 a = P.q.shadow[2 * (size_t)i + 0];
         float4 b = P.q.shadow[2 * (size_t)i + 1];
         int tag = __float_as_int(a.w);
-        Hit h = trace<true>(P.scene.geom, V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), 0.f, 1e30f);
+        Hit h = trace<true>(P.scene.geom, V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), 0.f, 1e30f, P.collect_stats ? &st : nullptr);
         if (h.prim >= 0) atomicAnd(P.paths.vis + (tag & 0x3fffffff), ~(1u << (tag >> 30)));
     }
+    if (P.collect_stats) flush_trav(P.q.trav + 2, st);
 }
 
 // ---------------------------------------------------------------------------------

@@ -42,7 +42,8 @@ struct Queues {
     int* shade[2];       // double-buffered slot lists
     int* extend;
     float4* shadow;      // 2 x float4 per entry: (o.xyz, slot|bit<<31) (d.xyz, -)
-    int* counts;         // [0],[1] shade ; [2] extend ; [3] shadow ; [4..7] stats
+    int* counts;         // [0],[1] shade ; [2] extend ; [3] shadow
+    unsigned long long* trav;   // [0],[1] extend nodes/prims ; [2],[3] shadow nodes/prims ; [4],[5] primary
 };
 
 // Everything a frame's kernels need, passed by value (fits the 4 KB param space).
@@ -53,7 +54,9 @@ struct FrameParams {
     Queues q;
     int W, H;            // full frame
     int row0, row1;      // this rank's rows [row0,row1)
-    int accum_id;
+    int accum_id;        // accumulation index of this renderer (0 = first sample in its buffers)
+    int frame_id;        // sample index that keys the RNG streams (== accum_id unless spp-sharded)
+    int collect_stats;   // accumulate nodes/prims visited into q.trav
     int v1_stop, v2_stop;
     int mode;
     // PT outputs

@@ -1,0 +1,4 @@
+// render_nrc <config.json> [BETA] — headless stand-in for the reference executable of the
+// same name (render_nrc.cu: main()).  See hm_main_common.h.
+#include "hm_main_common.h"
+int main(int argc, char** argv) { return hm_main(argc, argv, HM_RENDER_NRC, "render_nrc"); }

@@ -56,6 +56,8 @@ enum {
 
 const char* hm_last_error(void);
 int hm_device_count(void);
+/* bytes of the kernel parameter block a stage launch sends host->device (accounting only) */
+int hm_frame_param_bytes(void);
 
 /* ---- scene -------------------------------------------------------------------- */
 
@@ -166,12 +168,22 @@ typedef struct {
     double ms_primary, ms_shade, ms_extend, ms_shadow, ms_finalize, ms_train, ms_infer, ms_composite, ms_total;
     uint64_t rays_primary, rays_extend, rays_shadow, shade_items;
     uint64_t kernel_launches;
+    /* launches per stage: primary shade extend shadow finalize train infer composite */
+    uint64_t stage_launches[8];
+    /* instrumented traversal (hm_renderer_set_collect_stats): BVH nodes visited / primitives tested */
+    uint64_t trav_nodes_extend, trav_prims_extend, trav_nodes_shadow, trav_prims_shadow, trav_nodes_primary, trav_prims_primary;
     float last_loss;
     int frames;
 } hm_stats;
 int hm_renderer_get_stats(hm_renderer* r, hm_stats* out);
-/* per-stage CUDA-event timing on/off (adds one event pair per stage) */
+/* per-stage CUDA-event timing on/off (event pairs around each launch, resolved in hm_renderer_get_stats) */
 int hm_renderer_set_profiling(hm_renderer* r, int on);
+/* instrumented traversal + queue-size accounting (polls the queue counters every bounce) */
+int hm_renderer_set_collect_stats(hm_renderer* r, int on);
+int hm_renderer_reset_stats(hm_renderer* r);
+/* Sample schedule for spp-sharded rendering: the RNG frame id of this renderer's
+ * k-th sample is offset + k * stride (default 0, 1 == the reference's accumId). */
+int hm_renderer_set_frame_schedule(hm_renderer* r, int offset, int stride);
 
 /* ---- stand-alone kernels (parity tests, micro-benchmarks) ----------------------- */
 
