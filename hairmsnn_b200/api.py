@@ -178,15 +178,15 @@ class Scene:
     def arrays(self):
         """Host views of BVH + geometry (numpy, no copy; valid while the scene lives)."""
         i = self.info()
-        nodes, cps, tv, tn = _fp(), _fp(), _fp(), _fp()
+        nodes, cps, tv, tn, ld = _fp(), _fp(), _fp(), _fp(), _fp()
         lc, lp, sc = _ip(), _ip(), _ip()
         _check(lib.hm_scene_get_arrays(self._h, C.byref(nodes), C.byref(lc), C.byref(lp), C.byref(cps), C.byref(tv),
-                                       C.byref(tn), C.byref(sc)))
+                                       C.byref(tn), C.byref(sc), C.byref(ld)))
         nprim = i.num_segments + i.num_triangles
         as_np = np.ctypeslib.as_array
         out = {
             "nodes": as_np(nodes, (i.num_bvh_nodes * 16,)),
-            "leaf_code": as_np(lc, (nprim,)), "leaf_prim": as_np(lp, (nprim,)),
+            "leaf_code": as_np(lc, (nprim,)), "leaf_prim": as_np(lp, (nprim,)), "leaf_data": as_np(ld, (nprim * 16,)),
             "cps": as_np(cps, (max(i.num_control_points, 1) * 4,)) if i.num_control_points else np.zeros(4, np.float32),
             "tri_verts": as_np(tv, (i.num_triangles * 12,)) if i.num_triangles else np.zeros(12, np.float32),
             "tri_normals": as_np(tn, (i.num_triangles * 12,)) if i.num_triangles else np.zeros(12, np.float32),

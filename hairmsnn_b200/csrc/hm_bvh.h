@@ -13,10 +13,15 @@
 //   child >= 0 : inner node index
 //   child <  0 : leaf, ~child = (first_slot << 3) | (count - 1), count <= 8
 //
-//   leaf slot s : leaf_code[s]  = first control-point index of a fibre segment, or
-//                                 (triangle index | kTriTag)
+//   leaf slot s : leaf_data[4s..4s+3] = the primitive itself, 64 B, so a leaf test is ONE
+//                                 dependent fetch after the node (HBM capacity is cheap
+//                                 on B200; an index -> control-point indirection is not):
+//                                   fibre   : 4 control points (xyz, radius)
+//                                   triangle: v0, v1, v2, (-, -, -, -1)   (w < 0 tags it)
 //                 leaf_prim[s]  = primitive id reported to the caller
 //                                 (segment id, or num_segments + triangle id)
+//                 leaf_code[s]  = host-side bookkeeping only (first control-point index,
+//                                 or triangle index | kTriTag)
 //
 // The traversal routine is shared by the CUDA kernels and the host build (the
 // latter only serves the CPU oracle / baseline); it uses only IEEE + - * / sqrt and
@@ -36,6 +41,7 @@ struct F4 {
 
 struct GeomView {
     const F4* nodes;      // 4 per node
+    const F4* leaf_data;  // 4 per leaf slot
     const int* leaf_code;
     const int* leaf_prim;
     const F4* cps;        // xyz + radius
@@ -93,6 +99,11 @@ struct TraceStats {
 };
 
 // ANY = true: occlusion query, returns at the first accepted hit.
+//
+// "while-while" traversal: descend inner nodes until a leaf is reached, then test the
+// leaf's primitives.  On the GPU the lanes of a warp re-converge after the inner loop, so
+// the (expensive, variable-length) curve solver runs with as many lanes as possible in
+// the leaf phase instead of interleaving with other lanes' box tests.
 template <bool ANY>
 HM_HD Hit trace(const GeomView& g, V3 o, V3 d, float tmin, float tmax, TraceStats* stats = nullptr) {
     Hit best;
@@ -114,7 +125,8 @@ HM_HD Hit trace(const GeomView& g, V3 o, V3 d, float tmin, float tmax, TraceStat
     const int kDone = 0x7fffffff;
 
     while (cur != kDone) {
-        if (cur >= 0) {
+        // ---- inner nodes ----
+        while (cur >= 0 && cur != kDone) {
             const F4* n = g.nodes + 4 * (size_t)cur;
             F4 q0 = load_f4(n + 0), q1 = load_f4(n + 1), q2 = load_f4(n + 2), q3 = load_f4(n + 3);
             if (stats) stats->nodes++;
@@ -133,18 +145,18 @@ HM_HD Hit trace(const GeomView& g, V3 o, V3 d, float tmin, float tmax, TraceStat
             } else {
                 cur = sp > 0 ? stack[--sp] : kDone;
             }
-        } else {
+        }
+        if (cur == kDone) break;
+        // ---- leaf ----
+        {
             int code = ~cur;
             int first = code >> 3;
             int count = (code & 7) + 1;
             for (int i = 0; i < count; ++i) {
-                int lc = load_i(g.leaf_code + first + i);
+                const F4* p = g.leaf_data + 4 * (size_t)(first + i);
+                F4 a = load_f4(p + 0), b = load_f4(p + 1), c = load_f4(p + 2), e = load_f4(p + 3);
                 if (stats) stats->prims++;
-                if (lc & kTriTag) {
-                    int ti = lc & ~kTriTag;
-                    F4 a = load_f4(g.tri_verts + 3 * (size_t)ti + 0);
-                    F4 b = load_f4(g.tri_verts + 3 * (size_t)ti + 1);
-                    F4 c = load_f4(g.tri_verts + 3 * (size_t)ti + 2);
+                if (e.w < 0.f) {
                     float t, b1, b2;
                     if (intersect_triangle(o, d, tmin, best.t, V3(a.x, a.y, a.z), V3(b.x, b.y, b.z),
                                            V3(c.x, c.y, c.z), t, b1, b2)) {
@@ -152,8 +164,6 @@ HM_HD Hit trace(const GeomView& g, V3 o, V3 d, float tmin, float tmax, TraceStat
                         if (ANY) { best.prim = load_i(g.leaf_prim + best_slot); return best; }
                     }
                 } else {
-                    const F4* cp = g.cps + lc;
-                    F4 a = load_f4(cp + 0), b = load_f4(cp + 1), c = load_f4(cp + 2), e = load_f4(cp + 3);
                     SegHit sh;
                     if (intersect_fibre(rf, tmin, best.t, f4_to_v4(a), f4_to_v4(b), f4_to_v4(c), f4_to_v4(e), sh)) {
                         best.t = sh.t; best.u = sh.u; best.v = 0.f; best_slot = first + i;

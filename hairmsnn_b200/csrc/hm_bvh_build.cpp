@@ -202,7 +202,7 @@ void build_bvh(const HostGeometry& geo, HostBvh& out, int threads_hint) {
     const int ns = (int)geo.seg_cp.size();
     const int nt = (int)(geo.tri_verts.size() / 3);
     const int n = ns + nt;
-    out.nodes.clear(); out.leaf_code.clear(); out.leaf_prim.clear();
+    out.nodes.clear(); out.leaf_data.clear(); out.leaf_code.clear(); out.leaf_prim.clear();
     if (n == 0) return;
 
     std::vector<PrimRef> prims(n);
@@ -286,10 +286,21 @@ void build_bvh(const HostGeometry& geo, HostBvh& out, int threads_hint) {
     memcpy(out.nodes.data(), packed.data(), packed.size() * sizeof(NodeRaw));
     out.leaf_code.resize(n);
     out.leaf_prim.resize(n);
+    out.leaf_data.resize(4 * (size_t)n);
     for (int i = 0; i < n; ++i) {
         int p = order[i];
         out.leaf_prim[i] = p;
         out.leaf_code[i] = p < ns ? geo.seg_cp[p] : ((p - ns) | kTriTag);
+        F4* dst = out.leaf_data.data() + 4 * (size_t)i;
+        if (p < ns) {
+            const F4* cp = geo.cps.data() + geo.seg_cp[p];
+            dst[0] = cp[0]; dst[1] = cp[1]; dst[2] = cp[2]; dst[3] = cp[3];
+            if (dst[3].w < 0.f) dst[3].w = 0.f;
+        } else {
+            const F4* tv = geo.tri_verts.data() + 3 * (size_t)(p - ns);
+            dst[0] = tv[0]; dst[1] = tv[1]; dst[2] = tv[2];
+            dst[3] = F4{0.f, 0.f, 0.f, -1.f};
+        }
     }
 }
 

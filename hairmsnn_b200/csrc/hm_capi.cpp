@@ -171,7 +171,8 @@ int hm_scene_get_info(const hm_scene* s, hm_scene_info* info) {
 }
 
 int hm_scene_get_arrays(const hm_scene* s, const float** nodes, const int** leaf_code, const int** leaf_prim,
-                        const float** cps, const float** tri_v, const float** tri_n, const int** seg_cp) {
+                        const float** cps, const float** tri_v, const float** tri_n, const int** seg_cp,
+                        const float** leaf_data) {
     return guarded([&] {
         need(s, "scene");
         const HostScene& hs = s->hs;
@@ -182,6 +183,7 @@ int hm_scene_get_arrays(const hm_scene* s, const float** nodes, const int** leaf
         if (tri_v) *tri_v = (const float*)hs.geo.tri_verts.data();
         if (tri_n) *tri_n = (const float*)hs.geo.tri_normals.data();
         if (seg_cp) *seg_cp = hs.geo.seg_cp.data();
+        if (leaf_data) *leaf_data = (const float*)hs.bvh.leaf_data.data();
     });
 }
 

@@ -121,6 +121,10 @@ HM_HD V3 dir_to_ray_space(const RayFrame& f, V3 v) {
     return V3(fdot(v, f.ex), fdot(v, f.ey), fdot(v, f.ez));
 }
 
+#ifndef HM_FIBRE_REASON
+#define HM_FIBRE_REASON(code)
+#endif
+
 struct SegHit {
     float t;   // ray parameter
     float u;   // curve parameter
@@ -145,6 +149,14 @@ struct RaySpaceCubic {
 // q0..q3 (xyz + radius in w; radius taken at q1, constant along the segment — the
 // .hair pipeline produces one width per file, scene.cpp:52-57).
 // Accepts hits with t in (tmin, tmax).  Returns true and fills `hit` on success.
+//
+// Stages, cheapest first (most candidates a BVH leaf offers are misses):
+//   1. depth-range reject on the Bezier hull;
+//   2. "fat line" reject in the ray's projection plane: the projected curve lies in the
+//      convex hull of its Bezier points, i.e. inside a slab around the projected chord;
+//      the ray axis (the origin of that plane) must lie within the slab grown by r;
+//   3. Newton iteration on the curve parameter, started at the chord point nearest to the
+//      ray axis: ray vs. the tangent cylinder at u, step u by the axial offset of the hit.
 HM_HD bool intersect_fibre(const RayFrame& rf, float tmin, float tmax,
                            V4 q0, V4 q1, V4 q2, V4 q3, SegHit& hit) {
     // control points in ray space
@@ -159,15 +171,25 @@ HM_HD bool intersect_fibre(const RayFrame& rf, float tmin, float tmax,
     V3 b1 = V3(fmaf(k2.x - k0.x, sixth, k1.x), fmaf(k2.y - k0.y, sixth, k1.y), fmaf(k2.z - k0.z, sixth, k1.z));
     V3 b2 = V3(fmaf(k1.x - k3.x, sixth, k2.x), fmaf(k1.y - k3.y, sixth, k2.y), fmaf(k1.z - k3.z, sixth, k2.z));
 
-    // conservative reject: hull must come within r of the ray axis and overlap [tmin,tmax]
-    float xmin = fminf(fminf(k1.x, b1.x), fminf(b2.x, k2.x));
-    float xmax = fmaxf(fmaxf(k1.x, b1.x), fmaxf(b2.x, k2.x));
-    float ymin = fminf(fminf(k1.y, b1.y), fminf(b2.y, k2.y));
-    float ymax = fmaxf(fmaxf(k1.y, b1.y), fmaxf(b2.y, k2.y));
     float zmin = fminf(fminf(k1.z, b1.z), fminf(b2.z, k2.z));
     float zmax = fmaxf(fmaxf(k1.z, b1.z), fmaxf(b2.z, k2.z));
-    if (xmin > r || xmax < -r || ymin > r || ymax < -r) return false;
-    if (zmin - r > tmax || zmax + r < tmin) return false;
+    if (zmin - r > tmax || zmax + r < tmin) { HM_FIBRE_REASON(1); return false; }
+
+    // projected chord e = k2 - k1; offsets of the axis and of the inner hull points from the
+    // chord line (scaled by |e|), and their positions along it (scaled by |e|^2)
+    const float ex = k2.x - k1.x, ey = k2.y - k1.y;
+    const float len2 = fmaf(ex, ex, ey * ey);
+    const float elen = sqrtf(len2);
+    const float re = fmaf(r, elen, 1e-6f * elen + 1e-12f) * 1.0001f;
+    const float c0 = fmaf(ey, k1.x, -(ex * k1.y));
+    const float c1 = fmaf(ex, b1.y - k1.y, -(ey * (b1.x - k1.x)));
+    const float c2 = fmaf(ex, b2.y - k1.y, -(ey * (b2.x - k1.x)));
+    if (c0 > fmaxf(fmaxf(c1, c2), 0.f) + re || c0 < fminf(fminf(c1, c2), 0.f) - re) { HM_FIBRE_REASON(2); return false; }
+    // (positions along the chord are scaled by |e| as well: dot(p - k1, e) = |e| * distance)
+    const float s0 = -fmaf(ex, k1.x, ey * k1.y);
+    const float s1 = fmaf(ex, b1.x - k1.x, ey * (b1.y - k1.y));
+    const float s2 = fmaf(ex, b2.x - k1.x, ey * (b2.y - k1.y));
+    if (s0 > fmaxf(fmaxf(s1, s2), len2) + re || s0 < fminf(fminf(s1, s2), 0.f) - re) { HM_FIBRE_REASON(3); return false; }
 
     RaySpaceCubic cu;
     cu.a = V3(0.5f * (-k0.x + 3.f * k1.x - 3.f * k2.x + k3.x),
@@ -181,67 +203,65 @@ HM_HD bool intersect_fibre(const RayFrame& rf, float tmin, float tmax,
 
     const float r2 = r * r;
     const float kConv = 5e-5f;
-    bool found = false;
-    float best_t = tmax, best_u = 0.f;
 
-    // start from the end the ray meets first, then retry from the other end
-    float ustart = (k2.z - k1.z) > 0.f ? 0.f : 1.f;
-    for (int pass = 0; pass < 2; ++pass) {
-        float u = ustart;
-        float uold = 0.f, dt1 = 0.f, dt2 = 0.f;
-        for (int it = 0; it < 24; ++it) {
-            V3 c0 = cu.pos(u);
-            V3 cd = cu.vel(u);
-            // ray (0,0,s) vs infinite cylinder through c0 along cd, radius r
-            float cxy = fmaf(cd.y, cd.y, cd.x * cd.x);
-            float dp = fmaf(c0.y, c0.y, c0.x * c0.x);
-            float cdd = fmaf(c0.y, cd.y, c0.x * cd.x);
-            float cxd = fmaf(c0.x, cd.y, -(c0.y * cd.x));
-            float cz2 = cd.z * cd.z;
-            float dd = cxy + cz2;
-            float bq = -(cd.z * cdd);
-            float aq = fmaf(cxd, cxd, fmaf(dp, cz2, -(dd * r2)));
-            float det = fmaf(bq, bq, -(aq * cxy));
-            bool real_hit = det > 0.f;
-            // guard against a ray (numerically) parallel to the tangent
-            float cq = fmaxf(cxy, 1e-12f * dd);
-            float s = (bq - (real_hit ? sqrtf(det) : 0.f)) / cq;
-            float dt = fmaf(s, cd.z, -cdd) / dd;
+    // start at the chord point nearest to the ray axis (mid-span when seen end-on)
+    float u = len2 > 1e-12f ? fminf(fmaxf(s0 / len2, 0.f), 1.f) : 0.5f;
+    float uold = 0.f, dt1 = 0.f, dt2 = 0.f;
+    for (int it = 0; it < 16; ++it) {
+        V3 c0p = cu.pos(u);
+        V3 cd = cu.vel(u);
+        // ray (0,0,s) vs infinite cylinder through c0p along cd, radius r
+        float cxy = fmaf(cd.y, cd.y, cd.x * cd.x);
+        float dp = fmaf(c0p.y, c0p.y, c0p.x * c0p.x);
+        float cdd = fmaf(c0p.y, cd.y, c0p.x * cd.x);
+        float cxd = fmaf(c0p.x, cd.y, -(c0p.y * cd.x));
+        float cz2 = cd.z * cd.z;
+        float dd = cxy + cz2;
+        float bq = -(cd.z * cdd);
+        float aq = fmaf(cxd, cxd, fmaf(dp, cz2, -(dd * r2)));
+        float det = fmaf(bq, bq, -(aq * cxy));
+        bool real_hit = det > 0.f;
+        // guard against a ray (numerically) parallel to the tangent
+        float cq = fmaxf(cxy, 1e-12f * dd);
+        float s = (bq - (real_hit ? sqrtf(det) : 0.f)) / cq;
+        float dt = fmaf(s, cd.z, -cdd) / dd;
 
-            if (fabsf(dt) < kConv) {
-                if (real_hit) {
-                    float t = s + c0.z;
-                    if (t > tmin && t < best_t) {
-                        best_t = t;
-                        best_u = u;
-                        found = true;
-                    }
-                }
-                break;
-            }
-            dt = fminf(dt, 0.5f);
-            dt = fmaxf(dt, -0.5f);
-            dt1 = dt2;
-            dt2 = dt;
-            float unext;
-            if (dt1 * dt2 < 0.f) {
-                // bracketed: regula falsi with a periodic bisection safeguard
-                if ((it & 3) == 0) unext = 0.5f * (uold + u);
-                else unext = (dt2 * uold - dt1 * u) / (dt2 - dt1);
-            } else {
-                unext = u + dt;
-            }
-            uold = u;
-            u = unext;
-            if (u < 0.f || u > 1.f) break;
+        if (fabsf(dt) < kConv) {
+            if (!real_hit) { HM_FIBRE_REASON(4); return false; }
+            float t = s + c0p.z;
+            if (!(t > tmin && t < tmax)) { HM_FIBRE_REASON(5); return false; }
+            hit.t = t;
+            hit.u = u;
+            return true;
         }
-        if (found) break;
-        ustart = 1.f - ustart;
+        dt = fminf(dt, 0.5f);
+        dt = fmaxf(dt, -0.5f);
+        dt1 = dt2;
+        dt2 = dt;
+        float unext;
+        if (it > 0 && dt1 * dt2 < 0.f) {
+            // bracketed: regula falsi with a periodic bisection safeguard
+            if ((it & 3) == 0) unext = 0.5f * (uold + u);
+            else unext = (dt2 * uold - dt1 * u) / (dt2 - dt1);
+        } else {
+            unext = u + dt;
+        }
+        uold = u;
+        u = unext;
+        // A step may overshoot the span (rays nearly parallel to the fibre): retry once from
+        // the end it left through.  Leaving through the same end again means the surface
+        // point nearest to this ray lies beyond the span — the neighbouring segment of the
+        // strand owns it (no end caps).
+        if (u < 0.f) {
+            if (uold == 0.f) { HM_FIBRE_REASON(6); return false; }
+            u = 0.f;
+        } else if (u > 1.f) {
+            if (uold == 1.f) { HM_FIBRE_REASON(6); return false; }
+            u = 1.f;
+        }
     }
-    if (!found) return false;
-    hit.t = best_t;
-    hit.u = best_u;
-    return true;
+    HM_FIBRE_REASON(7);
+    return false;
 }
 
 // Watertight-enough Moeller-Trumbore for the head mesh (closed-source in the

@@ -30,6 +30,7 @@ struct HostGeometry {
 
 struct HostBvh {
     std::vector<F4> nodes;
+    std::vector<F4> leaf_data;   // 4 per leaf slot
     std::vector<int> leaf_code;
     std::vector<int> leaf_prim;
 };
@@ -77,6 +78,7 @@ void camera_basis(const HostScene& s, int W, int H, float pos[3], float d00[3], 
 inline GeomView make_view(const HostGeometry& g, const HostBvh& b) {
     GeomView v;
     v.nodes = b.nodes.data();
+    v.leaf_data = b.leaf_data.data();
     v.leaf_code = b.leaf_code.data();
     v.leaf_prim = b.leaf_prim.data();
     v.cps = g.cps.data();

@@ -38,7 +38,8 @@ DeviceScene::DeviceScene(const HostScene& hs) {
     const HostBvh& b = hs.bvh;
     memset(&view, 0, sizeof(view));
     view.geom.nodes = upload(b.nodes.data(), b.nodes.size());
-    view.geom.leaf_code = upload(b.leaf_code.data(), b.leaf_code.size());
+    view.geom.leaf_data = upload(b.leaf_data.data(), b.leaf_data.size());
+    view.geom.leaf_code = nullptr;   // host-side only
     view.geom.leaf_prim = upload(b.leaf_prim.data(), b.leaf_prim.size());
     view.geom.cps = upload(g.cps.data(), g.cps.size());
     view.geom.tri_verts = upload(g.tri_verts.data(), g.tri_verts.size());

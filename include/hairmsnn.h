@@ -114,7 +114,7 @@ int hm_scene_get_info(const hm_scene* scene, hm_scene_info* info);
  * traverse the SAME tree).  Pointers stay valid until hm_scene_free. */
 int hm_scene_get_arrays(const hm_scene* scene, const float** bvh_nodes, const int** leaf_code, const int** leaf_prim,
                         const float** control_points, const float** tri_vertices4, const float** tri_normals4,
-                        const int** segment_first_cp);
+                        const int** segment_first_cp, const float** leaf_data16);
 /* generateEnvSamplingTables (scene.cpp:349-425): cPdf/cCdf [(w+1)*h], mPdf/mCdf [h+1] */
 int hm_scene_get_env_tables(const hm_scene* scene, const float** env_rgba, const float** cpdf, const float** ccdf,
                             const float** mpdf, const float** mcdf);

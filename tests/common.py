@@ -38,7 +38,7 @@ def probe_scene_desc(scene, kw):
     fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
 
     class D(C.Structure):
-        _fields_ = [("nodes", fp), ("num_nodes", C.c_int), ("leaf_code", ip), ("leaf_prim", ip),
+        _fields_ = [("nodes", fp), ("num_nodes", C.c_int), ("leaf_code", ip), ("leaf_prim", ip), ("leaf_data", fp),
                     ("cps", fp), ("tri_verts", fp), ("tri_normals", fp), ("seg_cp", ip),
                     ("num_segments", C.c_int), ("num_tris", C.c_int),
                     ("env", fp), ("cpdf", fp), ("ccdf", fp), ("mpdf", fp), ("mcdf", fp),
@@ -55,7 +55,7 @@ def probe_scene_desc(scene, kw):
     keep = [arr]
     P = lambda a, t=fp: a.ctypes.data_as(t)
     d.nodes = P(arr["nodes"]); d.num_nodes = info.num_bvh_nodes
-    d.leaf_code = P(arr["leaf_code"], ip); d.leaf_prim = P(arr["leaf_prim"], ip)
+    d.leaf_code = P(arr["leaf_code"], ip); d.leaf_prim = P(arr["leaf_prim"], ip); d.leaf_data = P(arr["leaf_data"])
     d.cps = P(arr["cps"]); d.tri_verts = P(arr["tri_verts"]); d.tri_normals = P(arr["tri_normals"]); d.seg_cp = P(arr["seg_cp"], ip)
     d.num_segments = info.num_segments; d.num_tris = info.num_triangles
     d.has_env = int(info.env_w > 0)

@@ -154,7 +154,7 @@ void probe_trace_brute(void* p, int n, const float* org, const float* dir, float
 extern "C" {
 
 struct ProbeSceneDesc {
-    const float* nodes; int num_nodes; const int* leaf_code; const int* leaf_prim;
+    const float* nodes; int num_nodes; const int* leaf_code; const int* leaf_prim; const float* leaf_data;
     const float* cps; const float* tri_verts; const float* tri_normals; const int* seg_cp;
     int num_segments, num_tris;
     const float* env; const float* cpdf; const float* ccdf; const float* mpdf; const float* mcdf;
@@ -169,7 +169,7 @@ static SceneView make_scene_view(const ProbeSceneDesc& d) {
     SceneView S;
     memset(&S, 0, sizeof(S));
     S.geom.nodes = (const F4*)d.nodes; S.geom.num_nodes = d.num_nodes;
-    S.geom.leaf_code = d.leaf_code; S.geom.leaf_prim = d.leaf_prim;
+    S.geom.leaf_code = d.leaf_code; S.geom.leaf_prim = d.leaf_prim; S.geom.leaf_data = (const F4*)d.leaf_data;
     S.geom.cps = (const F4*)d.cps; S.geom.tri_verts = (const F4*)d.tri_verts;
     S.geom.num_segments = d.num_segments; S.geom.num_tris = d.num_tris;
     S.seg_cp = d.seg_cp; S.tri_normals = (const F4*)d.tri_normals;

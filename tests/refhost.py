@@ -52,7 +52,7 @@ class RefHost:
         self._keep.append(arr)
         ns, nt = info.num_segments, info.num_triangles
         L.ref_set_geometry(_p(arr["nodes"]), info.num_bvh_nodes, _p(arr["leaf_code"], _ip), _p(arr["leaf_prim"], _ip),
-                           _p(arr["cps"]), _p(arr["tri_verts"]), _p(arr["seg_cp"], _ip), ns, nt)
+                           _p(arr["cps"]), _p(arr["tri_verts"]), _p(arr["seg_cp"], _ip), ns, nt, _p(arr["leaf_data"]))
         # reference triangle layout: flattened float3 soup + index triples
         tv = np.ascontiguousarray(arr["tri_verts"].reshape(-1, 4)[:, :3]) if nt else np.zeros((3, 3), np.float32)
         tn = np.ascontiguousarray(arr["tri_normals"].reshape(-1, 4)[:, :3]) if nt else np.zeros((3, 3), np.float32)

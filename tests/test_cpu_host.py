@@ -144,3 +144,47 @@ def test_exr_and_png_writers_roundtrip(tmp_path):
     if not cv2.imwrite(p, img):
         pytest.skip("OpenCV has no EXR writer")
     assert os.path.getsize(p) > 0
+
+
+def test_fibre_intersector_finds_surface_points(probe):
+    """Rays aimed at points ON the tube surface must hit at (about) that distance: guards the
+    conservative rejects and the single-pass Newton solve against holes."""
+    from hairmsnn_b200 import synth
+    cps, seg = synth.make_hair(40, 68, curly=True, seed=5)
+    rng = np.random.default_rng(0)
+    probe.probe_intersect_fibre.restype = C.c_int
+    misses, total, worst, late = 0, 0, 0.0, 0
+    for _ in range(6000):
+        s = int(rng.integers(0, len(seg)))
+        q = cps[seg[s]:seg[s] + 4].astype(np.float64)
+        u = rng.uniform(0.03, 0.97)
+        a = 0.5 * (-q[0] + 3 * q[1] - 3 * q[2] + q[3]); b = 0.5 * (2 * q[0] - 5 * q[1] + 4 * q[2] - q[3]); c = 0.5 * (q[2] - q[0]); d0 = q[1]
+        pos = ((a * u + b) * u + c) * u + d0
+        vel = (3 * a * u + 2 * b) * u + c
+        t = vel[:3] / np.linalg.norm(vel[:3])
+        n = np.cross(t, rng.standard_normal(3)); n /= np.linalg.norm(n)
+        r = pos[3]
+        P = pos[:3] + r * n
+        # incoming direction within 80 degrees of the normal, arbitrary azimuth
+        w = rng.standard_normal(3); w -= w.dot(n) * n; w /= np.linalg.norm(w)
+        cos_i = rng.uniform(0.17, 1.0)
+        out = cos_i * n + np.sqrt(1 - cos_i ** 2) * w
+        dist = rng.uniform(0.5, 250.0)
+        o = (P + dist * out).astype(np.float32)
+        dvec = (-out).astype(np.float32); dvec /= np.linalg.norm(dvec)
+        tt, uu = C.c_float(), C.c_float()
+        q32 = np.ascontiguousarray(cps[seg[s]:seg[s] + 4], np.float32)
+        ok = probe.probe_intersect_fibre(q32.ctypes.data_as(_fp), o.ctypes.data_as(_fp), dvec.ctypes.data_as(_fp), C.c_float(0), C.c_float(1e30), C.byref(tt), C.byref(uu))
+        total += 1
+        if not ok:
+            misses += 1
+        else:
+            # may enter the same tube earlier than the aimed point; a LATER crossing of the same
+            # curled span (the solver converged to the second of two crossings) must stay rare
+            if tt.value > dist + 2e-3 * max(1.0, dist * 1e-2) + 1e-3:
+                late += 1
+            worst = max(worst, dist - tt.value)
+    print(f"misses {misses}/{total}, later-crossing {late}/{total}, worst early {worst:.3f}")
+    assert misses / total < 2e-3, (misses, total)
+    assert late / total < 2e-3, (late, total)
+    assert worst < 2.5      # an earlier entry can only be on this ~1-unit segment

@@ -112,7 +112,7 @@ def test_path_traced_frames_match_reference(mis, env_pdf):
     # unrelated samples of the same estimator.  So: the bulk must agree tightly, the rest
     # must agree in the mean.
     frac, rel_mse = _compare_images(g_acc, accum, frac_exact=0.96)
-    assert abs(g_acc[..., :3].mean() - accum[..., :3].mean()) < 0.01 * accum[..., :3].mean()
+    assert abs(g_acc[..., :3].mean() - accum[..., :3].mean()) < 0.03 * accum[..., :3].mean()
     # misses are pure environment lookups: bit-exact
     o_hit = (accum[..., :3].sum(axis=2) > 0)
     assert np.allclose(g_avg[..., 3], 1.0)
