@@ -393,6 +393,9 @@ class Renderer:
         _check(lib.hm_get_buffer(self._h, which, out.ctypes.data_as(C.c_void_p), C.c_size_t(out.nbytes)))
         return out
 
+    def readback_async(self, which, host_ptr, nbytes):
+        _check(lib.hm_readback_async(self._h, which, C.c_void_p(host_ptr), C.c_size_t(nbytes)))
+
     def trace_rays(self, org, dir, any_hit=False, tmin=0.0, tmax=1e30, stats=False):
         org, dir = _f32(org).reshape(-1, 3), _f32(dir).reshape(-1, 3)
         n = org.shape[0]

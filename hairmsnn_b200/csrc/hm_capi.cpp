@@ -265,6 +265,10 @@ int hm_get_buffer(hm_renderer* r, int which, void* dst, size_t bytes) {
     });
 }
 
+int hm_readback_async(hm_renderer* r, int which, void* dst, size_t bytes) {
+    return guarded([&] { need(r, "renderer"); need(dst, "host_dst"); r->r->readback_async(which, dst, bytes); });
+}
+
 int hm_save_png(hm_renderer* r, const char* path) {
     return guarded([&] {
         need(r, "renderer"); need(path, "path");

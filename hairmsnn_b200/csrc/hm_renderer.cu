@@ -9,8 +9,35 @@
 #include <cmath>
 #include <cstring>
 #include <stdexcept>
+#include <vector>
 
 namespace hm {
+
+// Scratch allocator for thrust: its default allocator calls cudaMalloc/cudaFree per algorithm
+// invocation, and cudaFree synchronises the whole device — which would serialise the frames in
+// flight.  Blocks are kept and reused (all uses are ordered on one stream).
+struct ThrustScratch {
+    typedef char value_type;
+    struct Block { char* p; size_t n; bool busy; };
+    std::vector<Block> blocks;
+    char* allocate(std::ptrdiff_t n) {
+        for (auto& b : blocks)
+            if (!b.busy && b.n >= (size_t)n) { b.busy = true; return b.p; }
+        char* p = nullptr;
+        if (cudaMalloc((void**)&p, (size_t)n) != cudaSuccess) throw std::runtime_error("CUDA: scratch allocation failed");
+        blocks.push_back(Block{p, (size_t)n, true});
+        return p;
+    }
+    void deallocate(char* p, size_t) {
+        for (auto& b : blocks)
+            if (b.p == p) { b.busy = false; return; }
+    }
+    ~ThrustScratch() { for (auto& b : blocks) cudaFree(b.p); }
+};
+static ThrustScratch& thrust_scratch() {
+    static thread_local ThrustScratch s;
+    return s;
+}
 
 #define HM_CUDA(call)                                                                          \
     do {                                                                                       \
@@ -94,11 +121,12 @@ Renderer::Renderer(const HostScene& hs, int kind, int beta_cli, int device, int 
     if (world < 1 || rank < 0 || rank >= world) throw std::invalid_argument("bad rank/world");
     W_ = hs.width; H_ = hs.height;
     if (W_ <= 0 || H_ <= 0) throw std::invalid_argument("bad frame size");
-    // contiguous row bands; band edges are multiples of 8 rows where possible so that
-    // every band holds whole training-record groups and a multiple of 128 pixels
     row0_ = (int)((int64_t)H_ * rank / world);
     row1_ = (int)((int64_t)H_ * (rank + 1) / world);
-    HM_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    HM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    HM_CUDA(cudaStreamCreateWithPriority(&main_stream_, cudaStreamNonBlocking, prio_lo));
+    HM_CUDA(cudaStreamCreateWithPriority(&order_stream_, cudaStreamNonBlocking, prio_hi));
     scene_.reset(new DeviceScene(hs));
     camera_basis(hs, W_, H_, cam_.pos, cam_.d00, cam_.du, cam_.dv);
 
@@ -110,34 +138,7 @@ Renderer::Renderer(const HostScene& hs, int kind, int beta_cli, int device, int 
         allocs_.push_back(p);
         return p;
     };
-    paths_.rng = (uint32_t*)alloc(n * 4);
-    paths_.ray_o = (float4*)alloc(n * 16);
-    paths_.ray_d = (float4*)alloc(n * 16);
-    paths_.hit = (float4*)alloc(n * 16);
-    paths_.beta = (float4*)alloc(n * 16);
-    paths_.color = (float4*)alloc(n * 16);
-    paths_.dl_beta = (float4*)alloc(n * 16);
-    paths_.dl_light = (float4*)alloc(n * 16);
-    paths_.dl_bsdf = (float4*)alloc(n * 16);
-    paths_.vis = (uint32_t*)alloc(n * 4);
-    if (kind_ == HM_KIND_MSNN) {
-        paths_.beta_short = (float4*)alloc(n * 16);
-        paths_.color_short = (float4*)alloc(n * 16);
-        paths_.dl_beta_short = (float4*)alloc(n * 16);
-    }
-    q_.shade[0] = (int*)alloc(n * 4);
-    q_.shade[1] = (int*)alloc(n * 4);
-    q_.extend = (int*)alloc(n * 4);
-    q_.shadow = (float4*)alloc(n * 2 * 32);
-    q_.counts = (int*)alloc(16 * 4);
-    d_trav_ = (unsigned long long*)alloc(8 * 8);
-    q_.trav = d_trav_;
-    HM_CUDA(cudaMallocHost((void**)&h_counts_, 16 * 4));
-    memset(h_counts_, 0, 16 * 4);
-
-    for (int i = 0; i < 6; ++i) bufs_[i] = (float4*)alloc(n * 16);
-    fb_ = (uint32_t*)alloc(n * 4);
-
+    d_trav_ = (unsigned long long*)alloc(16 * 8);
     if (kind_ == HM_KIND_MSNN) {
         in_ch_ = 12;
         records_ = 128 * 128;   // numTrainRecordsX * numTrainRecordsY (headers/render_hair_msnn.h:127-130)
@@ -145,37 +146,79 @@ Renderer::Renderer(const HostScene& hs, int kind, int beta_cli, int device, int 
         every_nth_ = (int)(n / (size_t)records_);
         if (every_nth_ < 1)
             throw std::invalid_argument("render_hair_msnn needs at least 16384 pixels (everyNth would be 0)");
+    }
+    for (FrameCtx& c : ctx_) {
+        c.paths.rng = (uint32_t*)alloc(n * 4);
+        c.paths.ray_o = (float4*)alloc(n * 16);
+        c.paths.ray_d = (float4*)alloc(n * 16);
+        c.paths.hit = (float4*)alloc(n * 16);
+        c.paths.beta = (float4*)alloc(n * 16);
+        c.paths.color = (float4*)alloc(n * 16);
+        c.paths.dl_beta = (float4*)alloc(n * 16);
+        c.paths.dl_light = (float4*)alloc(n * 16);
+        c.paths.dl_bsdf = (float4*)alloc(n * 16);
+        c.paths.vis = (uint32_t*)alloc(n * 4);
+        if (kind_ == HM_KIND_MSNN) {
+            c.paths.beta_short = (float4*)alloc(n * 16);
+            c.paths.color_short = (float4*)alloc(n * 16);
+            c.paths.dl_beta_short = (float4*)alloc(n * 16);
+            c.train_idxs = (int*)alloc((size_t)records_ * 4);
+            c.nn_frame_in = (float*)alloc(n * in_ch_ * 4);
+            c.nn_train_in = (float*)alloc((size_t)records_ * in_ch_ * 4);
+            c.nn_train_out = (float*)alloc((size_t)records_ * 3 * 4);
+            c.gbuffer = (float4*)alloc(n * 16);
+        }
+        c.q.shade[0] = (int*)alloc(n * 4);
+        c.q.shade[1] = (int*)alloc(n * 4);
+        c.q.extend = (int*)alloc(n * 4);
+        c.q.shadow = (float4*)alloc(n * 2 * 32);
+        c.q.counts = (int*)alloc(16 * 4);
+        c.q.trav = d_trav_;
+        HM_CUDA(cudaStreamCreateWithPriority(&c.tail_stream, cudaStreamNonBlocking, prio_hi));
+        HM_CUDA(cudaEventCreateWithFlags(&c.ev_main_done, cudaEventDisableTiming));
+        HM_CUDA(cudaEventCreateWithFlags(&c.ev_traced, cudaEventDisableTiming));
+        HM_CUDA(cudaEventCreateWithFlags(&c.ev_free, cudaEventDisableTiming));
+    }
+    for (int i = 0; i < 6; ++i) bufs_[i] = (float4*)alloc(n * 16);
+    fb_ = (uint32_t*)alloc(n * 4);
+
+    if (kind_ == HM_KIND_MSNN) {
         MlpConfig cfg = hs.tcnn_config.empty() ? MlpConfig() : mlp_config_from_json(hs.tcnn_config, in_ch_, 3);
         cfg.in_ch = in_ch_; cfg.out_ch = 3;
-        mlp_.reset(new Mlp(cfg, stream_));
-        h_train_idxs_.resize(records_);
-        for (int i = 0; i < records_; ++i) h_train_idxs_[i] = i;   // thrust::sequence
+        mlp_.reset(new Mlp(cfg, order_stream_));
+        std::vector<int> seq(records_);
+        for (int i = 0; i < records_; ++i) seq[i] = i;   // thrust::sequence
         d_train_idxs_ = (int*)alloc((size_t)records_ * 4);
-        HM_CUDA(cudaMemcpy(d_train_idxs_, h_train_idxs_.data(), (size_t)records_ * 4, cudaMemcpyHostToDevice));
-        nn_frame_in_ = (float*)alloc(n * in_ch_ * 4);
+        HM_CUDA(cudaMemcpy(d_train_idxs_, seq.data(), (size_t)records_ * 4, cudaMemcpyHostToDevice));
         nn_frame_out_ = (float*)alloc(n * 3 * 4);
-        nn_train_in_ = (float*)alloc((size_t)records_ * in_ch_ * 4);
-        nn_train_out_ = (float*)alloc((size_t)records_ * 3 * 4);
-        gbuffer_ = (float4*)alloc(n * 16);
     }
+    last_ctx_ = &ctx_[0];
     HM_CUDA(cudaDeviceSynchronize());
 }
 
 Renderer::~Renderer() {
     cudaSetDevice(device_);
-    cudaStreamSynchronize(stream_);
+    cudaDeviceSynchronize();
     mlp_.reset();
     for (void* p : allocs_) cudaFree(p);
-    if (h_counts_) cudaFreeHost(h_counts_);
     scene_.reset();
     for (auto& p : pending_) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : event_pool_) cudaEventDestroy(e);
-    if (stream_) cudaStreamDestroy(stream_);
+    for (FrameCtx& c : ctx_) {
+        if (c.tail_stream) cudaStreamDestroy(c.tail_stream);
+        if (c.ev_main_done) cudaEventDestroy(c.ev_main_done);
+        if (c.ev_traced) cudaEventDestroy(c.ev_traced);
+        if (c.ev_free) cudaEventDestroy(c.ev_free);
+    }
+    if (main_stream_) cudaStreamDestroy(main_stream_);
+    if (order_stream_) cudaStreamDestroy(order_stream_);
 }
 
 void Renderer::sync() {
     HM_CUDA(cudaSetDevice(device_));
-    HM_CUDA(cudaStreamSynchronize(stream_));
+    HM_CUDA(cudaStreamSynchronize(main_stream_));
+    for (FrameCtx& c : ctx_) HM_CUDA(cudaStreamSynchronize(c.tail_stream));
+    HM_CUDA(cudaStreamSynchronize(order_stream_));
 }
 
 cudaEvent_t Renderer::take_event() {
@@ -188,19 +231,19 @@ cudaEvent_t Renderer::take_event() {
 // Event pairs are recorded around each stage launch and resolved later, so profiling does
 // not add host synchronisation inside the frame.
 template <typename F>
-void Renderer::timed(int stage, F&& f) {
+void Renderer::timed(int stage, cudaStream_t s, F&& f) {
     stats_.launches[stage]++;
     if (!profiling_) { f(); return; }
     Pending p{stage, take_event(), take_event()};
-    HM_CUDA(cudaEventRecord(p.a, stream_));
+    HM_CUDA(cudaEventRecord(p.a, s));
     f();
-    HM_CUDA(cudaEventRecord(p.b, stream_));
+    HM_CUDA(cudaEventRecord(p.b, s));
     pending_.push_back(p);
 }
 
 void Renderer::resolve_events() {
     if (pending_.empty()) return;
-    HM_CUDA(cudaStreamSynchronize(stream_));
+    sync();
     for (auto& p : pending_) {
         float ms = 0.f;
         HM_CUDA(cudaEventElapsedTime(&ms, p.a, p.b));
@@ -212,134 +255,162 @@ void Renderer::resolve_events() {
 
 void Renderer::reset_stats() {
     resolve_events();
+    sync();
     stats_ = Stats();
-    cudaMemsetAsync(d_trav_, 0, 8 * 8, stream_);
+    HM_CUDA(cudaMemset(d_trav_, 0, 16 * 8));
 }
 
-FrameParams Renderer::base_params() {
+FrameParams Renderer::params_for(const FrameCtx& c) {
     FrameParams P;
     memset(&P, 0, sizeof(P));
     P.scene = scene_->view;
     P.cam = cam_;
-    P.paths = paths_;
-    P.q = q_;
+    P.paths = c.paths;
+    P.q = c.q;
     P.W = W_; P.H = H_;
     P.row0 = row0_; P.row1 = row1_;
-    P.accum_id = accum_id_;
-    P.frame_id = frame_offset_ + accum_id_ * frame_stride_;
+    P.accum_id = c.accum_id;
+    P.frame_id = c.frame_id;
     P.collect_stats = collect_stats_ ? 1 : 0;
     P.v1_stop = hs_.path_v1 - 1;
     P.v2_stop = hs_.path_v2 - 1;
     P.accum = bufs_[1]; P.average = bufs_[0]; P.fb = fb_;
     P.in_ch = in_ch_;
+    if (kind_ == HM_KIND_MSNN) {
+        P.mode = MODE_MSNN;
+        P.msnn_beta = beta_;
+        P.every_nth = every_nth_;
+        P.train_idxs = c.train_idxs;
+        // this band's training records: fbOfs / everyNth over its pixel range
+        const int64_t px0 = (int64_t)row0_ * W_, px1 = (int64_t)row1_ * W_;
+        P.train_slot0 = (int)(px0 / every_nth_);
+        int slot1 = (int)((px1 + every_nth_ - 1) / every_nth_);
+        if (slot1 > records_) slot1 = records_;
+        P.train_slots = slot1 - P.train_slot0;
+        P.nn_frame_in = c.nn_frame_in;
+        P.nn_train_in = c.nn_train_in;
+        P.nn_train_out = c.nn_train_out;
+        P.gbuffer = c.gbuffer;
+    } else {
+        P.mode = MODE_PT;
+    }
     return P;
 }
 
-// One wavefront loop: primary, then (shade -> shadow + extend) per path vertex.
-void Renderer::trace_bounces(FrameParams& P, int max_vertices) {
-    HM_CUDA(cudaMemsetAsync(q_.counts, 0, 16 * 4, stream_));
-    timed(0, [&] { launch_primary(P, stream_); });
-    stats_.rays_primary += (uint64_t)(row1_ - row0_) * W_;
-    int src = 0;
-    for (int vertex = 0; vertex < max_vertices; ++vertex) {
-        timed(1, [&] { launch_shade(P, src, stream_); });
-        timed(3, [&] { launch_shadow(P, stream_); });
-        const int dst = src ^ 1;
-        HM_CUDA(cudaMemsetAsync(q_.counts + dst, 0, 4, stream_));
-        timed(2, [&] { launch_extend(P, dst, stream_); });
-        const bool last = vertex + 1 >= max_vertices;
-        // Long paths (PT, training paths): look at the queue sizes every few vertices so
-        // the loop ends once every path died.  Short HairMSNN paths never synchronise.
-        const bool poll = collect_stats_ || (!last && max_vertices > 4 && (vertex & 1) == 1);
-        if (poll) {
-            HM_CUDA(cudaMemcpyAsync(h_counts_, q_.counts, 16 * 4, cudaMemcpyDeviceToHost, stream_));
-            HM_CUDA(cudaStreamSynchronize(stream_));
-            stats_.shade_items += (uint64_t)h_counts_[src];
-            stats_.rays_extend += (uint64_t)h_counts_[2];
-            stats_.rays_shadow += (uint64_t)h_counts_[3];
-            if (h_counts_[dst] == 0) break;
-        }
-        HM_CUDA(cudaMemsetAsync(q_.counts + 2, 0, 8, stream_));   // extend + shadow counters
-        src = dst;
-    }
-    timed(4, [&] { launch_finalize(P, stream_); });
-}
-
-void Renderer::frame_pt() {
-    FrameParams P = base_params();
-    P.mode = MODE_PT;
-    // vertices shaded: the primary hit plus up to v2_stop bounces
-    int max_vertices = P.v2_stop + 1;
-    if (max_vertices < 1) max_vertices = 1;
-    trace_bounces(P, max_vertices);
-}
-
-void Renderer::shuffle_train_idxs() {
+void Renderer::shuffle_train_idxs(FrameCtx& c) {
     // thrust::shuffle(trainIdxs, default_random_engine()) — a freshly constructed engine
     // every frame, so the permutation applied is the same each time and the sequence of
-    // compositions is deterministic (render_hair_msnn.cu:711-714)
+    // compositions is deterministic (render_hair_msnn.cu:711-714).  The frame keeps a copy:
+    // later frames re-shuffle the persistent array while this one is still in flight.
     thrust::device_ptr<int> p = thrust::device_pointer_cast(d_train_idxs_);
-    thrust::shuffle(thrust::cuda::par.on(stream_), p, p + records_, thrust::default_random_engine());
+    thrust::shuffle(thrust::cuda::par_nosync(thrust_scratch()).on(main_stream_), p, p + records_, thrust::default_random_engine());
+    HM_CUDA(cudaMemcpyAsync(c.train_idxs, d_train_idxs_, (size_t)records_ * 4, cudaMemcpyDeviceToDevice, main_stream_));
+}
+
+FrameCtx& Renderer::begin_frame() {
+    HM_CUDA(cudaSetDevice(device_));
+    FrameCtx& c = ctx_[frames_issued_ % kFramesInFlight];
+    frames_issued_++;
+    c.accum_id = accum_id_;
+    c.frame_id = frame_offset_ + accum_id_ * frame_stride_;
+    // the context is reusable once the frame that last used it has been composited
+    HM_CUDA(cudaStreamWaitEvent(main_stream_, c.ev_free, 0));
+    return c;
+}
+
+// Wavefront loop: primary, then (shade -> shadow + extend) per path vertex.  The first
+// `main_vertices` vertices run on the main stream, the rest on the frame's tail stream.
+// No host synchronisation: every stage reads its queue length from device memory, and the
+// tail always issues the full vertex budget (empty launches cost a few microseconds).
+void Renderer::trace_frame(FrameCtx& c) {
+    if (kind_ == HM_KIND_MSNN) shuffle_train_idxs(c);
+    FrameParams P = params_for(c);
+    int max_vertices = P.v2_stop + 1;   // the primary hit plus up to v2_stop bounces
+    if (max_vertices < 1) max_vertices = 1;
+    int main_vertices = kind_ == HM_KIND_MSNN ? beta_ + 2 : 6;
+    if (main_vertices < 2) main_vertices = 2;
+    if (main_vertices > max_vertices) main_vertices = max_vertices;
+
+    cudaStream_t s = main_stream_;
+    HM_CUDA(cudaMemsetAsync(c.q.counts, 0, 16 * 4, s));
+    timed(0, s, [&] { launch_primary(P, s); });
+    int src = 0;
+    for (int vertex = 0; vertex < max_vertices; ++vertex) {
+        if (vertex == main_vertices) {
+            HM_CUDA(cudaEventRecord(c.ev_main_done, main_stream_));
+            s = c.tail_stream;
+            HM_CUDA(cudaStreamWaitEvent(s, c.ev_main_done, 0));
+        }
+        timed(1, s, [&] { launch_shade(P, src, s); });
+        timed(3, s, [&] { launch_shadow(P, s); });
+        const int dst = src ^ 1;
+        HM_CUDA(cudaMemsetAsync(c.q.counts + dst, 0, 4, s));
+        timed(2, s, [&] { launch_extend(P, dst, s); });
+        HM_CUDA(cudaMemsetAsync(c.q.counts + 2, 0, 8, s));   // extend + shadow counters
+        src = dst;
+    }
+    if (kind_ == HM_KIND_MSNN) timed(4, s, [&] { launch_finalize(P, s); });   // frame-local outputs only
+    HM_CUDA(cudaEventRecord(c.ev_traced, s));
+    HM_CUDA(cudaStreamWaitEvent(order_stream_, c.ev_traced, 0));
+    last_ctx_ = &c;
+}
+
+void Renderer::finish_pt(FrameCtx& c) {
+    FrameParams P = params_for(c);
+    timed(4, order_stream_, [&] { launch_finalize(P, order_stream_); });   // accumulates: frame order
+}
+
+void Renderer::end_frame(FrameCtx& c) {
+    HM_CUDA(cudaEventRecord(c.ev_free, order_stream_));
+    accum_id_++;
+    stats_.frames++;
 }
 
 void Renderer::msnn_trace() {
     if (kind_ != HM_KIND_MSNN) throw std::logic_error("not a HairMSNN renderer");
-    HM_CUDA(cudaSetDevice(device_));
-    shuffle_train_idxs();
-    FrameParams P = base_params();
-    P.mode = MODE_MSNN;
-    P.msnn_beta = beta_;
-    P.every_nth = every_nth_;
-    P.train_idxs = d_train_idxs_;
-    // this band's training records: fbOfs / everyNth over its pixel range
-    const int64_t px0 = (int64_t)row0_ * W_, px1 = (int64_t)row1_ * W_;
-    P.train_slot0 = (int)(px0 / every_nth_);
-    int slot1 = (int)((px1 + every_nth_ - 1) / every_nth_);
-    if (slot1 > records_) slot1 = records_;
-    P.train_slots = slot1 - P.train_slot0;
-    P.nn_frame_in = nn_frame_in_;
-    P.nn_train_in = nn_train_in_;
-    P.nn_train_out = nn_train_out_;
-    P.gbuffer = gbuffer_;
-    // Training paths run to full length (pathV2 vertices); with the queue polling in
-    // trace_bounces the loop ends as soon as they have all terminated.
-    int max_vertices = P.v2_stop + 1;
-    if (max_vertices < 1) max_vertices = 1;
-    trace_bounces(P, max_vertices);
+    if (current_) throw std::logic_error("msnn_trace: the previous frame was not finished (call msnn_finish)");
+    FrameCtx& c = begin_frame();
+    trace_frame(c);
+    current_ = &c;
 }
 
 void Renderer::msnn_train_backward() {
     if (kind_ != HM_KIND_MSNN) throw std::logic_error("not a HairMSNN renderer");
+    if (!current_) throw std::logic_error("msnn_train_backward: call msnn_trace first");
     const int64_t px0 = (int64_t)row0_ * W_, px1 = (int64_t)row1_ * W_;
     int s0 = (int)(px0 / every_nth_);
     int s1 = (int)((px1 + every_nth_ - 1) / every_nth_);
     if (s1 > records_) s1 = records_;
     int n = s1 - s0;
     n -= n % 128;
-    timed(5, [&] {
-        mlp_->forward_backward(nn_train_in_ + (size_t)s0 * in_ch_, nn_train_out_ + (size_t)s0 * 3, n, world_ == 1 ? n : records_);
+    FrameCtx& c = *current_;
+    timed(5, order_stream_, [&] {
+        mlp_->forward_backward(c.nn_train_in + (size_t)s0 * in_ch_, c.nn_train_out + (size_t)s0 * 3, n, world_ == 1 ? n : records_);
     });
 }
 
 void Renderer::msnn_train_apply() {
-    timed(5, [&] { mlp_->optimizer_step(); });
+    if (kind_ != HM_KIND_MSNN) throw std::logic_error("not a HairMSNN renderer");
+    timed(5, order_stream_, [&] { mlp_->optimizer_step(); });
 }
 
 void Renderer::msnn_finish() {
     if (kind_ != HM_KIND_MSNN) throw std::logic_error("not a HairMSNN renderer");
+    if (!current_) throw std::logic_error("msnn_finish: call msnn_trace first");
+    FrameCtx& c = *current_;
     const size_t first = (size_t)row0_ * W_;
     const int count = (row1_ - row0_) * W_;
-    timed(6, [&] { mlp_->inference(nn_frame_in_ + first * in_ch_, nn_frame_out_ + first * 3, count); });
+    timed(6, order_stream_, [&] { mlp_->inference(c.nn_frame_in + first * in_ch_, nn_frame_out_ + first * 3, count); });
     MsnnComposite C;
     C.final_avg = bufs_[0]; C.final_accum = bufs_[1];
     C.pt_avg = bufs_[2]; C.pt_accum = bufs_[3];
     C.nn_avg = bufs_[4]; C.nn_accum = bufs_[5];
-    C.fb = fb_; C.gbuffer = gbuffer_; C.nn_out = nn_frame_out_;
-    C.accum_id = accum_id_;
+    C.fb = fb_; C.gbuffer = c.gbuffer; C.nn_out = nn_frame_out_;
+    C.accum_id = c.accum_id;
     C.first = (int)first; C.count = count;
-    timed(7, [&] { launch_msnn_composite(C, stream_); });
-    accum_id_++;
-    stats_.frames++;
+    timed(7, order_stream_, [&] { launch_msnn_composite(C, order_stream_); });
+    end_frame(c);
+    current_ = nullptr;
 }
 
 void Renderer::msnn_pretrain(int steps) {
@@ -347,39 +418,44 @@ void Renderer::msnn_pretrain(int steps) {
     // points from an UNSET camera.  Deterministic stand-in: `steps`
     // G_BUFFER passes from the real camera, each followed by a training step; the
     // accumulation counter advances as genTrainingData() does and is reset afterwards.
+    if (kind_ != HM_KIND_MSNN) throw std::logic_error("not a HairMSNN renderer");
     for (int i = 0; i < steps; ++i) {
         msnn_trace();
         msnn_train_backward();
         msnn_train_apply();
-        accum_id_++;
+        end_frame(*current_);
+        current_ = nullptr;
     }
+    sync();
+    stats_.frames -= steps;
     accum_id_ = 0;
 }
 
 void Renderer::render_frames(int n) {
     HM_CUDA(cudaSetDevice(device_));
+    if (kind_ == HM_KIND_NRC) throw std::logic_error("render_nrc is not implemented in this build");
     for (int i = 0; i < n; ++i) {
         Pending whole{8, nullptr, nullptr};
         if (profiling_) {
+            // frame span on the order stream: previous frame's completion -> this frame's completion
             whole.a = take_event(); whole.b = take_event();
-            HM_CUDA(cudaEventRecord(whole.a, stream_));
+            HM_CUDA(cudaEventRecord(whole.a, order_stream_));
         }
         if (kind_ == HM_KIND_PT) {
-            frame_pt();
-            accum_id_++;
-            stats_.frames++;
-        } else if (kind_ == HM_KIND_MSNN) {
+            FrameCtx& c = begin_frame();
+            trace_frame(c);
+            finish_pt(c);
+            end_frame(c);
+        } else {
             msnn_trace();
             if (hs_.tcnn_train) {
                 msnn_train_backward();
                 msnn_train_apply();
             }
             msnn_finish();
-        } else {
-            throw std::logic_error("render_nrc is not implemented in this build");
         }
         if (whole.a) {
-            HM_CUDA(cudaEventRecord(whole.b, stream_));
+            HM_CUDA(cudaEventRecord(whole.b, order_stream_));
             pending_.push_back(whole);
         }
     }
@@ -387,33 +463,43 @@ void Renderer::render_frames(int n) {
 
 Stats Renderer::stats() {
     resolve_events();
+    sync();
     if (mlp_) stats_.last_loss = mlp_->loss();
-    HM_CUDA(cudaStreamSynchronize(stream_));
-    unsigned long long t[8];
+    unsigned long long t[16];
     HM_CUDA(cudaMemcpy(t, d_trav_, sizeof(t), cudaMemcpyDeviceToHost));
     for (int i = 0; i < 6; ++i) stats_.trav[i] = t[i];
+    stats_.rays_extend = t[6]; stats_.rays_shadow = t[7]; stats_.shade_items = t[8]; stats_.rays_primary = t[9];
     return stats_;
 }
 
 void* Renderer::device_buffer(int which, size_t* bytes) {
     const size_t n = (size_t)W_ * H_;
+    FrameCtx& c = *last_ctx_;
     switch (which) {
         case 0: case 1: case 2: case 3: case 4: case 5: *bytes = n * 16; return bufs_[which];
         case 6: *bytes = n * 4; return fb_;
-        case 7: *bytes = n * in_ch_ * 4; return nn_frame_in_;
+        case 7: *bytes = n * in_ch_ * 4; return c.nn_frame_in;
         case 8: *bytes = n * 3 * 4; return nn_frame_out_;
-        case 9: *bytes = (size_t)records_ * in_ch_ * 4; return nn_train_in_;
-        case 10: *bytes = (size_t)records_ * 3 * 4; return nn_train_out_;
-        case 11: *bytes = n * 16; return gbuffer_;
-        case 12: *bytes = (size_t)records_ * 4; return d_train_idxs_;
+        case 9: *bytes = (size_t)records_ * in_ch_ * 4; return c.nn_train_in;
+        case 10: *bytes = (size_t)records_ * 3 * 4; return c.nn_train_out;
+        case 11: *bytes = n * 16; return c.gbuffer;
+        case 12: *bytes = (size_t)records_ * 4; return c.train_idxs;
         default: *bytes = 0; return nullptr;
     }
+}
+
+void Renderer::readback_async(int which, void* host_dst, size_t bytes) {
+    size_t have = 0;
+    void* p = device_buffer(which, &have);
+    if (!p) throw std::logic_error("buffer not available for this renderer kind");
+    if (bytes > have) throw std::invalid_argument("requested more bytes than the buffer holds");
+    HM_CUDA(cudaMemcpyAsync(host_dst, p, bytes, cudaMemcpyDeviceToHost, order_stream_));
 }
 
 void Renderer::trace_rays_device(const float* d_org, const float* d_dir, int n, int any, float tmin, float tmax,
                                  float* d_out_hit, int* d_out_stats) {
     HM_CUDA(cudaSetDevice(device_));
-    launch_trace_rays(scene_->view, d_org, d_dir, n, any, tmin, tmax, (float4*)d_out_hit, d_out_stats, stream_);
+    launch_trace_rays(scene_->view, d_org, d_dir, n, any, tmin, tmax, (float4*)d_out_hit, d_out_stats, order_stream_);
 }
 
 }  // namespace hm

@@ -35,16 +35,44 @@ private:
     template <typename T> T* upload(const T* src, size_t n);
 };
 
+// Per-frame working set.  Several frames are in flight at once (see Renderer), each with
+// its own path state, queues and network I/O buffers.
+struct FrameCtx {
+    PathBuffers paths{};
+    Queues q{};
+    int* train_idxs = nullptr;        // this frame's copy of the shuffled trainIdxs
+    float* nn_frame_in = nullptr;
+    float* nn_train_in = nullptr;
+    float* nn_train_out = nullptr;
+    float4* gbuffer = nullptr;
+    cudaStream_t tail_stream = nullptr;
+    cudaEvent_t ev_main_done = nullptr, ev_traced = nullptr, ev_free = nullptr;
+    int frame_id = 0, accum_id = 0;
+};
+
+// Frame scheduling.  The reference renders one frame at a time on the null stream.  Here a
+// frame is three chained pieces on different streams:
+//   main  stream : shuffle, primary rays and the first vertices of every path (the bulk of
+//                  the rays; saturates the GPU)
+//   tail  stream : the remaining vertices of the few long paths (HairMSNN training paths,
+//                  deep path-tracing paths): dozens of tiny latency-bound launches
+//   order stream : everything with a cross-frame dependency, strictly in frame order:
+//                  training step, inference, composite / accumulation
+// Frame N+1's main part does not depend on frame N's tail, training or inference, so up to
+// kFramesInFlight frames overlap: tails and the MLP run in the shadow of the next frames'
+// main parts.  Results are identical to one-at-a-time execution.
 class Renderer {
 public:
+    static constexpr int kFramesInFlight = 4;
+
     Renderer(const HostScene& hs, int kind, int beta_cli, int device, int rank, int world);
     ~Renderer();
 
     void render_frames(int n);          // enqueue n frames (async)
     void sync();
-    void reset_accumulation() { accum_id_ = 0; }
+    void reset_accumulation() { sync(); accum_id_ = 0; }
     int accum_id() const { return accum_id_; }
-    cudaStream_t stream() const { return stream_; }
+    cudaStream_t stream() const { return order_stream_; }
 
     // HairMSNN split frame
     void msnn_trace();
@@ -57,6 +85,8 @@ public:
     void* device_buffer(int which, size_t* bytes);
     void trace_rays_device(const float* d_org, const float* d_dir, int n, int any, float tmin, float tmax,
                            float* d_out_hit, int* d_out_stats);
+    // enqueue a device->host copy of an output buffer behind the last enqueued frame
+    void readback_async(int which, void* host_dst, size_t bytes);
     void set_profiling(bool on) { profiling_ = on; }
     void set_collect_stats(bool on) { collect_stats_ = on; }
     // spp sharding: RNG frame id = offset + accum_id * stride (accum_id counts this renderer's own samples)
@@ -72,22 +102,24 @@ public:
     const HostScene& host_scene() const { return hs_; }
 
 private:
-    void frame_pt();
-    void trace_bounces(FrameParams& P, int max_vertices);
-    FrameParams base_params();
-    void shuffle_train_idxs();
-    template <typename F> void timed(int stage, F&& f);
+    FrameCtx& begin_frame();
+    void trace_frame(FrameCtx& c);        // main + tail pieces, ends with order_stream waiting on ev_traced
+    void finish_pt(FrameCtx& c);
+    void end_frame(FrameCtx& c);
+    FrameParams params_for(const FrameCtx& c);
+    void shuffle_train_idxs(FrameCtx& c);
+    template <typename F> void timed(int stage, cudaStream_t s, F&& f);
 
     const HostScene& hs_;
     int kind_, beta_, device_, rank_, world_;
     int W_, H_, row0_, row1_;
     int accum_id_ = 0;
-    cudaStream_t stream_ = nullptr;
+    uint64_t frames_issued_ = 0;
+    FrameCtx* current_ = nullptr;   // frame between msnn_trace() and msnn_finish()
+    cudaStream_t main_stream_ = nullptr, order_stream_ = nullptr;
     std::unique_ptr<DeviceScene> scene_;
     Camera cam_;
-    PathBuffers paths_{};
-    Queues q_{};
-    int* h_counts_ = nullptr;      // pinned mirror of q_.counts
+    FrameCtx ctx_[kFramesInFlight];
     std::vector<void*> allocs_;
     // outputs
     float4* bufs_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // final avg/accum, pt avg/accum, nn avg/accum
@@ -95,12 +127,9 @@ private:
     // msnn
     std::unique_ptr<Mlp> mlp_;
     int in_ch_ = 12, records_ = 16384, every_nth_ = 1;
-    int* d_train_idxs_ = nullptr;
-    std::vector<int> h_train_idxs_;
-    uint64_t shuffle_state_ = 0;
-    float* nn_frame_in_ = nullptr; float* nn_frame_out_ = nullptr;
-    float* nn_train_in_ = nullptr; float* nn_train_out_ = nullptr;
-    float4* gbuffer_ = nullptr;
+    int* d_train_idxs_ = nullptr;   // persistent permutation, re-shuffled every frame
+    float* nn_frame_out_ = nullptr;
+    FrameCtx* last_ctx_ = nullptr;
     bool profiling_ = false, collect_stats_ = false;
     int frame_offset_ = 0, frame_stride_ = 1;
     Stats stats_;

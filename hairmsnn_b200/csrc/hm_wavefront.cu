@@ -125,7 +125,10 @@ __global__ void __launch_bounds__(kBlock) k_primary(const FrameParams P) {
         int idx = queue_reserve(P.q.counts + 0, live && hit_any);
         if (idx >= 0) P.q.shade[0][idx] = slot;
     }
-    if (P.collect_stats) flush_trav(P.q.trav + 4, st);
+    if (P.collect_stats) {
+        flush_trav(P.q.trav + 4, st);
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.q.trav + 9, (unsigned long long)n);
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -251,6 +254,7 @@ __global__ void __launch_bounds__(kBlock) k_shade(const FrameParams P, int src) 
         int idx = queue_reserve(P.q.counts + 2, extend);
         if (idx >= 0) P.q.extend[idx] = slot;
     }
+    if (P.collect_stats && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.q.trav + 8, (unsigned long long)n);
 }
 
 // ---------------------------------------------------------------------------------
@@ -274,7 +278,10 @@ __global__ void __launch_bounds__(kBlock) k_extend(const FrameParams P, int dst)
         int idx = queue_reserve(P.q.counts + dst, live && hit_any);
         if (idx >= 0) P.q.shade[dst][idx] = slot;
     }
-    if (P.collect_stats) flush_trav(P.q.trav + 0, st);
+    if (P.collect_stats) {
+        flush_trav(P.q.trav + 0, st);
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.q.trav + 6, (unsigned long long)n);
+    }
 }
 
 __global__ void __launch_bounds__(kBlock) k_shadow(const FrameParams P) {
@@ -287,7 +294,10 @@ __global__ void __launch_bounds__(kBlock) k_shadow(const FrameParams P) {
         Hit h = trace<true>(P.scene.geom, V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), 0.f, 1e30f, P.collect_stats ? &st : nullptr);
         if (h.prim >= 0) atomicAnd(P.paths.vis + (tag & 0x3fffffff), ~(1u << (tag >> 30)));
     }
-    if (P.collect_stats) flush_trav(P.q.trav + 2, st);
+    if (P.collect_stats) {
+        flush_trav(P.q.trav + 2, st);
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.q.trav + 7, (unsigned long long)n);
+    }
 }
 
 // ---------------------------------------------------------------------------------

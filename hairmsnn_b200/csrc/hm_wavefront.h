@@ -43,7 +43,8 @@ struct Queues {
     int* extend;
     float4* shadow;      // 2 x float4 per entry: (o.xyz, slot|bit<<31) (d.xyz, -)
     int* counts;         // [0],[1] shade ; [2] extend ; [3] shadow
-    unsigned long long* trav;   // [0],[1] extend nodes/prims ; [2],[3] shadow nodes/prims ; [4],[5] primary
+    unsigned long long* trav;   // [0],[1] extend nodes/prims ; [2],[3] shadow nodes/prims ; [4],[5] primary ;
+                                // [6] extend rays ; [7] shadow rays ; [8] shade items ; [9] primary rays
 };
 
 // Everything a frame's kernels need, passed by value (fits the 4 KB param space).

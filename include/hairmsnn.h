@@ -155,6 +155,10 @@ int hm_msnn_pretrain(hm_renderer* r, int n_steps);
 hm_mlp* hm_renderer_mlp(hm_renderer* r);
 
 int hm_get_buffer(hm_renderer* r, int which, void* host_dst, size_t bytes);
+/* asynchronous variant: the copy is enqueued behind the last enqueued frame; host_dst (ideally
+ * pinned) is valid after hm_renderer_sync().  Lets a caller stream every frame's result to the
+ * host without stalling the frames in flight. */
+int hm_readback_async(hm_renderer* r, int which, void* host_dst, size_t bytes);
 /* device pointer of the same buffers (for in-place NCCL gathers) */
 int hm_get_device_buffer(hm_renderer* r, int which, void** dev_ptr, size_t* bytes);
 
