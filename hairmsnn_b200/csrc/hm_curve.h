@@ -145,28 +145,37 @@ struct RaySpaceCubic {
     }
 };
 
-// Intersect the ray (o, d unit) with the swept tube of Catmull-Rom control points
-// q0..q3 (xyz + radius in w; radius taken at q1, constant along the segment — the
-// .hair pipeline produces one width per file, scene.cpp:52-57).
-// Accepts hits with t in (tmin, tmax).  Returns true and fills `hit` on success.
+// Ray vs. the swept tube of one Catmull-Rom span, control points q0..q3 (xyz + radius in w;
+// radius taken at q1, constant along the span — the .hair pipeline produces one width per
+// file, scene.cpp:52-57).  Split in two so that the GPU traversal can run the cheap part for
+// every candidate a leaf offers and batch the expensive part across the lanes of a warp:
 //
-// Stages, cheapest first (most candidates a BVH leaf offers are misses):
-//   1. depth-range reject on the Bezier hull;
-//   2. "fat line" reject in the ray's projection plane: the projected curve lies in the
-//      convex hull of its Bezier points, i.e. inside a slab around the projected chord;
-//      the ray axis (the origin of that plane) must lie within the slab grown by r;
-//   3. Newton iteration on the curve parameter, started at the chord point nearest to the
-//      ray axis: ray vs. the tangent cylinder at u, step u by the axial offset of the hit.
-HM_HD bool intersect_fibre(const RayFrame& rf, float tmin, float tmax,
-                           V4 q0, V4 q1, V4 q2, V4 q3, SegHit& hit) {
-    // control points in ray space
-    V3 k0 = to_ray_space(rf, q0.xyz());
-    V3 k1 = to_ray_space(rf, q1.xyz());
-    V3 k2 = to_ray_space(rf, q2.xyz());
-    V3 k3 = to_ray_space(rf, q3.xyz());
-    const float r = q1.w;
+//   fibre_candidate : conservative rejects
+//       1. depth range of the Bezier hull vs (tmin, tmax);
+//       2. "fat line" in the ray's projection plane: the projected curve lies in the convex
+//          hull of its Bezier points, i.e. inside a slab around the projected chord; the ray
+//          axis (the origin of that plane) must lie within the slab grown by r, and within
+//          the hull's extent along the chord.
+//       Also yields the Newton start: the chord point nearest to the ray axis.
+//   fibre_solve     : Newton iteration on the curve parameter — ray vs. the tangent cylinder
+//       at u, step u by the axial offset of the hit.  Accepts hits with t in (tmin, tmax).
+//
+// intersect_fibre = candidate && solve.  Only + - * / sqrt and explicit fmaf are used.
+struct FibreCandidate {
+    V3 k0, k1, k2, k3;   // control points in ray space
+    float r, u_start;
+};
 
-    // Bezier hull of the segment: b0=k1, b1=k1+(k2-k0)/6, b2=k2-(k3-k1)/6, b3=k2
+HM_HD bool fibre_candidate(const RayFrame& rf, float tmin, float tmax, V4 q0, V4 q1, V4 q2, V4 q3, FibreCandidate& c) {
+    c.k0 = to_ray_space(rf, q0.xyz());
+    c.k1 = to_ray_space(rf, q1.xyz());
+    c.k2 = to_ray_space(rf, q2.xyz());
+    c.k3 = to_ray_space(rf, q3.xyz());
+    const V3 k0 = c.k0, k1 = c.k1, k2 = c.k2, k3 = c.k3;
+    const float r = q1.w;
+    c.r = r;
+
+    // Bezier hull of the span: b0=k1, b1=k1+(k2-k0)/6, b2=k2-(k3-k1)/6, b3=k2
     const float sixth = 1.f / 6.f;
     V3 b1 = V3(fmaf(k2.x - k0.x, sixth, k1.x), fmaf(k2.y - k0.y, sixth, k1.y), fmaf(k2.z - k0.z, sixth, k1.z));
     V3 b2 = V3(fmaf(k1.x - k3.x, sixth, k2.x), fmaf(k1.y - k3.y, sixth, k2.y), fmaf(k1.z - k3.z, sixth, k2.z));
@@ -176,7 +185,7 @@ HM_HD bool intersect_fibre(const RayFrame& rf, float tmin, float tmax,
     if (zmin - r > tmax || zmax + r < tmin) { HM_FIBRE_REASON(1); return false; }
 
     // projected chord e = k2 - k1; offsets of the axis and of the inner hull points from the
-    // chord line (scaled by |e|), and their positions along it (scaled by |e|^2)
+    // chord line, and their positions along it (both scaled by |e|)
     const float ex = k2.x - k1.x, ey = k2.y - k1.y;
     const float len2 = fmaf(ex, ex, ey * ey);
     const float elen = sqrtf(len2);
@@ -185,12 +194,18 @@ HM_HD bool intersect_fibre(const RayFrame& rf, float tmin, float tmax,
     const float c1 = fmaf(ex, b1.y - k1.y, -(ey * (b1.x - k1.x)));
     const float c2 = fmaf(ex, b2.y - k1.y, -(ey * (b2.x - k1.x)));
     if (c0 > fmaxf(fmaxf(c1, c2), 0.f) + re || c0 < fminf(fminf(c1, c2), 0.f) - re) { HM_FIBRE_REASON(2); return false; }
-    // (positions along the chord are scaled by |e| as well: dot(p - k1, e) = |e| * distance)
     const float s0 = -fmaf(ex, k1.x, ey * k1.y);
     const float s1 = fmaf(ex, b1.x - k1.x, ey * (b1.y - k1.y));
     const float s2 = fmaf(ex, b2.x - k1.x, ey * (b2.y - k1.y));
     if (s0 > fmaxf(fmaxf(s1, s2), len2) + re || s0 < fminf(fminf(s1, s2), 0.f) - re) { HM_FIBRE_REASON(3); return false; }
 
+    // start at the chord point nearest to the ray axis (mid-span when seen end-on)
+    c.u_start = len2 > 1e-12f ? fminf(fmaxf(s0 / len2, 0.f), 1.f) : 0.5f;
+    return true;
+}
+
+HM_HD bool fibre_solve(const FibreCandidate& c, float tmin, float tmax, SegHit& hit) {
+    const V3 k0 = c.k0, k1 = c.k1, k2 = c.k2, k3 = c.k3;
     RaySpaceCubic cu;
     cu.a = V3(0.5f * (-k0.x + 3.f * k1.x - 3.f * k2.x + k3.x),
               0.5f * (-k0.y + 3.f * k1.y - 3.f * k2.y + k3.y),
@@ -201,11 +216,9 @@ HM_HD bool intersect_fibre(const RayFrame& rf, float tmin, float tmax,
     cu.c = V3(0.5f * (k2.x - k0.x), 0.5f * (k2.y - k0.y), 0.5f * (k2.z - k0.z));
     cu.d = k1;
 
-    const float r2 = r * r;
+    const float r2 = c.r * c.r;
     const float kConv = 5e-5f;
-
-    // start at the chord point nearest to the ray axis (mid-span when seen end-on)
-    float u = len2 > 1e-12f ? fminf(fmaxf(s0 / len2, 0.f), 1.f) : 0.5f;
+    float u = c.u_start;
     float uold = 0.f, dt1 = 0.f, dt2 = 0.f;
     for (int it = 0; it < 16; ++it) {
         V3 c0p = cu.pos(u);
@@ -262,6 +275,13 @@ HM_HD bool intersect_fibre(const RayFrame& rf, float tmin, float tmax,
     }
     HM_FIBRE_REASON(7);
     return false;
+}
+
+HM_HD bool intersect_fibre(const RayFrame& rf, float tmin, float tmax,
+                           V4 q0, V4 q1, V4 q2, V4 q3, SegHit& hit) {
+    FibreCandidate c;
+    if (!fibre_candidate(rf, tmin, tmax, q0, q1, q2, q3, c)) return false;
+    return fibre_solve(c, tmin, tmax, hit);
 }
 
 // Watertight-enough Moeller-Trumbore for the head mesh (closed-source in the

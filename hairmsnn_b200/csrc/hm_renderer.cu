@@ -342,11 +342,10 @@ void Renderer::trace_frame(FrameCtx& c) {
             HM_CUDA(cudaStreamWaitEvent(s, c.ev_main_done, 0));
         }
         timed(1, s, [&] { launch_shade(P, src, s); });
-        timed(3, s, [&] { launch_shadow(P, s); });
         const int dst = src ^ 1;
         HM_CUDA(cudaMemsetAsync(c.q.counts + dst, 0, 4, s));
-        timed(2, s, [&] { launch_extend(P, dst, s); });
-        HM_CUDA(cudaMemsetAsync(c.q.counts + 2, 0, 8, s));   // extend + shadow counters
+        timed(2, s, [&] { launch_trace(P, dst, s); });
+        HM_CUDA(cudaMemsetAsync(c.q.counts + 2, 0, 16, s));   // extend + shadow counters and their work cursors
         src = dst;
     }
     if (kind_ == HM_KIND_MSNN) timed(4, s, [&] { launch_finalize(P, s); });   // frame-local outputs only
@@ -499,7 +498,7 @@ void Renderer::readback_async(int which, void* host_dst, size_t bytes) {
 void Renderer::trace_rays_device(const float* d_org, const float* d_dir, int n, int any, float tmin, float tmax,
                                  float* d_out_hit, int* d_out_stats) {
     HM_CUDA(cudaSetDevice(device_));
-    launch_trace_rays(scene_->view, d_org, d_dir, n, any, tmin, tmax, (float4*)d_out_hit, d_out_stats, order_stream_);
+    launch_trace_rays(scene_->view, d_org, d_dir, n, any, tmin, tmax, (float4*)d_out_hit, d_out_stats, (int*)(d_trav_ + 15), order_stream_);
 }
 
 }  // namespace hm

@@ -16,7 +16,7 @@
 namespace hm {
 
 struct Stats {
-    double ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // primary shade extend shadow finalize train infer composite total
+    double ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // primary shade trace(shadow+extend) - finalize train infer composite total
     uint64_t launches[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t rays_primary = 0, rays_extend = 0, rays_shadow = 0, shade_items = 0;
     uint64_t trav[6] = {0, 0, 0, 0, 0, 0};        // extend nodes/prims, shadow nodes/prims, primary nodes/prims
@@ -63,7 +63,7 @@ struct FrameCtx {
 // main parts.  Results are identical to one-at-a-time execution.
 class Renderer {
 public:
-    static constexpr int kFramesInFlight = 4;
+    static constexpr int kFramesInFlight = 8;
 
     Renderer(const HostScene& hs, int kind, int beta_cli, int device, int rank, int world);
     ~Renderer();

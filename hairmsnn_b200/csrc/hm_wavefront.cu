@@ -14,6 +14,7 @@
 // shade/shadow/extend are persistent grids (148 SMs x resident CTAs) that pull their
 // item count from device memory, so the host never synchronises inside a bounce.
 #include "hm_wavefront.h"
+#include "hm_trace_dev.cuh"
 
 #include <atomic>
 
@@ -36,6 +37,7 @@ int wavefront_sm_count() {
 namespace {
 
 constexpr int kBlock = 128;
+constexpr int kTraceCtasPerSm = 6;   // persistent traversal grid: resident CTAs per SM at ~80 registers
 
 __device__ __forceinline__ float4 f4(V3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
 __device__ __forceinline__ V3 v3(float4 a) { return V3(a.x, a.y, a.z); }
@@ -76,34 +78,34 @@ __device__ __forceinline__ void write_nn_input(float* dst, V3 p, V3 wo, V3 t, fl
 // ---------------------------------------------------------------------------------
 // primary
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_primary(const FrameParams P) {
-    const int n = (P.row1 - P.row0) * P.W;
-    const int first = P.row0 * P.W;
-    TraceStats st; st.nodes = 0; st.prims = 0;
-    for (int base = blockIdx.x * kBlock; base < n; base += gridDim.x * kBlock) {
-        int i = base + threadIdx.x;
-        bool live = i < n;
-        bool hit_any = false;
-        int slot = first + i;
-        if (live) {
-            int px = slot % P.W, py = slot / P.W;
-            Rng rng = rng_seed(P.frame_id + 10007, (uint32_t)px, (uint32_t)py, (uint32_t)P.W);
-            float ox = rng_next(rng);
-            float oy = rng_next(rng);
-            float su = ((float)px + ox) / (float)P.W;
-            float sv = ((float)py + oy) / (float)P.H;
-            V3 o(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]);
-            V3 d = normalize(V3(P.cam.d00[0], P.cam.d00[1], P.cam.d00[2]) +
-                             su * V3(P.cam.du[0], P.cam.du[1], P.cam.du[2]) +
-                             sv * V3(P.cam.dv[0], P.cam.dv[1], P.cam.dv[2]));
-            Hit h = trace<false>(P.scene.geom, o, d, 0.f, 1e30f, P.collect_stats ? &st : nullptr);
-            hit_any = h.prim >= 0;
-            P.paths.rng[slot] = rng.state;
-            P.paths.ray_o[slot] = f4(o, 0.f);
-            P.paths.ray_d[slot] = f4(d, 0.f);
+struct PrimaryOps {
+    const FrameParams& P;
+    int first;
+    __device__ __forceinline__ bool fetch(int w, V3& o, V3& d) const {
+        const int slot = first + w;
+        const int px = slot % P.W, py = slot / P.W;
+        Rng rng = rng_seed(P.frame_id + 10007, (uint32_t)px, (uint32_t)py, (uint32_t)P.W);
+        float ox = rng_next(rng);
+        float oy = rng_next(rng);
+        float su = ((float)px + ox) / (float)P.W;
+        float sv = ((float)py + oy) / (float)P.H;
+        o = V3(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]);
+        d = normalize(V3(P.cam.d00[0], P.cam.d00[1], P.cam.d00[2]) +
+                      su * V3(P.cam.du[0], P.cam.du[1], P.cam.du[2]) +
+                      sv * V3(P.cam.dv[0], P.cam.dv[1], P.cam.dv[2]));
+        P.paths.rng[slot] = rng.state;
+        P.paths.ray_o[slot] = f4(o, 0.f);
+        P.paths.ray_d[slot] = f4(d, 0.f);
+        return false;
+    }
+    __device__ __forceinline__ void commit(int w, const Hit& h, bool finished) const {
+        const int slot = first + (finished ? w : 0);
+        const bool hit_any = finished && h.prim >= 0;
+        if (finished) {
             P.paths.hit[slot] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
             P.paths.beta[slot] = make_float4(1.f, 1.f, 1.f, __int_as_float(0));
             P.paths.dl_light[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const V3 d = v3(P.paths.ray_d[slot]);
             V3 c(0.f);
             if (!hit_any && P.scene.lights.env.has_env) c = env_radiance(P.scene.lights.env, d);
             P.paths.color[slot] = f4(c, 0.f);
@@ -122,11 +124,18 @@ __global__ void __launch_bounds__(kBlock) k_primary(const FrameParams P) {
                 }
             }
         }
-        int idx = queue_reserve(P.q.counts + 0, live && hit_any);
+        int idx = queue_reserve(P.q.counts + 0, hit_any);
         if (idx >= 0) P.q.shade[0][idx] = slot;
     }
+};
+
+__global__ void __launch_bounds__(kBlock) k_primary(const FrameParams P) {
+    const int n = (P.row1 - P.row0) * P.W;
+    TraceStats st[2] = {{0, 0}, {0, 0}};
+    PrimaryOps ops{P, P.row0 * P.W};
+    trace_queue(P.scene.geom, n, P.q.counts + 6, ops, 0.f, 1e30f, P.collect_stats ? st : nullptr);
     if (P.collect_stats) {
-        flush_trav(P.q.trav + 4, st);
+        flush_trav(P.q.trav + 4, st[0]);
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.q.trav + 9, (unsigned long long)n);
     }
 }
@@ -260,43 +269,57 @@ __global__ void __launch_bounds__(kBlock) k_shade(const FrameParams P, int src) 
 // ---------------------------------------------------------------------------------
 // extend / shadow
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_extend(const FrameParams P, int dst) {
-    const int n = P.q.counts[2];
-    const int rounds = (n + kBlock - 1) / kBlock;
-    TraceStats st; st.nodes = 0; st.prims = 0;
-    for (int r = blockIdx.x; r < rounds; r += gridDim.x) {
-        int i = r * kBlock + threadIdx.x;
-        bool live = i < n;
-        int slot = live ? P.q.extend[i] : 0;
-        bool hit_any = false;
-        if (live) {
-            V3 o = v3(P.paths.ray_o[slot]), d = v3(P.paths.ray_d[slot]);
-            Hit h = trace<false>(P.scene.geom, o, d, 0.f, 1e30f, P.collect_stats ? &st : nullptr);
-            hit_any = h.prim >= 0;
-            if (hit_any) P.paths.hit[slot] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
+// One launch traces a vertex's occlusion probes AND its continuation rays: work items
+// [0, n_shadow) are shadow-queue entries (any-hit), [n_shadow, n_shadow + n_extend) extend-queue
+// entries (closest-hit).  Fewer, fuller launches: the long-path tail is a chain of
+// latency-bound launches, and the two ray kinds share warps.
+struct TraceOps {
+    const FrameParams& P;
+    int n_shadow, dst;
+    __device__ __forceinline__ bool fetch(int w, V3& o, V3& d) const {
+        if (w < n_shadow) {
+            float4 a = P.q.shadow[2 * (size_t)w + 0];
+            float4 b = P.q.shadow[2 * (size_t)w + 1];
+            o = V3(a.x, a.y, a.z);
+            d = V3(b.x, b.y, b.z);
+            return true;
         }
-        int idx = queue_reserve(P.q.counts + dst, live && hit_any);
+        const int slot = P.q.extend[w - n_shadow];
+        o = v3(P.paths.ray_o[slot]);
+        d = v3(P.paths.ray_d[slot]);
+        return false;
+    }
+    __device__ __forceinline__ void commit(int w, const Hit& h, bool finished) const {
+        const bool got = finished && h.prim >= 0;
+        bool to_shade = false;
+        int slot = 0;
+        if (got) {
+            if (w < n_shadow) {
+                const int tag = __float_as_int(P.q.shadow[2 * (size_t)w].w);
+                atomicAnd(P.paths.vis + (tag & 0x3fffffff), ~(1u << (tag >> 30)));
+            } else {
+                slot = P.q.extend[w - n_shadow];
+                P.paths.hit[slot] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
+                to_shade = true;
+            }
+        }
+        int idx = queue_reserve(P.q.counts + dst, to_shade);
         if (idx >= 0) P.q.shade[dst][idx] = slot;
     }
-    if (P.collect_stats) {
-        flush_trav(P.q.trav + 0, st);
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.q.trav + 6, (unsigned long long)n);
-    }
-}
+};
 
-__global__ void __launch_bounds__(kBlock) k_shadow(const FrameParams P) {
-    const int n = P.q.counts[3];
-    TraceStats st; st.nodes = 0; st.prims = 0;
-    for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
-        float4 a = P.q.shadow[2 * (size_t)i + 0];
-        float4 b = P.q.shadow[2 * (size_t)i + 1];
-        int tag = __float_as_int(a.w);
-        Hit h = trace<true>(P.scene.geom, V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), 0.f, 1e30f, P.collect_stats ? &st : nullptr);
-        if (h.prim >= 0) atomicAnd(P.paths.vis + (tag & 0x3fffffff), ~(1u << (tag >> 30)));
-    }
+__global__ void __launch_bounds__(kBlock) k_trace(const FrameParams P, int dst) {
+    const int n_extend = P.q.counts[2], n_shadow = P.q.counts[3];
+    TraceStats st[2] = {{0, 0}, {0, 0}};
+    TraceOps ops{P, n_shadow, dst};
+    trace_queue(P.scene.geom, n_shadow + n_extend, P.q.counts + 4, ops, 0.f, 1e30f, P.collect_stats ? st : nullptr);
     if (P.collect_stats) {
-        flush_trav(P.q.trav + 2, st);
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.q.trav + 7, (unsigned long long)n);
+        flush_trav(P.q.trav + 0, st[0]);
+        flush_trav(P.q.trav + 2, st[1]);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            atomicAdd(P.q.trav + 6, (unsigned long long)n_extend);
+            atomicAdd(P.q.trav + 7, (unsigned long long)n_shadow);
+        }
     }
 }
 
@@ -377,15 +400,35 @@ __global__ void __launch_bounds__(256) k_msnn_composite(const MsnnComposite C) {
     }
 }
 
+struct HookOps {
+    const float* org; const float* dir; float4* out_hit; int any;
+    __device__ __forceinline__ bool fetch(int w, V3& o, V3& d) const {
+        o = V3(org[3 * w], org[3 * w + 1], org[3 * w + 2]);
+        d = V3(dir[3 * w], dir[3 * w + 1], dir[3 * w + 2]);
+        return any != 0;
+    }
+    __device__ __forceinline__ void commit(int w, const Hit& h, bool finished) const {
+        if (finished) out_hit[w] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
+    }
+};
+
+// Test hook.  With out_stats == nullptr the rays go through the production warp-cooperative
+// traversal; with per-ray statistics requested, through the portable one-thread-per-ray loop
+// (the counters are per ray there).
 __global__ void __launch_bounds__(kBlock) k_trace_rays(const SceneView S, const float* org, const float* dir, int n,
-                                                        int any, float tmin, float tmax, float4* out_hit, int* out_stats) {
+                                                        int any, float tmin, float tmax, float4* out_hit, int* out_stats,
+                                                        int* cursor) {
+    if (!out_stats) {
+        HookOps ops{org, dir, out_hit, any};
+        trace_queue(S.geom, n, cursor, ops, tmin, tmax, nullptr);
+        return;
+    }
     for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
         V3 o(org[3 * i], org[3 * i + 1], org[3 * i + 2]), d(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
         TraceStats st; st.nodes = 0; st.prims = 0;
-        Hit h = any ? trace<true>(S.geom, o, d, tmin, tmax, out_stats ? &st : nullptr)
-                    : trace<false>(S.geom, o, d, tmin, tmax, out_stats ? &st : nullptr);
+        Hit h = any ? trace<true>(S.geom, o, d, tmin, tmax, &st) : trace<false>(S.geom, o, d, tmin, tmax, &st);
         out_hit[i] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
-        if (out_stats) { out_stats[2 * i] = st.nodes; out_stats[2 * i + 1] = st.prims; }
+        out_stats[2 * i] = st.nodes; out_stats[2 * i + 1] = st.prims;
     }
 }
 
@@ -396,7 +439,7 @@ int persistent_grid(int ctas_per_sm) { return wavefront_sm_count() * ctas_per_sm
 void launch_primary(const FrameParams& P, cudaStream_t stream) {
     int n = (P.row1 - P.row0) * P.W;
     int blocks = (n + kBlock - 1) / kBlock;
-    int grid = blocks < persistent_grid(16) ? blocks : persistent_grid(16);
+    int grid = blocks < persistent_grid(kTraceCtasPerSm) ? blocks : persistent_grid(kTraceCtasPerSm);
     if (grid < 1) grid = 1;
     k_primary<<<grid, kBlock, 0, stream>>>(P);
     g_launches++;
@@ -405,12 +448,8 @@ void launch_shade(const FrameParams& P, int src, cudaStream_t stream) {
     k_shade<<<persistent_grid(8), kBlock, 0, stream>>>(P, src);
     g_launches++;
 }
-void launch_extend(const FrameParams& P, int dst, cudaStream_t stream) {
-    k_extend<<<persistent_grid(16), kBlock, 0, stream>>>(P, dst);
-    g_launches++;
-}
-void launch_shadow(const FrameParams& P, cudaStream_t stream) {
-    k_shadow<<<persistent_grid(16), kBlock, 0, stream>>>(P);
+void launch_trace(const FrameParams& P, int dst, cudaStream_t stream) {
+    k_trace<<<persistent_grid(kTraceCtasPerSm), kBlock, 0, stream>>>(P, dst);
     g_launches++;
 }
 void launch_finalize(const FrameParams& P, cudaStream_t stream) {
@@ -422,11 +461,12 @@ void launch_msnn_composite(const MsnnComposite& C, cudaStream_t stream) {
     g_launches++;
 }
 void launch_trace_rays(const SceneView& S, const float* org, const float* dir, int n, int any, float tmin, float tmax,
-                       float4* out_hit, int* out_stats, cudaStream_t stream) {
+                       float4* out_hit, int* out_stats, int* cursor, cudaStream_t stream) {
     int blocks = (n + kBlock - 1) / kBlock;
-    int grid = blocks < persistent_grid(16) ? blocks : persistent_grid(16);
+    int grid = blocks < persistent_grid(kTraceCtasPerSm) ? blocks : persistent_grid(kTraceCtasPerSm);
     if (grid < 1) grid = 1;
-    k_trace_rays<<<grid, kBlock, 0, stream>>>(S, org, dir, n, any, tmin, tmax, out_hit, out_stats);
+    cudaMemsetAsync(cursor, 0, sizeof(int), stream);
+    k_trace_rays<<<grid, kBlock, 0, stream>>>(S, org, dir, n, any, tmin, tmax, out_hit, out_stats, cursor);
     g_launches++;
 }
 

@@ -42,7 +42,7 @@ struct Queues {
     int* shade[2];       // double-buffered slot lists
     int* extend;
     float4* shadow;      // 2 x float4 per entry: (o.xyz, slot|bit<<31) (d.xyz, -)
-    int* counts;         // [0],[1] shade ; [2] extend ; [3] shadow
+    int* counts;         // [0],[1] shade ; [2] extend ; [3] shadow ; work cursors: [4] trace [6] primary
     unsigned long long* trav;   // [0],[1] extend nodes/prims ; [2],[3] shadow nodes/prims ; [4],[5] primary ;
                                 // [6] extend rays ; [7] shadow rays ; [8] shade items ; [9] primary rays
 };
@@ -87,13 +87,13 @@ struct MsnnComposite {
 // All launches are asynchronous on `stream`.
 void launch_primary(const FrameParams& P, cudaStream_t stream);
 void launch_shade(const FrameParams& P, int src_queue, cudaStream_t stream);
-void launch_extend(const FrameParams& P, int dst_queue, cudaStream_t stream);
-void launch_shadow(const FrameParams& P, cudaStream_t stream);
+// occlusion probes + continuation rays of one vertex in one launch
+void launch_trace(const FrameParams& P, int dst_queue, cudaStream_t stream);
 void launch_finalize(const FrameParams& P, cudaStream_t stream);
 void launch_msnn_composite(const MsnnComposite& C, cudaStream_t stream);
 // test hook: closest-hit / any-hit for caller-supplied rays (device pointers)
 void launch_trace_rays(const SceneView& S, const float* org, const float* dir, int n, int any,
-                       float tmin, float tmax, float4* out_hit, int* out_stats, cudaStream_t stream);
+                       float tmin, float tmax, float4* out_hit, int* out_stats, int* cursor, cudaStream_t stream);
 // test hook: vertex shading of caller-supplied hits
 int wavefront_sm_count();
 uint64_t wavefront_launch_count();
