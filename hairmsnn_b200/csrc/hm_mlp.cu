@@ -23,6 +23,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 #include <stdexcept>
@@ -145,8 +146,10 @@ __device__ __forceinline__ float quartic_cdf(float x, float inv_radius) {
     return fmaxf(0.0f, fminf(1.0f, (15.f / 16.f) * u * (1 - (2.f / 3.f) * u2 + (1.f / 5.f) * u4) + 0.5f));
 }
 
-// Encodes one input row into 64 halves at `dst` (shared memory row).
-__device__ __forceinline__ void encode_row(const NetShape& S, const __half2* __restrict__ table, const float* x, __half* dst) {
+// Encodes one input row into 64 halves; `at(col)` gives the address of column `col` (even
+// columns are 4-byte aligned and followed by their odd neighbour).
+template <class At>
+__device__ __forceinline__ void encode_row(const NetShape& S, const __half2* __restrict__ table, const float* x, At at) {
     const int nl = S.grid.n_levels;
     for (int l = 0; l < nl; ++l) {
         const float scale = S.grid.scale[l];
@@ -172,7 +175,7 @@ __device__ __forceinline__ void encode_row(const NetShape& S, const __half2* __r
             float2 v = __half22float2(__ldg(tl + idx));
             acc.x += w * v.x; acc.y += w * v.y;
         }
-        *reinterpret_cast<uint32_t*>(dst + 2 * l) = pack2(acc.x, acc.y);
+        *reinterpret_cast<uint32_t*>(at(2 * l)) = pack2(acc.x, acc.y);
     }
     int c0 = nl * 2;
     const int nb = S.blob_bins;
@@ -183,13 +186,13 @@ __device__ __forceinline__ void encode_row(const NetShape& S, const __half2* __r
         for (int k = 0; k < nb; ++k) {
             const float rb = (float)(k + 1) / (float)nb;
             const float right = quartic_cdf(rb - xv, inv_r) + quartic_cdf(rb - xv - 1.0f, inv_r) + quartic_cdf(rb - xv + 1.0f, inv_r);
-            dst[c0 + j * nb + k] = __float2half_rn(right - left);
+            *at(c0 + j * nb + k) = __float2half_rn(right - left);
             left = right;
         }
     }
     c0 += S.blob_dims * nb;
-    for (int j = 0; j < S.identity_dims; ++j) dst[c0 + j] = __float2half_rn(x[3 + S.blob_dims + j]);
-    for (int c = c0 + S.identity_dims; c < kW; ++c) dst[c] = __float2half_rn(1.0f);
+    for (int j = 0; j < S.identity_dims; ++j) *at(c0 + j) = __float2half_rn(x[3 + S.blob_dims + j]);
+    for (int c = c0 + S.identity_dims; c < kW; ++c) *at(c) = __float2half_rn(1.0f);
 }
 
 struct FwdArgs {
@@ -231,7 +234,8 @@ __global__ void __launch_bounds__(kTile) k_mlp_forward(const NetShape S, const _
             } else {
                 for (int i = 0; i < 12; ++i) x[i] = i < S.in_ch ? __ldg(src + i) : 0.f;
             }
-            encode_row(S, table, x, sAct + threadIdx.x * kStride);
+            __half* rowp = sAct + threadIdx.x * kStride;
+            encode_row(S, table, x, [rowp](int col) { return rowp + col; });
         }
         __syncwarp();
         if (TRAIN) {
@@ -307,6 +311,235 @@ __global__ void __launch_bounds__(kTile) k_mlp_forward(const NetShape S, const _
             if (lane == 0) atomicAdd(A.loss, lsum);
         }
         __syncwarp();
+    }
+}
+
+// ---- tcgen05 / TMEM forward -----------------------------------------------------------
+// Same computation as k_mlp_forward, with the three layers on the 5th-generation tensor
+// cores: a CTA owns 128 rows; the activation tile A [128 x 64] fp16 and the weights
+// W0, W1 [64 x 64], Wout [16 x 64] sit in shared memory in the canonical K-major
+// SWIZZLE_128B layout (row = 128 B; 8-row groups of 1024 B; 16-byte chunk c of row r is
+// stored at chunk c ^ (r & 7)); one elected thread issues 4 x tcgen05.mma (M=128, N=64|16,
+// K=16) per layer into a 64-column TMEM accumulator and commits to an mbarrier; the
+// epilogue is row-per-thread: tcgen05.ld 32x32b gives thread i the 64 fp32 accumulators of
+// row i, which are ReLU'd, packed to fp16 and written back into A (swizzled) as the next
+// layer's operand.  The encoded inputs are produced in-kernel, so A never touches HBM.
+namespace tc {
+
+constexpr uint32_t kABytes = 128 * 128, kWBytes = 64 * 128, kWoBytes = 16 * 128;
+constexpr uint32_t kSmemBytes = kABytes + 2 * kWBytes + kWoBytes + 64 /*barrier + tmem ptr*/ + 1024 /*alignment slack*/;
+constexpr uint32_t kTmemCols = 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t chunk) {
+    return (row >> 3) * 1024u + (row & 7u) * 128u + ((chunk ^ (row & 7u)) << 4);
+}
+// K-major, SWIZZLE_128B, 128-byte rows: LBO = 1 (16 B), SBO = 64 (1024 B), version 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)64 << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+    // c_format F32 (bit 4), A/B F16 K-major, N >> 3 at bit 17, M >> 4 at bit 24
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// weights [rows][64] fp16 (row-major = K-major) -> swizzled tile
+__device__ __forceinline__ void load_weights_sw(unsigned char* dst, const __half* src, int rows) {
+    for (int i = threadIdx.x; i < rows * 8; i += blockDim.x) {
+        const int r = i >> 3, c = i & 7;
+        *reinterpret_cast<uint4*>(dst + sw128(r, c)) = __ldg(reinterpret_cast<const uint4*>(src + r * kW + c * 8));
+    }
+}
+
+}  // namespace tc
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(kTile) k_mlp_forward_tc(const NetShape S, const __half* __restrict__ params, FwdArgs A) {
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t raw = tc::smem_u32(smem_dyn);
+    unsigned char* base = smem_dyn + ((1024u - (raw & 1023u)) & 1023u);
+    unsigned char* sA = base;
+    unsigned char* sW0 = sA + tc::kABytes;
+    unsigned char* sW1 = sW0 + tc::kWBytes;
+    unsigned char* sWo = sW1 + tc::kWBytes;
+    uint64_t* bar_ptr = reinterpret_cast<uint64_t*>(sWo + tc::kWoBytes);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_ptr + 1);
+    const uint32_t bar = tc::smem_u32(bar_ptr);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    tc::load_weights_sw(sW0, params, kW);
+    tc::load_weights_sw(sW1, params + kW * kW, kW);
+    tc::load_weights_sw(sWo, params + 2 * kW * kW, kOutPad);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tc::smem_u32(tmem_slot)), "r"(tc::kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc::fence_async_smem();          // weight tiles were written through the generic proxy
+    tc::fence_before();
+    __syncthreads();
+    tc::fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint64_t dA = tc::make_desc(tc::smem_u32(sA));
+    const uint64_t dW0 = tc::make_desc(tc::smem_u32(sW0));
+    const uint64_t dW1 = tc::make_desc(tc::smem_u32(sW1));
+    const uint64_t dWo = tc::make_desc(tc::smem_u32(sWo));
+    const uint32_t idesc64 = tc::make_idesc(64), idesc16 = tc::make_idesc(16);
+    const __half2* table = reinterpret_cast<const __half2*>(params + 2 * kW * kW + kOutPad * kW);
+    uint32_t parity = 0;
+    const uint32_t row = threadIdx.x;
+
+    // one layer on the tensor core: D[128 x n] = A[128 x 64] * W[n x 64]^T, K in 4 steps of 16
+    auto layer = [&](uint64_t dW, uint32_t idesc) {
+        tc::fence_async_smem();      // this thread's A-tile writes -> async proxy
+        tc::fence_before();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tc::fence_after();
+#pragma unroll
+            for (uint32_t kk = 0; kk < 4; ++kk) tc::mma_f16(tmem, dA + 2 * kk, dW + 2 * kk, idesc, kk);
+            tc::commit(bar);
+        }
+        tc::wait_bar(bar, parity);
+        parity ^= 1u;
+        tc::fence_after();
+    };
+    // TMEM row -> ReLU -> fp16 -> A tile (and optionally global)
+    auto epilogue_hidden = [&](__half* gdst) {
+        uint32_t v[32];
+        uint4 packed[8];
+#pragma unroll
+        for (int half_i = 0; half_i < 2; ++half_i) {
+            tc::ld32(tmem_lane + half_i * 32, v);
+            tc::wait_ld();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t w[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    w[j] = pack2(fmaxf(__uint_as_float(v[c * 8 + 2 * j]), 0.f), fmaxf(__uint_as_float(v[c * 8 + 2 * j + 1]), 0.f));
+                packed[half_i * 4 + c] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(sA + tc::sw128(row, c)) = packed[c];
+        if (gdst) {
+            uint4* d = reinterpret_cast<uint4*>(gdst);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) d[c] = packed[c];
+        }
+    };
+
+    for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+        const size_t grow = (size_t)tile * kTile + row;
+        {
+            float x[12];
+            const float* src = A.in + grow * S.in_ch;
+            if (S.in_ch == 12) {
+                const float4* s4 = reinterpret_cast<const float4*>(src);
+                float4 a = __ldg(s4), b = __ldg(s4 + 1), c = __ldg(s4 + 2);
+                x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+                x[8] = c.x; x[9] = c.y; x[10] = c.z; x[11] = c.w;
+            } else {
+                for (int i = 0; i < 12; ++i) x[i] = i < S.in_ch ? __ldg(src + i) : 0.f;
+            }
+            encode_row(S, table, x, [sA, row](int col) {
+                return reinterpret_cast<__half*>(sA + tc::sw128(row, (uint32_t)col >> 3) + ((uint32_t)col & 7u) * 2u);
+            });
+            if (TRAIN) {
+                uint4* d = reinterpret_cast<uint4*>(A.e + grow * kW);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) d[c] = *reinterpret_cast<const uint4*>(sA + tc::sw128(row, c));
+            }
+        }
+        layer(dW0, idesc64);
+        epilogue_hidden(TRAIN ? A.h1 + grow * kW : nullptr);
+        layer(dW1, idesc64);
+        epilogue_hidden(TRAIN ? A.h2 + grow * kW : nullptr);
+        layer(dWo, idesc16);
+        {
+            uint32_t v[16];
+            tc::ld16(tmem_lane, v);
+            tc::wait_ld();
+            // network output is held in fp16 by the reference (trim_and_cast_from)
+            const float pr = __half2float(__float2half_rn(__uint_as_float(v[0])));
+            const float pg = __half2float(__float2half_rn(__uint_as_float(v[1])));
+            const float pb = __half2float(__float2half_rn(__uint_as_float(v[2])));
+            if (!TRAIN) {
+                A.out[grow * 3 + 0] = pr; A.out[grow * 3 + 1] = pg; A.out[grow * 3 + 2] = pb;
+            } else {
+                const float lum = 0.299f * pr + 0.587f * pg + 0.114f * pb;
+                const float denom = lum * lum + 0.01f;
+                const float df0 = pr - __ldg(A.target + grow * 3 + 0);
+                const float df1 = pg - __ldg(A.target + grow * 3 + 1);
+                const float df2 = pb - __ldg(A.target + grow * 3 + 2);
+                float lsum = df0 * df0 / denom * A.inv_n_total + df1 * df1 / denom * A.inv_n_total + df2 * df2 / denom * A.inv_n_total;
+                uint2 dy;
+                dy.x = pack2(kLossScale * (2 * df0 / denom) * A.inv_n_total, kLossScale * (2 * df1 / denom) * A.inv_n_total);
+                dy.y = pack2(kLossScale * (2 * df2 / denom) * A.inv_n_total, 0.f);
+                *reinterpret_cast<uint2*>(A.dy + grow * 4) = dy;
+#pragma unroll
+                for (int ofs = 16; ofs > 0; ofs >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, ofs);
+                if (lane == 0) atomicAdd(A.loss, lsum);
+            }
+        }
+        // the next tile's encode overwrites A and its first MMA overwrites the accumulator:
+        // order them after every thread's TMEM reads
+        tc::fence_before();
+        __syncthreads();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(tc::kTmemCols) : "memory");
     }
 }
 
@@ -698,6 +931,11 @@ Mlp::Mlp(const MlpConfig& cfg, cudaStream_t stream) : cfg_(cfg), stream_(stream)
     HM_CUDA(cudaFuncSetAttribute(k_mlp_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
     HM_CUDA(cudaFuncSetAttribute(k_mlp_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
     HM_CUDA(cudaFuncSetAttribute(k_mlp_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
+    HM_CUDA(cudaFuncSetAttribute(k_mlp_forward_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
+    HM_CUDA(cudaFuncSetAttribute(k_mlp_forward_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
+    // forward implementation: tcgen05/TMEM by default; HM_MLP_IMPL=mma selects the mma.sync kernel
+    const char* impl = getenv("HM_MLP_IMPL");
+    use_tc_ = !(impl && std::string(impl) == "mma");
     reinitialize();
 }
 
@@ -766,7 +1004,8 @@ void Mlp::inference(const float* d_in, float* d_out, int n) {
     memset(&A, 0, sizeof(A));
     A.in = d_in; A.out = d_out; A.n_tiles = n / kTile;
     int grid = std::min(A.n_tiles, sm_count() * 4);
-    k_mlp_forward<false><<<grid, kTile, kFwdSmem, stream_>>>(S, (const __half*)d_half_, A);
+    if (use_tc_) k_mlp_forward_tc<false><<<grid, kTile, tc::kSmemBytes, stream_>>>(S, (const __half*)d_half_, A);
+    else k_mlp_forward<false><<<grid, kTile, kFwdSmem, stream_>>>(S, (const __half*)d_half_, A);
     launches_++;
     HM_CUDA(cudaGetLastError());
 }
@@ -785,7 +1024,8 @@ void Mlp::forward_backward(const float* d_in, const float* d_target, int n, int 
     A.inv_n_total = 1.f / (float)((size_t)n_total_records * cfg_.out_ch);
     A.n_tiles = n / kTile;
     int grid = std::min(A.n_tiles, sm_count() * 4);
-    k_mlp_forward<true><<<grid, kTile, kFwdSmem, stream_>>>(S, (const __half*)d_half_, A);
+    if (use_tc_) k_mlp_forward_tc<true><<<grid, kTile, tc::kSmemBytes, stream_>>>(S, (const __half*)d_half_, A);
+    else k_mlp_forward<true><<<grid, kTile, kFwdSmem, stream_>>>(S, (const __half*)d_half_, A);
     BwdArgs B;
     B.in = d_in; B.dy = (const __half*)d_dy_; B.h1 = h1; B.h2 = h2; B.dh1 = dh1; B.dh2 = dh2;
     B.grid_grads = d_grads_ + n_matrix_;

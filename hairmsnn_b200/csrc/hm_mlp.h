@@ -91,6 +91,7 @@ private:
     float lr_factor_ = 1.f;
     int step_ = 0;
     uint64_t launches_ = 0;
+    bool use_tc_ = true;
 };
 
 }  // namespace hm
