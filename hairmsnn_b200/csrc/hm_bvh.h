@@ -11,15 +11,21 @@
 //     q2 = (lo1.z hi1.x hi1.y hi1.z)
 //     q3 = (child0, child1, -, -) as int bits
 //   child >= 0 : inner node index
-//   child <  0 : leaf, ~child = (first_slot << 3) | (count - 1), count <= 8
+//   child <  0 : leaf holding ONE primitive reference, ~child = its leaf slot
+//
+//   A fibre segment enters the tree as several references (one per sub-span of its
+//   parameter range, each with the tight box of its piece of the curve — a thin diagonal
+//   tube fills a tiny fraction of its own box); all references of a segment name the same
+//   slot, so the primitive data exists once.
 //
 //   leaf slot s : leaf_data[4s..4s+3] = the primitive itself, 64 B, so a leaf test is ONE
 //                                 dependent fetch after the node (HBM capacity is cheap
 //                                 on B200; an index -> control-point indirection is not):
-//                                   fibre   : 4 control points (xyz, radius)
-//                                   triangle: v0, v1, v2, (-, -, -, -1)   (w < 0 tags it)
-//                 leaf_prim[s]  = primitive id reported to the caller
-//                                 (segment id, or num_segments + triangle id)
+//                                   fibre   : 4 control points (xyz, w); w of point 1 is the
+//                                             radius, w of point 0 carries the primitive id
+//                                             (int bits), w of point 3 is >= 0
+//                                   triangle: v0, v1, v2, (id bits, -, -, -1)   (w < 0 tags it)
+//                 leaf_prim[s]  = primitive id (segment id, or num_segments + triangle id)
 //                 leaf_code[s]  = host-side bookkeeping only (first control-point index,
 //                                 or triangle index | kTriTag)
 //
@@ -32,7 +38,6 @@
 namespace hm {
 
 static constexpr int kTriTag = 0x40000000;
-static constexpr int kMaxLeaf = 8;
 static constexpr int kStackDepth = 64;
 
 struct F4 {
@@ -98,18 +103,36 @@ struct TraceStats {
     int prims;
 };
 
-// ANY = true: occlusion query, returns at the first accepted hit.
-//
-// "while-while" traversal: descend inner nodes until a leaf is reached, then test the
-// leaf's primitives.  On the GPU the lanes of a warp re-converge after the inner loop, so
-// the (expensive, variable-length) curve solver runs with as many lanes as possible in
-// the leaf phase instead of interleaving with other lanes' box tests.
+// One primitive of a leaf slot against the ray; updates `best` on an accepted hit.  A
+// segment is reachable through several references: once it holds the current best hit the
+// others are skipped (they would find the same (t, u) again).
+HM_HD bool test_slot(const GeomView& g, int slot, V3 o, V3 d, const RayFrame& rf, float tmin, Hit& best) {
+    const F4* p = g.leaf_data + 4 * (size_t)slot;
+    F4 a = load_f4(p + 0), b = load_f4(p + 1), c = load_f4(p + 2), e = load_f4(p + 3);
+    if (e.w < 0.f) {
+        float t, b1, b2;
+        if (intersect_triangle(o, d, tmin, best.t, V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), V3(c.x, c.y, c.z), t, b1, b2)) {
+            best.t = t; best.u = b1; best.v = b2; best.prim = f_as_i(e.x);
+            return true;
+        }
+    } else if (f_as_i(a.w) != best.prim) {
+        SegHit sh;
+        if (intersect_fibre(rf, tmin, best.t, f4_to_v4(a), f4_to_v4(b), f4_to_v4(c), f4_to_v4(e), sh)) {
+            best.t = sh.t; best.u = sh.u; best.v = 0.f; best.prim = f_as_i(a.w);
+            return true;
+        }
+    }
+    return false;
+}
+
+// ANY = true: occlusion query, returns at the first accepted hit.  Portable one-ray loop
+// (host oracle/baseline, and the per-ray statistics hook); the production kernels run the
+// warp-cooperative schedule of hm_trace_dev.cuh over the same per-primitive arithmetic.
 template <bool ANY>
 HM_HD Hit trace(const GeomView& g, V3 o, V3 d, float tmin, float tmax, TraceStats* stats = nullptr) {
     Hit best;
     best.t = tmax; best.prim = -1; best.u = 0.f; best.v = 0.f;
     if (g.num_nodes == 0) return best;
-    int best_slot = -1;
 
     const float eps = 1e-20f;
     V3 dd = V3(fabsf(d.x) > eps ? d.x : (d.x < 0.f ? -eps : eps),
@@ -125,8 +148,7 @@ HM_HD Hit trace(const GeomView& g, V3 o, V3 d, float tmin, float tmax, TraceStat
     const int kDone = 0x7fffffff;
 
     while (cur != kDone) {
-        // ---- inner nodes ----
-        while (cur >= 0 && cur != kDone) {
+        if (cur >= 0) {
             const F4* n = g.nodes + 4 * (size_t)cur;
             F4 q0 = load_f4(n + 0), q1 = load_f4(n + 1), q2 = load_f4(n + 2), q3 = load_f4(n + 3);
             if (stats) stats->nodes++;
@@ -145,36 +167,12 @@ HM_HD Hit trace(const GeomView& g, V3 o, V3 d, float tmin, float tmax, TraceStat
             } else {
                 cur = sp > 0 ? stack[--sp] : kDone;
             }
-        }
-        if (cur == kDone) break;
-        // ---- leaf ----
-        {
-            int code = ~cur;
-            int first = code >> 3;
-            int count = (code & 7) + 1;
-            for (int i = 0; i < count; ++i) {
-                const F4* p = g.leaf_data + 4 * (size_t)(first + i);
-                F4 a = load_f4(p + 0), b = load_f4(p + 1), c = load_f4(p + 2), e = load_f4(p + 3);
-                if (stats) stats->prims++;
-                if (e.w < 0.f) {
-                    float t, b1, b2;
-                    if (intersect_triangle(o, d, tmin, best.t, V3(a.x, a.y, a.z), V3(b.x, b.y, b.z),
-                                           V3(c.x, c.y, c.z), t, b1, b2)) {
-                        best.t = t; best.u = b1; best.v = b2; best_slot = first + i;
-                        if (ANY) { best.prim = load_i(g.leaf_prim + best_slot); return best; }
-                    }
-                } else {
-                    SegHit sh;
-                    if (intersect_fibre(rf, tmin, best.t, f4_to_v4(a), f4_to_v4(b), f4_to_v4(c), f4_to_v4(e), sh)) {
-                        best.t = sh.t; best.u = sh.u; best.v = 0.f; best_slot = first + i;
-                        if (ANY) { best.prim = load_i(g.leaf_prim + best_slot); return best; }
-                    }
-                }
-            }
+        } else {
+            if (stats) stats->prims++;
+            if (test_slot(g, ~cur, o, d, rf, tmin, best) && ANY) return best;
             cur = sp > 0 ? stack[--sp] : kDone;
         }
     }
-    if (best_slot >= 0) best.prim = load_i(g.leaf_prim + best_slot);
     return best;
 }
 
