@@ -4,7 +4,7 @@ CSRC := hairmsnn_b200/csrc
 LIB := hairmsnn_b200/lib/libhairmsnn.so
 ARCH := -gencode arch=compute_100a,code=sm_100a
 # -fmad=false: the traversal/intersection code must round like its host build (hit-id parity)
-NVFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC,-O3,-ffp-contract=off -fmad=false --expt-relaxed-constexpr -Xptxas -v
+NVFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC,-O3,-ffp-contract=off -fmad=false --expt-relaxed-constexpr -Xptxas -v $(EXTRA)
 NVFLAGS_MLP := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC,-O3 --expt-relaxed-constexpr -Xptxas -v
 CXXFLAGS := -O2 -std=c++17 -fPIC -ffp-contract=off -mfma -pthread -I/usr/local/cuda/include
 OBJ := build/hm_wavefront.o build/hm_renderer.o build/hm_mlp.o build/hm_capi.o build/hm_io.o build/hm_piz.o build/hm_scene_util.o build/hm_bvh_build.o

@@ -138,7 +138,7 @@ def cpu_baseline(sc, kw, seconds_target=12.0):
     while True:
         ref.render_msnn_gbuffer(n, W, H, BETA_CLI - 1, every_nth, idxs, y0=y0, y1=y1, threads=cores)
         n += 1
-        if time.perf_counter() - t0 > seconds_target or n >= 64:
+        if time.perf_counter() - t0 > seconds_target or n >= 4096:
             break
     dt = time.perf_counter() - t0
     paths = (y1 - y0) * W * n
@@ -285,8 +285,16 @@ def main():
     launches_dom = stage_launches[dominant] / args.steps
     avg_launch_ms = stage_ms[dominant] / max(stage_launches[dominant], 1)
     achieved = alg_bytes_per_step / max(launches_dom, 1) / (avg_launch_ms * 1e-3) / 1e9
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/)
+    traffic, traffic_note = None, None
+    tp = os.path.join(ROOT, "profiles", f"k_{dominant}_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        traffic = tj["traffic_bytes_per_launch"]
+        traffic_note = tj["source"]
     roofline = {"kernel": f"k_{dominant}", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "peak_source": peaks["src"], "traffic": None,
+                "frac": achieved / peaks["hbm_gbs"], "peak_source": peaks["src"], "traffic": traffic, "traffic_note": traffic_note,
+                "algorithmic_bytes_per_step": alg_bytes_per_step,
                 "rays_per_step": rays[dominant] / n_inst, "nodes_per_ray": nodes[dominant] / max(rays[dominant], 1),
                 "prims_per_ray": prims[dominant] / max(rays[dominant], 1), "avg_launch_ms": avg_launch_ms,
                 "launches_per_step": launches_dom,

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libhairmsnn.so")
+LIB_PATH = os.environ.get("HM_LIB") or os.path.join(_HERE, "lib", "libhairmsnn.so")   # HM_LIB: A/B builds of the same library
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -102,6 +102,19 @@ def _f32(a):
 
 def _ptr(a, t=_fp):
     return a.ctypes.data_as(t)
+
+
+def band_partition(width, height, records, rank, world):
+    """hm_band_partition: (row0, row1, first record, records owned, records trained on)."""
+    out = (C.c_int * 5)()
+    _check(lib.hm_band_partition(width, height, records, rank, world, out))
+    return tuple(out)
+
+
+def sample_schedule(rank, world, k):
+    """spp sharding: RNG frame id (the reference's accumId) of rank `rank`'s k-th
+    sample; ranks interleave, so the union over ranks of k = 0..K-1 is accumId 0..K*world-1."""
+    return rank + k * world
 
 
 def device_count():

@@ -329,6 +329,14 @@ int hm_renderer_set_frame_schedule(hm_renderer* r, int offset, int stride) {
         r->r->set_frame_schedule(offset, stride);
     });
 }
+int hm_band_partition(int width, int height, int records, int rank, int world, int* out5) {
+    return guarded([&] {
+        if (!out5 || width <= 0 || height <= 0 || records < 0 || world < 1 || rank < 0 || rank >= world)
+            throw std::invalid_argument("bad partition arguments");
+        const hm::BandPartition b = hm::band_partition(width, height, records, rank, world);
+        out5[0] = b.row0; out5[1] = b.row1; out5[2] = b.slot0; out5[3] = b.slots; out5[4] = b.train_n;
+    });
+}
 int hm_renderer_set_profiling(hm_renderer* r, int on) {
     return guarded([&] { need(r, "renderer"); r->r->set_profiling(on != 0); });
 }

@@ -75,6 +75,34 @@ void finalize_geometry(HostScene& s);
 // round trip (owlViewer/Camera.cpp:94-120, Camera.h:55)
 void camera_basis(const HostScene& s, int W, int H, float pos[3], float d00[3], float du[3], float dv[3]);
 
+// Multi-GPU partition of one frame: `world` contiguous row bands; a band owns the
+// training records whose pixel group (fbOfs / everyNth, cuda/hair_msnn.cu:199-203) lies wholly
+// inside it (a group straddling a band edge is left out of that step's batch: its training
+// pixel may fall on either side; with W % everyNth == 0, as in every shipped config, none do).  train_n = the band's record count rounded down to tcnn's batch granularity of 128
+// (common.h:280) — what its backward pass consumes.  Pure host arithmetic: the renderer and the
+// CPU-side multi-rank tests share it.
+struct BandPartition {
+    int row0, row1;          // rows [row0, row1)
+    int slot0, slots;        // training records [slot0, slot0 + slots)
+    int train_n;             // records fed to forward/backward
+};
+inline BandPartition band_partition(int W, int H, int records, int rank, int world) {
+    BandPartition b;
+    b.row0 = (int)((long long)H * rank / world);
+    b.row1 = (int)((long long)H * (rank + 1) / world);
+    const long long n = (long long)W * H;
+    const int every_nth = records > 0 ? (int)(n / records) : 0;
+    if (every_nth < 1) { b.slot0 = 0; b.slots = 0; b.train_n = 0; return b; }
+    const long long px0 = (long long)b.row0 * W, px1 = (long long)b.row1 * W;
+    b.slot0 = (int)((px0 + every_nth - 1) / every_nth);
+    int slot1 = (int)(px1 / every_nth);
+    if (slot1 > records) slot1 = records;
+    if (b.slot0 > slot1) b.slot0 = slot1;
+    b.slots = slot1 - b.slot0;
+    b.train_n = b.slots - b.slots % 128;
+    return b;
+}
+
 inline GeomView make_view(const HostGeometry& g, const HostBvh& b) {
     GeomView v;
     v.nodes = b.nodes.data();

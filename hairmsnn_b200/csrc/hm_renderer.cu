@@ -121,8 +121,8 @@ Renderer::Renderer(const HostScene& hs, int kind, int beta_cli, int device, int 
     if (world < 1 || rank < 0 || rank >= world) throw std::invalid_argument("bad rank/world");
     W_ = hs.width; H_ = hs.height;
     if (W_ <= 0 || H_ <= 0) throw std::invalid_argument("bad frame size");
-    row0_ = (int)((int64_t)H_ * rank / world);
-    row1_ = (int)((int64_t)H_ * (rank + 1) / world);
+    row0_ = band_partition(W_, H_, 0, rank, world).row0;
+    row1_ = band_partition(W_, H_, 0, rank, world).row1;
     int prio_lo = 0, prio_hi = 0;
     HM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     HM_CUDA(cudaStreamCreateWithPriority(&main_stream_, cudaStreamNonBlocking, prio_lo));
@@ -281,12 +281,9 @@ FrameParams Renderer::params_for(const FrameCtx& c) {
         P.msnn_beta = beta_;
         P.every_nth = every_nth_;
         P.train_idxs = c.train_idxs;
-        // this band's training records: fbOfs / everyNth over its pixel range
-        const int64_t px0 = (int64_t)row0_ * W_, px1 = (int64_t)row1_ * W_;
-        P.train_slot0 = (int)(px0 / every_nth_);
-        int slot1 = (int)((px1 + every_nth_ - 1) / every_nth_);
-        if (slot1 > records_) slot1 = records_;
-        P.train_slots = slot1 - P.train_slot0;
+        const BandPartition bp = band_partition(W_, H_, records_, rank_, world_);
+        P.train_slot0 = bp.slot0;
+        P.train_slots = bp.slots;
         P.nn_frame_in = c.nn_frame_in;
         P.nn_train_in = c.nn_train_in;
         P.nn_train_out = c.nn_train_out;
@@ -376,12 +373,8 @@ void Renderer::msnn_trace() {
 void Renderer::msnn_train_backward() {
     if (kind_ != HM_KIND_MSNN) throw std::logic_error("not a HairMSNN renderer");
     if (!current_) throw std::logic_error("msnn_train_backward: call msnn_trace first");
-    const int64_t px0 = (int64_t)row0_ * W_, px1 = (int64_t)row1_ * W_;
-    int s0 = (int)(px0 / every_nth_);
-    int s1 = (int)((px1 + every_nth_ - 1) / every_nth_);
-    if (s1 > records_) s1 = records_;
-    int n = s1 - s0;
-    n -= n % 128;
+    const BandPartition bp = band_partition(W_, H_, records_, rank_, world_);
+    const int s0 = bp.slot0, n = bp.train_n;
     FrameCtx& c = *current_;
     timed(5, order_stream_, [&] {
         mlp_->forward_backward(c.nn_train_in + (size_t)s0 * in_ch_, c.nn_train_out + (size_t)s0 * 3, n, world_ == 1 ? n : records_);

@@ -42,6 +42,15 @@ constexpr int kRefillLanes = 8;    // refill when this many lanes are idle
 #define HM_TRACE_NODE_LANES 10     // below this many node-ready lanes, parked work goes first
 #endif
 
+#ifndef HM_TRACE_PREFETCH
+#define HM_TRACE_PREFETCH 0        // 1: prefetch parked primitives and pushed far children into L2/L1
+#endif
+__device__ __forceinline__ void prefetch_line(const void* p) {
+#if HM_TRACE_PREFETCH
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
+
 // Ops must provide, all __device__:
 //   bool fetch(int work, V3& o, V3& d)                 — ray of work item `work`; returns true for
 //                                                         an occlusion (any-hit) query
@@ -160,13 +169,13 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
                 if (h1 && (!h0 || t1 < t0)) { int tmp = c0; c0 = c1; c1 = tmp; bool th = h0; h0 = h1; h1 = th; }
                 // c0 = nearer hit child (if any), c1 = the other hit child (if any)
                 if (h1) {
-                    if (c1 < 0) s_leaf[nleaf++][tx] = ~c1;
-                    else stack[sp++] = c1;
+                    if (c1 < 0) { s_leaf[nleaf++][tx] = ~c1; prefetch_line(g.leaf_data + 4 * (size_t)(~c1)); }
+                    else { stack[sp++] = c1; prefetch_line(g.nodes + 4 * (size_t)c1); }
                 }
                 if (h0 && c0 >= 0) {
                     cur = c0;
                 } else {
-                    if (h0) s_leaf[nleaf++][tx] = ~c0;     // parked last: popped first
+                    if (h0) { s_leaf[nleaf++][tx] = ~c0; prefetch_line(g.leaf_data + 4 * (size_t)(~c0)); }     // parked last: popped first
                     cur = sp > 0 ? stack[--sp] : kDone;
                 }
             }

@@ -37,7 +37,10 @@ int wavefront_sm_count() {
 namespace {
 
 constexpr int kBlock = 128;
-constexpr int kTraceCtasPerSm = 6;   // persistent traversal grid: resident CTAs per SM at ~80 registers
+#ifndef HM_TRACE_CTAS
+#define HM_TRACE_CTAS 6
+#endif
+constexpr int kTraceCtasPerSm = HM_TRACE_CTAS;   // persistent traversal grid: resident CTAs per SM (launch bounds cap the registers)
 
 __device__ __forceinline__ float4 f4(V3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
 __device__ __forceinline__ V3 v3(float4 a) { return V3(a.x, a.y, a.z); }
@@ -129,7 +132,7 @@ struct PrimaryOps {
     }
 };
 
-__global__ void __launch_bounds__(kBlock) k_primary(const FrameParams P) {
+__global__ void __launch_bounds__(kBlock, kTraceCtasPerSm) k_primary(const FrameParams P) {
     const int n = (P.row1 - P.row0) * P.W;
     TraceStats st[2] = {{0, 0}, {0, 0}};
     PrimaryOps ops{P, P.row0 * P.W};
@@ -308,7 +311,7 @@ struct TraceOps {
     }
 };
 
-__global__ void __launch_bounds__(kBlock) k_trace(const FrameParams P, int dst) {
+__global__ void __launch_bounds__(kBlock, kTraceCtasPerSm) k_trace(const FrameParams P, int dst) {
     const int n_extend = P.q.counts[2], n_shadow = P.q.counts[3];
     TraceStats st[2] = {{0, 0}, {0, 0}};
     TraceOps ops{P, n_shadow, dst};

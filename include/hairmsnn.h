@@ -188,6 +188,11 @@ int hm_renderer_reset_stats(hm_renderer* r);
 /* Sample schedule for spp-sharded rendering: the RNG frame id of this renderer's
  * k-th sample is offset + k * stride (default 0, 1 == the reference's accumId). */
 int hm_renderer_set_frame_schedule(hm_renderer* r, int offset, int stride);
+/* Row-band partition used by hm_renderer_create(rank, world) (pure host arithmetic, no
+ * device needed): out5 = row0, row1, first training record, training records owned, records fed
+ * to the backward pass (rounded down to tcnn's 128-row granularity, common.h:280).  `records` is
+ * numTrainRecordsX*Y = 16384 for render_hair_msnn (headers/render_hair_msnn.h:127-130). */
+int hm_band_partition(int width, int height, int records, int rank, int world, int* out5);
 
 /* ---- stand-alone kernels (parity tests, micro-benchmarks) ----------------------- */
 
