@@ -23,6 +23,8 @@ lib = C.CDLL(LIB_PATH)
 PATH_TRACING, NRC, HAIR_MSNN = 0, 1, 2
 BUF_FINAL_AVG, BUF_FINAL_ACCUM, BUF_PT_AVG, BUF_PT_ACCUM, BUF_NN_AVG, BUF_NN_ACCUM, BUF_FB8 = range(7)
 BUF_NN_FRAME_INPUT, BUF_NN_FRAME_OUTPUT, BUF_NN_TRAIN_INPUT, BUF_NN_TRAIN_OUTPUT, BUF_GBUFFER, BUF_TRAIN_IDXS = range(7, 13)
+BUF_GBUFFER_B, BUF_NRC_TRAIN_RECORDS = 13, 14
+NRC_MAX_BOUNCES = 40
 
 _fp = C.POINTER(C.c_float)
 _ip = C.POINTER(C.c_int)
@@ -79,7 +81,8 @@ lib.hm_mlp_n_params.restype = C.c_size_t
 lib.hm_mlp_launch_count.restype = C.c_uint64
 for _name in ("hm_renderer_stream", "hm_renderer_mlp", "hm_renderer_destroy", "hm_render_frames", "hm_render_frames_async",
               "hm_renderer_sync", "hm_renderer_reset_accumulation", "hm_renderer_accum_id", "hm_msnn_trace",
-              "hm_msnn_train_backward", "hm_msnn_train_apply", "hm_msnn_finish", "hm_mlp_stream", "hm_mlp_n_params",
+              "hm_msnn_train_backward", "hm_msnn_train_apply", "hm_msnn_finish", "hm_nrc_trace", "hm_nrc_query",
+              "hm_nrc_train_backward", "hm_nrc_train_apply", "hm_nrc_end", "hm_mlp_stream", "hm_mlp_n_params",
               "hm_mlp_launch_count", "hm_mlp_destroy", "hm_mlp_optimizer_step", "hm_mlp_reset", "hm_mlp_reinitialize",
               "hm_scene_free"):
     getattr(lib, _name).argtypes = [C.c_void_p]
@@ -380,6 +383,7 @@ class Renderer:
         if not h:
             raise HairMSNNError(-4, "this renderer kind has no MLP")
         m = Mlp(h, owned=False)
+        m.in_ch = self.layout()[0]
         return m
 
     def msnn_trace(self): _check(lib.hm_msnn_trace(self._h))
@@ -387,6 +391,31 @@ class Renderer:
     def msnn_train_apply(self): _check(lib.hm_msnn_train_apply(self._h))
     def msnn_finish(self): _check(lib.hm_msnn_finish(self._h))
     def msnn_pretrain(self, steps): _check(lib.hm_msnn_pretrain(self._h, steps))
+
+    # render_nrc split frame (render_nrc.cu:640-700)
+    def nrc_trace(self): _check(lib.hm_nrc_trace(self._h))
+    def nrc_query(self): _check(lib.hm_nrc_query(self._h))
+    def nrc_train_backward(self): _check(lib.hm_nrc_train_backward(self._h))
+    def nrc_train_apply(self): _check(lib.hm_nrc_train_apply(self._h))
+    def nrc_end(self): _check(lib.hm_nrc_end(self._h))
+    def nrc_set_all_unbiased(self, on): _check(lib.hm_nrc_set_all_unbiased(self._h, int(on)))
+
+    def layout(self):
+        """(MLP input channels, inference rows per frame, training records per step, everyNth)"""
+        out = (C.c_int * 4)()
+        _check(lib.hm_renderer_get_layout(self._h, out))
+        return tuple(out)
+
+    def nrc_train_records(self):
+        """TrainBuffer contents after nrc_trace(): dict of arrays [pixels][40][3] + bounces/hit [pixels]."""
+        _, nbytes = self.device_buffer(BUF_NRC_TRAIN_RECORDS)
+        raw = np.empty(nbytes, np.uint8)
+        _check(lib.hm_get_buffer(self._h, BUF_NRC_TRAIN_RECORDS, raw.ctypes.data_as(C.c_void_p), C.c_size_t(nbytes)))
+        rec = raw.view(np.float32).reshape(-1, 5 * NRC_MAX_BOUNCES * 3 + 2)
+        body = rec[:, :-2].reshape(-1, 5, NRC_MAX_BOUNCES, 3)
+        tail = rec[:, -2:].copy().view(np.int32)
+        return {"vert": body[:, 0], "wo": body[:, 1], "n": body[:, 2], "radiance": body[:, 3], "beta": body[:, 4],
+                "bounces": tail[:, 0], "hit": tail[:, 1]}
 
     def device_buffer(self, which):
         p = C.c_void_p(); n = C.c_size_t()

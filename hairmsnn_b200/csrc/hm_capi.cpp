@@ -203,13 +203,10 @@ int hm_scene_get_env_tables(const hm_scene* s, const float** env, const float** 
 
 // ---- renderer -----------------------------------------------------------------------
 int hm_renderer_create(hm_scene* s, int kind, int beta_cli, int device, int rank, int world, hm_renderer** out) {
-    if (kind == HM_RENDER_NRC) {
-        g_err = "render_nrc is not built yet (SURVEY §8f row 1)";
-        return HM_ERR_UNSUPPORTED;
-    }
     return guarded([&] {
         need(s, "scene"); need(out, "out");
-        if (kind != HM_RENDER_PATH_TRACING && kind != HM_RENDER_HAIR_MSNN) throw std::invalid_argument("unknown renderer kind");
+        if (kind != HM_RENDER_PATH_TRACING && kind != HM_RENDER_HAIR_MSNN && kind != HM_RENDER_NRC)
+            throw std::invalid_argument("unknown renderer kind");
         std::unique_ptr<hm_renderer> h(new hm_renderer);
         h->r.reset(new Renderer(s->hs, kind, beta_cli, device, rank, world));
         h->mlp_view.m = h->r->mlp();
@@ -239,6 +236,20 @@ int hm_msnn_trace(hm_renderer* r) { return guarded([&] { need(r, "renderer"); r-
 int hm_msnn_train_backward(hm_renderer* r) { return guarded([&] { need(r, "renderer"); r->r->msnn_train_backward(); }); }
 int hm_msnn_train_apply(hm_renderer* r) { return guarded([&] { need(r, "renderer"); r->r->msnn_train_apply(); }); }
 int hm_msnn_finish(hm_renderer* r) { return guarded([&] { need(r, "renderer"); r->r->msnn_finish(); }); }
+int hm_nrc_trace(hm_renderer* r) { return guarded([&] { need(r, "renderer"); r->r->nrc_trace(); }); }
+int hm_nrc_query(hm_renderer* r) { return guarded([&] { need(r, "renderer"); r->r->nrc_query(); }); }
+int hm_nrc_train_backward(hm_renderer* r) { return guarded([&] { need(r, "renderer"); r->r->nrc_train_backward(); }); }
+int hm_nrc_train_apply(hm_renderer* r) { return guarded([&] { need(r, "renderer"); r->r->nrc_train_apply(); }); }
+int hm_nrc_end(hm_renderer* r) { return guarded([&] { need(r, "renderer"); r->r->nrc_end(); }); }
+int hm_nrc_set_all_unbiased(hm_renderer* r, int on) {
+    return guarded([&] { need(r, "renderer"); r->r->set_nrc_all_unbiased(on != 0); });
+}
+int hm_renderer_get_layout(const hm_renderer* r, int* out4) {
+    return guarded([&] {
+        need(r, "renderer"); need(out4, "out4");
+        out4[0] = r->r->in_channels(); out4[1] = r->r->nn_frame_rows(); out4[2] = r->r->train_records(); out4[3] = r->r->every_nth();
+    });
+}
 int hm_msnn_pretrain(hm_renderer* r, int n) {
     return guarded([&] { need(r, "renderer"); r->r->msnn_pretrain(n); r->r->sync(); });
 }

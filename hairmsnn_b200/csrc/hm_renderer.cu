@@ -147,6 +147,17 @@ Renderer::Renderer(const HostScene& hs, int kind, int beta_cli, int device, int 
         if (every_nth_ < 1)
             throw std::invalid_argument("render_hair_msnn needs at least 16384 pixels (everyNth would be 0)");
     }
+    if (kind_ == HM_KIND_NRC) {
+        // RenderWindowNRC::initialize (render_nrc.cu:116-160); std::ceil of INTEGER divisions throughout
+        if (world != 1) throw std::invalid_argument("render_nrc shards by samples (hm_renderer_set_frame_schedule), not by row bands");
+        in_ch_ = 9;
+        records_ = kNrcTrainRecords;
+        nrc_train_pixels_ = records_ / kNrcMaxBounces;
+        every_nth_ = (int)(n / (size_t)nrc_train_pixels_);
+        if (every_nth_ < 1) throw std::invalid_argument("render_nrc needs at least 1638 pixels (everyNth would be 0)");
+        if (n % 128) throw std::invalid_argument("render_nrc needs W*H to be a multiple of 128 (scene.cpp:302-306)");
+        nn_frame_rows_ = (int)n + nrc_train_pixels_ - nrc_train_pixels_ % 128 + 128;
+    }
     for (FrameCtx& c : ctx_) {
         c.paths.rng = (uint32_t*)alloc(n * 4);
         c.paths.ray_o = (float4*)alloc(n * 16);
@@ -168,6 +179,17 @@ Renderer::Renderer(const HostScene& hs, int kind, int beta_cli, int device, int 
             c.nn_train_out = (float*)alloc((size_t)records_ * 3 * 4);
             c.gbuffer = (float4*)alloc(n * 16);
         }
+        if (kind_ == HM_KIND_NRC) {
+            c.paths.nrc_state = (float4*)alloc(n * 16);
+            c.paths.nrc_prev = (float4*)alloc(n * 16);
+            c.train_idxs = (int*)alloc((size_t)nrc_train_pixels_ * 4);
+            c.nn_frame_in = (float*)alloc((size_t)nn_frame_rows_ * in_ch_ * 4);
+            c.nn_train_in = (float*)alloc((size_t)records_ * in_ch_ * 4);
+            c.nn_train_out = (float*)alloc((size_t)records_ * 3 * 4);
+            c.gbuffer = (float4*)alloc(n * 16);
+            c.gbuffer_b = (float4*)alloc(n * 16);
+            c.tbuffer = (NrcTrainRec*)alloc((size_t)nrc_train_pixels_ * sizeof(NrcTrainRec));
+        }
         c.q.shade[0] = (int*)alloc(n * 4);
         c.q.shade[1] = (int*)alloc(n * 4);
         c.q.extend = (int*)alloc(n * 4);
@@ -182,15 +204,17 @@ Renderer::Renderer(const HostScene& hs, int kind, int beta_cli, int device, int 
     for (int i = 0; i < 6; ++i) bufs_[i] = (float4*)alloc(n * 16);
     fb_ = (uint32_t*)alloc(n * 4);
 
-    if (kind_ == HM_KIND_MSNN) {
+    if (kind_ == HM_KIND_MSNN || kind_ == HM_KIND_NRC) {
         MlpConfig cfg = hs.tcnn_config.empty() ? MlpConfig() : mlp_config_from_json(hs.tcnn_config, in_ch_, 3);
         cfg.in_ch = in_ch_; cfg.out_ch = 3;
         mlp_.reset(new Mlp(cfg, order_stream_));
-        std::vector<int> seq(records_);
-        for (int i = 0; i < records_; ++i) seq[i] = i;   // thrust::sequence
-        d_train_idxs_ = (int*)alloc((size_t)records_ * 4);
-        HM_CUDA(cudaMemcpy(d_train_idxs_, seq.data(), (size_t)records_ * 4, cudaMemcpyHostToDevice));
-        nn_frame_out_ = (float*)alloc(n * 3 * 4);
+        n_idxs_ = kind_ == HM_KIND_NRC ? nrc_train_pixels_ : records_;
+        if (kind_ == HM_KIND_MSNN) nn_frame_rows_ = (int)n;
+        std::vector<int> seq(n_idxs_);
+        for (int i = 0; i < n_idxs_; ++i) seq[i] = i;   // thrust::sequence
+        d_train_idxs_ = (int*)alloc((size_t)n_idxs_ * 4);
+        HM_CUDA(cudaMemcpy(d_train_idxs_, seq.data(), (size_t)n_idxs_ * 4, cudaMemcpyHostToDevice));
+        nn_frame_out_ = (float*)alloc((size_t)nn_frame_rows_ * 3 * 4);
     }
     last_ctx_ = &ctx_[0];
     HM_CUDA(cudaDeviceSynchronize());
@@ -288,6 +312,17 @@ FrameParams Renderer::params_for(const FrameCtx& c) {
         P.nn_train_in = c.nn_train_in;
         P.nn_train_out = c.nn_train_out;
         P.gbuffer = c.gbuffer;
+    } else if (kind_ == HM_KIND_NRC) {
+        P.mode = MODE_NRC;
+        P.every_nth = every_nth_;
+        P.train_idxs = c.train_idxs;
+        P.nn_frame_in = c.nn_frame_in;
+        P.gbuffer = c.gbuffer;
+        P.gbuffer_b = c.gbuffer_b;
+        P.tbuffer = c.tbuffer;
+        P.nrc_train_pixels = nrc_train_pixels_;
+        P.nrc_all_unbiased = nrc_all_unbiased_ ? 1 : 0;
+        P.nrc_c = nrc_c_;
     } else {
         P.mode = MODE_PT;
     }
@@ -300,8 +335,8 @@ void Renderer::shuffle_train_idxs(FrameCtx& c) {
     // compositions is deterministic (render_hair_msnn.cu:711-714).  The frame keeps a copy:
     // later frames re-shuffle the persistent array while this one is still in flight.
     thrust::device_ptr<int> p = thrust::device_pointer_cast(d_train_idxs_);
-    thrust::shuffle(thrust::cuda::par_nosync(thrust_scratch()).on(main_stream_), p, p + records_, thrust::default_random_engine());
-    HM_CUDA(cudaMemcpyAsync(c.train_idxs, d_train_idxs_, (size_t)records_ * 4, cudaMemcpyDeviceToDevice, main_stream_));
+    thrust::shuffle(thrust::cuda::par_nosync(thrust_scratch()).on(main_stream_), p, p + n_idxs_, thrust::default_random_engine());
+    HM_CUDA(cudaMemcpyAsync(c.train_idxs, d_train_idxs_, (size_t)n_idxs_ * 4, cudaMemcpyDeviceToDevice, main_stream_));
 }
 
 FrameCtx& Renderer::begin_frame() {
@@ -320,9 +355,17 @@ FrameCtx& Renderer::begin_frame() {
 // No host synchronisation: every stage reads its queue length from device memory, and the
 // tail always issues the full vertex budget (empty launches cost a few microseconds).
 void Renderer::trace_frame(FrameCtx& c) {
-    if (kind_ == HM_KIND_MSNN) shuffle_train_idxs(c);
+    if (kind_ == HM_KIND_MSNN || kind_ == HM_KIND_NRC) shuffle_train_idxs(c);
     FrameParams P = params_for(c);
     int max_vertices = P.v2_stop + 1;   // the primary hit plus up to v2_stop bounces
+    if (kind_ == HM_KIND_NRC) {
+        max_vertices = kNrcMaxBounces;  // vertices 0..39; path_v1/path_v2 do not apply (cuda/nrc.cu:169)
+        // what render() clears after every frame (render_nrc.cu:683-689: owlBufferClear x4 + RESET pass)
+        HM_CUDA(cudaMemsetAsync(c.nn_frame_in, 0, (size_t)nn_frame_rows_ * in_ch_ * 4, main_stream_));
+        HM_CUDA(cudaMemsetAsync(c.nn_train_in, 0, (size_t)records_ * in_ch_ * 4, main_stream_));
+        HM_CUDA(cudaMemsetAsync(c.nn_train_out, 0, (size_t)records_ * 3 * 4, main_stream_));
+        HM_CUDA(cudaMemsetAsync(c.tbuffer, 0, (size_t)nrc_train_pixels_ * sizeof(NrcTrainRec), main_stream_));
+    }
     if (max_vertices < 1) max_vertices = 1;
     int main_vertices = kind_ == HM_KIND_MSNN ? beta_ + 2 : 6;
     if (main_vertices < 2) main_vertices = 2;
@@ -345,7 +388,7 @@ void Renderer::trace_frame(FrameCtx& c) {
         HM_CUDA(cudaMemsetAsync(c.q.counts + 2, 0, 16, s));   // extend + shadow counters and their work cursors
         src = dst;
     }
-    if (kind_ == HM_KIND_MSNN) timed(4, s, [&] { launch_finalize(P, s); });   // frame-local outputs only
+    if (kind_ != HM_KIND_PT) timed(4, s, [&] { launch_finalize(P, s); });   // frame-local outputs only
     HM_CUDA(cudaEventRecord(c.ev_traced, s));
     HM_CUDA(cudaStreamWaitEvent(order_stream_, c.ev_traced, 0));
     last_ctx_ = &c;
@@ -405,6 +448,51 @@ void Renderer::msnn_finish() {
     current_ = nullptr;
 }
 
+// ---- render_nrc (render_nrc.cu:640-700) ------------------------------------------------
+void Renderer::nrc_trace() {
+    if (kind_ != HM_KIND_NRC) throw std::logic_error("not an NRC renderer");
+    if (current_) throw std::logic_error("nrc_trace: the previous frame was not finished (call nrc_end)");
+    FrameCtx& c = begin_frame();
+    trace_frame(c);
+    current_ = &c;
+}
+
+void Renderer::nrc_query() {
+    if (kind_ != HM_KIND_NRC) throw std::logic_error("not an NRC renderer");
+    if (!current_) throw std::logic_error("nrc_query: call nrc_trace first");
+    FrameCtx& c = *current_;
+    timed(6, order_stream_, [&] { mlp_->inference(c.nn_frame_in, nn_frame_out_, nn_frame_rows_); });
+    NrcRender R;
+    R.accum = bufs_[1]; R.average = bufs_[0]; R.fb = fb_;
+    R.gbuffer = c.gbuffer; R.gbuffer_b = c.gbuffer_b; R.tbuffer = c.tbuffer;
+    R.train_idxs = c.train_idxs;
+    R.nn_out = nn_frame_out_;
+    R.train_in = c.nn_train_in; R.train_gt = c.nn_train_out;
+    R.W = W_; R.H = H_; R.in_ch = in_ch_; R.every_nth = every_nth_;
+    R.train_pixels = nrc_train_pixels_; R.all_unbiased = nrc_all_unbiased_ ? 1 : 0;
+    R.accum_id = c.accum_id;
+    timed(7, order_stream_, [&] { launch_nrc_render(R, order_stream_); });
+}
+
+void Renderer::nrc_train_backward() {
+    if (kind_ != HM_KIND_NRC) throw std::logic_error("not an NRC renderer");
+    if (!current_) throw std::logic_error("nrc_train_backward: call nrc_trace first");
+    FrameCtx& c = *current_;
+    timed(5, order_stream_, [&] { mlp_->forward_backward(c.nn_train_in, c.nn_train_out, records_, records_); });
+}
+
+void Renderer::nrc_train_apply() {
+    if (kind_ != HM_KIND_NRC) throw std::logic_error("not an NRC renderer");
+    timed(5, order_stream_, [&] { mlp_->optimizer_step(); });
+}
+
+void Renderer::nrc_end() {
+    if (kind_ != HM_KIND_NRC) throw std::logic_error("not an NRC renderer");
+    if (!current_) throw std::logic_error("nrc_end: call nrc_trace first");
+    end_frame(*current_);
+    current_ = nullptr;
+}
+
 void Renderer::msnn_pretrain(int steps) {
     // The reference pre-trains for one wall-clock second on rays towards random strand
     // points from an UNSET camera.  Deterministic stand-in: `steps`
@@ -425,7 +513,6 @@ void Renderer::msnn_pretrain(int steps) {
 
 void Renderer::render_frames(int n) {
     HM_CUDA(cudaSetDevice(device_));
-    if (kind_ == HM_KIND_NRC) throw std::logic_error("render_nrc is not implemented in this build");
     for (int i = 0; i < n; ++i) {
         Pending whole{8, nullptr, nullptr};
         if (profiling_) {
@@ -438,6 +525,14 @@ void Renderer::render_frames(int n) {
             trace_frame(c);
             finish_pt(c);
             end_frame(c);
+        } else if (kind_ == HM_KIND_NRC) {
+            nrc_trace();
+            nrc_query();
+            if (hs_.tcnn_train) {
+                nrc_train_backward();
+                nrc_train_apply();
+            }
+            nrc_end();
         } else {
             msnn_trace();
             if (hs_.tcnn_train) {
@@ -470,12 +565,14 @@ void* Renderer::device_buffer(int which, size_t* bytes) {
     switch (which) {
         case 0: case 1: case 2: case 3: case 4: case 5: *bytes = n * 16; return bufs_[which];
         case 6: *bytes = n * 4; return fb_;
-        case 7: *bytes = n * in_ch_ * 4; return c.nn_frame_in;
-        case 8: *bytes = n * 3 * 4; return nn_frame_out_;
+        case 7: *bytes = (kind_ == HM_KIND_NRC ? (size_t)nn_frame_rows_ : n) * in_ch_ * 4; return c.nn_frame_in;
+        case 8: *bytes = (kind_ == HM_KIND_NRC ? (size_t)nn_frame_rows_ : n) * 3 * 4; return nn_frame_out_;
         case 9: *bytes = (size_t)records_ * in_ch_ * 4; return c.nn_train_in;
         case 10: *bytes = (size_t)records_ * 3 * 4; return c.nn_train_out;
         case 11: *bytes = n * 16; return c.gbuffer;
-        case 12: *bytes = (size_t)records_ * 4; return c.train_idxs;
+        case 12: *bytes = (size_t)n_idxs_ * 4; return c.train_idxs;
+        case 13: *bytes = n * 16; return c.gbuffer_b;
+        case 14: *bytes = (size_t)nrc_train_pixels_ * sizeof(NrcTrainRec); return c.tbuffer;
         default: *bytes = 0; return nullptr;
     }
 }

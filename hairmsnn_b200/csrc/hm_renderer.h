@@ -45,6 +45,8 @@ struct FrameCtx {
     float* nn_train_in = nullptr;
     float* nn_train_out = nullptr;
     float4* gbuffer = nullptr;
+    float4* gbuffer_b = nullptr;      // NRC: throughput + bounce count at the cache query
+    NrcTrainRec* tbuffer = nullptr;   // NRC: per-training-pixel path records
     cudaStream_t tail_stream = nullptr;
     cudaEvent_t ev_main_done = nullptr, ev_traced = nullptr, ev_free = nullptr;
     int frame_id = 0, accum_id = 0;
@@ -81,6 +83,20 @@ public:
     void msnn_finish();
     void msnn_pretrain(int steps);
     Mlp* mlp() { return mlp_.get(); }
+
+    // NRC split frame (render_nrc.cu:640-700): trace = G_BUFFER pass; query = inference over the
+    // frame + training suffixes, then the RENDER pass (training records + composite);
+    // train_backward / train_apply = training_step; end = buffer clears + RESET pass + accumId++
+    void nrc_trace();
+    void nrc_query();
+    void nrc_train_backward();
+    void nrc_train_apply();
+    void nrc_end();
+    void set_nrc_all_unbiased(bool on) { nrc_all_unbiased_ = on; }
+    int nn_frame_rows() const { return nn_frame_rows_; }
+    int train_records() const { return records_; }
+    int in_channels() const { return in_ch_; }
+    int every_nth() const { return every_nth_; }
 
     void* device_buffer(int which, size_t* bytes);
     void trace_rays_device(const float* d_org, const float* d_dir, int n, int any, float tmin, float tmax,
@@ -128,7 +144,13 @@ private:
     std::unique_ptr<Mlp> mlp_;
     int in_ch_ = 12, records_ = 16384, every_nth_ = 1;
     int* d_train_idxs_ = nullptr;   // persistent permutation, re-shuffled every frame
+    int n_idxs_ = 0;                // its length (training records for HairMSNN, training pixels for NRC)
     float* nn_frame_out_ = nullptr;
+    // nrc
+    int nrc_train_pixels_ = 0;      // numTrainingPixels = numTrainingRecords / MAX_BOUNCES
+    int nn_frame_rows_ = 0;         // rows fed to inference (nnFrameSize for NRC, W*H for HairMSNN)
+    bool nrc_all_unbiased_ = false;
+    float nrc_c_ = 0.01f;           // headers/render_nrc.h:132
     FrameCtx* last_ctx_ = nullptr;
     bool profiling_ = false, collect_stats_ = false;
     int frame_offset_ = 0, frame_stride_ = 1;

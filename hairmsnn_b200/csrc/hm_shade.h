@@ -221,9 +221,12 @@ HM_HD V3 resolve_direct(V3 light_value, bool light_visible, V3 bsdf_value, bool 
 
 // Continuation ray and throughput factor.  Always produces a ray (the reference traces
 // even when a surface sample points below the horizon).
-HM_HD V3 sample_continuation(const SceneView& S, const Vertex& v, Rng& rng, V3& ray_o, V3& ray_d) {
+// pdf_out (optional) receives the sampling density (nextPathVertexNRC's return value,
+// cuda/nrc.cu:18-67).
+HM_HD V3 sample_continuation(const SceneView& S, const Vertex& v, Rng& rng, V3& ray_o, V3& ray_d, float* pdf_out = nullptr) {
     V3 wi; float pdf = 1.f;
     V3 f = sample_bsdf_dir(S, v, rng, wi, pdf);
+    if (pdf_out) *pdf_out = pdf;
     V3 mul = (pdf == 0.f) ? f : f / pdf;
     if (any_nan(mul)) mul = V3(1.f);
     V3 wo_next = -wi;

@@ -375,6 +375,261 @@ __global__ void __launch_bounds__(256) k_finalize(const FrameParams P) {
     }
 }
 
+// ---------------------------------------------------------------------------------
+// render_nrc: nrcTracePaths in wavefront form (cuda/nrc.cu:135-310)
+// ---------------------------------------------------------------------------------
+// The reference loop body for bounce b is: direct light at vertex b -> sample + trace to
+// vertex b+1 -> [training pixel: record vertex b] -> spread update with the NEW vertex ->
+// terminate / query the cache / continue.  Here the shade of vertex b first finishes
+// bounce b-1 (everything that needed the new hit), then starts bounce b.  No Russian
+// roulette: paths end on the spread heuristic, on leaving the scene, or at kNrcMaxBounces.
+__device__ __forceinline__ bool nrc_training_pixel(const FrameParams& P, int fb_ofs, int& tr_ofs, bool& unbiased) {
+    tr_ofs = fb_ofs / P.every_nth;
+    unbiased = false;
+    // the reference indexes one group past the end when W*H % everyNth != 0 (trOfs == numTrainingPixels,
+    // SURVEY §8 a18): that group has no training pixel here
+    if (tr_ofs >= P.nrc_train_pixels) return false;
+    const int train_idx = __ldg(P.train_idxs + tr_ofs) % P.every_nth;
+    const bool training = fb_ofs % P.every_nth == train_idx;
+    unbiased = training && (tr_ofs % 16 == 0 || P.nrc_all_unbiased);
+    return training;
+}
+
+__device__ __forceinline__ void write3(float* dst, V3 v) { dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; }
+
+__device__ __forceinline__ void write_nrc_query(float* dst, V3 p, V3 wo, V3 n, float scene_scale) {
+    V3 point = p / scene_scale;
+    dst[0] = point.x; dst[1] = point.y; dst[2] = point.z;
+    dst[3] = wo.x; dst[4] = wo.y; dst[5] = wo.z;
+    dst[6] = n.x; dst[7] = n.y; dst[8] = n.z;
+}
+
+// pow(length(d), 2) / (4 Pi) / |cos|   (cuda/nrc.cu:153,186)
+__device__ __forceinline__ float nrc_area(V3 a, V3 b, float abscos) {
+    float l = length(a - b);
+    return l * l / (4.f * kPi) / abscos;
+}
+
+__global__ void __launch_bounds__(kBlock) k_shade_nrc(const FrameParams P, int src) {
+    const int n = P.q.counts[src];
+    const int* queue = P.q.shade[src];
+    const int rounds = (n + kBlock - 1) / kBlock;
+    const size_t frame_size = (size_t)P.W * P.H;
+    for (int r = blockIdx.x; r < rounds; r += gridDim.x) {
+        int i = r * kBlock + threadIdx.x;
+        bool live = i < n;
+        int slot = live ? queue[i] : 0;
+
+        DirectSample ds;
+        ds.light.active = false; ds.bsdf.active = false;
+        bool extend = false;
+
+        if (live) {
+            Rng rng; rng.state = P.paths.rng[slot];
+            V3 ro = v3(P.paths.ray_o[slot]), rd = v3(P.paths.ray_d[slot]);
+            float4 hr = P.paths.hit[slot];
+            Hit hit; hit.t = hr.x; hit.prim = __float_as_int(hr.y); hit.u = hr.z; hit.v = hr.w;
+            float4 b4 = P.paths.beta[slot];
+            V3 beta = v3(b4);
+            const int b = __float_as_int(b4.w);       // index of this vertex == bounce about to start
+            V3 color = v3(P.paths.color[slot]);
+
+            int tr_ofs = 0;
+            bool unbiased = false;
+            const bool training = nrc_training_pixel(P, slot, tr_ofs, unbiased);
+            NrcTrainRec* rec = P.tbuffer + tr_ofs;
+
+            // direct light of vertex b-1, now that its probes are back
+            {
+                float4 dl = P.paths.dl_light[slot];
+                if (dl.w != 0.f) {
+                    uint32_t vis = P.paths.vis[slot];
+                    V3 d = resolve_direct(v3(dl), (vis & 1u) != 0, v3(P.paths.dl_bsdf[slot]), (vis & 2u) != 0);
+                    color += v3(P.paths.dl_beta[slot]) * d;
+                    if (training) write3(rec->radiance[b - 1], d);
+                }
+            }
+
+            Vertex v = vertex_from_hit(P.scene, hit, ro, rd);
+            const float abscos = fabsf(v.wo_local.z);
+
+            float spread = 0.f, a0 = 0.f, c = P.nrc_c;
+            int flags = 0;
+            bool terminated = false;
+            if (b == 0) {
+                if (v.surface && v.wo_local.z < 0.f) {
+                    // a head triangle seen from behind counts as a miss (cuda/nrc.cu:353-360); si.Le is 0 on a hit
+                    P.gbuffer[slot] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+                    P.gbuffer_b[slot] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+                    terminated = true;
+                } else {
+                    a0 = nrc_area(v.p, V3(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]), abscos);
+                }
+            } else {
+                float4 st = P.paths.nrc_state[slot];
+                spread = st.x; a0 = st.y; c = st.z; flags = __float_as_int(st.w);
+                float4 pv = P.paths.nrc_prev[slot];
+                const V3 prev_point = v3(pv);
+                if (training && (flags & kNrcRecalcA0)) {
+                    a0 = nrc_area(v.p, prev_point, abscos);
+                    flags &= ~kNrcRecalcA0;
+                }
+                {   // nrcSpread (cuda_headers/utils.cuh:86-90)
+                    float l = length(v.p - prev_point);
+                    spread = spread + sqrtf(l * l / pv.w / abscos);
+                }
+                const bool cond = spread * spread > c * a0;
+                if (cond && !(flags & kNrcSuffix)) {
+                    P.gbuffer[slot] = f4(color, __int_as_float(1));
+                    P.gbuffer_b[slot] = f4(beta, __int_as_float(b - 1));
+                    write_nrc_query(P.nn_frame_in + (size_t)slot * P.in_ch, v.p, v.wo, v.n, P.scene.scene_scale);
+                    if (training) { flags |= kNrcSuffix | kNrcRecalcA0; spread = 0.f; }
+                    else terminated = true;
+                } else if (cond) {
+                    write_nrc_query(P.nn_frame_in + (frame_size + tr_ofs) * P.in_ch, v.p, v.wo, v.n, P.scene.scene_scale);
+                    rec->bounces = b - 1;
+                    rec->hit = 1;
+                    if (!unbiased) terminated = true;
+                    else c = 1e30f;
+                }
+            }
+
+            if (terminated) {
+                flags |= kNrcTerminated;
+                P.paths.dl_light[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                sample_direct(P.scene, v, rng, ds);
+                P.paths.dl_beta[slot] = f4(beta, 0.f);
+                P.paths.dl_light[slot] = f4(ds.light.value, 1.f);
+                P.paths.dl_bsdf[slot] = f4(ds.bsdf.value, 0.f);
+                P.paths.vis[slot] = (ds.light.active ? 1u : 0u) | (ds.bsdf.active ? 2u : 0u);
+
+                V3 no, nd;
+                float pdf = 1.f;
+                V3 mul = sample_continuation(P.scene, v, rng, no, nd, &pdf);
+                beta = beta * mul;
+                P.paths.nrc_prev[slot] = f4(v.p, pdf);
+                if (training) {
+                    write3(rec->vert[b], v.p / P.scene.scene_scale);
+                    write3(rec->wo[b], v.wo);
+                    write3(rec->n[b], v.n);
+                    write3(rec->beta[b], mul);
+                }
+                if (b < kNrcMaxBounces - 1) {   // the last bounce's ray cannot change anything (cuda/nrc.cu:200)
+                    P.paths.ray_o[slot] = f4(no, 0.f);
+                    P.paths.ray_d[slot] = f4(nd, 0.f);
+                    extend = true;
+                }
+            }
+            P.paths.rng[slot] = rng.state;
+            P.paths.beta[slot] = f4(beta, __int_as_float(b + 1));
+            P.paths.color[slot] = f4(color, 0.f);
+            P.paths.nrc_state[slot] = make_float4(spread, a0, c, __int_as_float(flags));
+        }
+        push_probe(P, ds.light, slot, 0);
+        push_probe(P, ds.bsdf, slot, 1);
+        int idx = queue_reserve(P.q.counts + 2, extend);
+        if (idx >= 0) P.q.extend[idx] = slot;
+    }
+    if (P.collect_stats && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.q.trav + 8, (unsigned long long)n);
+}
+
+// End of the G_BUFFER pass: paths that left the scene (or reached the bounce cap) fold their last
+// direct sample and write their G-buffer entry; primary misses show the environment.
+__global__ void __launch_bounds__(256) k_finalize_nrc(const FrameParams P) {
+    const int n = (P.row1 - P.row0) * P.W;
+    const int first = P.row0 * P.W;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int slot = first + i;
+        V3 color = v3(P.paths.color[slot]);
+        const bool hit = __float_as_int(P.paths.hit[slot].y) >= 0;   // only a primary miss leaves prim < 0
+        if (!hit) {
+            P.gbuffer[slot] = f4(color, __int_as_float(0));
+            P.gbuffer_b[slot] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+            continue;
+        }
+        const int flags = __float_as_int(P.paths.nrc_state[slot].w);
+        if (flags & kNrcTerminated) continue;
+        const int b = __float_as_int(P.paths.beta[slot].w) - 1;     // last shaded vertex
+        int tr_ofs = 0;
+        bool unbiased = false;
+        const bool training = nrc_training_pixel(P, slot, tr_ofs, unbiased);
+        float4 dl = P.paths.dl_light[slot];
+        if (dl.w != 0.f) {
+            uint32_t vis = P.paths.vis[slot];
+            V3 d = resolve_direct(v3(dl), (vis & 1u) != 0, v3(P.paths.dl_bsdf[slot]), (vis & 2u) != 0);
+            color += v3(P.paths.dl_beta[slot]) * d;
+            if (training) write3(P.tbuffer[tr_ofs].radiance[b], d);
+        }
+        if (!(flags & kNrcSuffix)) {
+            P.gbuffer[slot] = f4(color, __int_as_float(1));
+            P.gbuffer_b[slot] = make_float4(0.f, 0.f, 0.f, __int_as_float(b));
+        }
+        if (training) {
+            // the reference lets every pixel of the group race on these two fields
+            // (cuda/nrc.cu:210-211); only the training pixel's own values are meaningful
+            P.tbuffer[tr_ofs].bounces = b;
+            P.tbuffer[tr_ofs].hit = 0;
+        }
+    }
+}
+
+// RENDER pass: nrcGenerateTrainingData (cuda/nrc.cu:69-133) + composite (cuda/nrc.cu:367-381).
+__global__ void __launch_bounds__(256) k_nrc_render(const NrcRender R) {
+    const int n = R.W * R.H;
+    for (int px = blockIdx.x * blockDim.x + threadIdx.x; px < n; px += gridDim.x * blockDim.x) {
+        const float4 g = R.gbuffer[px];
+        const float4 gb = R.gbuffer_b[px];
+        const bool hit = (__float_as_int(g.w) & 1) != 0;
+        const int tr_ofs = px / R.every_nth;
+        bool training = false, unbiased = false;
+        if (tr_ofs < R.train_pixels) {
+            training = px % R.every_nth == __ldg(R.train_idxs + tr_ofs) % R.every_nth;
+            unbiased = training && (tr_ofs % 16 == 0 || R.all_unbiased);
+        }
+        if (training) {
+            float* tin = R.train_in + (size_t)tr_ofs * R.in_ch * kNrcMaxBounces;
+            float* tgt = R.train_gt + (size_t)tr_ofs * 3 * kNrcMaxBounces;
+            if (hit) {
+                const NrcTrainRec& t = R.tbuffer[tr_ofs];
+                V3 cache(0.f);
+                if (t.hit && !unbiased) {
+                    const float* o = R.nn_out + 3 * ((size_t)n + tr_ofs);
+                    cache = V3(o[0], o[1], o[2]);
+                }
+                const int nb = t.bounces;
+                for (int bounce = 0; bounce < nb; ++bounce) {
+                    V3 color(0.f), beta(1.f);
+                    for (int sub = bounce; sub < nb; ++sub) {
+                        color = color + beta * V3(t.radiance[sub][0], t.radiance[sub][1], t.radiance[sub][2]);
+                        beta = beta * V3(t.beta[sub][0], t.beta[sub][1], t.beta[sub][2]);
+                    }
+                    float* d = tin + bounce * R.in_ch;
+                    d[0] = t.vert[bounce][0]; d[1] = t.vert[bounce][1]; d[2] = t.vert[bounce][2];
+                    d[3] = t.wo[bounce][0]; d[4] = t.wo[bounce][1]; d[5] = t.wo[bounce][2];
+                    d[6] = t.n[bounce][0]; d[7] = t.n[bounce][1]; d[8] = t.n[bounce][2];
+                    V3 tc = color + beta * cache;
+                    if (any_nan(tc)) tc = V3(0.f);
+                    write3(tgt + 3 * bounce, tc);
+                }
+            } else {
+                for (int k = 0; k < kNrcMaxBounces * R.in_ch; ++k) tin[k] = 0.f;
+                for (int k = 0; k < kNrcMaxBounces * 3; ++k) tgt[k] = 0.f;
+            }
+        }
+        V3 cache(R.nn_out[3 * (size_t)px + 0], R.nn_out[3 * (size_t)px + 1], R.nn_out[3 * (size_t)px + 2]);
+        if (any_nan(cache)) cache = V3(0.f);
+        V3 color = V3(g.x, g.y, g.z) + V3(gb.x, gb.y, gb.z) * V3(fmaxf(cache.x, 0.f), fmaxf(cache.y, 0.f), fmaxf(cache.z, 0.f));
+        // writePixel (cuda_headers/utils.cuh:13-35)
+        if (any_nan(color)) color = V3(0.f);
+        if (R.accum_id > 0) color = color + v3(R.accum[px]);
+        R.accum[px] = f4(color, 1.f);
+        color = (1.f / (R.accum_id + 1)) * color;
+        R.average[px] = f4(color, 1.f);
+        R.fb[px] = pack_rgba8(V3(linear_to_srgb(color.x), linear_to_srgb(color.y), linear_to_srgb(color.z)));
+    }
+}
+
 // RENDER pass of the HairMSNN program (cuda/hair_msnn.cu:314-356).
 __global__ void __launch_bounds__(256) k_msnn_composite(const MsnnComposite C) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C.count; i += gridDim.x * blockDim.x) {
@@ -448,7 +703,8 @@ void launch_primary(const FrameParams& P, cudaStream_t stream) {
     g_launches++;
 }
 void launch_shade(const FrameParams& P, int src, cudaStream_t stream) {
-    k_shade<<<persistent_grid(8), kBlock, 0, stream>>>(P, src);
+    if (P.mode == MODE_NRC) k_shade_nrc<<<persistent_grid(8), kBlock, 0, stream>>>(P, src);
+    else k_shade<<<persistent_grid(8), kBlock, 0, stream>>>(P, src);
     g_launches++;
 }
 void launch_trace(const FrameParams& P, int dst, cudaStream_t stream) {
@@ -456,11 +712,16 @@ void launch_trace(const FrameParams& P, int dst, cudaStream_t stream) {
     g_launches++;
 }
 void launch_finalize(const FrameParams& P, cudaStream_t stream) {
-    k_finalize<<<persistent_grid(8), 256, 0, stream>>>(P);
+    if (P.mode == MODE_NRC) k_finalize_nrc<<<persistent_grid(8), 256, 0, stream>>>(P);
+    else k_finalize<<<persistent_grid(8), 256, 0, stream>>>(P);
     g_launches++;
 }
 void launch_msnn_composite(const MsnnComposite& C, cudaStream_t stream) {
     k_msnn_composite<<<persistent_grid(8), 256, 0, stream>>>(C);
+    g_launches++;
+}
+void launch_nrc_render(const NrcRender& R, cudaStream_t stream) {
+    k_nrc_render<<<persistent_grid(8), 256, 0, stream>>>(R);
     g_launches++;
 }
 void launch_trace_rays(const SceneView& S, const float* org, const float* dir, int n, int any, float tmin, float tmax,

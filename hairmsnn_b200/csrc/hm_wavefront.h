@@ -36,6 +36,26 @@ struct PathBuffers {
     float4* beta_short;
     float4* color_short;
     float4* dl_beta_short;
+    // NRC: spread heuristic state (cuda/nrc.cu:135-310)
+    float4* nrc_state;   // spread, a0, c, flags (int bits: kNrc*)
+    float4* nrc_prev;    // previous vertex position (before the spawn offset), w = its sampling pdf
+};
+
+// render_nrc constants (cuda_headers/nrc.cuh:13, headers/render_nrc.h:126,132)
+constexpr int kNrcMaxBounces = 40;
+constexpr int kNrcTrainRecords = 65536;
+enum { kNrcSuffix = 1, kNrcRecalcA0 = 2, kNrcTerminated = 4 };
+
+// One training pixel's path record (TrainBuffer, cuda_headers/nrc.cuh:29-40, without the
+// `color` member nothing reads).
+struct NrcTrainRec {
+    float vert[kNrcMaxBounces][3];
+    float wo[kNrcMaxBounces][3];
+    float n[kNrcMaxBounces][3];
+    float radiance[kNrcMaxBounces][3];
+    float beta[kNrcMaxBounces][3];
+    int bounces;
+    int hit;
 };
 
 struct Queues {
@@ -70,8 +90,26 @@ struct FrameParams {
     float* nn_frame_in;  // [W*H][12]
     float* nn_train_in;  // [records][12]
     float* nn_train_out; // [records][3]
-    float4* gbuffer;     // rgb = short-path colour, w = flags (bit0 hit, bit1 surface)
+    float4* gbuffer;     // rgb = short-path colour (NRC: pathRadiance), w = flags (bit0 hit, bit1 surface)
     int in_ch;
+    // NRC
+    float4* gbuffer_b;   // rgb = throughput at the cache query (GBuffer::beta), w = bounces (int bits)
+    NrcTrainRec* tbuffer;        // [nrc_train_pixels]
+    int nrc_train_pixels;
+    int nrc_all_unbiased;
+    float nrc_c;
+};
+
+// RENDER pass of the NRC program (cuda/nrc.cu:69-133,367-381)
+struct NrcRender {
+    float4* accum; float4* average; uint32_t* fb;
+    const float4* gbuffer; const float4* gbuffer_b;
+    const NrcTrainRec* tbuffer;
+    const int* train_idxs;
+    const float* nn_out;   // [nn_frame_size][3]
+    float* train_in;       // [records][in_ch]
+    float* train_gt;       // [records][3]
+    int W, H, in_ch, every_nth, train_pixels, all_unbiased, accum_id;
 };
 
 struct MsnnComposite {
@@ -91,6 +129,7 @@ void launch_shade(const FrameParams& P, int src_queue, cudaStream_t stream);
 void launch_trace(const FrameParams& P, int dst_queue, cudaStream_t stream);
 void launch_finalize(const FrameParams& P, cudaStream_t stream);
 void launch_msnn_composite(const MsnnComposite& C, cudaStream_t stream);
+void launch_nrc_render(const NrcRender& R, cudaStream_t stream);
 // test hook: closest-hit / any-hit for caller-supplied rays (device pointers)
 void launch_trace_rays(const SceneView& S, const float* org, const float* dir, int n, int any,
                        float tmin, float tmax, float4* out_hit, int* out_stats, int* cursor, cudaStream_t stream);

@@ -51,7 +51,10 @@ enum {
     HM_BUF_NN_TRAIN_INPUT = 9,   /* float[records][in_ch]              */
     HM_BUF_NN_TRAIN_OUTPUT = 10, /* float[records][3]                  */
     HM_BUF_GBUFFER = 11,         /* float4[W*H]: rgb short-path colour, w = flags */
-    HM_BUF_TRAIN_IDXS = 12       /* int[records] (trainIdxs after this frame's shuffle) */
+    HM_BUF_TRAIN_IDXS = 12,      /* int[records] (trainIdxs after this frame's shuffle; NRC: int[training pixels]) */
+    HM_BUF_GBUFFER_B = 13,       /* render_nrc: float4[W*H]: rgb GBuffer::beta, w = GBuffer::bounces (int bits) */
+    HM_BUF_NRC_TRAIN_RECORDS = 14 /* render_nrc: TrainBuffer[training pixels] as 5 x float[40][3] (vert wo n
+                                    vertRadiance vertBeta) + int bounces + int hit = 2408 bytes each */
 };
 
 const char* hm_last_error(void);
@@ -153,6 +156,26 @@ int hm_msnn_finish(hm_renderer* r);
  * (render_hair_msnn.cu:633-641): n_steps of render-free G_BUFFER + train */
 int hm_msnn_pretrain(hm_renderer* r, int n_steps);
 hm_mlp* hm_renderer_mlp(hm_renderer* r);
+
+/* render_nrc only: the pieces of RenderWindowNRC::render() (render_nrc.cu:640-700) in the reference's
+ * order.  trace = shuffle + G_BUFFER pass (nrcTracePaths, cuda/nrc.cu:135-310); query = inference over
+ * the frame's cache queries and the training suffixes (nnFrameSize rows) + RENDER pass
+ * (nrcGenerateTrainingData + composite, cuda/nrc.cu:69-133,367-381); train_backward / train_apply =
+ * trainer->training_step over the 65536 records (a multi-GPU caller all-reduces hm_mlp_gradients()
+ * in between); end = accumId++ (the buffer clears and the RESET pass happen at the next trace).
+ * For render_nrc BUF_GBUFFER holds rgb = GBuffer::pathRadiance, w = hit; with the 9 input channels the
+ * tcnn composite encoding has no identity part and the 8 padding inputs of the 64-wide network are 1
+ * (the reference leaves them uninitialised). */
+int hm_nrc_trace(hm_renderer* r);
+int hm_nrc_query(hm_renderer* r);
+int hm_nrc_train_backward(hm_renderer* r);
+int hm_nrc_train_apply(hm_renderer* r);
+int hm_nrc_end(hm_renderer* r);
+/* LaunchParams::allUnbiased (cuda_headers/nrc.cuh:77): every training pixel traces its full path */
+int hm_nrc_set_all_unbiased(hm_renderer* r, int on);
+/* out4 = MLP input channels, rows fed to inference per frame (W*H, or nnFrameSize for render_nrc,
+ * render_nrc.cu:140-145), training records per step, everyNth */
+int hm_renderer_get_layout(const hm_renderer* r, int* out4);
 
 int hm_get_buffer(hm_renderer* r, int which, void* host_dst, size_t bytes);
 /* asynchronous variant: the copy is enqueued behind the last enqueued frame; host_dst (ideally

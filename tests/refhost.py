@@ -17,7 +17,7 @@ _up = C.POINTER(C.c_uint32)
 def ensure_built():
     """Builds oracle/_ref when the reference tree is present; otherwise the prebuilt
     libraries shipped with the snapshot must exist."""
-    need = [os.path.join(REF_DIR, "libref_pt.so"), os.path.join(REF_DIR, "libref_msnn.so")]
+    need = [os.path.join(REF_DIR, f"libref_{k}.so") for k in ("pt", "msnn", "nrc")]
     if os.path.isdir("/root/reference"):
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
     for p in need:
@@ -129,6 +129,43 @@ class RefHost:
         self.lib.ref_render_msnn_gbuffer(accum_id, y0, y1, W, H, beta, every_nth, _p(train_idxs, _ip), in_ch, _p(nn_in),
                                          _p(tr_in), _p(tr_out), _p(gb), threads or os.cpu_count())
         return nn_in, tr_in, tr_out, gb
+
+    def render_nrc_gbuffer(self, accum_id, W, H, every_nth, train_idxs, nn_frame_rows, c=0.01, all_unbiased=False,
+                           in_ch=9, threads=0):
+        """G_BUFFER pass of cuda/nrc.cu.  Returns (nn_frame_in [rows][in_ch], gbuffer [W*H][8] = hit,
+        pathRadiance, beta, bounces).  The path records stay inside the library for render_nrc_render /
+        nrc_train_record."""
+        assert self.which == "nrc"
+        ntp = len(train_idxs)
+        # the reference reads trainIdxs[ntp] when W*H is not a multiple of everyNth; give that
+        # group an index no pixel of it can match
+        idx = np.concatenate([np.asarray(train_idxs, np.int32), np.array([every_nth - 1], np.int32)])
+        assert W * H - ntp * every_nth < every_nth
+        self._nrc_idx = np.ascontiguousarray(idx)
+        nn_in = np.zeros((nn_frame_rows, in_ch), np.float32)
+        gb = np.zeros((W * H, 8), np.float32)
+        self.lib.ref_render_nrc_gbuffer(accum_id, W, H, every_nth, _p(self._nrc_idx, _ip), ntp, C.c_float(c),
+                                        int(all_unbiased), in_ch, _p(nn_in), _p(gb), threads or os.cpu_count())
+        return nn_in, gb
+
+    def nrc_train_record(self, tr_ofs):
+        out = np.zeros(2 + 15 * 40, np.float32)
+        self.lib.ref_nrc_train_record(tr_ofs, _p(out))
+        body = out[2:].reshape(40, 5, 3)
+        return {"bounces": int(out[0]), "hit": int(out[1]), "vert": body[:, 0], "wo": body[:, 1], "n": body[:, 2],
+                "radiance": body[:, 3], "beta": body[:, 4]}
+
+    def render_nrc_render(self, accum_id, W, H, every_nth, nn_out, records, in_ch=9, accum=None, average=None):
+        """RENDER pass of cuda/nrc.cu on the state left by render_nrc_gbuffer."""
+        assert self.which == "nrc"
+        nn_out = _f(nn_out)
+        tr_in = np.zeros((records, in_ch), np.float32); tr_gt = np.zeros((records, 3), np.float32)
+        accum = np.zeros((H, W, 4), np.float32) if accum is None else accum
+        average = np.zeros((H, W, 4), np.float32) if average is None else average
+        fb = np.zeros((H, W), np.uint32)
+        self.lib.ref_render_nrc_render(accum_id, W, H, every_nth, _p(self._nrc_idx, _ip), in_ch, _p(nn_out), _p(tr_in),
+                                       _p(tr_gt), _p(accum), _p(average), _p(fb, _up))
+        return tr_in, tr_gt, accum, average, fb
 
     def trace_radiance(self, org, dir):
         org, dir = _f(org).reshape(-1, 3), _f(dir).reshape(-1, 3)
