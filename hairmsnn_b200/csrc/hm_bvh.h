@@ -54,6 +54,10 @@ struct GeomView {
     int num_segments;
     int num_tris;
     int num_nodes;
+    // 8-wide quantised tree (the structure the sm_100a kernels traverse; see WideNode below)
+    const F4* wnodes;     // 5 per wide node (80 B)
+    const F4* wleaf_data; // 4 per wide leaf reference (64 B, same content as a leaf slot)
+    int num_wnodes;
 };
 
 struct Hit {
@@ -171,6 +175,203 @@ HM_HD Hit trace(const GeomView& g, V3 o, V3 d, float tmin, float tmax, TraceStat
             if (stats) stats->prims++;
             if (test_slot(g, ~cur, o, d, rf, tmin, best) && ANY) return best;
             cur = sp > 0 ? stack[--sp] : kDone;
+        }
+    }
+    return best;
+}
+
+// ---------------------------------------------------------------------------------
+// 8-wide tree with boxes quantised to 8 bits against the node's own bounds (after Ylitie,
+// Karras, Laine 2017, "Efficient incoherent ray traversal on GPUs through compressed wide
+// BVHs" — their idea, this layout and code).  Why: the binary tree above is 215 MB of nodes
+// for the curly scene and misses the 126 MB L2 on nearly every warp-wide step; this one is
+// ~5x smaller (80 B per ~6 children), stays L2-resident, and a ray visits ~3x fewer nodes.
+//
+//   wide node = 5 x 16 B
+//     w0 : origin.x, origin.y, origin.z, (ex | ey << 8 | ez << 16 | imask << 24)
+//          ex/ey/ez = IEEE-biased exponents: cell size on an axis = 2^(e-127)
+//          imask    = bit i set: child slot i is an inner node
+//     w1 : child_base, leaf_base, lmask (bit i: child slot i is a leaf), unused
+//          inner child of slot i = child_base + popc(imask & ((1 << i) - 1))
+//          leaf reference of slot i = leaf_base + popc(lmask & ((1 << i) - 1))
+//     w2 : qlo_x[8], qlo_y[8]      one byte per child slot; box = origin + q * cell
+//     w3 : qlo_z[8], qhi_x[8]
+//     w4 : qhi_y[8], qhi_z[8]
+//   Children sit in the slot whose bits name their octant relative to the node centre
+//   (bit k set = towards +axis k), so visiting slots in the order of (slot ^ octinv),
+//   highest first, walks them roughly front to back for any ray direction without sorting
+//   (octinv: bit k set when the ray travels towards +axis k).
+//   Every leaf reference owns a 64-byte copy of its primitive (wleaf_data): the references of
+//   one node are contiguous, so a leaf test is one dependent fetch with no index array.
+// The wide tree is derived from the binary one (hm_bvh_build.cpp: collapse), holds the same
+// references with the same (or looser, by < 1 cell) boxes, and the primitive tests are
+// shared — both trees return bit-identical closest hits.
+static constexpr int kWideStack = 32;
+
+HM_HD unsigned f_as_u(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    union { float f; unsigned u; } c; c.f = f; return c.u;
+#endif
+}
+HM_HD float u_as_f(unsigned u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    union { float f; unsigned u; } c; c.u = u; return c.f;
+#endif
+}
+// 32768 + byte k of w, as a float (exact).  On the device one PRMT drops the byte into mantissa
+// bits 8..15 of 2^15 (LSB weight 1 there); the bias is folded into the constant term of the
+// slab FMA, so a quantised plane costs PRMT + FFMA.  Folding rounds the constant once more:
+// at most 1/512 of a cell, which the builder's 1/64-cell margin covers.
+static constexpr float kQBias = 32768.f;
+HM_HD float byte_biased(unsigned w, int k) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(__byte_perm(w, 0x47000000u, 0x7504 | (k << 4)));
+#else
+    return kQBias + (float)((w >> (8 * k)) & 0xffu);
+#endif
+}
+HM_HD int popc_u(unsigned v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+HM_HD int top_bit(unsigned v) {   // index of the highest set bit, v != 0
+#if defined(__CUDA_ARCH__)
+    return 31 - __clz((int)v);
+#else
+    return 31 - __builtin_clz(v);
+#endif
+}
+// bit i of m -> bit (i ^ x), x in [0,7], m 8 bits wide
+HM_HD unsigned xor_permute8(unsigned m, int x) {
+    if (x & 1) m = ((m & 0x55u) << 1) | ((m & 0xAAu) >> 1);
+    if (x & 2) m = ((m & 0x33u) << 2) | ((m & 0xCCu) >> 2);
+    if (x & 4) m = ((m & 0x0Fu) << 4) | ((m & 0xF0u) >> 4);
+    return m;
+}
+
+struct WideRay {
+    V3 idir, ood;       // 1/d and o/d
+    int octinv;         // bit k: d[k] >= 0
+};
+HM_HD WideRay make_wide_ray(V3 o, V3 d) {
+    const float eps = 1e-20f;
+    V3 dd = V3(fabsf(d.x) > eps ? d.x : (d.x < 0.f ? -eps : eps),
+               fabsf(d.y) > eps ? d.y : (d.y < 0.f ? -eps : eps),
+               fabsf(d.z) > eps ? d.z : (d.z < 0.f ? -eps : eps));
+    WideRay r;
+    r.idir = V3(1.f / dd.x, 1.f / dd.y, 1.f / dd.z);
+    r.ood = V3(o.x * r.idir.x, o.y * r.idir.y, o.z * r.idir.z);
+    r.octinv = (dd.x >= 0.f ? 1 : 0) | (dd.y >= 0.f ? 2 : 0) | (dd.z >= 0.f ? 4 : 0);
+    return r;
+}
+
+// Slab test of the 8 child boxes of one wide node; returns the slots hit (bit i = slot i).
+HM_HD unsigned wide_node_hits(F4 w0, F4 w2, F4 w3, F4 w4, const WideRay& r, float tmin, float tmax) {
+    const unsigned em = f_as_u(w0.w);
+    // t(q) = (q + bias) * (cell * idir) + (origin * idir - o * idir - bias * cell * idir)
+    const float ax = u_as_f((em & 0xffu) << 23) * r.idir.x, bx = fmaf(-kQBias, ax, fmaf(w0.x, r.idir.x, -r.ood.x));
+    const float ay = u_as_f(((em >> 8) & 0xffu) << 23) * r.idir.y, by = fmaf(-kQBias, ay, fmaf(w0.y, r.idir.y, -r.ood.y));
+    const float az = u_as_f(((em >> 16) & 0xffu) << 23) * r.idir.z, bz = fmaf(-kQBias, az, fmaf(w0.z, r.idir.z, -r.ood.z));
+    // near / far planes per axis by ray direction
+    const bool px = (r.octinv & 1) != 0, py = (r.octinv & 2) != 0, pz = (r.octinv & 4) != 0;
+    const unsigned lox[2] = {f_as_u(w2.x), f_as_u(w2.y)}, loy[2] = {f_as_u(w2.z), f_as_u(w2.w)};
+    const unsigned loz[2] = {f_as_u(w3.x), f_as_u(w3.y)}, hix[2] = {f_as_u(w3.z), f_as_u(w3.w)};
+    const unsigned hiy[2] = {f_as_u(w4.x), f_as_u(w4.y)}, hiz[2] = {f_as_u(w4.z), f_as_u(w4.w)};
+    unsigned hits = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int h = 0; h < 2; ++h) {
+        const unsigned nx = px ? lox[h] : hix[h], fx = px ? hix[h] : lox[h];
+        const unsigned ny = py ? loy[h] : hiy[h], fy = py ? hiy[h] : loy[h];
+        const unsigned nz = pz ? loz[h] : hiz[h], fz = pz ? hiz[h] : loz[h];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 4; ++k) {
+            const float tnx = fmaf(byte_biased(nx, k), ax, bx), tfx = fmaf(byte_biased(fx, k), ax, bx);
+            const float tny = fmaf(byte_biased(ny, k), ay, by), tfy = fmaf(byte_biased(fy, k), ay, by);
+            const float tnz = fmaf(byte_biased(nz, k), az, bz), tfz = fmaf(byte_biased(fz, k), az, bz);
+            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+            if (tn <= tf) hits |= 1u << (4 * h + k);
+        }
+    }
+    return hits;
+}
+
+// Primitive of one wide leaf reference against the ray (same tests as test_slot).
+HM_HD bool test_wide_leaf(const GeomView& g, int ref, V3 o, V3 d, const RayFrame& rf, float tmin, Hit& best) {
+    const F4* p = g.wleaf_data + 4 * (size_t)ref;
+    F4 a = load_f4(p + 0), b = load_f4(p + 1), c = load_f4(p + 2), e = load_f4(p + 3);
+    if (e.w < 0.f) {
+        float t, b1, b2;
+        if (intersect_triangle(o, d, tmin, best.t, V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), V3(c.x, c.y, c.z), t, b1, b2)) {
+            best.t = t; best.u = b1; best.v = b2; best.prim = f_as_i(e.x);
+            return true;
+        }
+    } else if (f_as_i(a.w) != best.prim) {
+        SegHit sh;
+        if (intersect_fibre(rf, tmin, best.t, f4_to_v4(a), f4_to_v4(b), f4_to_v4(c), f4_to_v4(e), sh)) {
+            best.t = sh.t; best.u = sh.u; best.v = 0.f; best.prim = f_as_i(a.w);
+            return true;
+        }
+    }
+    return false;
+}
+
+// Portable one-ray traversal of the wide tree (host tests, per-ray statistics hook); the
+// production kernels run the warp-cooperative schedule of hm_trace_dev.cuh over the same
+// node and primitive arithmetic.
+template <bool ANY>
+HM_HD Hit trace_wide(const GeomView& g, V3 o, V3 d, float tmin, float tmax, TraceStats* stats = nullptr) {
+    Hit best;
+    best.t = tmax; best.prim = -1; best.u = 0.f; best.v = 0.f;
+    if (g.num_wnodes == 0) return best;
+    const WideRay wr = make_wide_ray(o, d);
+    const RayFrame rf = make_ray_frame(o, d);
+
+    // a "group" = the not-yet-visited hit children of one node: base indices + masks
+    struct Group { int child_base, leaf_base; unsigned bits; };   // bits = imask | lmask << 8 | hits(permuted) << 16
+    Group stack[kWideStack];
+    int sp = 0;
+    Group cur;
+    cur.child_base = 0; cur.leaf_base = 0; cur.bits = 1u | (1u << (16 + (0 ^ wr.octinv)));   // pseudo-node whose slot 0 is the root
+
+    while (true) {
+        unsigned hits = cur.bits >> 16;
+        if (hits == 0) {
+            if (sp == 0) break;
+            cur = stack[--sp];
+            continue;
+        }
+        const int b = top_bit(hits);
+        cur.bits &= ~(1u << (16 + b));
+        const int slot = b ^ wr.octinv;
+        const unsigned below = (1u << slot) - 1u;
+        if ((cur.bits >> slot) & 1u) {
+            const int ni = cur.child_base + popc_u(cur.bits & 0xffu & below);
+            const F4* n = g.wnodes + 5 * (size_t)ni;
+            F4 w0 = load_f4(n + 0), w1 = load_f4(n + 1), w2 = load_f4(n + 2), w3 = load_f4(n + 3), w4 = load_f4(n + 4);
+            if (stats) stats->nodes++;
+            const unsigned imask = f_as_u(w0.w) >> 24, lmask = f_as_u(w1.z) & 0xffu;
+            unsigned h = wide_node_hits(w0, w2, w3, w4, wr, tmin, best.t) & (imask | lmask);
+            if (h) {
+                if (cur.bits >> 16) stack[sp++] = cur;
+                cur.child_base = f_as_i(w1.x); cur.leaf_base = f_as_i(w1.y);
+                cur.bits = imask | (lmask << 8) | (xor_permute8(h, wr.octinv) << 16);
+            }
+        } else {
+            const int ref = cur.leaf_base + popc_u((cur.bits >> 8) & 0xffu & below);
+            if (stats) stats->prims++;
+            if (test_wide_leaf(g, ref, o, d, rf, tmin, best) && ANY) return best;
         }
     }
     return best;

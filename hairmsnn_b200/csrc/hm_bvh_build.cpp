@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
+#include <stdexcept>
 #include <thread>
 
 namespace hm {
@@ -194,6 +195,150 @@ void triangle_bounds(const F4* tv, int ti, PrimRef& pr) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------
+// Binary tree -> 8-wide quantised tree (layout: hm_bvh.h).
+// ---------------------------------------------------------------------------------
+struct WideChild {
+    int code;      // binary child code: inner node index, or ~leaf slot
+    Box box;
+};
+
+struct WideBuilder {
+    const std::vector<NodeRaw>& bin;
+    const std::vector<F4>& leaf_data;   // binary leaf slots (64 B each)
+    std::vector<F4>& wnodes;
+    std::vector<F4>& wleaf;
+    int max_depth = 0;
+
+    static Box child_box(const NodeRaw& n, int k) {
+        Box b;
+        for (int a = 0; a < 3; ++a) { b.lo[a] = n.q[6 * k + a]; b.hi[a] = n.q[6 * k + 3 + a]; }
+        return b;
+    }
+
+    // children of the wide node that replaces binary node `bi`: open the inner child with the
+    // largest surface area until there are 8 (or only leaves are left)
+    int gather(int bi, WideChild* out) const {
+        const NodeRaw& n = bin[bi];
+        int cnt = 0;
+        out[cnt++] = WideChild{n.c0, child_box(n, 0)};
+        if (!(n.q[6] > n.q[9])) out[cnt++] = WideChild{n.c1, child_box(n, 1)};   // inverted box: the unreachable twin of a single-reference tree
+        while (cnt < 8) {
+            int pick = -1; float best = -1.f;
+            for (int i = 0; i < cnt; ++i)
+                if (out[i].code >= 0) { float a = out[i].box.half_area(); if (a > best) { best = a; pick = i; } }
+            if (pick < 0) break;
+            const NodeRaw& c = bin[out[pick].code];
+            out[pick] = WideChild{c.c0, child_box(c, 0)};
+            out[cnt++] = WideChild{c.c1, child_box(c, 1)};
+        }
+        return cnt;
+    }
+
+    // Fills wide node `wi` from binary node `bi`; children blocks are reserved here, so the inner
+    // children of a node are contiguous (child_base + rank) and so are its leaf references.
+    void emit(int wi, int bi, const Box& bounds, int depth) {
+        struct Item { int wi, bi, depth; Box bounds; };
+        std::vector<Item> todo;
+        todo.push_back(Item{wi, bi, depth, bounds});
+        while (!todo.empty()) {
+            Item it = todo.back(); todo.pop_back();
+            max_depth = std::max(max_depth, it.depth);
+            WideChild ch[8];
+            const int cnt = gather(it.bi, ch);
+
+            // octant slots: greedy assignment maximising sum of (slot sign) . (child centre - node centre)
+            float nc[3];
+            for (int a = 0; a < 3; ++a) nc[a] = 0.5f * (it.bounds.lo[a] + it.bounds.hi[a]);
+            int slot_of_child[8]; bool slot_used[8] = {false, false, false, false, false, false, false, false};
+            bool child_done[8] = {false, false, false, false, false, false, false, false};
+            float cost[8][8];
+            for (int c = 0; c < cnt; ++c)
+                for (int sl = 0; sl < 8; ++sl) {
+                    float v = 0.f;
+                    for (int a = 0; a < 3; ++a) {
+                        float rel = 0.5f * (ch[c].box.lo[a] + ch[c].box.hi[a]) - nc[a];
+                        v += ((sl >> a) & 1) ? rel : -rel;
+                    }
+                    cost[c][sl] = v;
+                }
+            for (int round = 0; round < cnt; ++round) {
+                int bc = -1, bs = -1; float bv = -FLT_MAX;
+                for (int c = 0; c < cnt; ++c) {
+                    if (child_done[c]) continue;
+                    for (int sl = 0; sl < 8; ++sl)
+                        if (!slot_used[sl] && cost[c][sl] > bv) { bv = cost[c][sl]; bc = c; bs = sl; }
+                }
+                child_done[bc] = true; slot_used[bs] = true; slot_of_child[bc] = bs;
+            }
+            int child_in_slot[8];
+            for (int sl = 0; sl < 8; ++sl) child_in_slot[sl] = -1;
+            for (int c = 0; c < cnt; ++c) child_in_slot[slot_of_child[c]] = c;
+
+            // quantisation frame: cell = 2^e per axis with 255 cells covering the node
+            unsigned ebits[3]; float cell[3];
+            for (int a = 0; a < 3; ++a) {
+                float ext = it.bounds.hi[a] - it.bounds.lo[a];
+                int e = -100;
+                if (ext > 0.f) e = std::max(-100, (int)ceilf(log2f(ext / 255.f)));
+                while (it.bounds.lo[a] + 255.f * ldexpf(1.f, e) < it.bounds.hi[a]) e++;
+                cell[a] = ldexpf(1.f, e);
+                ebits[a] = (unsigned)(e + 127);
+            }
+            unsigned imask = 0, lmask = 0;
+            unsigned char qlo[3][8], qhi[3][8];
+            for (int sl = 0; sl < 8; ++sl) {
+                const int c = child_in_slot[sl];
+                for (int a = 0; a < 3; ++a) { qlo[a][sl] = 255; qhi[a][sl] = 0; }   // empty slot: inverted box
+                if (c < 0) continue;
+                if (ch[c].code >= 0) imask |= 1u << sl; else lmask |= 1u << sl;
+                for (int a = 0; a < 3; ++a) {
+                    const float org = it.bounds.lo[a];
+                    int lo = (int)floorf((ch[c].box.lo[a] - org) / cell[a] - 1.f / 64.f);   // margin: hm_bvh.h byte_biased
+                    lo = std::max(0, std::min(255, lo));
+                    while (lo > 0 && org + (float)lo * cell[a] > ch[c].box.lo[a]) lo--;
+                    int hi = (int)ceilf((ch[c].box.hi[a] - org) / cell[a] + 1.f / 64.f);
+                    hi = std::max(0, std::min(255, hi));
+                    while (hi < 255 && org + (float)hi * cell[a] < ch[c].box.hi[a]) hi++;
+                    qlo[a][sl] = (unsigned char)lo; qhi[a][sl] = (unsigned char)hi;
+                }
+            }
+            const int n_inner = __builtin_popcount(imask), n_leaf = __builtin_popcount(lmask);
+            const int child_base = (int)(wnodes.size() / 5);
+            const int leaf_base = (int)(wleaf.size() / 4);
+            wnodes.resize(wnodes.size() + 5 * (size_t)n_inner);
+            wleaf.resize(wleaf.size() + 4 * (size_t)n_leaf);
+
+            auto as_f = [](unsigned u) { float f; memcpy(&f, &u, 4); return f; };
+            auto pack4 = [](const unsigned char* q) { return (unsigned)q[0] | ((unsigned)q[1] << 8) | ((unsigned)q[2] << 16) | ((unsigned)q[3] << 24); };
+            F4* w = wnodes.data() + 5 * (size_t)it.wi;
+            w[0] = F4{it.bounds.lo[0], it.bounds.lo[1], it.bounds.lo[2], as_f(ebits[0] | (ebits[1] << 8) | (ebits[2] << 16) | (imask << 24))};
+            w[1] = F4{as_f((unsigned)child_base), as_f((unsigned)leaf_base), as_f(lmask), 0.f};
+            w[2] = F4{as_f(pack4(qlo[0])), as_f(pack4(qlo[0] + 4)), as_f(pack4(qlo[1])), as_f(pack4(qlo[1] + 4))};
+            w[3] = F4{as_f(pack4(qlo[2])), as_f(pack4(qlo[2] + 4)), as_f(pack4(qhi[0])), as_f(pack4(qhi[0] + 4))};
+            w[4] = F4{as_f(pack4(qhi[1])), as_f(pack4(qhi[1] + 4)), as_f(pack4(qhi[2])), as_f(pack4(qhi[2] + 4))};
+
+            int ri = 0, rl = 0;
+            for (int sl = 0; sl < 8; ++sl) {
+                const int c = child_in_slot[sl];
+                if (c < 0) continue;
+                if (ch[c].code >= 0) {
+                    // the child's own frame is its DEQUANTISED box clipped to nothing tighter than its true
+                    // bounds: use the true bounds (they lie inside the dequantised box)
+                    todo.push_back(Item{child_base + ri, ch[c].code, it.depth + 1, ch[c].box});
+                    ri++;
+                } else {
+                    const F4* src = leaf_data.data() + 4 * (size_t)(~ch[c].code);
+                    F4* dst = wleaf.data() + 4 * (size_t)(leaf_base + rl);
+                    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+                    rl++;
+                }
+            }
+        }
+    }
+};
+
 }  // namespace
 
 void build_bvh(const HostGeometry& geo, HostBvh& out, int threads_hint) {
@@ -201,6 +346,7 @@ void build_bvh(const HostGeometry& geo, HostBvh& out, int threads_hint) {
     const int nt = (int)(geo.tri_verts.size() / 3);
     const int nprim = ns + nt;
     out.nodes.clear(); out.leaf_data.clear(); out.leaf_code.clear(); out.leaf_prim.clear();
+    out.wnodes.clear(); out.wleaf_data.clear();
     if (nprim == 0) return;
 
     // References.  Each fibre segment enters the tree as k references, one per sub-span of its
@@ -208,10 +354,13 @@ void build_bvh(const HostGeometry& geo, HostBvh& out, int threads_hint) {
     // tube fills a tiny fraction of its own box, and k pieces cut the total box area ~k-fold
     // (measured on the curly scene, k = 4: 128 -> 82 nodes and 30 -> 7 primitive tests per
     // incoherent ray).  k follows the chord length in units of `span_len` (HM_BVH_SPAN,
-    // default 20 radii), capped by HM_BVH_SPLIT (default 4).  Triangles get one reference.
-    int max_split = 4;
+    // default 5 radii), capped by HM_BVH_SPLIT (default 16).  Triangles get one reference.
+    // Swept on the bench scene with the 8-wide tree (gpurun_out/sweep*.txt, B200): split/span
+    // 4/20 -> 176, 8/10 -> 190, 16/5 -> 194 Mpaths/s (9.1 -> 4.6 primitive tests per ray at the
+    // same ~33 node visits).
+    int max_split = 16;
     if (const char* e = getenv("HM_BVH_SPLIT")) max_split = std::max(1, std::min(16, atoi(e)));
-    float span_radii = 20.f;
+    float span_radii = 5.f;
     if (const char* e = getenv("HM_BVH_SPAN")) span_radii = std::max(1.f, (float)atof(e));
     std::vector<int> ref_first(ns + 1);
     ref_first[0] = 0;
@@ -335,6 +484,15 @@ void build_bvh(const HostGeometry& geo, HostBvh& out, int threads_hint) {
             dst[3] = F4{id_bits(p), 0.f, 0.f, -1.f};
         }
     }
+
+    // the structure the GPU traverses
+    out.wnodes.clear(); out.wleaf_data.clear();
+    out.wnodes.resize(5);
+    WideBuilder wb{packed, out.leaf_data, out.wnodes, out.wleaf_data};
+    wb.emit(0, 0, root, 1);
+    out.wide_depth = wb.max_depth;
+    if (wb.max_depth > kWideStack)
+        throw std::runtime_error("BVH: wide tree deeper than the traversal stack");
 }
 
 }  // namespace hm

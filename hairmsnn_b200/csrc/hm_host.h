@@ -33,6 +33,10 @@ struct HostBvh {
     std::vector<F4> leaf_data;   // 4 per leaf slot
     std::vector<int> leaf_code;
     std::vector<int> leaf_prim;
+    // 8-wide quantised tree derived from the binary one (hm_bvh.h: WideNode)
+    std::vector<F4> wnodes;      // 5 per wide node
+    std::vector<F4> wleaf_data;  // 4 per wide leaf reference
+    int wide_depth = 0;
 };
 
 void build_bvh(const HostGeometry& geo, HostBvh& out, int threads_hint = 0);
@@ -114,6 +118,9 @@ inline GeomView make_view(const HostGeometry& g, const HostBvh& b) {
     v.num_segments = (int)g.seg_cp.size();
     v.num_tris = (int)(g.tri_verts.size() / 3);
     v.num_nodes = (int)(b.nodes.size() / 4);
+    v.wnodes = b.wnodes.data();
+    v.wleaf_data = b.wleaf_data.data();
+    v.num_wnodes = (int)(b.wnodes.size() / 5);
     return v;
 }
 

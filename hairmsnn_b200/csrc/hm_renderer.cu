@@ -64,10 +64,14 @@ DeviceScene::DeviceScene(const HostScene& hs) {
     const HostGeometry& g = hs.geo;
     const HostBvh& b = hs.bvh;
     memset(&view, 0, sizeof(view));
-    view.geom.nodes = upload(b.nodes.data(), b.nodes.size());
-    view.geom.leaf_data = upload(b.leaf_data.data(), b.leaf_data.size());
+    // the kernels traverse the 8-wide quantised tree only; the binary tree stays on the host (oracle hook)
+    view.geom.nodes = nullptr;
+    view.geom.leaf_data = nullptr;
+    view.geom.wnodes = upload(b.wnodes.data(), b.wnodes.size());
+    view.geom.wleaf_data = upload(b.wleaf_data.data(), b.wleaf_data.size());
+    view.geom.num_wnodes = (int)(b.wnodes.size() / 5);
     view.geom.leaf_code = nullptr;   // host-side only
-    view.geom.leaf_prim = upload(b.leaf_prim.data(), b.leaf_prim.size());
+    view.geom.leaf_prim = nullptr;
     view.geom.cps = upload(g.cps.data(), g.cps.size());
     view.geom.tri_verts = upload(g.tri_verts.data(), g.tri_verts.size());
     view.geom.num_segments = (int)g.seg_cp.size();

@@ -8,8 +8,9 @@
 // in the node loop because every lane waited for the slowest descent.  This schedule makes
 // every warp iteration ONE kind of unit step, taken by as many lanes as possible:
 //
-//   node step  : fetch one inner node, test both child boxes; inner children go to the
-//                lane's stack, leaf children (one primitive reference each) are PARKED in a
+//   node step  : fetch one 8-wide quantised node (80 B, hm_bvh.h), test its 8 child boxes; hit
+//                inner children become the lane's current group (older groups go to its
+//                stack), hit leaf children (one primitive reference each) are PARKED in a
 //                small per-lane list in shared memory and the lane keeps descending;
 //   prim step  : pop one parked reference, fetch its 64-byte primitive; triangles are
 //                intersected directly, fibre spans go through the cheap conservative
@@ -29,14 +30,14 @@
 namespace hm {
 
 constexpr int kTraceBlock = 128;   // threads per CTA of every kernel that calls trace_queue
-constexpr int kLeafCap = 8;        // parked primitive references per lane
+constexpr int kLeafCap = 16;       // parked primitive references per lane (a wide node can park 8)
 constexpr int kSolveCap = 4;       // parked solver candidates per lane
 constexpr int kRefillLanes = 8;    // refill when this many lanes are idle
 #ifndef HM_TRACE_PRIM_LANES
-#define HM_TRACE_PRIM_LANES 20     // prim step when this many lanes hold a parked reference
+#define HM_TRACE_PRIM_LANES 16     // prim step when this many lanes hold a parked reference
 #endif
 #ifndef HM_TRACE_SOLVE_LANES
-#define HM_TRACE_SOLVE_LANES 12    // solve step when this many lanes hold a candidate
+#define HM_TRACE_SOLVE_LANES 10    // solve step when this many lanes hold a candidate
 #endif
 #ifndef HM_TRACE_NODE_LANES
 #define HM_TRACE_NODE_LANES 10     // below this many node-ready lanes, parked work goes first
@@ -63,24 +64,27 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
                                             TraceStats* stats) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int kDone = 0x7fffffff;
     __shared__ int s_leaf[kLeafCap][kTraceBlock];
     __shared__ int s_solve[kSolveCap][kTraceBlock];
     const int tx = threadIdx.x;
 
     int id = -1;
-    V3 o, d, idir, ood;
+    V3 o, d;
+    WideRay wr;
     RayFrame rf;
     Hit best;
     best.t = tmax; best.prim = -1; best.u = 0.f; best.v = 0.f;
-    int cur = kDone, sp = 0, nleaf = 0, nsolve = 0;
-    int stack[kStackDepth];
+    // current group of pending inner children: base index + (imask | permuted hits << 8); older groups on the stack
+    int g_base = 0;
+    unsigned g_bits = 0;
+    int sp = 0, nleaf = 0, nsolve = 0;
+    int2 stack[kWideStack];
     bool exhausted = false;
     bool any = false;
 
     while (true) {
         // ---- commit finished rays, refill idle lanes ----
-        const bool finished = id >= 0 && cur == kDone && nleaf == 0 && nsolve == 0;
+        const bool finished = id >= 0 && (g_bits >> 8) == 0 && sp == 0 && nleaf == 0 && nsolve == 0;
         if (__any_sync(FULL, finished)) {
             ops.commit(id, best, finished);
             if (finished) id = -1;
@@ -97,15 +101,12 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
                 if (w < n) {
                     id = w;
                     any = ops.fetch(w, o, d);
-                    const float eps = 1e-20f;
-                    V3 dd = V3(fabsf(d.x) > eps ? d.x : (d.x < 0.f ? -eps : eps),
-                               fabsf(d.y) > eps ? d.y : (d.y < 0.f ? -eps : eps),
-                               fabsf(d.z) > eps ? d.z : (d.z < 0.f ? -eps : eps));
-                    idir = V3(1.f / dd.x, 1.f / dd.y, 1.f / dd.z);
-                    ood = V3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+                    wr = make_wide_ray(o, d);
                     rf = make_ray_frame(o, d);
                     best.t = tmax; best.prim = -1; best.u = 0.f; best.v = 0.f;
-                    cur = g.num_nodes > 0 ? 0 : kDone;
+                    // pseudo-group whose slot 0 is the root
+                    g_base = 0;
+                    g_bits = g.num_wnodes > 0 ? (1u | (1u << (8 + wr.octinv))) : 0u;
                     sp = 0; nleaf = 0; nsolve = 0;
                 }
             }
@@ -113,7 +114,7 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
         if (__all_sync(FULL, id < 0)) break;
 
         // ---- vote on the step kind ----
-        const bool can_node = cur != kDone && nleaf <= kLeafCap - 2;          // a node parks at most 2 references
+        const bool can_node = id >= 0 && ((g_bits >> 8) != 0 || sp > 0) && nleaf <= kLeafCap - 8;   // a node parks at most 8 references
         const bool can_prim = nleaf > 0 && nsolve < kSolveCap;
         const bool can_solve = nsolve > 0;
         const int n_node = __popc(__ballot_sync(FULL, can_node));
@@ -124,8 +125,8 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
         if (n_solve >= HM_TRACE_SOLVE_LANES || (n_solve > 0 && few_nodes && n_solve >= n_prim)) {
             // ---- solve step ----
             if (can_solve) {
-                const int slot = s_solve[--nsolve][tx];
-                const F4* p = g.leaf_data + 4 * (size_t)slot;
+                const int ref = s_solve[--nsolve][tx];
+                const F4* p = g.wleaf_data + 4 * (size_t)ref;
                 F4 a = load_f4(p + 0), b = load_f4(p + 1), c = load_f4(p + 2), e = load_f4(p + 3);
                 FibreCandidate fc;
                 // re-run the rejects: best.t may have shrunk since the span was parked
@@ -134,49 +135,57 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
                     SegHit sh;
                     if (fibre_solve(fc, tmin, best.t, sh)) {
                         best.t = sh.t; best.u = sh.u; best.v = 0.f; best.prim = f_as_i(a.w);
-                        if (any) { cur = kDone; sp = 0; nleaf = 0; nsolve = 0; }
+                        if (any) { g_bits = 0; sp = 0; nleaf = 0; nsolve = 0; }
                     }
                 }
             }
         } else if (n_prim >= HM_TRACE_PRIM_LANES || (n_prim > 0 && few_nodes)) {
             // ---- prim step ----
             if (can_prim) {
-                const int slot = s_leaf[--nleaf][tx];
-                const F4* p = g.leaf_data + 4 * (size_t)slot;
+                const int ref = s_leaf[--nleaf][tx];
+                const F4* p = g.wleaf_data + 4 * (size_t)ref;
                 F4 a = load_f4(p + 0), b = load_f4(p + 1), c = load_f4(p + 2), e = load_f4(p + 3);
                 if (stats) stats[any ? 1 : 0].prims++;
                 if (e.w < 0.f) {
                     float t, b1, b2;
                     if (intersect_triangle(o, d, tmin, best.t, V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), V3(c.x, c.y, c.z), t, b1, b2)) {
                         best.t = t; best.u = b1; best.v = b2; best.prim = f_as_i(e.x);
-                        if (any) { cur = kDone; sp = 0; nleaf = 0; nsolve = 0; }
+                        if (any) { g_bits = 0; sp = 0; nleaf = 0; nsolve = 0; }
                     }
                 } else if (f_as_i(a.w) != best.prim) {
                     FibreCandidate fc;
-                    if (fibre_candidate(rf, tmin, best.t, f4_to_v4(a), f4_to_v4(b), f4_to_v4(c), f4_to_v4(e), fc)) s_solve[nsolve++][tx] = slot;
+                    if (fibre_candidate(rf, tmin, best.t, f4_to_v4(a), f4_to_v4(b), f4_to_v4(c), f4_to_v4(e), fc)) s_solve[nsolve++][tx] = ref;
                 }
             }
         } else {
             // ---- node step ----
             if (can_node) {
-                const F4* nd = g.nodes + 4 * (size_t)cur;
-                F4 q0 = load_f4(nd + 0), q1 = load_f4(nd + 1), q2 = load_f4(nd + 2), q3 = load_f4(nd + 3);
+                if ((g_bits >> 8) == 0) { const int2 e = stack[--sp]; g_base = e.x; g_bits = (unsigned)e.y; }
+                const int bit = top_bit(g_bits >> 8);
+                g_bits &= ~(1u << (8 + bit));
+                const int slot = bit ^ wr.octinv;
+                const int ni = g_base + __popc(g_bits & 0xffu & ((1u << slot) - 1u));
+                const F4* nd = g.wnodes + 5 * (size_t)ni;
+                F4 w0 = load_f4(nd + 0), w1 = load_f4(nd + 1), w2 = load_f4(nd + 2), w3 = load_f4(nd + 3), w4 = load_f4(nd + 4);
                 if (stats) stats[any ? 1 : 0].nodes++;
-                float t0 = slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, idir, ood, tmin, best.t);
-                float t1 = slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, idir, ood, tmin, best.t);
-                int c0 = f_as_i(q3.x), c1 = f_as_i(q3.y);
-                bool h0 = t0 < 2.9e38f, h1 = t1 < 2.9e38f;
-                if (h1 && (!h0 || t1 < t0)) { int tmp = c0; c0 = c1; c1 = tmp; bool th = h0; h0 = h1; h1 = th; }
-                // c0 = nearer hit child (if any), c1 = the other hit child (if any)
-                if (h1) {
-                    if (c1 < 0) { s_leaf[nleaf++][tx] = ~c1; prefetch_line(g.leaf_data + 4 * (size_t)(~c1)); }
-                    else { stack[sp++] = c1; prefetch_line(g.nodes + 4 * (size_t)c1); }
+                const unsigned imask = f_as_u(w0.w) >> 24, lmask = f_as_u(w1.z) & 0xffu;
+                const unsigned h = wide_node_hits(w0, w2, w3, w4, wr, tmin, best.t);
+                // leaves: park far-to-near, so the nearest is popped first
+                unsigned pl = xor_permute8(h & lmask, wr.octinv);
+                const int leaf_base = f_as_i(w1.y);
+                while (pl) {
+                    const int b = __ffs((int)pl) - 1;
+                    pl &= pl - 1;
+                    const int sl = b ^ wr.octinv;
+                    const int ref = leaf_base + __popc(lmask & ((1u << sl) - 1u));
+                    s_leaf[nleaf++][tx] = ref;
+                    prefetch_line(g.wleaf_data + 4 * (size_t)ref);
                 }
-                if (h0 && c0 >= 0) {
-                    cur = c0;
-                } else {
-                    if (h0) { s_leaf[nleaf++][tx] = ~c0; prefetch_line(g.leaf_data + 4 * (size_t)(~c0)); }     // parked last: popped first
-                    cur = sp > 0 ? stack[--sp] : kDone;
+                const unsigned hi = h & imask;
+                if (hi) {
+                    if (g_bits >> 8) stack[sp++] = make_int2(g_base, (int)g_bits);
+                    g_base = f_as_i(w1.x);
+                    g_bits = imask | (xor_permute8(hi, wr.octinv) << 8);
                 }
             }
         }

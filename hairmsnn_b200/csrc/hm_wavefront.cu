@@ -684,7 +684,7 @@ __global__ void __launch_bounds__(kBlock) k_trace_rays(const SceneView S, const 
     for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
         V3 o(org[3 * i], org[3 * i + 1], org[3 * i + 2]), d(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
         TraceStats st; st.nodes = 0; st.prims = 0;
-        Hit h = any ? trace<true>(S.geom, o, d, tmin, tmax, &st) : trace<false>(S.geom, o, d, tmin, tmax, &st);
+        Hit h = any ? trace_wide<true>(S.geom, o, d, tmin, tmax, &st) : trace_wide<false>(S.geom, o, d, tmin, tmax, &st);
         out_hit[i] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
         out_stats[2 * i] = st.nodes; out_stats[2 * i + 1] = st.prims;
     }

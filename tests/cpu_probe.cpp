@@ -117,6 +117,21 @@ void probe_trace(void* p, int n, const float* org, const float* dir, float tmin,
         if (out_nodes) { out_nodes[i] = st.nodes; out_prims[i] = st.prims; }
     }
 }
+// same through the 8-wide quantised tree (what the CUDA kernels traverse)
+int probe_scene_num_wide_nodes(void* p) { return (int)(((ProbeScene*)p)->bvh.wnodes.size() / 5); }
+int probe_scene_wide_depth(void* p) { return ((ProbeScene*)p)->bvh.wide_depth; }
+void probe_trace_wide(void* p, int n, const float* org, const float* dir, float tmin, float tmax, int any,
+                      float* out_t, int* out_prim, float* out_u, float* out_v, int* out_nodes, int* out_prims) {
+    ProbeScene* s = (ProbeScene*)p;
+    GeomView g = make_view(s->geo, s->bvh);
+    for (int i = 0; i < n; ++i) {
+        TraceStats st{0, 0};
+        V3 o(org[3 * i], org[3 * i + 1], org[3 * i + 2]), d(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+        Hit h = any ? trace_wide<true>(g, o, d, tmin, tmax, &st) : trace_wide<false>(g, o, d, tmin, tmax, &st);
+        out_t[i] = h.t; out_prim[i] = h.prim; out_u[i] = h.u; out_v[i] = h.v;
+        if (out_nodes) { out_nodes[i] = st.nodes; out_prims[i] = st.prims; }
+    }
+}
 // exhaustive reference: test every primitive, no BVH
 void probe_trace_brute(void* p, int n, const float* org, const float* dir, float tmin, float tmax,
                        float* out_t, int* out_prim, float* out_u) {
@@ -245,3 +260,39 @@ void probe_render_pt(const ProbeSceneDesc* d, int accum_id, int W, int H, int y0
 }
 
 }  // extern "C"
+
+// debug aid: walk the wide tree for references of `prim`, report per level whether the ray hits the child's box
+extern "C" void probe_wide_debug(void* p, const float* org, const float* dir, int prim) {
+    ProbeScene* s = (ProbeScene*)p;
+    GeomView g = make_view(s->geo, s->bvh);
+    V3 o(org[0], org[1], org[2]), d(dir[0], dir[1], dir[2]);
+    WideRay wr = make_wide_ray(o, d);
+    struct E { int ni; int depth; };
+    std::vector<E> st; st.push_back({0, 0});
+    std::vector<int> parent(g.num_wnodes, -1), pslot(g.num_wnodes, -1);
+    while (!st.empty()) {
+        E e = st.back(); st.pop_back();
+        const F4* n = g.wnodes + 5 * (size_t)e.ni;
+        unsigned imask = f_as_u(n[0].w) >> 24, lmask = f_as_u(n[1].z) & 0xff;
+        unsigned h = wide_node_hits(n[0], n[2], n[3], n[4], wr, 0.f, 1e30f);
+        for (int sl = 0; sl < 8; ++sl) {
+            unsigned below = (1u << sl) - 1u;
+            if ((imask >> sl) & 1) { int c = f_as_i(n[1].x) + popc_u(imask & below); parent[c] = e.ni; pslot[c] = sl; st.push_back({c, e.depth + 1}); }
+            if ((lmask >> sl) & 1) {
+                int ref = f_as_i(n[1].y) + popc_u(lmask & below);
+                const F4* q = g.wleaf_data + 4 * (size_t)ref;
+                int id = q[3].w < 0.f ? f_as_i(q[3].x) : f_as_i(q[0].w);
+                if (id == prim) {
+                    printf("ref %d of prim %d in node %d slot %d (depth %d) box hit=%d\n", ref, prim, e.ni, sl, e.depth, (h >> sl) & 1);
+                    int c = e.ni;
+                    while (parent[c] >= 0) {
+                        const F4* pn = g.wnodes + 5 * (size_t)parent[c];
+                        unsigned ph = wide_node_hits(pn[0], pn[2], pn[3], pn[4], wr, 0.f, 1e30f);
+                        printf("   node %d is slot %d of node %d: box hit=%d\n", c, pslot[c], parent[c], (ph >> pslot[c]) & 1);
+                        c = parent[c];
+                    }
+                }
+            }
+        }
+    }
+}

@@ -112,6 +112,35 @@ def test_bvh_trace_equals_brute_force(probe):
     assert np.array_equal(t1.view(np.uint32), t2.view(np.uint32))
     assert np.array_equal(u1.view(np.uint32), u2.view(np.uint32))
     assert nodes.mean() < 400
+    # the 8-wide quantised tree (the one the kernels traverse) returns the same hits, bit for bit
+    t3 = np.zeros(n, np.float32); p3 = np.zeros(n, np.int32); u3 = np.zeros(n, np.float32); v3 = np.zeros(n, np.float32)
+    wn = np.zeros(n, np.int32); wp = np.zeros(n, np.int32)
+    probe.probe_trace_wide(h, n, o.ctypes.data_as(_fp), d.ctypes.data_as(_fp), C.c_float(0), C.c_float(1e30), 0, t3.ctypes.data_as(_fp),
+                           p3.ctypes.data_as(_ip), u3.ctypes.data_as(_fp), v3.ctypes.data_as(_fp), wn.ctypes.data_as(_ip), wp.ctypes.data_as(_ip))
+    assert np.array_equal(p3, p2)
+    assert np.array_equal(t3.view(np.uint32), t2.view(np.uint32))
+    assert np.array_equal(u3.view(np.uint32), u2.view(np.uint32))
+    assert 0 < probe.probe_scene_num_wide_nodes(h) < probe.probe_scene_num_nodes(h) / 2
+    assert wn.mean() < 0.6 * nodes.mean(), (wn.mean(), nodes.mean())
+    # occlusion queries agree on hit / no hit
+    probe.probe_trace_wide(h, n, o.ctypes.data_as(_fp), d.ctypes.data_as(_fp), C.c_float(0), C.c_float(1e30), 1, t3.ctypes.data_as(_fp),
+                           p3.ctypes.data_as(_ip), u3.ctypes.data_as(_fp), v3.ctypes.data_as(_fp), None, None)
+    assert np.array_equal(p3 >= 0, p2 >= 0)
+    # secondary-style rays from inside the volume, random directions
+    rng = np.random.default_rng(5)
+    hit = p2 >= 0
+    o2 = (o[hit] + t2[hit, None] * d[hit]).astype(np.float32)
+    d2 = rng.normal(size=o2.shape).astype(np.float32); d2 /= np.linalg.norm(d2, axis=1, keepdims=True)
+    o2 = np.ascontiguousarray(o2 + 0.05 * d2); d2 = np.ascontiguousarray(d2)
+    m = len(o2)
+    ta = np.zeros(m, np.float32); pa = np.zeros(m, np.int32); ua = np.zeros(m, np.float32); va = np.zeros(m, np.float32)
+    tb = np.zeros(m, np.float32); pb = np.zeros(m, np.int32); ub = np.zeros(m, np.float32); vb = np.zeros(m, np.float32)
+    probe.probe_trace(h, m, o2.ctypes.data_as(_fp), d2.ctypes.data_as(_fp), C.c_float(0), C.c_float(1e30), 0, ta.ctypes.data_as(_fp),
+                      pa.ctypes.data_as(_ip), ua.ctypes.data_as(_fp), va.ctypes.data_as(_fp), None, None)
+    probe.probe_trace_wide(h, m, o2.ctypes.data_as(_fp), d2.ctypes.data_as(_fp), C.c_float(0), C.c_float(1e30), 0, tb.ctypes.data_as(_fp),
+                           pb.ctypes.data_as(_ip), ub.ctypes.data_as(_fp), vb.ctypes.data_as(_fp), None, None)
+    assert (pa >= 0).sum() > 20
+    assert np.array_equal(pa, pb) and np.array_equal(ta.view(np.uint32), tb.view(np.uint32)) and np.array_equal(ua.view(np.uint32), ub.view(np.uint32))
     probe.probe_scene_destroy(h)
 
 
