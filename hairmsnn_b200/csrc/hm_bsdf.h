@@ -90,7 +90,7 @@ HM_HD float log_bessel_i0(float x) {
 }
 
 // longitudinal scattering M_p
-HM_HD float longitudinal(float cos_i, float cos_o, float sin_i, float sin_o, float v) {
+static HM_HD_OUTLINE float longitudinal(float cos_i, float cos_o, float sin_i, float sin_o, float v) {
     float a = cos_i * cos_o / v;
     float b = sin_i * sin_o / v;
     if (v <= 0.1f)
@@ -132,7 +132,7 @@ struct FibreGeom {
     V3 ap[4];        // attenuations A_0..A_2, residual
 };
 
-HM_HD void fibre_geom(const HairLobes& L, V3 wo, float h, FibreGeom& g) {
+static HM_HD_OUTLINE void fibre_geom(const HairLobes& L, V3 wo, float h, FibreGeom& g) {
     g.sin_o = wo.x;
     g.cos_o = safe_sqrt(1 - sqr(g.sin_o));
     g.phi_o = atan2f(wo.z, wo.y);
@@ -184,7 +184,10 @@ HM_HD void tilt(const HairLobes& L, int p, float sin_o, float cos_o, float& sin_
     }
 }
 
-HM_HD V3 eval_with_geom(const HairLobes& L, const FibreGeom& g, V3 wi, float* pdf) {
+// Outlined on the device: a vertex evaluates the model up to three times (light sample, BSDF
+// sample, continuation) and the inlined copies made k_shade 16.6 k instructions — ncu showed it
+// stalled on instruction fetch (stall_no_instruction 9 of 19 cycles per issue).
+static HM_HD_OUTLINE V3 eval_with_geom(const HairLobes& L, const FibreGeom& g, V3 wi, float* pdf) {
     float sin_i = wi.x;
     float cos_i = safe_sqrt(1 - sqr(sin_i));
     float phi_i = atan2f(wi.z, wi.y);
@@ -223,10 +226,21 @@ HM_HD V3 hair_eval(const HairLobes& L, V3 wo_local, V3 wi_local, float h, float*
 // Draws wi_local from the lobe mixture with u = (lobe, theta, phi-of-theta, dphi).
 // The caller maps it to world space, renormalises, and evaluates with hair_eval on
 // the *local* direction returned here (as the reference does).
+// Same two entry points with the per-vertex part (hairdetail::FibreGeom: everything that depends on
+// wo and h only) computed once by the caller and shared by all evaluations at the vertex.
+HM_HD V3 hair_eval_geom(const HairLobes& L, const hairdetail::FibreGeom& g, V3 wi_local, float* pdf) {
+    return hairdetail::eval_with_geom(L, g, wi_local, pdf);
+}
+static HM_HD_OUTLINE V3 hair_sample_dir_geom(const HairLobes& L, const hairdetail::FibreGeom& g, float u0, float u1, float u2, float u3);
+
 HM_HD V3 hair_sample_dir(const HairLobes& L, V3 wo_local, float h, float u0, float u1, float u2, float u3) {
+    hairdetail::FibreGeom g;
+    hairdetail::fibre_geom(L, wo_local, h, g);
+    return hair_sample_dir_geom(L, g, u0, u1, u2, u3);
+}
+
+static HM_HD_OUTLINE V3 hair_sample_dir_geom(const HairLobes& L, const hairdetail::FibreGeom& g, float u0, float u1, float u2, float u3) {
     using namespace hairdetail;
-    FibreGeom g;
-    fibre_geom(L, wo_local, h, g);
 
     int p = 0;
     float eps1 = u0;
@@ -300,7 +314,7 @@ HM_HD V3 sample_vndf(float a, V3 v, float u1, float u2) {
 }  // namespace surfdetail
 
 // f * cos
-HM_HD V3 surf_eval(V3 wo, V3 wi, V3 kd, float alpha) {
+static HM_HD_OUTLINE V3 surf_eval(V3 wo, V3 wi, V3 kd, float alpha) {
     V3 brdf(0.f);
     if (wo.z > 0.f && wi.z > 0.f) {
         brdf += 0.5f * kd / kPi;
@@ -309,7 +323,7 @@ HM_HD V3 surf_eval(V3 wo, V3 wi, V3 kd, float alpha) {
     return brdf * fabsf(wi.z);
 }
 
-HM_HD float surf_pdf(float alpha, V3 v, V3 ne) {
+static HM_HD_OUTLINE float surf_pdf(float alpha, V3 v, V3 ne) {
     float g1 = surfdetail::ggx_g1(alpha, v);
     float m = fmaxf(0.f, dot(v, ne));
     float d = surfdetail::ggx_d(alpha, ne);
@@ -317,7 +331,7 @@ HM_HD float surf_pdf(float alpha, V3 v, V3 ne) {
     return dv / (4.f * dot(v, ne));
 }
 
-HM_HD V3 surf_sample(float u1, float u2, float alpha, V3 v, float* pdf) {
+static HM_HD_OUTLINE V3 surf_sample(float u1, float u2, float alpha, V3 v, float* pdf) {
     V3 n = surfdetail::sample_vndf(alpha, v, u1, u2);
     V3 l = -v + 2.0f * n * dot(v, n);
     *pdf = surf_pdf(alpha, v, n);

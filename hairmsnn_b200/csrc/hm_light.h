@@ -82,7 +82,7 @@ HM_HD float spherical_phi(V3 v) {
 }
 HM_HD float spherical_theta(V3 v) { return acosf(v.z); }
 
-HM_HD V3 env_radiance(const EnvView& e, V3 dir) {
+static HM_HD_OUTLINE V3 env_radiance(const EnvView& e, V3 dir) {
     float theta = spherical_theta(dir);
     float phi = spherical_phi(dir) + e.rot_phi;
     if (phi > kTwoPiLoose) phi = phi - kTwoPiLoose;
@@ -140,7 +140,7 @@ HM_HD V3 uniform_sample_sphere(float u0, float u1) {
 
 // u0 = first draw (pairs with the conditional/u axis), u1 = second draw.
 // Returns radiance; wi and pdf by reference.
-HM_HD V3 env_sample(const EnvView& e, float u0, float u1, V3& wi, float& pdf) {
+static HM_HD_OUTLINE V3 env_sample(const EnvView& e, float u0, float u1, V3& wi, float& pdf) {
     if (!e.pdf_sampling) {
         wi = uniform_sample_sphere(u0, u1);
         pdf = 1.f / (4.f * kPi);

@@ -11,9 +11,12 @@
 #if defined(__CUDACC__)
 #define HM_HD __host__ __device__ __forceinline__
 #define HM_D __device__ __forceinline__
+// one shared copy per kernel instead of one per call site (instruction-cache footprint)
+#define HM_HD_OUTLINE __host__ __device__ __noinline__
 #else
 #define HM_HD inline
 #define HM_D inline
+#define HM_HD_OUTLINE inline
 #endif
 
 namespace hm {

@@ -45,6 +45,8 @@ struct Vertex {
     float h;         // fibres: dot(Y, n)
     float alpha;     // surfaces: squared roughness
     bool surface;
+    hairdetail::FibreGeom geom;   // fibres: the wo/h-dependent part of the scattering model, shared by
+                                  // every evaluation at this vertex (same arithmetic, computed once)
 };
 
 // orthonormalBasis (cuda_headers/utils.cuh:232-259) — note the double-precision
@@ -85,6 +87,7 @@ HM_HD Vertex vertex_from_hit(const SceneView& S, const Hit& hit, V3 ray_o, V3 ra
         v.h = dot(Y, v.n);
         v.alpha = 0.f;
         v.surface = false;
+        hairdetail::fibre_geom(S.lobes, v.wo_local, v.h, v.geom);
     } else {
         const int ti = hit.prim - ns;
         const float bu = hit.u, bv = hit.v;
@@ -121,7 +124,7 @@ struct DirectSample {
 };
 
 HM_HD V3 eval_bsdf(const SceneView& S, const Vertex& v, V3 wi_local, float* pdf) {
-    if (!v.surface) return hair_eval(S.lobes, v.wo_local, wi_local, v.h, pdf);
+    if (!v.surface) return hair_eval_geom(S.lobes, v.geom, wi_local, pdf);
     V3 f = surf_eval(v.wo_local, wi_local, V3(S.kd[0], S.kd[1], S.kd[2]), v.alpha);
     *pdf = surf_pdf(v.alpha, v.wo_local, normalize(v.wo_local + wi_local));
     return f;
@@ -134,9 +137,9 @@ HM_HD V3 sample_bsdf_dir(const SceneView& S, const Vertex& v, Rng& rng, V3& wi, 
     if (!v.surface) {
         float r2 = rng_next(rng);
         float r3 = rng_next(rng);
-        V3 wl = hair_sample_dir(S.lobes, v.wo_local, v.h, r0, r1, r2, r3);
+        V3 wl = hair_sample_dir_geom(S.lobes, v.geom, r0, r1, r2, r3);
         wi = normalize(v.to_local.transposed().apply(wl));
-        return hair_eval(S.lobes, v.wo_local, wl, v.h, &pdf);
+        return hair_eval_geom(S.lobes, v.geom, wl, &pdf);
     }
     V3 wl = surf_sample(r0, r1, v.alpha, v.wo_local, &pdf);
     wi = normalize(v.to_local.transposed().apply(wl));

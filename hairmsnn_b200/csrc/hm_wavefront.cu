@@ -132,7 +132,7 @@ struct PrimaryOps {
     }
 };
 
-__global__ void __launch_bounds__(kBlock, kTraceCtasPerSm) k_primary(const FrameParams P) {
+__global__ void __launch_bounds__(kBlock, kTraceCtasPerSm) k_primary(const __grid_constant__ FrameParams P) {
     const int n = (P.row1 - P.row0) * P.W;
     TraceStats st[2] = {{0, 0}, {0, 0}};
     PrimaryOps ops{P, P.row0 * P.W};
@@ -163,7 +163,7 @@ __device__ __forceinline__ void fold_pending(const FrameParams& P, int slot, boo
     if (training) color_short += v3(P.paths.dl_beta_short[slot]) * d;
 }
 
-__global__ void __launch_bounds__(kBlock) k_shade(const FrameParams P, int src) {
+__global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ FrameParams P, int src) {
     const int n = P.q.counts[src];
     const int* queue = P.q.shade[src];
     const int rounds = (n + kBlock - 1) / kBlock;
@@ -311,7 +311,7 @@ struct TraceOps {
     }
 };
 
-__global__ void __launch_bounds__(kBlock, kTraceCtasPerSm) k_trace(const FrameParams P, int dst) {
+__global__ void __launch_bounds__(kBlock, kTraceCtasPerSm) k_trace(const __grid_constant__ FrameParams P, int dst) {
     const int n_extend = P.q.counts[2], n_shadow = P.q.counts[3];
     TraceStats st[2] = {{0, 0}, {0, 0}};
     TraceOps ops{P, n_shadow, dst};
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(kBlock, kTraceCtasPerSm) k_trace(const FramePa
 // ---------------------------------------------------------------------------------
 // finalize
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_finalize(const FrameParams P) {
+__global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ FrameParams P) {
     const int n = (P.row1 - P.row0) * P.W;
     const int first = P.row0 * P.W;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -410,7 +410,7 @@ __device__ __forceinline__ float nrc_area(V3 a, V3 b, float abscos) {
     return l * l / (4.f * kPi) / abscos;
 }
 
-__global__ void __launch_bounds__(kBlock) k_shade_nrc(const FrameParams P, int src) {
+__global__ void __launch_bounds__(kBlock) k_shade_nrc(const __grid_constant__ FrameParams P, int src) {
     const int n = P.q.counts[src];
     const int* queue = P.q.shade[src];
     const int rounds = (n + kBlock - 1) / kBlock;
@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(kBlock) k_shade_nrc(const FrameParams P, int s
 
 // End of the G_BUFFER pass: paths that left the scene (or reached the bounce cap) fold their last
 // direct sample and write their G-buffer entry; primary misses show the environment.
-__global__ void __launch_bounds__(256) k_finalize_nrc(const FrameParams P) {
+__global__ void __launch_bounds__(256) k_finalize_nrc(const __grid_constant__ FrameParams P) {
     const int n = (P.row1 - P.row0) * P.W;
     const int first = P.row0 * P.W;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {

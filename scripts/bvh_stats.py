@@ -49,12 +49,15 @@ def load_hair(path):
     return np.concatenate([cps, w], axis=1), np.concatenate(seg_first).astype(np.int32)
 
 
+WIDE = os.environ.get("HM_STATS_WIDE", "1") != "0"
+
+
 def trace(probe, h, o, d, any_hit=False):
     n = len(o)
     o = np.ascontiguousarray(o, np.float32); d = np.ascontiguousarray(d, np.float32)
     t = np.zeros(n, np.float32); p = np.zeros(n, np.int32); u = np.zeros(n, np.float32); v = np.zeros(n, np.float32)
     nodes = np.zeros(n, np.int32); prims = np.zeros(n, np.int32)
-    probe.probe_trace(h, n, o.ctypes.data_as(fp), d.ctypes.data_as(fp), C.c_float(0), C.c_float(1e30), int(any_hit),
+    (probe.probe_trace_wide if WIDE else probe.probe_trace)(h, n, o.ctypes.data_as(fp), d.ctypes.data_as(fp), C.c_float(0), C.c_float(1e30), int(any_hit),
                       t.ctypes.data_as(fp), p.ctypes.data_as(ip), u.ctypes.data_as(fp), v.ctypes.data_as(fp),
                       nodes.ctypes.data_as(ip), prims.ctypes.data_as(ip))
     return t, p, nodes, prims
@@ -75,7 +78,11 @@ def main():
     h = C.c_void_p(probe.probe_scene_create(cps.ctypes.data_as(fp), len(cps), seg.ctypes.data_as(ip), len(seg),
                                            tv4.ctypes.data_as(fp), len(tv4) // 3, 0))
     probe.probe_scene_num_nodes.argtypes = [C.c_void_p]
-    print(f"segments {len(seg)} nodes {probe.probe_scene_num_nodes(h)} build {time.time() - t0:.1f}s split={os.environ.get('HM_BVH_SPLIT', '1')}")
+    probe.probe_scene_num_wide_nodes.argtypes = [C.c_void_p]; probe.probe_scene_wide_depth.argtypes = [C.c_void_p]
+    nb, nw = probe.probe_scene_num_nodes(h), probe.probe_scene_num_wide_nodes(h)
+    print(f"segments {len(seg)} binary nodes {nb} ({nb * 64 / 1e6:.0f} MB) = references - 1; wide nodes {nw} ({nw * 80 / 1e6:.0f} MB), "
+          f"wide leaf copies {(nb + 1) * 64 / 1e6:.0f} MB, wide depth {probe.probe_scene_wide_depth(h)}, build {time.time() - t0:.1f}s "
+          f"split={os.environ.get('HM_BVH_SPLIT', 'default')} span={os.environ.get('HM_BVH_SPAN', 'default')} tree={'wide' if WIDE else 'binary'}")
     # camera rays (config.json camera, 1024x1024)
     rng = np.random.default_rng(0)
     cam = np.array(synth.CAMERA_FROM, np.float32)
