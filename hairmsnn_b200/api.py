@@ -231,6 +231,15 @@ class Scene:
             pass
 
 
+def load_exr(path):
+    """RGBA32F image [h][w][4] through the library's OpenEXR reader (hm_image_load_exr)."""
+    w, h = C.c_int(), C.c_int()
+    _check(lib.hm_image_load_exr(os.fsencode(path), None, C.c_size_t(0), C.byref(w), C.byref(h)))
+    out = np.empty((h.value, w.value, 4), np.float32)
+    _check(lib.hm_image_load_exr(os.fsencode(path), _ptr(out), C.c_size_t(out.size), C.byref(w), C.byref(h)))
+    return out
+
+
 class Mlp:
     """TINY_MLP stand-in.  `inference` / `train_step` take HOST numpy arrays; the
     `*_device` variants take raw device pointers (ints), e.g. torch tensors' data_ptr()."""

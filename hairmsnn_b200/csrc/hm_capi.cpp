@@ -201,6 +201,20 @@ int hm_scene_get_env_tables(const hm_scene* s, const float** env, const float** 
     });
 }
 
+int hm_image_load_exr(const char* path, float* rgba, size_t capacity_floats, int* width, int* height) {
+    return guarded([&] {
+        need(path, "path"); need(width, "width"); need(height, "height");
+        std::vector<float> img;
+        int w = 0, h = 0;
+        load_exr_rgba(path, img, w, h);
+        *width = w; *height = h;
+        if (rgba) {
+            if (capacity_floats < img.size()) throw std::invalid_argument("hm_image_load_exr: buffer too small");
+            memcpy(rgba, img.data(), img.size() * sizeof(float));
+        }
+    });
+}
+
 // ---- renderer -----------------------------------------------------------------------
 int hm_renderer_create(hm_scene* s, int kind, int beta_cli, int device, int rank, int world, hm_renderer** out) {
     return guarded([&] {

@@ -43,6 +43,9 @@ constexpr int kRefillLanes = 8;    // refill when this many lanes are idle
 #define HM_TRACE_NODE_LANES 10     // below this many node-ready lanes, parked work goes first
 #endif
 
+#ifndef HM_TRACE_NODE_REPEAT
+#define HM_TRACE_NODE_REPEAT 2     // node steps per vote
+#endif
 #ifndef HM_TRACE_PREFETCH
 #define HM_TRACE_PREFETCH 0        // 1: prefetch parked primitives and pushed far children into L2/L1
 #endif
@@ -158,34 +161,41 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
                 }
             }
         } else {
-            // ---- node step ----
-            if (can_node) {
-                if ((g_bits >> 8) == 0) { const int2 e = stack[--sp]; g_base = e.x; g_bits = (unsigned)e.y; }
-                const int bit = top_bit(g_bits >> 8);
-                g_bits &= ~(1u << (8 + bit));
-                const int slot = bit ^ wr.octinv;
-                const int ni = g_base + __popc(g_bits & 0xffu & ((1u << slot) - 1u));
-                const F4* nd = g.wnodes + 5 * (size_t)ni;
-                F4 w0 = load_f4(nd + 0), w1 = load_f4(nd + 1), w2 = load_f4(nd + 2), w3 = load_f4(nd + 3), w4 = load_f4(nd + 4);
-                if (stats) stats[any ? 1 : 0].nodes++;
-                const unsigned imask = f_as_u(w0.w) >> 24, lmask = f_as_u(w1.z) & 0xffu;
-                const unsigned h = wide_node_hits(w0, w2, w3, w4, wr, tmin, best.t);
-                // leaves: park far-to-near, so the nearest is popped first
-                unsigned pl = xor_permute8(h & lmask, wr.octinv);
-                const int leaf_base = f_as_i(w1.y);
-                while (pl) {
-                    const int b = __ffs((int)pl) - 1;
-                    pl &= pl - 1;
-                    const int sl = b ^ wr.octinv;
-                    const int ref = leaf_base + __popc(lmask & ((1u << sl) - 1u));
-                    s_leaf[nleaf++][tx] = ref;
-                    prefetch_line(g.wleaf_data + 4 * (size_t)ref);
-                }
-                const unsigned hi = h & imask;
-                if (hi) {
-                    if (g_bits >> 8) stack[sp++] = make_int2(g_base, (int)g_bits);
-                    g_base = f_as_i(w1.x);
-                    g_bits = imask | (xor_permute8(hi, wr.octinv) << 8);
+            // ---- node step(s) ----
+            // HM_TRACE_NODE_REPEAT unit steps per vote: most iterations are node steps, and the
+            // commit/refill/vote preamble costs about a quarter of a node test.
+#pragma unroll 1
+            for (int rep = 0; rep < HM_TRACE_NODE_REPEAT; ++rep) {
+                const bool go = id >= 0 && ((g_bits >> 8) != 0 || sp > 0) && nleaf <= kLeafCap - 8;
+                if (rep > 0 && __popc(__ballot_sync(FULL, go)) < HM_TRACE_NODE_LANES) break;
+                if (go) {
+                    if ((g_bits >> 8) == 0) { const int2 e = stack[--sp]; g_base = e.x; g_bits = (unsigned)e.y; }
+                    const int bit = top_bit(g_bits >> 8);
+                    g_bits &= ~(1u << (8 + bit));
+                    const int slot = bit ^ wr.octinv;
+                    const int ni = g_base + __popc(g_bits & 0xffu & ((1u << slot) - 1u));
+                    const F4* nd = g.wnodes + 5 * (size_t)ni;
+                    F4 w0 = load_f4(nd + 0), w1 = load_f4(nd + 1), w2 = load_f4(nd + 2), w3 = load_f4(nd + 3), w4 = load_f4(nd + 4);
+                    if (stats) stats[any ? 1 : 0].nodes++;
+                    const unsigned imask = f_as_u(w0.w) >> 24, lmask = f_as_u(w1.z) & 0xffu;
+                    const unsigned h = wide_node_hits(w0, w2, w3, w4, wr, tmin, best.t);
+                    // leaves: park far-to-near, so the nearest is popped first
+                    unsigned pl = xor_permute8(h & lmask, wr.octinv);
+                    const int leaf_base = f_as_i(w1.y);
+                    while (pl) {
+                        const int b = __ffs((int)pl) - 1;
+                        pl &= pl - 1;
+                        const int sl = b ^ wr.octinv;
+                        const int ref = leaf_base + __popc(lmask & ((1u << sl) - 1u));
+                        s_leaf[nleaf++][tx] = ref;
+                        prefetch_line(g.wleaf_data + 4 * (size_t)ref);
+                    }
+                    const unsigned hi = h & imask;
+                    if (hi) {
+                        if (g_bits >> 8) stack[sp++] = make_int2(g_base, (int)g_bits);
+                        g_base = f_as_i(w1.x);
+                        g_bits = imask | (xor_permute8(hi, wr.octinv) << 8);
+                    }
                 }
             }
         }

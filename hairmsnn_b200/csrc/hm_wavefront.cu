@@ -163,7 +163,13 @@ __device__ __forceinline__ void fold_pending(const FrameParams& P, int slot, boo
     if (training) color_short += v3(P.paths.dl_beta_short[slot]) * d;
 }
 
-__global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ FrameParams P, int src) {
+#ifndef HM_SHADE_GRID
+#define HM_SHADE_GRID 8
+#endif
+#ifndef HM_SHADE_CTAS
+#define HM_SHADE_CTAS 4
+#endif
+__global__ void __launch_bounds__(kBlock, HM_SHADE_CTAS) k_shade(const __grid_constant__ FrameParams P, int src) {
     const int n = P.q.counts[src];
     const int* queue = P.q.shade[src];
     const int rounds = (n + kBlock - 1) / kBlock;
@@ -704,7 +710,7 @@ void launch_primary(const FrameParams& P, cudaStream_t stream) {
 }
 void launch_shade(const FrameParams& P, int src, cudaStream_t stream) {
     if (P.mode == MODE_NRC) k_shade_nrc<<<persistent_grid(8), kBlock, 0, stream>>>(P, src);
-    else k_shade<<<persistent_grid(8), kBlock, 0, stream>>>(P, src);
+    else k_shade<<<persistent_grid(HM_SHADE_GRID), kBlock, 0, stream>>>(P, src);
     g_launches++;
 }
 void launch_trace(const FrameParams& P, int dst, cudaStream_t stream) {

@@ -103,6 +103,11 @@ typedef struct {
 } hm_scene_desc;
 
 int hm_scene_create(const hm_scene_desc* desc, hm_scene** out);
+/* loadEnvTexture's file reader (model.cpp:158-231, tinyexr LoadEXR): single-part scanline OpenEXR,
+ * HALF/FLOAT/UINT channels, NONE/ZIPS/ZIP/PIZ compression -> RGBA32F, top row first, alpha 1 when
+ * the file has none.  Call with rgba = NULL to get the size, then with a buffer of
+ * capacity_floats >= 4*w*h. */
+int hm_image_load_exr(const char* path, float* rgba, size_t capacity_floats, int* width, int* height);
 void hm_scene_free(hm_scene* scene);
 
 typedef struct {

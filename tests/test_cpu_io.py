@@ -1,0 +1,56 @@
+"""Asset readers either side of the path: the OpenEXR reader incl. the PIZ decoder
+(hm_piz.cpp) against fixtures written and read back by OpenCV's OpenEXR (tests/golden/gen_piz_fixture.py),
+and — where the reference tree is mounted — the shipped scenes themselves."""
+import os
+
+import numpy as np
+import pytest
+
+from hairmsnn_b200 import api
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REF = "/root/reference/scenes"
+
+
+@pytest.mark.parametrize("name", ["piz_f32", "piz_f16"])
+def test_piz_fixture_decodes_bit_exact(name):
+    img = api.load_exr(os.path.join(GOLD, name + ".exr"))
+    want = np.load(os.path.join(GOLD, name + ".npy"))
+    assert img.shape == (77, 131, 4)
+    assert np.array_equal(img[..., :3].view(np.uint32), want.view(np.uint32))
+    assert np.all(img[..., 3] == 1.0)
+
+
+def test_corrupt_piz_block_is_an_error_not_a_crash(tmp_path):
+    raw = bytearray(open(os.path.join(GOLD, "piz_f32.exr"), "rb").read())
+    for k in range(len(raw) - 4000, len(raw) - 3000):
+        raw[k] ^= 0x5A
+    p = tmp_path / "bad.exr"
+    p.write_bytes(bytes(raw))
+    try:
+        img = api.load_exr(str(p))          # damage may decode to wrong pixels, but must not crash
+        assert img.shape == (77, 131, 4)
+    except api.HairMSNNError as e:
+        assert e.code == -1
+    p2 = tmp_path / "short.exr"
+    p2.write_bytes(bytes(raw[:5000]))
+    with pytest.raises(api.HairMSNNError):
+        api.load_exr(str(p2))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference scenes are not mounted here")
+def test_shipped_straight_scene_loads_unchanged():
+    """scenes/straight/config.json as shipped: Windows absolute paths, wrong-case .hair name, PIZ env map."""
+    sc = api.Scene.load(os.path.join(REF, "straight", "config.json"))
+    i = sc.info()
+    assert (i.num_segments, i.num_strands, i.num_triangles) == (1200000, 50000, 78520)
+    assert (i.width, i.height, i.spp, i.path_v1, i.path_v2) == (1024, 1024, 500, 1, 40)
+    assert (i.env_w, i.env_h, i.num_dlights) == (4096, 2048, 1)
+    assert 170 < i.scene_scale < 182                      # ~176
+    env = sc.env_tables()["env"].reshape(2048, 4096, 4)
+    cv2 = pytest.importorskip("cv2")
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    ref = cv2.imread(os.path.join(REF, "envmaps", "christmas_photo_studio_07_4k.exr"), cv2.IMREAD_UNCHANGED)
+    if ref is None:
+        pytest.skip("OpenCV build has no OpenEXR")
+    assert np.array_equal(env[..., :3], ref[..., ::-1])
