@@ -35,6 +35,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 W = H = 1024
 BETA_CLI = 1
 RECORDS = 16384
+NODE_BYTES = 80          # 8-wide quantised BVH node (hm_bvh.h)
 FLOPS_PER_QUERY = 16768           # 2*(64*64 + 64*64 + 64*3)
 
 
@@ -85,7 +86,7 @@ def make_scene(num_strands):
 
 
 CONFIG = {"workload": "render_hair_msnn synthetic-curly 1024x1024 BETA=1 (50k strands, 3.4M segments, env 4096x2048 + 1 directional, MIS+ENV_PDF, online training 16384 records/step, 1048576 MLP queries/step)",
-          "l2": "working set (BVH 215 MB + control points 57 MB + env tables 200 MB + path state 180 MB) exceeds the 126 MB L2; no flush needed",
+          "l2": "working set (wide BVH nodes 1.1 GB + leaf primitive copies 2.8 GB + control points 57 MB + env tables 200 MB + path state 180 MB per frame in flight) exceeds the 126 MB L2; no flush needed",
           "sharding": "spp"}
 
 
@@ -122,7 +123,7 @@ def run_reference(args, rank):
                              "sample": f"rows {y0}..{y1 - 1} of the 1024x1024 frame ({paths} paths) per step: G_BUFFER pass of cuda/hair_msnn.cu compiled for the host, all host threads"},
             "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 def cpu_baseline(sc, kw, seconds_target=12.0):
@@ -146,6 +147,24 @@ def cpu_baseline(sc, kw, seconds_target=12.0):
             "sample": f"{n} samples of rows {y0}..{y1 - 1} ({paths} paths, {dt:.1f} s): the reference's hair_msnn.cu G_BUFFER pass compiled for the host (oracle/_ref), {cores} threads"}
 
 
+_REAL_STDOUT = None
+
+
+def redirect_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(text):
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        print(text, flush=True)
+    else:
+        os.write(_REAL_STDOUT, (text + "\n").encode())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -160,6 +179,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries exactly one JSON line (rank 0): libraries that write to fd 1 (NCCL prints its
+    # version banner there) are sent to stderr for the duration of the run
+    redirect_stdout()
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -170,7 +192,8 @@ def main():
 
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
     peaks = load_peaks()
 
     t0 = time.time()
@@ -258,30 +281,36 @@ def main():
     frame_param_bytes = int(api.lib.hm_frame_param_bytes())
     launches_per_step = launches / max(args.steps, 1)
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
     # ---- roofline of the dominant kernel -------------------------------------------------
-    # instrumented pass: nodes visited / primitives tested per stage (SURVEY §8d per-ray bytes)
+    # instrumented pass: nodes visited / primitives tested per stage (SURVEY §8d per-ray bytes).
+    # Every rank takes part (the step holds a collective when world > 1); rank 0 reports.
     r.reset_stats()
     r.set_collect_stats(True)
     n_inst = 2
     for _ in range(n_inst):
-        r.render_frames(1) if world == 1 else (step(), r.sync())
+        step()
+        r.sync()
     si = r.stats()
     r.set_collect_stats(False)
-    # stage "trace" = k_trace: one launch per path vertex tracing its occlusion probes and continuation rays
-    stage_ms = {"primary": st.ms_primary, "shade": st.ms_shade, "trace": st.ms_extend,
+    if rank != 0:
+        barrier()
+        dist.destroy_process_group()
+        return
+    if world > 1:
+        barrier()
+    # k_trace: one launch per path vertex tracing its occlusion probes and continuation rays.  A frame's
+    # launches split into the main piece (vertices 0..BETA of every path: ~97% of the secondary rays, on
+    # the main stream) and the tail piece (the few training paths' deeper vertices: dozens of tiny
+    # latency-bound launches on a side stream).  The roofline line is about the main-piece launches.
+    stage_ms = {"primary": st.ms_primary, "shade": st.ms_shade, "trace": st.ms_extend, "trace_tail": st.ms_shadow,
                 "train": st.ms_train, "infer": st.ms_infer, "composite": st.ms_composite, "finalize": st.ms_finalize}
-    stage_launches = dict(zip(("primary", "shade", "trace", "-", "finalize", "train", "infer", "composite"), st.stage_launches))
+    stage_launches = dict(zip(("primary", "shade", "trace", "trace_tail", "finalize", "train", "infer", "composite"), st.stage_launches))
     dominant = max(("primary", "trace"), key=lambda k: stage_ms[k])
-    rays = {"primary": si.rays_primary, "trace": si.rays_extend + si.rays_shadow}
-    nodes = {"primary": si.trav_nodes_primary, "trace": si.trav_nodes_extend + si.trav_nodes_shadow}
-    prims = {"primary": si.trav_prims_primary, "trace": si.trav_prims_extend + si.trav_prims_shadow}
-    # algorithmic bytes per ray: 32 B ray + 16 B hit + 64 B per node visited + 64 B per primitive tested
-    alg_bytes_per_step = (rays[dominant] * 48 + nodes[dominant] * 64 + prims[dominant] * 64) / n_inst
+    rays = {"primary": si.rays_primary, "trace": si.rays_extend + si.rays_shadow - si.rays_tail}
+    nodes = {"primary": si.trav_nodes_primary, "trace": si.trav_nodes_extend + si.trav_nodes_shadow - si.trav_nodes_tail}
+    prims = {"primary": si.trav_prims_primary, "trace": si.trav_prims_extend + si.trav_prims_shadow - si.trav_prims_tail}
+    # algorithmic bytes per ray: 32 B ray + 16 B hit + 80 B per wide node visited + 64 B per primitive tested
+    alg_bytes_per_step = (rays[dominant] * 48 + nodes[dominant] * NODE_BYTES + prims[dominant] * 64) / n_inst
     launches_dom = stage_launches[dominant] / args.steps
     avg_launch_ms = stage_ms[dominant] / max(stage_launches[dominant], 1)
     achieved = alg_bytes_per_step / max(launches_dom, 1) / (avg_launch_ms * 1e-3) / 1e9
@@ -295,10 +324,15 @@ def main():
     roofline = {"kernel": f"k_{dominant}", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "peak_source": peaks["src"], "traffic": traffic, "traffic_note": traffic_note,
                 "algorithmic_bytes_per_step": alg_bytes_per_step,
+                "algorithmic_bytes_per_launch": alg_bytes_per_step / max(launches_dom, 1),
                 "rays_per_step": rays[dominant] / n_inst, "nodes_per_ray": nodes[dominant] / max(rays[dominant], 1),
                 "prims_per_ray": prims[dominant] / max(rays[dominant], 1), "avg_launch_ms": avg_launch_ms,
                 "launches_per_step": launches_dom,
-                "note": "frames overlap (8 in flight): per-launch durations are measured while other frames' kernels share the GPU; the sum over stages exceeds ms_per_step"}
+                "tail_piece": {"launches_per_step": stage_launches["trace_tail"] / args.steps, "rays_per_step": si.rays_tail / n_inst,
+                               "ms_per_step_sum": stage_ms["trace_tail"] / args.steps},
+                "note": "main-piece k_trace launches (2 per frame at BETA=1), CUDA events around each launch inside the timed region; "
+                        "8 frames are in flight, so a launch shares the GPU with other frames' tail-piece and MLP kernels; the kernel is "
+                        "bound by dependent-fetch latency and SIMT divergence, not by bandwidth (profiles/)"}
     mlp_qps = W * H / (stage_ms["infer"] / args.steps * 1e-3) if stage_ms["infer"] > 0 else None
     mlp_info = {"queries_per_s": mlp_qps, "tflops": mlp_qps * FLOPS_PER_QUERY / 1e12 if mlp_qps else None,
                 "frac_of_tensor_peak": (mlp_qps * FLOPS_PER_QUERY / 1e12 / peaks["bf16_tflops"]) if mlp_qps else None,
@@ -318,7 +352,7 @@ def main():
             "roofline": roofline, "mlp": mlp_info, "cpu_baseline": cb,
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
             "training_loss": st.last_loss}
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

@@ -69,6 +69,7 @@ class Stats(C.Structure):
         ("stage_launches", C.c_uint64 * 8),
         ("trav_nodes_extend", C.c_uint64), ("trav_prims_extend", C.c_uint64), ("trav_nodes_shadow", C.c_uint64),
         ("trav_prims_shadow", C.c_uint64), ("trav_nodes_primary", C.c_uint64), ("trav_prims_primary", C.c_uint64),
+        ("trav_nodes_tail", C.c_uint64), ("trav_prims_tail", C.c_uint64), ("rays_tail", C.c_uint64),
         ("last_loss", C.c_float), ("frames", C.c_int),
     ]
 

@@ -337,6 +337,7 @@ int hm_renderer_get_stats(hm_renderer* r, hm_stats* out) {
         out->trav_nodes_extend = s.trav[0]; out->trav_prims_extend = s.trav[1];
         out->trav_nodes_shadow = s.trav[2]; out->trav_prims_shadow = s.trav[3];
         out->trav_nodes_primary = s.trav[4]; out->trav_prims_primary = s.trav[5];
+        out->trav_nodes_tail = s.tail_nodes; out->trav_prims_tail = s.tail_prims; out->rays_tail = s.tail_rays;
         out->last_loss = s.last_loss;
         out->frames = s.frames;
     });
@@ -379,8 +380,8 @@ int hm_write_stats(hm_renderer* r, const char* path) {
         f << "  \"paths\": " << paths << ",\n";
         f << "  \"ms_total\": " << s.ms[8] << ",\n";
         f << "  \"mpaths_per_s\": " << (s.ms[8] > 0 ? paths / (s.ms[8] * 1e-3) / 1e6 : 0.0) << ",\n";
-        f << "  \"ms\": {\"primary\": " << s.ms[0] << ", \"shade\": " << s.ms[1] << ", \"extend\": " << s.ms[2]
-          << ", \"shadow\": " << s.ms[3] << ", \"finalize\": " << s.ms[4] << ", \"train\": " << s.ms[5]
+        f << "  \"ms\": {\"primary\": " << s.ms[0] << ", \"shade\": " << s.ms[1] << ", \"trace_main\": " << s.ms[2]
+          << ", \"trace_tail\": " << s.ms[3] << ", \"finalize\": " << s.ms[4] << ", \"train\": " << s.ms[5]
           << ", \"infer\": " << s.ms[6] << ", \"composite\": " << s.ms[7] << "},\n";
         f << "  \"rays\": {\"primary\": " << s.rays_primary << ", \"extend\": " << s.rays_extend << ", \"shadow\": "
           << s.rays_shadow << "},\n";

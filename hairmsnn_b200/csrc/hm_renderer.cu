@@ -384,11 +384,12 @@ void Renderer::trace_frame(FrameCtx& c) {
             HM_CUDA(cudaEventRecord(c.ev_main_done, main_stream_));
             s = c.tail_stream;
             HM_CUDA(cudaStreamWaitEvent(s, c.ev_main_done, 0));
+            P.tail = 1;
         }
         timed(1, s, [&] { launch_shade(P, src, s); });
         const int dst = src ^ 1;
         HM_CUDA(cudaMemsetAsync(c.q.counts + dst, 0, 4, s));
-        timed(2, s, [&] { launch_trace(P, dst, s); });
+        timed(P.tail ? 3 : 2, s, [&] { launch_trace(P, dst, s); });   // stage 2: main piece, stage 3: tail piece
         HM_CUDA(cudaMemsetAsync(c.q.counts + 2, 0, 16, s));   // extend + shadow counters and their work cursors
         src = dst;
     }
@@ -559,6 +560,7 @@ Stats Renderer::stats() {
     unsigned long long t[16];
     HM_CUDA(cudaMemcpy(t, d_trav_, sizeof(t), cudaMemcpyDeviceToHost));
     for (int i = 0; i < 6; ++i) stats_.trav[i] = t[i];
+    stats_.tail_nodes = t[10]; stats_.tail_prims = t[11]; stats_.tail_rays = t[12];
     stats_.rays_extend = t[6]; stats_.rays_shadow = t[7]; stats_.shade_items = t[8]; stats_.rays_primary = t[9];
     return stats_;
 }

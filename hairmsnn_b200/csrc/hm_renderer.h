@@ -16,10 +16,11 @@
 namespace hm {
 
 struct Stats {
-    double ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // primary shade trace(shadow+extend) - finalize train infer composite total
+    double ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // primary shade trace(main piece) trace(tail piece) finalize train infer composite total
     uint64_t launches[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t rays_primary = 0, rays_extend = 0, rays_shadow = 0, shade_items = 0;
     uint64_t trav[6] = {0, 0, 0, 0, 0, 0};        // extend nodes/prims, shadow nodes/prims, primary nodes/prims
+    uint64_t tail_nodes = 0, tail_prims = 0, tail_rays = 0;   // share of extend+shadow traced by tail-piece launches
     float last_loss = 0.f;
     int frames = 0;
 };

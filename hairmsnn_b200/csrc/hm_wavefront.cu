@@ -325,9 +325,14 @@ __global__ void __launch_bounds__(kBlock, kTraceCtasPerSm) k_trace(const __grid_
     if (P.collect_stats) {
         flush_trav(P.q.trav + 0, st[0]);
         flush_trav(P.q.trav + 2, st[1]);
+        if (P.tail) {
+            TraceStats both{st[0].nodes + st[1].nodes, st[0].prims + st[1].prims};
+            flush_trav(P.q.trav + 10, both);
+        }
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             atomicAdd(P.q.trav + 6, (unsigned long long)n_extend);
             atomicAdd(P.q.trav + 7, (unsigned long long)n_shadow);
+            if (P.tail) atomicAdd(P.q.trav + 12, (unsigned long long)(n_extend + n_shadow));
         }
     }
 }

@@ -64,7 +64,8 @@ struct Queues {
     float4* shadow;      // 2 x float4 per entry: (o.xyz, slot|bit<<31) (d.xyz, -)
     int* counts;         // [0],[1] shade ; [2] extend ; [3] shadow ; work cursors: [4] trace [6] primary
     unsigned long long* trav;   // [0],[1] extend nodes/prims ; [2],[3] shadow nodes/prims ; [4],[5] primary ;
-                                // [6] extend rays ; [7] shadow rays ; [8] shade items ; [9] primary rays
+                                // [6] extend rays ; [7] shadow rays ; [8] shade items ; [9] primary rays ;
+                                // tail-piece share of the above: [10] nodes [11] prims [12] rays
 };
 
 // Everything a frame's kernels need, passed by value (fits the 4 KB param space).
@@ -78,6 +79,7 @@ struct FrameParams {
     int accum_id;        // accumulation index of this renderer (0 = first sample in its buffers)
     int frame_id;        // sample index that keys the RNG streams (== accum_id unless spp-sharded)
     int collect_stats;   // accumulate nodes/prims visited into q.trav
+    int tail;            // this launch belongs to the frame's tail piece (long paths only): separate counters
     int v1_stop, v2_stop;
     int mode;
     // PT outputs

@@ -196,6 +196,8 @@ int hm_save_exr(hm_renderer* r, int which, const char* path);
 /* integrator.stats_output — parsed by the reference (scene.cpp:295) but never written */
 int hm_write_stats(hm_renderer* r, const char* path);
 
+/* ms_extend / ms_shadow: k_trace launches (each traces a vertex's occlusion probes AND continuation
+ * rays) of a frame's main piece / of its tail piece (vertices past beta+1, long paths only). */
 typedef struct {
     double ms_primary, ms_shade, ms_extend, ms_shadow, ms_finalize, ms_train, ms_infer, ms_composite, ms_total;
     uint64_t rays_primary, rays_extend, rays_shadow, shade_items;
@@ -204,6 +206,8 @@ typedef struct {
     uint64_t stage_launches[8];
     /* instrumented traversal (hm_renderer_set_collect_stats): BVH nodes visited / primitives tested */
     uint64_t trav_nodes_extend, trav_prims_extend, trav_nodes_shadow, trav_prims_shadow, trav_nodes_primary, trav_prims_primary;
+    /* share of the extend+shadow totals traced by tail-piece launches */
+    uint64_t trav_nodes_tail, trav_prims_tail, rays_tail;
     float last_loss;
     int frames;
 } hm_stats;
