@@ -23,7 +23,7 @@ lib = C.CDLL(LIB_PATH)
 PATH_TRACING, NRC, HAIR_MSNN = 0, 1, 2
 BUF_FINAL_AVG, BUF_FINAL_ACCUM, BUF_PT_AVG, BUF_PT_ACCUM, BUF_NN_AVG, BUF_NN_ACCUM, BUF_FB8 = range(7)
 BUF_NN_FRAME_INPUT, BUF_NN_FRAME_OUTPUT, BUF_NN_TRAIN_INPUT, BUF_NN_TRAIN_OUTPUT, BUF_GBUFFER, BUF_TRAIN_IDXS = range(7, 13)
-BUF_GBUFFER_B, BUF_NRC_TRAIN_RECORDS = 13, 14
+BUF_GBUFFER_B, BUF_NRC_TRAIN_RECORDS, BUF_SCENE_INDICES, BUF_SCENE_POINTS = 13, 14, 15, 16
 NRC_MAX_BOUNCES = 40
 
 _fp = C.POINTER(C.c_float)
@@ -329,6 +329,10 @@ class Mlp:
     def load(self, path):
         _check(lib.hm_mlp_load(self._h, os.fsencode(path)))
 
+    def save_snapshot(self, path):
+        """tiny-cuda-nn Trainer::serialize as text JSON (what TINY_MLP::loadWeights reads)."""
+        _check(lib.hm_mlp_save_snapshot(self._h, os.fsencode(path)))
+
     def close(self):
         if self._h and self._owned:
             lib.hm_mlp_destroy(self._h)
@@ -401,6 +405,7 @@ class Renderer:
     def msnn_train_apply(self): _check(lib.hm_msnn_train_apply(self._h))
     def msnn_finish(self): _check(lib.hm_msnn_finish(self._h))
     def msnn_pretrain(self, steps): _check(lib.hm_msnn_pretrain(self._h, steps))
+    def msnn_train_data_gen(self): _check(lib.hm_msnn_train_data_gen(self._h))
 
     # render_nrc split frame (render_nrc.cu:640-700)
     def nrc_trace(self): _check(lib.hm_nrc_trace(self._h))
@@ -436,9 +441,9 @@ class Renderer:
         _, nbytes = self.device_buffer(which)
         if which in (BUF_FB8,):
             out = np.empty((self.H, self.W), np.uint32)
-        elif which == BUF_TRAIN_IDXS:
+        elif which in (BUF_TRAIN_IDXS, BUF_SCENE_INDICES):
             out = np.empty(nbytes // 4, np.int32)
-        elif which in (BUF_NN_FRAME_INPUT, BUF_NN_FRAME_OUTPUT, BUF_NN_TRAIN_INPUT, BUF_NN_TRAIN_OUTPUT):
+        elif which in (BUF_NN_FRAME_INPUT, BUF_NN_FRAME_OUTPUT, BUF_NN_TRAIN_INPUT, BUF_NN_TRAIN_OUTPUT, BUF_SCENE_POINTS):
             out = np.empty(nbytes // 4, np.float32)
         else:
             out = np.empty((self.H, self.W, 4), np.float32)

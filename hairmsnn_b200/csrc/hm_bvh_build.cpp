@@ -11,6 +11,8 @@
 #include <cfloat>
 #include <cstdlib>
 #include <cmath>
+#include <chrono>
+#include <cstdio>
 #include <cstring>
 #include <stdexcept>
 #include <thread>
@@ -238,12 +240,15 @@ struct WideBuilder {
 
     // Fills wide node `wi` from binary node `bi`; children blocks are reserved here, so the inner
     // children of a node are contiguous (child_base + rank) and so are its leaf references.
-    void emit(int wi, int bi, const Box& bounds, int depth) {
-        struct Item { int wi, bi, depth; Box bounds; };
+    struct Item { int wi, bi, depth; Box bounds; };
+    // `deferred` (optional): subtrees rooted at depth > defer_below are not expanded here; their
+    // root slots stay reserved and the items are handed back for parallel expansion.
+    void emit(int wi, int bi, const Box& bounds, int depth, std::vector<Item>* deferred = nullptr, int defer_below = 0) {
         std::vector<Item> todo;
         todo.push_back(Item{wi, bi, depth, bounds});
         while (!todo.empty()) {
             Item it = todo.back(); todo.pop_back();
+            if (deferred && it.depth > defer_below) { deferred->push_back(it); continue; }
             max_depth = std::max(max_depth, it.depth);
             WideChild ch[8];
             const int cnt = gather(it.bi, ch);
@@ -345,6 +350,14 @@ void build_bvh(const HostGeometry& geo, HostBvh& out, int threads_hint) {
     const int ns = (int)geo.seg_cp.size();
     const int nt = (int)(geo.tri_verts.size() / 3);
     const int nprim = ns + nt;
+    const bool verbose = getenv("HM_BVH_VERBOSE") != nullptr;
+    auto t_start = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!verbose) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[bvh] %-28s %.2f s\n", what, std::chrono::duration<double>(now - t_start).count());
+        t_start = now;
+    };
     out.nodes.clear(); out.leaf_data.clear(); out.leaf_code.clear(); out.leaf_prim.clear();
     out.wnodes.clear(); out.wleaf_data.clear();
     if (nprim == 0) return;
@@ -400,6 +413,7 @@ void build_bvh(const HostGeometry& geo, HostBvh& out, int threads_hint) {
         for (auto& th : pool) th.join();
     }
 
+    lap("references");
     std::vector<int> order(n);
     for (int i = 0; i < n; ++i) order[i] = i;
     std::vector<NodeRaw> nodes((size_t)std::max(n + 1, 2));   // n single-reference leaves -> n - 1 inner nodes (+ root slot)
@@ -413,6 +427,7 @@ void build_bvh(const HostGeometry& geo, HostBvh& out, int threads_hint) {
     for (int i = 0; i < n; ++i) root.grow(prims[i].box);
 
     int code = bld.build_range(0, n, root, 0);
+    lap("binary SAH build");
     int used = bld.next_node.load();
     if (code < 0) {
         // a single reference: root with child0 = the leaf and an unreachable child1
@@ -462,6 +477,7 @@ void build_bvh(const HostGeometry& geo, HostBvh& out, int threads_hint) {
         }
     }
 
+    lap("depth-first relayout");
     out.nodes.resize(packed.size() * 4);
     memcpy(out.nodes.data(), packed.data(), packed.size() * sizeof(NodeRaw));
     out.leaf_code.resize(nprim);
@@ -485,12 +501,53 @@ void build_bvh(const HostGeometry& geo, HostBvh& out, int threads_hint) {
         }
     }
 
+    lap("leaf slots");
     // the structure the GPU traverses
     out.wnodes.clear(); out.wleaf_data.clear();
     out.wnodes.resize(5);
     WideBuilder wb{packed, out.leaf_data, out.wnodes, out.wleaf_data};
-    wb.emit(0, 0, root, 1);
-    out.wide_depth = wb.max_depth;
+    // top levels sequentially, then one task per deferred subtree: each expands into private arrays
+    // (its root at local index 0) that are appended to the global ones with their base indices shifted
+    std::vector<WideBuilder::Item> subtrees;
+    wb.emit(0, 0, root, 1, &subtrees, hw > 1 ? 3 : kWideStack + 1);
+    int max_depth = wb.max_depth;
+    if (!subtrees.empty()) {
+        struct Local { std::vector<F4> nodes, leaves; int depth = 0; };
+        std::vector<Local> loc(subtrees.size());
+        std::atomic<size_t> next{0};
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < hw; ++t)
+            pool.emplace_back([&]() {
+                for (size_t i; (i = next.fetch_add(1)) < subtrees.size();) {
+                    loc[i].nodes.resize(5);
+                    WideBuilder lb{packed, out.leaf_data, loc[i].nodes, loc[i].leaves};
+                    lb.emit(0, subtrees[i].bi, subtrees[i].bounds, subtrees[i].depth);
+                    loc[i].depth = lb.max_depth;
+                }
+            });
+        for (auto& th : pool) th.join();
+        auto as_u = [](float f) { unsigned u; memcpy(&u, &f, 4); return u; };
+        auto as_f = [](unsigned u) { float f; memcpy(&f, &u, 4); return f; };
+        for (size_t i = 0; i < subtrees.size(); ++i) {
+            max_depth = std::max(max_depth, loc[i].depth);
+            const size_t n_local = loc[i].nodes.size() / 5;
+            const unsigned node_off = (unsigned)(out.wnodes.size() / 5);       // local index k >= 1 -> node_off + k - 1
+            const unsigned leaf_off = (unsigned)(out.wleaf_data.size() / 4);
+            for (size_t k = 0; k < n_local; ++k) {
+                F4* w = loc[i].nodes.data() + 5 * k;
+                w[1].x = as_f(as_u(w[1].x) + node_off - 1u);
+                w[1].y = as_f(as_u(w[1].y) + leaf_off);
+            }
+            memcpy(out.wnodes.data() + 5 * (size_t)subtrees[i].wi, loc[i].nodes.data(), 5 * sizeof(F4));
+            out.wnodes.insert(out.wnodes.end(), loc[i].nodes.begin() + 5, loc[i].nodes.end());
+            out.wleaf_data.insert(out.wleaf_data.end(), loc[i].leaves.begin(), loc[i].leaves.end());
+            std::vector<F4>().swap(loc[i].nodes);
+            std::vector<F4>().swap(loc[i].leaves);
+        }
+    }
+    out.wide_depth = max_depth;
+    wb.max_depth = max_depth;
+    lap("wide collapse");
     if (wb.max_depth > kWideStack)
         throw std::runtime_error("BVH: wide tree deeper than the traversal stack");
 }

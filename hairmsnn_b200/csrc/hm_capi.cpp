@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <fstream>
 #include <memory>
@@ -215,6 +216,8 @@ int hm_image_load_exr(const char* path, float* rgba, size_t capacity_floats, int
     });
 }
 
+static void load_tcnn_snapshot(hm::Mlp& mlp, const std::string& path);
+
 // ---- renderer -----------------------------------------------------------------------
 int hm_renderer_create(hm_scene* s, int kind, int beta_cli, int device, int rank, int world, hm_renderer** out) {
     return guarded([&] {
@@ -226,6 +229,9 @@ int hm_renderer_create(hm_scene* s, int kind, int beta_cli, int device, int rank
         h->mlp_view.m = h->r->mlp();
         h->mlp_view.stream = h->r->stream();
         h->mlp_view.device = device;
+        // tcnn.init_weights (scene.cpp:318-322; loaded right after the TINY_MLP ctor, render_nrc.cu:148-150)
+        if (h->r->mlp() && !s->hs.tcnn_weights.empty())
+            load_tcnn_snapshot(*h->r->mlp(), hm::resolve_scene_path(s->hs.tcnn_weights, s->hs.base_dir));
         *out = h.release();
     });
 }
@@ -263,6 +269,9 @@ int hm_renderer_get_layout(const hm_renderer* r, int* out4) {
         need(r, "renderer"); need(out4, "out4");
         out4[0] = r->r->in_channels(); out4[1] = r->r->nn_frame_rows(); out4[2] = r->r->train_records(); out4[3] = r->r->every_nth();
     });
+}
+int hm_msnn_train_data_gen(hm_renderer* r) {
+    return guarded([&] { need(r, "renderer"); r->r->msnn_train_data_gen(); r->r->sync(); });
 }
 int hm_msnn_pretrain(hm_renderer* r, int n) {
     return guarded([&] { need(r, "renderer"); r->r->msnn_pretrain(n); r->r->sync(); });
@@ -526,19 +535,94 @@ int hm_mlp_save(hm_mlp* m, const char* path) {
         f.write(magic, 8); f.write((const char*)&n, 8); f.write((const char*)p.data(), n * 4);
     });
 }
+// half bits -> float (snapshots of type "__half")
+static float snapshot_half_to_float(uint16_t h) {
+    uint32_t s = (h >> 15) & 1, e = (h >> 10) & 0x1f, mnt = h & 0x3ff, bits;
+    if (e == 0) {
+        if (mnt == 0) bits = s << 31;
+        else {
+            int ee = -1;
+            do { ee++; mnt <<= 1; } while (!(mnt & 0x400));
+            bits = (s << 31) | ((uint32_t)(127 - 15 - ee) << 23) | ((mnt & 0x3ff) << 13);
+        }
+    } else if (e == 31) bits = (s << 31) | 0x7f800000u | (mnt << 13);
+    else bits = (s << 31) | ((e + 112) << 23) | (mnt << 13);
+    float f; memcpy(&f, &bits, 4);
+    return f;
+}
+
+// Trainer::deserialize (trainer.h:285-310) over the TEXT form TINY_MLP::loadWeights reads
+// (cuda/neural_network.cu:23-32): {"n_params": N, "params_type": "float" | "__half",
+// "params_binary": {"bytes": [...], "subtype": null}} — nlohmann's JSON rendering of a binary value,
+// accepted by tcnn's from_json (gpu_memory_json.h:58-67).  An "optimizer" member, if present, is ignored
+// (the reference never writes one: serialize_optimizer defaults to false).
+static void load_tcnn_snapshot(hm::Mlp& mlp, const std::string& path) {
+    hm::Json j = hm::parse_json_file(path);
+    std::string type = "__half";                       // type_to_string<precision_t>() of the reference build
+    if (const hm::Json* t = j.find("params_type")) type = t->string();
+    const hm::Json& pb = j.at("params_binary");
+    const hm::Json* bytes = pb.type == hm::Json::Object ? pb.find("bytes") : nullptr;
+    if (!bytes || bytes->type != hm::Json::Array) throw std::invalid_argument("snapshot: params_binary must be {\"bytes\": [...]}");
+    const size_t nb = bytes->arr.size();
+    std::vector<uint8_t> raw(nb);
+    for (size_t i = 0; i < nb; ++i) raw[i] = (uint8_t)bytes->arr[i].number();
+    std::vector<float> p;
+    if (type == "float") {
+        if (nb % 4) throw std::invalid_argument("snapshot: byte count is not a multiple of 4");
+        p.resize(nb / 4);
+        memcpy(p.data(), raw.data(), nb);
+    } else if (type == "__half") {
+        if (nb % 2) throw std::invalid_argument("snapshot: byte count is not a multiple of 2");
+        p.resize(nb / 2);
+        for (size_t i = 0; i < p.size(); ++i) { uint16_t h; memcpy(&h, raw.data() + 2 * i, 2); p[i] = snapshot_half_to_float(h); }
+    } else {
+        throw std::invalid_argument("Trainer: snapshot parameters must be of type float of __half");   // the reference's message
+    }
+    if (p.size() != mlp.n_params()) throw std::invalid_argument("snapshot has a different parameter count");
+    mlp.set_params(p.data(), p.size());
+}
+
 int hm_mlp_load(hm_mlp* m, const char* path) {
     return guarded([&] {
         need(m, "mlp"); need(path, "path");
         std::ifstream f(path, std::ios::binary);
         if (!f) throw hm::IoError(std::string("cannot read ") + path);
         char magic[8]; uint64_t n = 0;
-        f.read(magic, 8); f.read((char*)&n, 8);
-        if (!f || memcmp(magic, "HMSNNW1", 7) != 0) throw std::invalid_argument("not a HairMSNN-B200 weight file");
+        f.read(magic, 8);
+        if (f && memcmp(magic, "HMSNNW1", 7) != 0) {   // not the raw blob: tiny-cuda-nn's JSON snapshot
+            f.close();
+            load_tcnn_snapshot(*m->m, path);
+            return;
+        }
+        f.read((char*)&n, 8);
+        if (!f) throw std::invalid_argument("not a weight file");
         if (n != m->m->n_params()) throw std::invalid_argument("weight file has a different parameter count");
         std::vector<float> p(n);
         f.read((char*)p.data(), n * 4);
         if (!f) throw hm::IoError("truncated weight file");
         m->m->set_params(p.data(), p.size());
+    });
+}
+// Trainer::serialize (trainer.h:270-283) as text JSON, params_type "float"
+int hm_mlp_save_snapshot(hm_mlp* m, const char* path) {
+    return guarded([&] {
+        need(m, "mlp"); need(path, "path");
+        std::vector<float> p(m->m->n_params());
+        m->m->get_params(p.data(), p.size());
+        std::ofstream f(path, std::ios::binary);
+        if (!f) throw hm::IoError(std::string("cannot write ") + path);
+        std::string out;
+        out.reserve(p.size() * 16 + 256);
+        out += "{\"n_params\":" + std::to_string(p.size()) + ",\"params_binary\":{\"bytes\":[";
+        const uint8_t* b = (const uint8_t*)p.data();
+        char tmp[8];
+        for (size_t i = 0; i < p.size() * 4; ++i) {
+            int len = snprintf(tmp, sizeof(tmp), i ? ",%u" : "%u", (unsigned)b[i]);
+            out.append(tmp, (size_t)len);
+        }
+        out += "],\"subtype\":null},\"params_type\":\"float\"}";
+        f.write(out.data(), (std::streamsize)out.size());
+        if (!f) throw hm::IoError(std::string("cannot write ") + path);
     });
 }
 void* hm_mlp_stream(hm_mlp* m) { return m ? (void*)m->stream : nullptr; }

@@ -73,6 +73,8 @@ struct HostScene {
 
 // scene.cpp:349-425
 void build_env_tables(HostScene& s);
+// fetchSceneSamples (render_hair_msnn.cu:34-97): points on the strands for the TRAIN_DATA_GEN pass
+void build_scene_samples(const HostGeometry& g, int num_samples, unsigned seed, std::vector<float>& points3);
 // bounds / scales as the frame drivers compute them (render_hair_msnn.cu:414-430)
 void finalize_geometry(HostScene& s);
 // cameraChanged() (render_path_tracing.cu:767-797) through the viewer's camera

@@ -304,14 +304,21 @@ FrameParams Renderer::params_for(const FrameCtx& c) {
     P.v2_stop = hs_.path_v2 - 1;
     P.accum = bufs_[1]; P.average = bufs_[0]; P.fb = fb_;
     P.in_ch = in_ch_;
+    P.n_primary = (row1_ - row0_) * W_;
+    if (c.pretrain) {
+        P.pretrain = 1;
+        P.n_primary = records_;
+        P.sampled_points = d_scene_points_;
+        P.scene_indices = d_scene_indices_;
+    }
     if (kind_ == HM_KIND_MSNN) {
         P.mode = MODE_MSNN;
         P.msnn_beta = beta_;
         P.every_nth = every_nth_;
         P.train_idxs = c.train_idxs;
         const BandPartition bp = band_partition(W_, H_, records_, rank_, world_);
-        P.train_slot0 = bp.slot0;
-        P.train_slots = bp.slots;
+        P.train_slot0 = c.pretrain ? 0 : bp.slot0;
+        P.train_slots = c.pretrain ? records_ : bp.slots;
         P.nn_frame_in = c.nn_frame_in;
         P.nn_train_in = c.nn_train_in;
         P.nn_train_out = c.nn_train_out;
@@ -349,6 +356,7 @@ FrameCtx& Renderer::begin_frame() {
     frames_issued_++;
     c.accum_id = accum_id_;
     c.frame_id = frame_offset_ + accum_id_ * frame_stride_;
+    c.pretrain = false;
     // the context is reusable once the frame that last used it has been composited
     HM_CUDA(cudaStreamWaitEvent(main_stream_, c.ev_free, 0));
     return c;
@@ -359,7 +367,7 @@ FrameCtx& Renderer::begin_frame() {
 // No host synchronisation: every stage reads its queue length from device memory, and the
 // tail always issues the full vertex budget (empty launches cost a few microseconds).
 void Renderer::trace_frame(FrameCtx& c) {
-    if (kind_ == HM_KIND_MSNN || kind_ == HM_KIND_NRC) shuffle_train_idxs(c);
+    if ((kind_ == HM_KIND_MSNN || kind_ == HM_KIND_NRC) && !c.pretrain) shuffle_train_idxs(c);
     FrameParams P = params_for(c);
     int max_vertices = P.v2_stop + 1;   // the primary hit plus up to v2_stop bounces
     if (kind_ == HM_KIND_NRC) {
@@ -498,17 +506,58 @@ void Renderer::nrc_end() {
     current_ = nullptr;
 }
 
-void Renderer::msnn_pretrain(int steps) {
-    // The reference pre-trains for one wall-clock second on rays towards random strand
-    // points from an UNSET camera.  Deterministic stand-in: `steps`
-    // G_BUFFER passes from the real camera, each followed by a training step; the
-    // accumulation counter advances as genTrainingData() does and is reset afterwards.
+void Renderer::ensure_scene_samples() {
+    if (d_scene_points_) return;
+    std::vector<float> pts;
+    build_scene_samples(hs_.geo, 1000000, 1337u, pts);      // numSamples = 1e6 (headers/render_hair_msnn.h:127-130)
+    n_scene_samples_ = (int)(pts.size() / 3);
+    if (n_scene_samples_ < records_) throw std::invalid_argument("TRAIN_DATA_GEN needs at least 16384 strand samples");
+    HM_CUDA(cudaMalloc((void**)&d_scene_points_, pts.size() * 4));
+    allocs_.push_back(d_scene_points_);
+    HM_CUDA(cudaMemcpy(d_scene_points_, pts.data(), pts.size() * 4, cudaMemcpyHostToDevice));
+    std::vector<int> seq(n_scene_samples_);
+    for (int i = 0; i < n_scene_samples_; ++i) seq[i] = i;   // thrust::sequence
+    HM_CUDA(cudaMalloc((void**)&d_scene_indices_, (size_t)n_scene_samples_ * 4));
+    allocs_.push_back(d_scene_indices_);
+    HM_CUDA(cudaMemcpy(d_scene_indices_, seq.data(), (size_t)n_scene_samples_ * 4, cudaMemcpyHostToDevice));
+    // the initial shuffle of sceneIndices (render_hair_msnn.cu:395-400)
+    thrust::device_ptr<int> p = thrust::device_pointer_cast(d_scene_indices_);
+    thrust::shuffle(thrust::cuda::par_nosync(thrust_scratch()).on(main_stream_), p, p + n_scene_samples_, thrust::default_random_engine());
+}
+
+void Renderer::msnn_train_data_gen() {
     if (kind_ != HM_KIND_MSNN) throw std::logic_error("not a HairMSNN renderer");
+    if (current_) throw std::logic_error("msnn_train_data_gen: a frame is in flight");
+    HM_CUDA(cudaSetDevice(device_));
+    ensure_scene_samples();
+    FrameCtx& c = begin_frame();
+    c.pretrain = true;
+    trace_frame(c);
+    end_frame(c);
+}
+
+void Renderer::msnn_pretrain(int steps) {
+    // The reference's initial training (render_hair_msnn.cu:633-641): genTrainingData() = the
+    // TRAIN_DATA_GEN pass — 128 x 128 full-length training paths whose first ray runs from the camera
+    // position to a random point on the strands — followed by train() = shuffle(sceneIndices) +
+    // training_step, repeated for one WALL-CLOCK second, before cameraChanged() has set the launch
+    // parameters' camera (the rays start wherever the uninitialised camera.pos points).
+    // Here: the scene file's camera position, a fixed number of steps, and strand samples from a fixed
+    // seed instead of the wall clock.  accumId advances per pass and is reset afterwards (cameraChanged).
+    if (kind_ != HM_KIND_MSNN) throw std::logic_error("not a HairMSNN renderer");
+    if (current_) throw std::logic_error("msnn_pretrain: a frame is in flight");
+    HM_CUDA(cudaSetDevice(device_));
+    ensure_scene_samples();
     for (int i = 0; i < steps; ++i) {
-        msnn_trace();
-        msnn_train_backward();
-        msnn_train_apply();
-        end_frame(*current_);
+        FrameCtx& c = begin_frame();
+        c.pretrain = true;
+        trace_frame(c);
+        current_ = &c;
+        thrust::device_ptr<int> p = thrust::device_pointer_cast(d_scene_indices_);
+        thrust::shuffle(thrust::cuda::par_nosync(thrust_scratch()).on(main_stream_), p, p + n_scene_samples_, thrust::default_random_engine());
+        timed(5, order_stream_, [&] { mlp_->forward_backward(c.nn_train_in, c.nn_train_out, records_, records_); });
+        timed(5, order_stream_, [&] { mlp_->optimizer_step(); });
+        end_frame(c);
         current_ = nullptr;
     }
     sync();
@@ -579,6 +628,8 @@ void* Renderer::device_buffer(int which, size_t* bytes) {
         case 12: *bytes = (size_t)n_idxs_ * 4; return c.train_idxs;
         case 13: *bytes = n * 16; return c.gbuffer_b;
         case 14: *bytes = (size_t)nrc_train_pixels_ * sizeof(NrcTrainRec); return c.tbuffer;
+        case 15: *bytes = (size_t)n_scene_samples_ * 4; return d_scene_indices_;
+        case 16: *bytes = (size_t)n_scene_samples_ * 12; return d_scene_points_;
         default: *bytes = 0; return nullptr;
     }
 }

@@ -51,6 +51,7 @@ struct FrameCtx {
     cudaStream_t tail_stream = nullptr;
     cudaEvent_t ev_main_done = nullptr, ev_traced = nullptr, ev_free = nullptr;
     int frame_id = 0, accum_id = 0;
+    bool pretrain = false;            // this frame is a TRAIN_DATA_GEN pass
 };
 
 // Frame scheduling.  The reference renders one frame at a time on the null stream.  Here a
@@ -83,6 +84,7 @@ public:
     void msnn_train_apply();
     void msnn_finish();
     void msnn_pretrain(int steps);
+    void msnn_train_data_gen();        // one TRAIN_DATA_GEN pass (genTrainingData), no training step
     Mlp* mlp() { return mlp_.get(); }
 
     // NRC split frame (render_nrc.cu:640-700): trace = G_BUFFER pass; query = inference over the
@@ -147,6 +149,11 @@ private:
     int* d_train_idxs_ = nullptr;   // persistent permutation, re-shuffled every frame
     int n_idxs_ = 0;                // its length (training records for HairMSNN, training pixels for NRC)
     float* nn_frame_out_ = nullptr;
+    // TRAIN_DATA_GEN pass: points on the strands + their shuffled index list (fetchSceneSamples)
+    float* d_scene_points_ = nullptr;
+    int* d_scene_indices_ = nullptr;
+    int n_scene_samples_ = 0;
+    void ensure_scene_samples();
     // nrc
     int nrc_train_pixels_ = 0;      // numTrainingPixels = numTrainingRecords / MAX_BOUNCES
     int nn_frame_rows_ = 0;         // rows fed to inference (nnFrameSize for NRC, W*H for HairMSNN)

@@ -2,6 +2,8 @@
 // importance tables, scene bounds/scale, camera basis.  Load-time CPU work.
 #include <algorithm>
 #include <cmath>
+#include <limits>
+#include <random>
 #include <thread>
 
 #include "hm_host.h"
@@ -59,6 +61,42 @@ void build_env_tables(HostScene& s) {
     if (total > 0.f)
         for (int i = 1; i < H; ++i) s.mcdf[i] /= total;
     s.mcdf[H] = 1.0f;
+}
+
+// RenderWindow_HairMSNN::fetchSceneSamples (render_hair_msnn.cu:34-97), the part the TRAIN_DATA_GEN
+// pass reads: ~num_samples points on the strands, each segment getting
+// int(len / total_len * num_samples) of them (at least one), len = control-polygon length
+// (render_hair_msnn.cu:359-368); positions at uniform random curve parameters.  The reference seeds
+// std::default_random_engine from the wall clock; `seed` makes the set reproducible.
+void build_scene_samples(const HostGeometry& g, int num_samples, unsigned seed, std::vector<float>& points3) {
+    points3.clear();
+    const size_t ns = g.seg_cp.size();
+    std::vector<float> len(ns);
+    float total = 0.f;
+    auto dist = [](const F4& a, const F4& b) {
+        V3 d = V3(a.x, a.y, a.z) - V3(b.x, b.y, b.z);
+        return length(d);
+    };
+    for (size_t i = 0; i < ns; ++i) {
+        const F4* c = g.cps.data() + g.seg_cp[i];
+        float l = dist(c[0], c[1]) + dist(c[2], c[1]) + dist(c[3], c[2]);
+        total += l;
+        len[i] = l;
+    }
+    std::default_random_engine gen(seed);
+    points3.reserve(3 * (size_t)(num_samples + ns));
+    for (size_t i = 0; i < ns; ++i) {
+        int k = (int)(len[i] / total * (float)num_samples);
+        if (k == 0) k = 1;
+        const F4* c = g.cps.data() + g.seg_cp[i];
+        CubicSeg seg;
+        seg.from_catmull_rom(f4_to_v4(c[0]), f4_to_v4(c[1]), f4_to_v4(c[2]), f4_to_v4(c[3]));
+        for (int j = 0; j < k; ++j) {
+            float u = std::generate_canonical<float, std::numeric_limits<float>::digits>(gen);
+            V4 p = seg.pos4(u);
+            points3.push_back(p.x); points3.push_back(p.y); points3.push_back(p.z);
+        }
+    }
 }
 
 void finalize_geometry(HostScene& s) {

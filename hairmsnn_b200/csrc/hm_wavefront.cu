@@ -58,6 +58,7 @@ __device__ __forceinline__ int queue_reserve(int* counter, bool want) {
 }
 
 __device__ __forceinline__ bool is_training_pixel(const FrameParams& P, int fb_ofs, int& tr_ofs) {
+    if (P.pretrain) { tr_ofs = fb_ofs; return true; }   // TRAIN_DATA_GEN: every work item is a training record
     tr_ofs = fb_ofs / P.every_nth;
     int train_idx = __ldg(P.train_idxs + tr_ofs) % P.every_nth;
     return fb_ofs % P.every_nth == train_idx;
@@ -86,16 +87,24 @@ struct PrimaryOps {
     int first;
     __device__ __forceinline__ bool fetch(int w, V3& o, V3& d) const {
         const int slot = first + w;
-        const int px = slot % P.W, py = slot / P.W;
-        Rng rng = rng_seed(P.frame_id + 10007, (uint32_t)px, (uint32_t)py, (uint32_t)P.W);
-        float ox = rng_next(rng);
-        float oy = rng_next(rng);
-        float su = ((float)px + ox) / (float)P.W;
-        float sv = ((float)py + oy) / (float)P.H;
         o = V3(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]);
-        d = normalize(V3(P.cam.d00[0], P.cam.d00[1], P.cam.d00[2]) +
-                      su * V3(P.cam.du[0], P.cam.du[1], P.cam.du[2]) +
-                      sv * V3(P.cam.dv[0], P.cam.dv[1], P.cam.dv[2]));
+        Rng rng;
+        if (P.pretrain) {
+            // launch index = (w % numTrainRecordsX, w / numTrainRecordsX) in a frame W wide; no pixel jitter is drawn
+            rng = rng_seed(P.frame_id + 10007, (uint32_t)(w % 128), (uint32_t)(w / 128), (uint32_t)P.W);
+            const float* sp = P.sampled_points + 3 * (size_t)__ldg(P.scene_indices + w);
+            d = normalize(V3(__ldg(sp), __ldg(sp + 1), __ldg(sp + 2)) - o);
+        } else {
+            const int px = slot % P.W, py = slot / P.W;
+            rng = rng_seed(P.frame_id + 10007, (uint32_t)px, (uint32_t)py, (uint32_t)P.W);
+            float ox = rng_next(rng);
+            float oy = rng_next(rng);
+            float su = ((float)px + ox) / (float)P.W;
+            float sv = ((float)py + oy) / (float)P.H;
+            d = normalize(V3(P.cam.d00[0], P.cam.d00[1], P.cam.d00[2]) +
+                          su * V3(P.cam.du[0], P.cam.du[1], P.cam.du[2]) +
+                          sv * V3(P.cam.dv[0], P.cam.dv[1], P.cam.dv[2]));
+        }
         P.paths.rng[slot] = rng.state;
         P.paths.ray_o[slot] = f4(o, 0.f);
         P.paths.ray_d[slot] = f4(d, 0.f);
@@ -133,9 +142,9 @@ struct PrimaryOps {
 };
 
 __global__ void __launch_bounds__(kBlock, kTraceCtasPerSm) k_primary(const __grid_constant__ FrameParams P) {
-    const int n = (P.row1 - P.row0) * P.W;
+    const int n = P.n_primary;
     TraceStats st[2] = {{0, 0}, {0, 0}};
-    PrimaryOps ops{P, P.row0 * P.W};
+    PrimaryOps ops{P, P.pretrain ? 0 : P.row0 * P.W};
     trace_queue(P.scene.geom, n, P.q.counts + 6, ops, 0.f, 1e30f, P.collect_stats ? st : nullptr);
     if (P.collect_stats) {
         flush_trav(P.q.trav + 4, st[0]);
@@ -341,8 +350,8 @@ __global__ void __launch_bounds__(kBlock, kTraceCtasPerSm) k_trace(const __grid_
 // finalize
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ FrameParams P) {
-    const int n = (P.row1 - P.row0) * P.W;
-    const int first = P.row0 * P.W;
+    const int n = P.n_primary;
+    const int first = P.pretrain ? 0 : P.row0 * P.W;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         int slot = first + i;
         V3 color = v3(P.paths.color[slot]);
@@ -706,7 +715,7 @@ int persistent_grid(int ctas_per_sm) { return wavefront_sm_count() * ctas_per_sm
 }  // namespace
 
 void launch_primary(const FrameParams& P, cudaStream_t stream) {
-    int n = (P.row1 - P.row0) * P.W;
+    int n = P.n_primary;
     int blocks = (n + kBlock - 1) / kBlock;
     int grid = blocks < persistent_grid(kTraceCtasPerSm) ? blocks : persistent_grid(kTraceCtasPerSm);
     if (grid < 1) grid = 1;

@@ -80,6 +80,12 @@ struct FrameParams {
     int frame_id;        // sample index that keys the RNG streams (== accum_id unless spp-sharded)
     int collect_stats;   // accumulate nodes/prims visited into q.trav
     int tail;            // this launch belongs to the frame's tail piece (long paths only): separate counters
+    int n_primary;       // primary work items (rows * W; numTrainRecords in the TRAIN_DATA_GEN pass)
+    // HairMSNN TRAIN_DATA_GEN pass (cuda/hair_msnn.cu:222-233): work item i is training record i, its
+    // ray runs from the camera position to sampled_points[scene_indices[i]]
+    int pretrain;
+    const float* sampled_points;   // [numSamples][3]
+    const int* scene_indices;      // [numSamples] shuffled
     int v1_stop, v2_stop;
     int mode;
     // PT outputs

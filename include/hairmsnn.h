@@ -53,8 +53,10 @@ enum {
     HM_BUF_GBUFFER = 11,         /* float4[W*H]: rgb short-path colour, w = flags */
     HM_BUF_TRAIN_IDXS = 12,      /* int[records] (trainIdxs after this frame's shuffle; NRC: int[training pixels]) */
     HM_BUF_GBUFFER_B = 13,       /* render_nrc: float4[W*H]: rgb GBuffer::beta, w = GBuffer::bounces (int bits) */
-    HM_BUF_NRC_TRAIN_RECORDS = 14 /* render_nrc: TrainBuffer[training pixels] as 5 x float[40][3] (vert wo n
+    HM_BUF_NRC_TRAIN_RECORDS = 14,/* render_nrc: TrainBuffer[training pixels] as 5 x float[40][3] (vert wo n
                                     vertRadiance vertBeta) + int bounces + int hit = 2408 bytes each */
+    HM_BUF_SCENE_INDICES = 15,   /* render_hair_msnn: int[numSamples] sceneIndices (after the first pre-training call) */
+    HM_BUF_SCENE_POINTS = 16     /* render_hair_msnn: float[numSamples][3] sampledPoints */
 };
 
 const char* hm_last_error(void);
@@ -157,9 +159,14 @@ int hm_msnn_trace(hm_renderer* r);
 int hm_msnn_train_backward(hm_renderer* r);
 int hm_msnn_train_apply(hm_renderer* r);
 int hm_msnn_finish(hm_renderer* r);
-/* deterministic stand-in for the wall-clock pre-training loop
- * (render_hair_msnn.cu:633-641): n_steps of render-free G_BUFFER + train */
+/* The initial training of RenderWindow_HairMSNN::initialize (render_hair_msnn.cu:633-641): n_steps of
+ * genTrainingData() [the TRAIN_DATA_GEN pass, cuda/hair_msnn.cu:222-233: 128 x 128 training paths towards
+ * random points on the strands (fetchSceneSamples, render_hair_msnn.cu:34-97)] + train().  The reference
+ * runs it for one wall-clock second from an unset camera with time-seeded samples; here the step count is
+ * the caller's, the rays start at the scene's camera position and the samples come from a fixed seed.
+ * hm_msnn_train_data_gen runs one pass without the training step (records: HM_BUF_NN_TRAIN_INPUT/OUTPUT). */
 int hm_msnn_pretrain(hm_renderer* r, int n_steps);
+int hm_msnn_train_data_gen(hm_renderer* r);
 hm_mlp* hm_renderer_mlp(hm_renderer* r);
 
 /* render_nrc only: the pieces of RenderWindowNRC::render() (render_nrc.cu:640-700) in the reference's
@@ -267,8 +274,13 @@ size_t hm_mlp_n_params(const hm_mlp* m);
  * (network_with_input_encoding.h:113-130) */
 int hm_mlp_get_params(hm_mlp* m, float* host_dst, size_t count);
 int hm_mlp_set_params(hm_mlp* m, const float* host_src, size_t count);
-/* Trainer::serialize / deserialize subset (trainer.h:270-310): raw little-endian blob */
+/* hm_mlp_save: raw little-endian fp32 blob.  hm_mlp_save_snapshot: Trainer::serialize (trainer.h:270-283)
+ * as the text JSON TINY_MLP::loadWeights reads (cuda/neural_network.cu:23-32): n_params, params_type
+ * "float", params_binary {"bytes": [...]}.  hm_mlp_load accepts both, and snapshots of params_type
+ * "__half" (Trainer::deserialize, trainer.h:285-310).  scene.tcnn.init_weights is loaded this way by
+ * hm_renderer_create (render_nrc.cu:148-150). */
 int hm_mlp_save(hm_mlp* m, const char* path);
+int hm_mlp_save_snapshot(hm_mlp* m, const char* path);
 int hm_mlp_load(hm_mlp* m, const char* path);
 void* hm_mlp_stream(hm_mlp* m);
 uint64_t hm_mlp_launch_count(const hm_mlp* m);

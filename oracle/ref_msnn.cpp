@@ -65,6 +65,37 @@ void ref_render_msnn_gbuffer(int accum_id, int y0, int y1, int W, int H, int bet
         }
 }
 
+// TRAIN_DATA_GEN pass (cuda/hair_msnn.cu:222-233 + the shared training-path block :234-277): a
+// 128 x 128 launch inside a W x H frame; record i's ray runs from the camera position to
+// sampled_points[scene_indices[i]].  nn_train_in: float[16384*in_ch], nn_train_out: float[16384*3].
+void ref_render_msnn_train_data_gen(int accum_id, int W, int H, int beta, const int* scene_indices, const float* sampled_points3,
+                                    int in_ch, float* nn_train_in, float* nn_train_out, int threads) {
+    LaunchParams& P = optixLaunchParams;
+    P.accumId = accum_id;
+    P.pass = TRAIN_DATA_GEN;
+    P.beta = beta;
+    P.numTrainRecordsX = 128; P.numTrainRecordsY = 128;
+    P.sceneIndices = (int*)scene_indices;
+    P.sampledPoints = (float3*)sampled_points3;
+    P.mlpInputCh = in_ch; P.mlpOutputCh = 3;
+    P.nnTrainInput = nn_train_in; P.nnTrainOutput = nn_train_out;
+    g_raygen_data.frameBuffer = nullptr;
+    g_raygen_data.frameBufferSize = vec2i(W, H);
+    if (threads < 1) threads = 1;
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) {
+        pool.emplace_back([=]() {
+            for (int y = t; y < 128; y += threads)
+                for (int x = 0; x < 128; ++x) {
+                    refemu::g_ctx.launch_x = x; refemu::g_ctx.launch_y = y;
+                    refemu::g_ctx.program_data = &g_raygen_data;
+                    ref_raygen_rayGenCam();
+                }
+        });
+    }
+    for (auto& th : pool) th.join();
+}
+
 // RENDER pass (cuda/hair_msnn.cu:314-356) over all pixels; buffers are float4[W*H].
 void ref_render_msnn_composite(int accum_id, int W, int H, const float* gbuf8, const float* nn_out3,
                                float* pt_accum, float* nn_accum, float* final_accum,

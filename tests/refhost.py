@@ -130,6 +130,15 @@ class RefHost:
                                          _p(tr_in), _p(tr_out), _p(gb), threads or os.cpu_count())
         return nn_in, tr_in, tr_out, gb
 
+    def render_msnn_train_data_gen(self, accum_id, W, H, beta, scene_indices, sampled_points, in_ch=12, threads=0):
+        assert self.which == "msnn"
+        idx = np.ascontiguousarray(scene_indices, dtype=np.int32)
+        pts = _f(sampled_points).reshape(-1, 3)
+        tr_in = np.zeros((16384, in_ch), np.float32); tr_out = np.zeros((16384, 3), np.float32)
+        self.lib.ref_render_msnn_train_data_gen(accum_id, W, H, beta, _p(idx, _ip), _p(pts), in_ch, _p(tr_in), _p(tr_out),
+                                                threads or os.cpu_count())
+        return tr_in, tr_out
+
     def render_nrc_gbuffer(self, accum_id, W, H, every_nth, train_idxs, nn_frame_rows, c=0.01, all_unbiased=False,
                            in_ch=9, threads=0):
         """G_BUFFER pass of cuda/nrc.cu.  Returns (nn_frame_in [rows][in_ch], gbuffer [W*H][8] = hit,

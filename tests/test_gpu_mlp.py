@@ -165,3 +165,40 @@ def test_save_and_load_roundtrip(tmp_path):
     assert np.array_equal(m2.inference(x), m.inference(x))
     with pytest.raises(api.HairMSNNError):
         m2.load(str(tmp_path / "missing.bin"))
+
+
+def test_tcnn_snapshot_roundtrip_and_half_snapshots(tmp_path):
+    """Trainer::serialize / deserialize (trainer.h:270-310) in the text-JSON form TINY_MLP::loadWeights reads."""
+    import json
+    a = api.Mlp.create()
+    x = np.random.default_rng(3).uniform(-0.5, 0.5, (256, 12)).astype(np.float32)
+    y = np.random.default_rng(4).uniform(0, 1, (256, 3)).astype(np.float32)
+    for _ in range(3):
+        a.train_step(x, y)
+    pa = a.get_params()
+    p = str(tmp_path / "snap.json")
+    a.save_snapshot(p)
+    j = json.load(open(p))
+    assert j["n_params"] == 1000448 and j["params_type"] == "float" and len(j["params_binary"]["bytes"]) == 4 * 1000448
+    b = api.Mlp.create()
+    assert not np.array_equal(b.get_params(), pa)
+    b.load(p)
+    assert np.array_equal(b.get_params(), pa)
+    assert np.array_equal(b.inference(x), a.inference(x))
+    # a snapshot as the reference build writes it: params_type "__half"
+    half = pa.astype(np.float16)
+    j2 = {"n_params": int(pa.size), "params_type": "__half", "params_binary": {"bytes": half.view(np.uint8).tolist(), "subtype": None}}
+    p2 = str(tmp_path / "snap_half.json")
+    json.dump(j2, open(p2, "w"))
+    c = api.Mlp.create()
+    c.load(p2)
+    assert np.array_equal(c.get_params(), half.astype(np.float32))
+    # wrong size / wrong type are errors
+    j2["params_binary"]["bytes"] = j2["params_binary"]["bytes"][:-2]
+    json.dump(j2, open(p2, "w"))
+    with pytest.raises(api.HairMSNNError):
+        c.load(p2)
+    j2["params_type"] = "double"
+    json.dump(j2, open(p2, "w"))
+    with pytest.raises(api.HairMSNNError):
+        c.load(p2)
