@@ -197,7 +197,25 @@ def main():
     peaks = load_peaks()
 
     t0 = time.time()
-    sc, kw = make_scene(args.strands)
+    if world == 1:
+        sc, kw = make_scene(args.strands)
+    else:
+        # one rank builds the acceleration structure (and keeps the binary tree the CPU arm needs), the others
+        # restore the GPU-side tree from a RAM-backed cache instead of N concurrent 40-second builds
+        cache = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp", f"hm_bvh_cache_{os.environ.get('MASTER_PORT', '0')}")
+        os.makedirs(cache, exist_ok=True)
+        if rank == 0:
+            sc, kw = make_scene(args.strands)
+            sc.save_bvh_cache(cache)
+        dist.barrier()
+        if rank != 0:
+            os.environ["HM_BVH_CACHE"] = cache
+            sc, kw = make_scene(args.strands)
+            del os.environ["HM_BVH_CACHE"]
+        dist.barrier()
+        if rank == 0:
+            import shutil
+            shutil.rmtree(cache, ignore_errors=True)
     r = api.Renderer(sc, api.HAIR_MSNN, beta_cli=BETA_CLI, device=local_rank)
     r.set_frame_schedule(rank, world)
     mlp = r.mlp()

@@ -56,6 +56,7 @@ class SceneInfo(C.Structure):
         ("scene_scale", C.c_float),
         ("cam_pos", C.c_float * 3), ("cam_d00", C.c_float * 3), ("cam_du", C.c_float * 3), ("cam_dv", C.c_float * 3),
         ("env_w", C.c_int), ("env_h", C.c_int), ("num_dlights", C.c_int),
+        ("num_wide_nodes", C.c_int), ("num_wide_leaf_refs", C.c_int), ("wide_depth", C.c_int),
     ]
 
 
@@ -186,6 +187,9 @@ class Scene:
         h = C.c_void_p()
         _check(lib.hm_scene_create(C.byref(d), C.byref(h)))
         return cls(h.value)
+
+    def save_bvh_cache(self, directory):
+        _check(lib.hm_scene_save_bvh_cache(self._h, os.fsencode(directory)))
 
     def info(self):
         i = SceneInfo()

@@ -15,7 +15,9 @@
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
+#include <string>
 #include <thread>
+#include <unistd.h>
 
 namespace hm {
 
@@ -550,6 +552,81 @@ void build_bvh(const HostGeometry& geo, HostBvh& out, int threads_hint) {
     lap("wide collapse");
     if (wb.max_depth > kWideStack)
         throw std::runtime_error("BVH: wide tree deeper than the traversal stack");
+}
+
+// ---------------------------------------------------------------------------------
+// On-disk cache of the tree the GPU traverses (build once, reuse).
+// ---------------------------------------------------------------------------------
+namespace {
+constexpr uint64_t kCacheMagic = 0x31485642574d4848ull;   // "HHMWBVH1"
+
+uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
+    // 8 bytes per step (word-wise FNV variant): this is a cache key, not a cryptographic digest
+    const unsigned char* p = (const unsigned char*)data;
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) { uint64_t w; memcpy(&w, p + i, 8); h = (h ^ w) * 0x100000001b3ull; }
+    for (; i < n; ++i) h = (h ^ p[i]) * 0x100000001b3ull;
+    return h;
+}
+}  // namespace
+
+uint64_t bvh_cache_key(const HostGeometry& geo) {
+    uint64_t h = 0xcbf29ce484222325ull;
+    h = fnv1a(h, geo.cps.data(), geo.cps.size() * sizeof(F4));
+    h = fnv1a(h, geo.seg_cp.data(), geo.seg_cp.size() * sizeof(int));
+    h = fnv1a(h, geo.tri_verts.data(), geo.tri_verts.size() * sizeof(F4));
+    const char* split = getenv("HM_BVH_SPLIT");
+    const char* span = getenv("HM_BVH_SPAN");
+    std::string params = std::string("v3|") + (split ? split : "-") + "|" + (span ? span : "-");
+    h = fnv1a(h, params.data(), params.size());
+    return h;
+}
+
+// Wide tree only: a scene restored from the cache has no binary tree (hm_scene_get_arrays reports 0 nodes).
+bool load_bvh_cache(const std::string& path, uint64_t key, HostBvh& out) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    uint64_t hdr[6];
+    bool ok = fread(hdr, 8, 6, f) == 6 && hdr[0] == kCacheMagic && hdr[1] == key;
+    if (ok) {
+        out.nodes.clear(); out.leaf_data.clear(); out.leaf_code.clear();
+        out.wnodes.resize((size_t)hdr[2]); out.wleaf_data.resize((size_t)hdr[3]);
+        out.wide_depth = (int)hdr[4];
+        out.leaf_prim.resize((size_t)hdr[5]);
+        ok = fread(out.wnodes.data(), sizeof(F4), out.wnodes.size(), f) == out.wnodes.size() &&
+             fread(out.wleaf_data.data(), sizeof(F4), out.wleaf_data.size(), f) == out.wleaf_data.size() &&
+             fread(out.leaf_prim.data(), sizeof(int), out.leaf_prim.size(), f) == out.leaf_prim.size();
+    }
+    fclose(f);
+    if (!ok) { out.wnodes.clear(); out.wleaf_data.clear(); out.leaf_prim.clear(); }
+    return ok;
+}
+
+void save_bvh_cache(const std::string& path, uint64_t key, const HostBvh& b) {
+    const std::string tmp = path + ".tmp" + std::to_string((unsigned long long)(uintptr_t)&b) + std::to_string((long long)getpid());
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return;                                        // an unwritable cache directory is not an error
+    uint64_t hdr[6] = {kCacheMagic, key, b.wnodes.size(), b.wleaf_data.size(), (uint64_t)b.wide_depth, b.leaf_prim.size()};
+    bool ok = fwrite(hdr, 8, 6, f) == 6 &&
+              fwrite(b.wnodes.data(), sizeof(F4), b.wnodes.size(), f) == b.wnodes.size() &&
+              fwrite(b.wleaf_data.data(), sizeof(F4), b.wleaf_data.size(), f) == b.wleaf_data.size() &&
+              fwrite(b.leaf_prim.data(), sizeof(int), b.leaf_prim.size(), f) == b.leaf_prim.size();
+    ok = fclose(f) == 0 && ok;
+    if (ok) ok = rename(tmp.c_str(), path.c_str()) == 0;   // atomic: readers see a whole file or none
+    if (!ok) remove(tmp.c_str());
+}
+
+// build_bvh through the cache directory named by HM_BVH_CACHE (unset: always build).
+void build_bvh_cached(const HostGeometry& geo, HostBvh& out, int threads_hint) {
+    const char* dir = getenv("HM_BVH_CACHE");
+    if (!dir || !*dir) { build_bvh(geo, out, threads_hint); return; }
+    const uint64_t key = bvh_cache_key(geo);
+    char name[64];
+    snprintf(name, sizeof(name), "/hm_bvh_%016llx.bin", (unsigned long long)key);
+    const std::string path = std::string(dir) + name;
+    if (load_bvh_cache(path, key, out)) return;
+    build_bvh(geo, out, threads_hint);
+    save_bvh_cache(path, key, out);
 }
 
 }  // namespace hm

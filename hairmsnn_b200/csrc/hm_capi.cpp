@@ -84,7 +84,7 @@ int hm_scene_load(const char* path, hm_scene** out) {
         load_scene_file(path, s->hs);
         finalize_geometry(s->hs);
         if (s->hs.has_env) build_env_tables(s->hs);
-        build_bvh(s->hs.geo, s->hs.bvh);
+        build_bvh_cached(s->hs.geo, s->hs.bvh);
         *out = s.release();
     });
 }
@@ -145,13 +145,22 @@ int hm_scene_create(const hm_scene_desc* d, hm_scene** out) {
         if (d->tcnn_config_path) hs.tcnn_config = d->tcnn_config_path;
         finalize_geometry(hs);
         if (hs.has_env) build_env_tables(hs);
-        build_bvh(hs.geo, hs.bvh);
+        build_bvh_cached(hs.geo, hs.bvh);
         *out = s.release();
     });
 }
 
 void hm_scene_free(hm_scene* s) { delete s; }
 
+int hm_scene_save_bvh_cache(const hm_scene* s, const char* dir) {
+    return guarded([&] {
+        need(s, "scene"); need(dir, "dir");
+        const uint64_t key = bvh_cache_key(s->hs.geo);
+        char name[64];
+        snprintf(name, sizeof(name), "/hm_bvh_%016llx.bin", (unsigned long long)key);
+        save_bvh_cache(std::string(dir) + name, key, s->hs.bvh);
+    });
+}
 int hm_scene_get_info(const hm_scene* s, hm_scene_info* info) {
     return guarded([&] {
         need(s, "scene"); need(info, "info");
@@ -168,6 +177,9 @@ int hm_scene_get_info(const hm_scene* s, hm_scene_info* info) {
         camera_basis(hs, hs.width, hs.height, info->cam_pos, info->cam_d00, info->cam_du, info->cam_dv);
         info->env_w = hs.env_w; info->env_h = hs.env_h;
         info->num_dlights = (int)(hs.dl_from.size() / 3);
+        info->num_wide_nodes = (int)(hs.bvh.wnodes.size() / 5);
+        info->num_wide_leaf_refs = (int)(hs.bvh.wleaf_data.size() / 4);
+        info->wide_depth = hs.bvh.wide_depth;
     });
 }
 

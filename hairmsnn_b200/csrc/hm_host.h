@@ -1,6 +1,7 @@
 // hm_host.h — host-side scene containers shared by the loaders, the BVH builder and
 // the C-ABI implementation.
 #pragma once
+#include <cstdint>
 #include <string>
 #include <vector>
 
@@ -40,6 +41,13 @@ struct HostBvh {
 };
 
 void build_bvh(const HostGeometry& geo, HostBvh& out, int threads_hint = 0);
+// Same through an on-disk cache of the GPU-side (8-wide) tree: directory from the environment variable
+// HM_BVH_CACHE, file hm_bvh_<hash of geometry + build parameters>.bin, written atomically.  A scene
+// restored from the cache carries no binary tree (only the builder's process has one).
+void build_bvh_cached(const HostGeometry& geo, HostBvh& out, int threads_hint = 0);
+uint64_t bvh_cache_key(const HostGeometry& geo);
+bool load_bvh_cache(const std::string& path, uint64_t key, HostBvh& out);
+void save_bvh_cache(const std::string& path, uint64_t key, const HostBvh& b);
 
 // Everything parseScene produces (scene.cpp:119-339, headers/scene.h) plus the tables
 // the frame drivers derive at start-up.

@@ -997,13 +997,23 @@ void Mlp::ensure_train_buffers(int n) {
 }
 
 // ---- compute -------------------------------------------------------------------------------
+// resident CTAs per SM of the persistent forward grid (HM_MLP_CTAS overrides; swept on B200)
+static int fwd_ctas_per_sm() {
+    static int v = 0;
+    if (!v) {
+        v = 4;
+        if (const char* e = getenv("HM_MLP_CTAS")) v = std::max(1, std::min(16, atoi(e)));
+    }
+    return v;
+}
+
 void Mlp::inference(const float* d_in, float* d_out, int n) {
     if (n % kTile != 0) throw std::invalid_argument("batch size must be a multiple of 128");
     NetShape S = make_shape(cfg_, layout_);
     FwdArgs A;
     memset(&A, 0, sizeof(A));
     A.in = d_in; A.out = d_out; A.n_tiles = n / kTile;
-    int grid = std::min(A.n_tiles, sm_count() * 4);
+    int grid = std::min(A.n_tiles, sm_count() * fwd_ctas_per_sm());
     if (use_tc_) k_mlp_forward_tc<false><<<grid, kTile, tc::kSmemBytes, stream_>>>(S, (const __half*)d_half_, A);
     else k_mlp_forward<false><<<grid, kTile, kFwdSmem, stream_>>>(S, (const __half*)d_half_, A);
     launches_++;

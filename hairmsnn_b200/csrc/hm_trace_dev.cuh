@@ -32,7 +32,10 @@ namespace hm {
 constexpr int kTraceBlock = 128;   // threads per CTA of every kernel that calls trace_queue
 constexpr int kLeafCap = 16;       // parked primitive references per lane (a wide node can park 8)
 constexpr int kSolveCap = 4;       // parked solver candidates per lane
-constexpr int kRefillLanes = 8;    // refill when this many lanes are idle
+#ifndef HM_TRACE_REFILL
+#define HM_TRACE_REFILL 8
+#endif
+constexpr int kRefillLanes = HM_TRACE_REFILL;    // refill when this many lanes are idle
 #ifndef HM_TRACE_PRIM_LANES
 #define HM_TRACE_PRIM_LANES 16     // prim step when this many lanes hold a parked reference
 #endif

@@ -104,12 +104,18 @@ typedef struct {
     const char* tcnn_config_path;
 } hm_scene_desc;
 
+/* Both constructors build the acceleration structure (owlGroupBuildAccel's job in the reference,
+ * render_hair_msnn.cu:401,412).  With the environment variable HM_BVH_CACHE naming a directory, the built
+ * tree is stored there (file name = hash of geometry + build parameters, written atomically) and later
+ * constructions of the same geometry — other ranks of a multi-GPU job, later runs — load it instead. */
 int hm_scene_create(const hm_scene_desc* desc, hm_scene** out);
 /* loadEnvTexture's file reader (model.cpp:158-231, tinyexr LoadEXR): single-part scanline OpenEXR,
  * HALF/FLOAT/UINT channels, NONE/ZIPS/ZIP/PIZ compression -> RGBA32F, top row first, alpha 1 when
  * the file has none.  Call with rgba = NULL to get the size, then with a buffer of
  * capacity_floats >= 4*w*h. */
 int hm_image_load_exr(const char* path, float* rgba, size_t capacity_floats, int* width, int* height);
+/* stores the scene's wide tree in `dir` under the name HM_BVH_CACHE lookups use (no-op if it came from there) */
+int hm_scene_save_bvh_cache(const hm_scene* scene, const char* dir);
 void hm_scene_free(hm_scene* scene);
 
 typedef struct {
@@ -118,6 +124,10 @@ typedef struct {
     float scene_scale;
     float cam_pos[3], cam_d00[3], cam_du[3], cam_dv[3];  /* cameraChanged(), render_path_tracing.cu:767-797 */
     int env_w, env_h, num_dlights;
+    /* the 8-wide quantised tree the kernels traverse (80 B nodes), its leaf references (64 B each) and
+     * depth.  num_bvh_nodes counts the binary SAH tree it is derived from: 0 when the scene came from the
+     * HM_BVH_CACHE directory (the cache stores the wide tree only). */
+    int num_wide_nodes, num_wide_leaf_refs, wide_depth;
 } hm_scene_info;
 int hm_scene_get_info(const hm_scene* scene, hm_scene_info* info);
 /* host copies of the acceleration structure + geometry (test hook: lets the oracle

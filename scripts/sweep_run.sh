@@ -1,6 +1,6 @@
 source scripts/sweep.sh
-run rep2 HM_X=1
-run rep1 HM_LIB=$V/libhairmsnn_rep1.so
-run rep3 HM_LIB=$V/libhairmsnn_rep3.so
-run rep2n16 HM_LIB=$V/libhairmsnn_rep2n16.so
-run rep4n20 HM_LIB=$V/libhairmsnn_rep4n20.so
+run refill8 HM_X=1
+run refill4 HM_LIB=$V/libhairmsnn_refill4.so
+run refill2 HM_LIB=$V/libhairmsnn_refill2.so
+run refill12 HM_LIB=$V/libhairmsnn_refill12.so
+run refill16 HM_LIB=$V/libhairmsnn_refill16.so

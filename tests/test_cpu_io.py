@@ -54,3 +54,30 @@ def test_shipped_straight_scene_loads_unchanged():
     if ref is None:
         pytest.skip("OpenCV build has no OpenEXR")
     assert np.array_equal(env[..., :3], ref[..., ::-1])
+
+
+def test_bvh_cache_roundtrip(tmp_path, monkeypatch):
+    """HM_BVH_CACHE: the second construction of the same geometry loads the wide tree instead of building."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from common import small_scene_kwargs
+    kw = small_scene_kwargs(strands=200, segs=10)
+    a = api.Scene.from_arrays(**kw)                       # no cache
+    monkeypatch.setenv("HM_BVH_CACHE", str(tmp_path))
+    b = api.Scene.from_arrays(**kw)                       # builds and stores
+    files = [f for f in os.listdir(tmp_path) if f.startswith("hm_bvh_") and f.endswith(".bin")]
+    assert len(files) == 1
+    c = api.Scene.from_arrays(**kw)                       # restored
+    ia, ib, ic = a.info(), b.info(), c.info()
+    assert ib.num_bvh_nodes == ia.num_bvh_nodes > 0 and ic.num_bvh_nodes == 0
+    assert (ic.num_wide_nodes, ic.num_wide_leaf_refs, ic.wide_depth) == (ia.num_wide_nodes, ia.num_wide_leaf_refs, ia.wide_depth)
+    assert ia.num_wide_nodes > 0 and ia.wide_depth >= 2
+    # other geometry -> other key
+    kw2 = small_scene_kwargs(strands=201, segs=10)
+    api.Scene.from_arrays(**kw2)
+    assert len([f for f in os.listdir(tmp_path) if f.endswith(".bin")]) == 2
+    # a damaged file is ignored and rebuilt over
+    path = os.path.join(tmp_path, files[0])
+    open(path, "r+b").write(b"garbage!")
+    d = api.Scene.from_arrays(**kw)
+    assert d.info().num_bvh_nodes == ia.num_bvh_nodes

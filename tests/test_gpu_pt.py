@@ -159,3 +159,15 @@ def test_row_bands_reproduce_full_frame():
         img = r.buffer(api.BUF_FINAL_ACCUM)
         out[rank * 32:(rank + 1) * 32] = img[rank * 32:(rank + 1) * 32]
     assert np.array_equal(out.view(np.uint32), ref_img.view(np.uint32))
+
+
+def test_scene_restored_from_bvh_cache_renders_identically(tmp_path, monkeypatch):
+    kw = small_scene_kwargs(width=128, height=128, strands=600, segs=12, path_v2=6)
+    a = api.Scene.from_arrays(**kw)
+    a.save_bvh_cache(str(tmp_path))
+    monkeypatch.setenv("HM_BVH_CACHE", str(tmp_path))
+    b = api.Scene.from_arrays(**kw)
+    assert b.info().num_bvh_nodes == 0 and b.info().num_wide_nodes == a.info().num_wide_nodes
+    ra = api.Renderer(a, api.PATH_TRACING); rb = api.Renderer(b, api.PATH_TRACING)
+    ra.render_frames(2); rb.render_frames(2)
+    assert np.array_equal(ra.buffer(api.BUF_FINAL_ACCUM), rb.buffer(api.BUF_FINAL_ACCUM))
