@@ -385,6 +385,9 @@ class Renderer:
     def set_collect_stats(self, on):
         _check(lib.hm_renderer_set_collect_stats(self._h, int(on)))
 
+    def set_skip_unused_queries(self, on):
+        _check(lib.hm_renderer_set_skip_unused_queries(self._h, int(on)))
+
     def reset_stats(self):
         _check(lib.hm_renderer_reset_stats(self._h))
 

@@ -204,6 +204,7 @@ struct FwdArgs {
     float* loss;            // [1]
     float inv_n_total;      // 1 / (records * 3)
     int n_tiles;
+    const int* tile_mask;   // optional [n_tiles]: tiles whose flag is 0 are skipped (their outputs are not written)
 };
 
 template <bool TRAIN>
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(kTile) k_mlp_forward(const NetShape S, const _
     __half* wAct = sAct + warp * 32 * kStride;
 
     for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+        if (A.tile_mask && __ldg(A.tile_mask + tile) == 0) continue;
         const size_t row = (size_t)tile * kTile + threadIdx.x;
         {
             float x[12];
@@ -480,6 +482,7 @@ __global__ void __launch_bounds__(kTile) k_mlp_forward_tc(const NetShape S, cons
     };
 
     for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+        if (A.tile_mask && __ldg(A.tile_mask + tile) == 0) continue;
         const size_t grow = (size_t)tile * kTile + row;
         {
             float x[12];
@@ -1007,12 +1010,13 @@ static int fwd_ctas_per_sm() {
     return v;
 }
 
-void Mlp::inference(const float* d_in, float* d_out, int n) {
+void Mlp::inference(const float* d_in, float* d_out, int n, const int* d_tile_mask) {
     if (n % kTile != 0) throw std::invalid_argument("batch size must be a multiple of 128");
     NetShape S = make_shape(cfg_, layout_);
     FwdArgs A;
     memset(&A, 0, sizeof(A));
     A.in = d_in; A.out = d_out; A.n_tiles = n / kTile;
+    A.tile_mask = d_tile_mask;
     int grid = std::min(A.n_tiles, sm_count() * fwd_ctas_per_sm());
     if (use_tc_) k_mlp_forward_tc<false><<<grid, kTile, tc::kSmemBytes, stream_>>>(S, (const __half*)d_half_, A);
     else k_mlp_forward<false><<<grid, kTile, kFwdSmem, stream_>>>(S, (const __half*)d_half_, A);

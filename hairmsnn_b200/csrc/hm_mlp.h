@@ -53,7 +53,9 @@ public:
     cudaStream_t stream() const { return stream_; }
 
     // AoS fp32 [n][in_ch] -> [n][out_ch]; n % 128 == 0
-    void inference(const float* d_in, float* d_out, int n);
+    // d_tile_mask (optional, [n / 128] ints): 128-row tiles whose flag is 0 are skipped and their outputs
+    // left untouched — for callers that know which rows' results are never read
+    void inference(const float* d_in, float* d_out, int n, const int* d_tile_mask = nullptr);
     // forward + loss + backward into the fp32 gradient buffer (loss-scaled by 128).
     // n_total_records normalises the loss (global batch for data-parallel training).
     void forward_backward(const float* d_in, const float* d_target, int n, int n_total_records);

@@ -130,6 +130,11 @@ Renderer::Renderer(const HostScene& hs, int kind, int beta_cli, int device, int 
     int prio_lo = 0, prio_hi = 0;
     HM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     HM_CUDA(cudaStreamCreateWithPriority(&main_stream_, cudaStreamNonBlocking, prio_lo));
+    // HM_MAIN_STREAMS > 1 spreads the main pieces of consecutive frames over several streams.  Measured on
+    // B200 (profiles/r1k_sweep_main_streams.txt): 1 -> 194-201, 2 -> 178, 3 -> 151 Mpaths/s — concurrent
+    // persistent traversal grids fight over the SMs and the L2, so the default stays 1.
+    if (const char* e = getenv("HM_MAIN_STREAMS")) n_work_ = std::max(1, std::min((int)kMaxWorkStreams, atoi(e)));
+    for (int i = 0; i < n_work_ && n_work_ > 1; ++i) HM_CUDA(cudaStreamCreateWithPriority(&work_streams_[i], cudaStreamNonBlocking, prio_lo));
     HM_CUDA(cudaStreamCreateWithPriority(&order_stream_, cudaStreamNonBlocking, prio_hi));
     scene_.reset(new DeviceScene(hs));
     camera_basis(hs, W_, H_, cam_.pos, cam_.d00, cam_.du, cam_.dv);
@@ -162,7 +167,10 @@ Renderer::Renderer(const HostScene& hs, int kind, int beta_cli, int device, int 
         if (n % 128) throw std::invalid_argument("render_nrc needs W*H to be a multiple of 128 (scene.cpp:302-306)");
         nn_frame_rows_ = (int)n + nrc_train_pixels_ - nrc_train_pixels_ % 128 + 128;
     }
-    for (FrameCtx& c : ctx_) {
+    if (const char* e = getenv("HM_TAIL_MEGA")) tail_mega_ = atoi(e) != 0;
+    if (const char* e = getenv("HM_FRAMES_IN_FLIGHT")) frames_in_flight_ = std::max(1, std::min((int)kFramesInFlight, atoi(e)));
+    for (int ci = 0; ci < frames_in_flight_; ++ci) {
+        FrameCtx& c = ctx_[ci];
         c.paths.rng = (uint32_t*)alloc(n * 4);
         c.paths.ray_o = (float4*)alloc(n * 16);
         c.paths.ray_d = (float4*)alloc(n * 16);
@@ -182,6 +190,7 @@ Renderer::Renderer(const HostScene& hs, int kind, int beta_cli, int device, int 
             c.nn_train_in = (float*)alloc((size_t)records_ * in_ch_ * 4);
             c.nn_train_out = (float*)alloc((size_t)records_ * 3 * 4);
             c.gbuffer = (float4*)alloc(n * 16);
+            c.query_tiles = (int*)alloc((n / 128 + 1) * 4);
         }
         if (kind_ == HM_KIND_NRC) {
             c.paths.nrc_state = (float4*)alloc(n * 16);
@@ -204,6 +213,7 @@ Renderer::Renderer(const HostScene& hs, int kind, int beta_cli, int device, int 
         HM_CUDA(cudaEventCreateWithFlags(&c.ev_main_done, cudaEventDisableTiming));
         HM_CUDA(cudaEventCreateWithFlags(&c.ev_traced, cudaEventDisableTiming));
         HM_CUDA(cudaEventCreateWithFlags(&c.ev_free, cudaEventDisableTiming));
+        HM_CUDA(cudaEventCreateWithFlags(&c.ev_shuffled, cudaEventDisableTiming));
     }
     for (int i = 0; i < 6; ++i) bufs_[i] = (float4*)alloc(n * 16);
     fb_ = (uint32_t*)alloc(n * 4);
@@ -237,14 +247,17 @@ Renderer::~Renderer() {
         if (c.ev_main_done) cudaEventDestroy(c.ev_main_done);
         if (c.ev_traced) cudaEventDestroy(c.ev_traced);
         if (c.ev_free) cudaEventDestroy(c.ev_free);
+        if (c.ev_shuffled) cudaEventDestroy(c.ev_shuffled);
     }
     if (main_stream_) cudaStreamDestroy(main_stream_);
+    for (auto w : work_streams_) if (w) cudaStreamDestroy(w);
     if (order_stream_) cudaStreamDestroy(order_stream_);
 }
 
 void Renderer::sync() {
     HM_CUDA(cudaSetDevice(device_));
     HM_CUDA(cudaStreamSynchronize(main_stream_));
+    for (int i = 0; i < n_work_; ++i) if (work_streams_[i]) HM_CUDA(cudaStreamSynchronize(work_streams_[i]));
     for (FrameCtx& c : ctx_) HM_CUDA(cudaStreamSynchronize(c.tail_stream));
     HM_CUDA(cudaStreamSynchronize(order_stream_));
 }
@@ -323,6 +336,7 @@ FrameParams Renderer::params_for(const FrameCtx& c) {
         P.nn_train_in = c.nn_train_in;
         P.nn_train_out = c.nn_train_out;
         P.gbuffer = c.gbuffer;
+        P.query_tiles = c.pretrain ? nullptr : c.query_tiles;
     } else if (kind_ == HM_KIND_NRC) {
         P.mode = MODE_NRC;
         P.every_nth = every_nth_;
@@ -346,19 +360,26 @@ void Renderer::shuffle_train_idxs(FrameCtx& c) {
     // compositions is deterministic (render_hair_msnn.cu:711-714).  The frame keeps a copy:
     // later frames re-shuffle the persistent array while this one is still in flight.
     thrust::device_ptr<int> p = thrust::device_pointer_cast(d_train_idxs_);
+    // on main_stream_ (frame order); the frame's own stream picks the copy up through ev_shuffled
+    if (c.main != main_stream_) HM_CUDA(cudaStreamWaitEvent(main_stream_, c.ev_free, 0));
     thrust::shuffle(thrust::cuda::par_nosync(thrust_scratch()).on(main_stream_), p, p + n_idxs_, thrust::default_random_engine());
     HM_CUDA(cudaMemcpyAsync(c.train_idxs, d_train_idxs_, (size_t)n_idxs_ * 4, cudaMemcpyDeviceToDevice, main_stream_));
+    if (c.main != main_stream_) {
+        HM_CUDA(cudaEventRecord(c.ev_shuffled, main_stream_));
+        HM_CUDA(cudaStreamWaitEvent(c.main, c.ev_shuffled, 0));
+    }
 }
 
-FrameCtx& Renderer::begin_frame() {
+FrameCtx& Renderer::begin_frame(bool pretrain) {
     HM_CUDA(cudaSetDevice(device_));
-    FrameCtx& c = ctx_[frames_issued_ % kFramesInFlight];
+    FrameCtx& c = ctx_[frames_issued_ % frames_in_flight_];
+    c.main = (pretrain || n_work_ <= 1) ? main_stream_ : work_streams_[frames_issued_ % n_work_];
     frames_issued_++;
     c.accum_id = accum_id_;
     c.frame_id = frame_offset_ + accum_id_ * frame_stride_;
-    c.pretrain = false;
     // the context is reusable once the frame that last used it has been composited
-    HM_CUDA(cudaStreamWaitEvent(main_stream_, c.ev_free, 0));
+    HM_CUDA(cudaStreamWaitEvent(c.main, c.ev_free, 0));
+    c.pretrain = pretrain;
     return c;
 }
 
@@ -373,31 +394,42 @@ void Renderer::trace_frame(FrameCtx& c) {
     if (kind_ == HM_KIND_NRC) {
         max_vertices = kNrcMaxBounces;  // vertices 0..39; path_v1/path_v2 do not apply (cuda/nrc.cu:169)
         // what render() clears after every frame (render_nrc.cu:683-689: owlBufferClear x4 + RESET pass)
-        HM_CUDA(cudaMemsetAsync(c.nn_frame_in, 0, (size_t)nn_frame_rows_ * in_ch_ * 4, main_stream_));
-        HM_CUDA(cudaMemsetAsync(c.nn_train_in, 0, (size_t)records_ * in_ch_ * 4, main_stream_));
-        HM_CUDA(cudaMemsetAsync(c.nn_train_out, 0, (size_t)records_ * 3 * 4, main_stream_));
-        HM_CUDA(cudaMemsetAsync(c.tbuffer, 0, (size_t)nrc_train_pixels_ * sizeof(NrcTrainRec), main_stream_));
+        HM_CUDA(cudaMemsetAsync(c.nn_frame_in, 0, (size_t)nn_frame_rows_ * in_ch_ * 4, c.main));
+        HM_CUDA(cudaMemsetAsync(c.nn_train_in, 0, (size_t)records_ * in_ch_ * 4, c.main));
+        HM_CUDA(cudaMemsetAsync(c.nn_train_out, 0, (size_t)records_ * 3 * 4, c.main));
+        HM_CUDA(cudaMemsetAsync(c.tbuffer, 0, (size_t)nrc_train_pixels_ * sizeof(NrcTrainRec), c.main));
     }
     if (max_vertices < 1) max_vertices = 1;
     int main_vertices = kind_ == HM_KIND_MSNN ? beta_ + 2 : 6;
     if (main_vertices < 2) main_vertices = 2;
     if (main_vertices > max_vertices) main_vertices = max_vertices;
 
-    cudaStream_t s = main_stream_;
+    cudaStream_t s = c.main;
     HM_CUDA(cudaMemsetAsync(c.q.counts, 0, 16 * 4, s));
+    if (c.query_tiles && !c.pretrain) HM_CUDA(cudaMemsetAsync(c.query_tiles, 0, ((size_t)W_ * H_ / 128 + 1) * 4, s));
     timed(0, s, [&] { launch_primary(P, s); });
     int src = 0;
+    // HairMSNN: past the main piece only training paths are alive (16384 at most; all records in a pre-training pass)
+    long long tail_bound = 0;
     for (int vertex = 0; vertex < max_vertices; ++vertex) {
         if (vertex == main_vertices) {
-            HM_CUDA(cudaEventRecord(c.ev_main_done, main_stream_));
+            HM_CUDA(cudaEventRecord(c.ev_main_done, c.main));
             s = c.tail_stream;
             HM_CUDA(cudaStreamWaitEvent(s, c.ev_main_done, 0));
             P.tail = 1;
+            if (kind_ == HM_KIND_MSNN) tail_bound = records_;
+            if (kind_ == HM_KIND_MSNN && tail_mega_) {
+                // HM_TAIL_MEGA=1: the whole tail piece in one launch (k_tail_mega) instead of a launch pair per vertex.
+                // Measured equal on B200 (profiles/r1k_sweep_tail_mega.txt: 202-205 Mpaths/s either way, 245 instead of
+                // 320 launches per frame), so the launch-pair form every parity test was written against stays the default.
+                timed(3, s, [&] { launch_tail_mega(P, src, records_, s); });
+                break;
+            }
         }
-        timed(1, s, [&] { launch_shade(P, src, s); });
+        timed(1, s, [&] { launch_shade(P, src, s, tail_bound); });
         const int dst = src ^ 1;
         HM_CUDA(cudaMemsetAsync(c.q.counts + dst, 0, 4, s));
-        timed(P.tail ? 3 : 2, s, [&] { launch_trace(P, dst, s); });   // stage 2: main piece, stage 3: tail piece
+        timed(P.tail ? 3 : 2, s, [&] { launch_trace(P, dst, s, tail_bound); });   // stage 2: main piece, stage 3: tail piece
         HM_CUDA(cudaMemsetAsync(c.q.counts + 2, 0, 16, s));   // extend + shadow counters and their work cursors
         src = dst;
     }
@@ -448,7 +480,9 @@ void Renderer::msnn_finish() {
     FrameCtx& c = *current_;
     const size_t first = (size_t)row0_ * W_;
     const int count = (row1_ - row0_) * W_;
-    timed(6, order_stream_, [&] { mlp_->inference(c.nn_frame_in + first * in_ch_, nn_frame_out_ + first * 3, count); });
+    // rows whose output nobody reads (background, head) are skipped tile-wise; results are identical
+    const int* mask = (skip_unused_queries_ && first % 128 == 0) ? c.query_tiles + first / 128 : nullptr;
+    timed(6, order_stream_, [&] { mlp_->inference(c.nn_frame_in + first * in_ch_, nn_frame_out_ + first * 3, count, mask); });
     MsnnComposite C;
     C.final_avg = bufs_[0]; C.final_accum = bufs_[1];
     C.pt_avg = bufs_[2]; C.pt_accum = bufs_[3];
@@ -529,9 +563,9 @@ void Renderer::msnn_train_data_gen() {
     if (kind_ != HM_KIND_MSNN) throw std::logic_error("not a HairMSNN renderer");
     if (current_) throw std::logic_error("msnn_train_data_gen: a frame is in flight");
     HM_CUDA(cudaSetDevice(device_));
+    sync();
     ensure_scene_samples();
-    FrameCtx& c = begin_frame();
-    c.pretrain = true;
+    FrameCtx& c = begin_frame(true);
     trace_frame(c);
     end_frame(c);
 }
@@ -547,10 +581,10 @@ void Renderer::msnn_pretrain(int steps) {
     if (kind_ != HM_KIND_MSNN) throw std::logic_error("not a HairMSNN renderer");
     if (current_) throw std::logic_error("msnn_pretrain: a frame is in flight");
     HM_CUDA(cudaSetDevice(device_));
+    sync();
     ensure_scene_samples();
     for (int i = 0; i < steps; ++i) {
-        FrameCtx& c = begin_frame();
-        c.pretrain = true;
+        FrameCtx& c = begin_frame(true);
         trace_frame(c);
         current_ = &c;
         thrust::device_ptr<int> p = thrust::device_pointer_cast(d_scene_indices_);

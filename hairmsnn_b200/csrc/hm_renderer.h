@@ -47,9 +47,12 @@ struct FrameCtx {
     float* nn_train_out = nullptr;
     float4* gbuffer = nullptr;
     float4* gbuffer_b = nullptr;      // NRC: throughput + bounce count at the cache query
+    int* query_tiles = nullptr;       // HairMSNN: 128-pixel tiles holding at least one hair hit (the only rows whose
+                                      // network output the RENDER pass reads)
     NrcTrainRec* tbuffer = nullptr;   // NRC: per-training-pixel path records
+    cudaStream_t main = nullptr;      // the stream this frame's main piece runs on
     cudaStream_t tail_stream = nullptr;
-    cudaEvent_t ev_main_done = nullptr, ev_traced = nullptr, ev_free = nullptr;
+    cudaEvent_t ev_main_done = nullptr, ev_traced = nullptr, ev_free = nullptr, ev_shuffled = nullptr;
     int frame_id = 0, accum_id = 0;
     bool pretrain = false;            // this frame is a TRAIN_DATA_GEN pass
 };
@@ -67,7 +70,8 @@ struct FrameCtx {
 // main parts.  Results are identical to one-at-a-time execution.
 class Renderer {
 public:
-    static constexpr int kFramesInFlight = 8;
+    static constexpr int kFramesInFlight = 24;   // contexts allocated lazily: frames_in_flight_ of them are used
+    int frames_in_flight_ = 8;                   // HM_FRAMES_IN_FLIGHT overrides
 
     Renderer(const HostScene& hs, int kind, int beta_cli, int device, int rank, int world);
     ~Renderer();
@@ -108,6 +112,8 @@ public:
     void readback_async(int which, void* host_dst, size_t bytes);
     void set_profiling(bool on) { profiling_ = on; }
     void set_collect_stats(bool on) { collect_stats_ = on; }
+    // off: evaluate the cache for every pixel as the reference does (default: skip 128-pixel tiles without a hair hit)
+    void set_skip_unused_queries(bool on) { skip_unused_queries_ = on; }
     // spp sharding: RNG frame id = offset + accum_id * stride (accum_id counts this renderer's own samples)
     void set_frame_schedule(int offset, int stride) { frame_offset_ = offset; frame_stride_ = stride; }
     void reset_stats();
@@ -121,7 +127,7 @@ public:
     const HostScene& host_scene() const { return hs_; }
 
 private:
-    FrameCtx& begin_frame();
+    FrameCtx& begin_frame(bool pretrain = false);
     void trace_frame(FrameCtx& c);        // main + tail pieces, ends with order_stream waiting on ev_traced
     void finish_pt(FrameCtx& c);
     void end_frame(FrameCtx& c);
@@ -135,7 +141,12 @@ private:
     int accum_id_ = 0;
     uint64_t frames_issued_ = 0;
     FrameCtx* current_ = nullptr;   // frame between msnn_trace() and msnn_finish()
+    // main_stream_: shuffles (strictly in frame order), pre-training frames and — by default — every frame's main
+    // piece; work_streams_ (HM_MAIN_STREAMS > 1, an experiment that lost): main pieces round-robin
+    static constexpr int kMaxWorkStreams = 4;
     cudaStream_t main_stream_ = nullptr, order_stream_ = nullptr;
+    cudaStream_t work_streams_[kMaxWorkStreams] = {nullptr, nullptr, nullptr, nullptr};
+    int n_work_ = 1;
     std::unique_ptr<DeviceScene> scene_;
     Camera cam_;
     FrameCtx ctx_[kFramesInFlight];
@@ -160,7 +171,7 @@ private:
     bool nrc_all_unbiased_ = false;
     float nrc_c_ = 0.01f;           // headers/render_nrc.h:132
     FrameCtx* last_ctx_ = nullptr;
-    bool profiling_ = false, collect_stats_ = false;
+    bool profiling_ = false, collect_stats_ = false, skip_unused_queries_ = true, tail_mega_ = false;
     int frame_offset_ = 0, frame_stride_ = 1;
     Stats stats_;
     struct Pending { int stage; cudaEvent_t a, b; };

@@ -166,7 +166,7 @@ __device__ __forceinline__ void push_probe(const FrameParams& P, const Probe& pr
 __device__ __forceinline__ void fold_pending(const FrameParams& P, int slot, bool training, V3& color, V3& color_short) {
     float4 dl = P.paths.dl_light[slot];
     if (dl.w == 0.f) return;
-    uint32_t vis = P.paths.vis[slot];
+    uint32_t vis = __ldcg(P.paths.vis + slot);   // cleared by whichever thread traced the probe: bypass L1
     V3 d = resolve_direct(v3(dl), (vis & 1u) != 0, v3(P.paths.dl_bsdf[slot]), (vis & 2u) != 0);
     color += v3(P.paths.dl_beta[slot]) * d;
     if (training) color_short += v3(P.paths.dl_beta_short[slot]) * d;
@@ -178,6 +178,95 @@ __device__ __forceinline__ void fold_pending(const FrameParams& P, int slot, boo
 #ifndef HM_SHADE_CTAS
 #define HM_SHADE_CTAS 4
 #endif
+// One path vertex of render_path_tracing / render_hair_msnn: everything k_shade does for a live queue
+// item except the queue pushes.  Reads and writes the slot's path state in HBM; the caller gets the two
+// direct-light probes and whether a continuation ray was written to paths.ray_o / ray_d.
+__device__ __forceinline__ void shade_item(const FrameParams& P, int slot, DirectSample& ds, bool& extend) {
+    Rng rng; rng.state = P.paths.rng[slot];
+    V3 ro = v3(P.paths.ray_o[slot]), rd = v3(P.paths.ray_d[slot]);
+    float4 hr = __ldcg(P.paths.hit + slot);   // written by whichever thread traced the ray: bypass L1
+    Hit hit; hit.t = hr.x; hit.prim = __float_as_int(hr.y); hit.u = hr.z; hit.v = hr.w;
+    float4 b4 = P.paths.beta[slot];
+    V3 beta = v3(b4);
+    int bounces = __float_as_int(b4.w);
+    V3 color = v3(P.paths.color[slot]);
+
+    int tr_ofs = 0;
+    bool training = false;
+    V3 beta_short(1.f), color_short(0.f);
+    if (P.mode == MODE_MSNN) {
+        training = is_training_pixel(P, slot, tr_ofs);
+        if (training) {
+            beta_short = v3(P.paths.beta_short[slot]);
+            color_short = v3(P.paths.color_short[slot]);
+        }
+    }
+
+    fold_pending(P, slot, training, color, color_short);
+
+    Vertex v = vertex_from_hit(P.scene, hit, ro, rd);
+
+    if (P.mode == MODE_MSNN && bounces == 0) {
+        write_nn_input(P.nn_frame_in + (size_t)slot * P.in_ch, v.p, v.wo, v.t, P.scene.scene_scale);
+        P.gbuffer[slot].w = __int_as_float(1 | (v.surface ? 2 : 0));
+        if (training && tr_ofs >= P.train_slot0 && tr_ofs < P.train_slot0 + P.train_slots)
+            write_nn_input(P.nn_train_in + (size_t)tr_ofs * P.in_ch, v.p, v.wo, v.t, P.scene.scene_scale);
+    }
+
+    // direct lighting
+    const bool degenerate = P.mode == MODE_PT && P.v2_stop < P.v1_stop;   // pathTrace returns 0
+    bool do_dl = (P.mode == MODE_PT) ? (bounces >= P.v1_stop && !degenerate) : true;
+    if (do_dl) {
+        sample_direct(P.scene, v, rng, ds);
+        P.paths.dl_beta[slot] = f4(beta, 0.f);
+        if (training) P.paths.dl_beta_short[slot] = f4(beta_short, 0.f);
+        P.paths.dl_light[slot] = f4(ds.light.value, 1.f);
+        P.paths.dl_bsdf[slot] = f4(ds.bsdf.value, 0.f);
+        P.paths.vis[slot] = (ds.light.active ? 1u : 0u) | (ds.bsdf.active ? 2u : 0u);
+    } else {
+        P.paths.dl_light[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    // Russian roulette (after the direct sample of every vertex but the first)
+    bool alive = !degenerate;
+    if (bounces >= 1) {
+        float q = fmaxf(0.05f, 1.f - luminance709(beta));
+        if (training) {
+            float qs = fmaxf(0.05f, 1.f - luminance709(beta_short));
+            float eps = rng_next(rng);
+            if (eps < qs || bounces > P.msnn_beta) beta_short = V3(0.f);
+            if (eps < q) alive = false;
+            else {
+                beta = beta / (1.f - q);
+                if (!(beta_short == V3(0.f))) beta_short = beta_short / (1.f - qs);
+            }
+        } else {
+            float eps = rng_next(rng);
+            if (eps < q) alive = false;
+            else if (P.mode == MODE_MSNN && bounces > P.msnn_beta) alive = false;
+            else beta = beta / (1.f - q);
+        }
+    }
+    if (alive && bounces + 1 > P.v2_stop) alive = false;
+
+    if (alive) {
+        V3 no, nd;
+        V3 mul = sample_continuation(P.scene, v, rng, no, nd);
+        beta = beta * mul;
+        if (training) beta_short = beta_short * mul;
+        P.paths.ray_o[slot] = f4(no, 0.f);
+        P.paths.ray_d[slot] = f4(nd, 0.f);
+        extend = true;
+    }
+    P.paths.rng[slot] = rng.state;
+    P.paths.beta[slot] = f4(beta, __int_as_float(bounces + 1));
+    P.paths.color[slot] = f4(color, 0.f);
+    if (training) {
+        P.paths.beta_short[slot] = f4(beta_short, 0.f);
+        P.paths.color_short[slot] = f4(color_short, 0.f);
+    }
+}
+
 __global__ void __launch_bounds__(kBlock, HM_SHADE_CTAS) k_shade(const __grid_constant__ FrameParams P, int src) {
     const int n = P.q.counts[src];
     const int* queue = P.q.shade[src];
@@ -190,92 +279,7 @@ __global__ void __launch_bounds__(kBlock, HM_SHADE_CTAS) k_shade(const __grid_co
         DirectSample ds;
         ds.light.active = false; ds.bsdf.active = false;
         bool extend = false;
-
-        if (live) {
-            Rng rng; rng.state = P.paths.rng[slot];
-            V3 ro = v3(P.paths.ray_o[slot]), rd = v3(P.paths.ray_d[slot]);
-            float4 hr = P.paths.hit[slot];
-            Hit hit; hit.t = hr.x; hit.prim = __float_as_int(hr.y); hit.u = hr.z; hit.v = hr.w;
-            float4 b4 = P.paths.beta[slot];
-            V3 beta = v3(b4);
-            int bounces = __float_as_int(b4.w);
-            V3 color = v3(P.paths.color[slot]);
-
-            int tr_ofs = 0;
-            bool training = false;
-            V3 beta_short(1.f), color_short(0.f);
-            if (P.mode == MODE_MSNN) {
-                training = is_training_pixel(P, slot, tr_ofs);
-                if (training) {
-                    beta_short = v3(P.paths.beta_short[slot]);
-                    color_short = v3(P.paths.color_short[slot]);
-                }
-            }
-
-            fold_pending(P, slot, training, color, color_short);
-
-            Vertex v = vertex_from_hit(P.scene, hit, ro, rd);
-
-            if (P.mode == MODE_MSNN && bounces == 0) {
-                write_nn_input(P.nn_frame_in + (size_t)slot * P.in_ch, v.p, v.wo, v.t, P.scene.scene_scale);
-                P.gbuffer[slot].w = __int_as_float(1 | (v.surface ? 2 : 0));
-                if (training && tr_ofs >= P.train_slot0 && tr_ofs < P.train_slot0 + P.train_slots)
-                    write_nn_input(P.nn_train_in + (size_t)tr_ofs * P.in_ch, v.p, v.wo, v.t, P.scene.scene_scale);
-            }
-
-            // direct lighting
-            const bool degenerate = P.mode == MODE_PT && P.v2_stop < P.v1_stop;   // pathTrace returns 0
-            bool do_dl = (P.mode == MODE_PT) ? (bounces >= P.v1_stop && !degenerate) : true;
-            if (do_dl) {
-                sample_direct(P.scene, v, rng, ds);
-                P.paths.dl_beta[slot] = f4(beta, 0.f);
-                if (training) P.paths.dl_beta_short[slot] = f4(beta_short, 0.f);
-                P.paths.dl_light[slot] = f4(ds.light.value, 1.f);
-                P.paths.dl_bsdf[slot] = f4(ds.bsdf.value, 0.f);
-                P.paths.vis[slot] = (ds.light.active ? 1u : 0u) | (ds.bsdf.active ? 2u : 0u);
-            } else {
-                P.paths.dl_light[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-
-            // Russian roulette (after the direct sample of every vertex but the first)
-            bool alive = !degenerate;
-            if (bounces >= 1) {
-                float q = fmaxf(0.05f, 1.f - luminance709(beta));
-                if (training) {
-                    float qs = fmaxf(0.05f, 1.f - luminance709(beta_short));
-                    float eps = rng_next(rng);
-                    if (eps < qs || bounces > P.msnn_beta) beta_short = V3(0.f);
-                    if (eps < q) alive = false;
-                    else {
-                        beta = beta / (1.f - q);
-                        if (!(beta_short == V3(0.f))) beta_short = beta_short / (1.f - qs);
-                    }
-                } else {
-                    float eps = rng_next(rng);
-                    if (eps < q) alive = false;
-                    else if (P.mode == MODE_MSNN && bounces > P.msnn_beta) alive = false;
-                    else beta = beta / (1.f - q);
-                }
-            }
-            if (alive && bounces + 1 > P.v2_stop) alive = false;
-
-            if (alive) {
-                V3 no, nd;
-                V3 mul = sample_continuation(P.scene, v, rng, no, nd);
-                beta = beta * mul;
-                if (training) beta_short = beta_short * mul;
-                P.paths.ray_o[slot] = f4(no, 0.f);
-                P.paths.ray_d[slot] = f4(nd, 0.f);
-                extend = true;
-            }
-            P.paths.rng[slot] = rng.state;
-            P.paths.beta[slot] = f4(beta, __int_as_float(bounces + 1));
-            P.paths.color[slot] = f4(color, 0.f);
-            if (training) {
-                P.paths.beta_short[slot] = f4(beta_short, 0.f);
-                P.paths.color_short[slot] = f4(color_short, 0.f);
-            }
-        }
+        if (live) shade_item(P, slot, ds, extend);
         push_probe(P, ds.light, slot, 0);
         push_probe(P, ds.bsdf, slot, 1);
         int idx = queue_reserve(P.q.counts + 2, extend);
@@ -347,6 +351,123 @@ __global__ void __launch_bounds__(kBlock, kTraceCtasPerSm) k_trace(const __grid_
 }
 
 // ---------------------------------------------------------------------------------
+// tail piece of a HairMSNN frame in ONE launch
+// ---------------------------------------------------------------------------------
+// Past vertex beta+1 only the <= 16384 training paths are alive, for up to 38 more vertices.  As
+// (shade, trace) launch pairs that is 76 tiny latency-bound launches per frame, each sweeping the GPU
+// with persistent CTAs that find almost no work while other frames' main pieces are running (measured:
+// 0.73 ms of a 5.0 ms frame).  Here a warp keeps 32 such paths and walks them to the end: shade the 32
+// vertices (shade_item, the code k_shade runs), put their <= 96 rays into a warp-private list in shared
+// memory, trace the list with the warp-cooperative traversal, repeat while any path is alive.  Path
+// state stays in the HBM arrays between steps exactly as the launch-per-vertex form leaves it, so
+// k_finalize and the parity tests see no difference.
+constexpr int kTailRaysPerWarp = 96;
+
+struct TailOps {
+    const FrameParams& P;
+    float4* rays;        // warp-private: [kTailRaysPerWarp][2]  (o.xyz, slot | bit << 30) (d.xyz, kind | lane << 8)
+    int* alive;          // warp-private [32]: set when a lane's continuation ray hit something
+    __device__ __forceinline__ bool fetch(int w, V3& o, V3& d) const {
+        const float4 a = rays[2 * w], b = rays[2 * w + 1];
+        o = V3(a.x, a.y, a.z);
+        d = V3(b.x, b.y, b.z);
+        return (__float_as_int(b.w) & 0xff) == 0;      // kind 0: occlusion probe
+    }
+    __device__ __forceinline__ void commit(int w, const Hit& h, bool finished) const {
+        if (!finished || h.prim < 0) return;
+        const int tag = __float_as_int(rays[2 * w].w), info = __float_as_int(rays[2 * w + 1].w);
+        const int slot = tag & 0x3fffffff;
+        if ((info & 0xff) == 0) {
+            atomicAnd(P.paths.vis + slot, ~(1u << (tag >> 30)));
+        } else {
+            P.paths.hit[slot] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
+            alive[info >> 8] = 1;
+        }
+    }
+};
+
+__global__ void __launch_bounds__(kBlock) k_tail_mega(const __grid_constant__ FrameParams P, int src) {
+    __shared__ float4 s_rays[kBlock / 32][kTailRaysPerWarp][2];
+    __shared__ int s_alive[kBlock / 32][32];
+    __shared__ int s_cursor[kBlock / 32];
+    const int n = P.q.counts[src];
+    const int* queue = P.q.shade[src];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    TraceStats st[2] = {{0, 0}, {0, 0}};
+    unsigned long long n_shade = 0, n_extend = 0, n_shadow = 0;
+
+    // persistent warps: a lane whose path has ended takes the next queue entry, so few warps stay resident
+    // (8 frames are in flight; idle lanes of long-lived warps would pin registers the main pieces need)
+    int* cursor = P.q.counts + 7;
+    int slot = -1;
+    bool live = false, exhausted = false;
+    while (true) {
+        const unsigned want = __ballot_sync(0xffffffffu, !live);
+        if (want && !exhausted) {
+            const int cnt = __popc(want);
+            int base = 0;
+            if (lane == 0) base = atomicAdd(cursor, cnt);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + cnt >= n) exhausted = true;
+            if (!live) {
+                const int i = base + __popc(want & ((1u << lane) - 1u));
+                if (i < n) { slot = queue[i]; live = true; }
+            }
+        }
+        if (!__any_sync(0xffffffffu, live)) break;
+        {
+            DirectSample ds;
+            ds.light.active = false; ds.bsdf.active = false;
+            bool extend = false;
+            if (live) shade_item(P, slot, ds, extend);
+            // warp-private ray list: probes first (they end early), then continuation rays
+            const unsigned m0 = __ballot_sync(0xffffffffu, ds.light.active), m1 = __ballot_sync(0xffffffffu, ds.bsdf.active);
+            const unsigned m2 = __ballot_sync(0xffffffffu, extend);
+            const unsigned below = (1u << lane) - 1u;
+            const int n0 = __popc(m0), n1 = __popc(m1), n2 = __popc(m2);
+            if (ds.light.active) {
+                const int w = __popc(m0 & below);
+                s_rays[wib][w][0] = make_float4(ds.light.o.x, ds.light.o.y, ds.light.o.z, __int_as_float(slot));
+                s_rays[wib][w][1] = make_float4(ds.light.d.x, ds.light.d.y, ds.light.d.z, __int_as_float(lane << 8));
+            }
+            if (ds.bsdf.active) {
+                const int w = n0 + __popc(m1 & below);
+                s_rays[wib][w][0] = make_float4(ds.bsdf.o.x, ds.bsdf.o.y, ds.bsdf.o.z, __int_as_float(slot | (1 << 30)));
+                s_rays[wib][w][1] = make_float4(ds.bsdf.d.x, ds.bsdf.d.y, ds.bsdf.d.z, __int_as_float(lane << 8));
+            }
+            if (extend) {
+                const int w = n0 + n1 + __popc(m2 & below);
+                const float4 o = P.paths.ray_o[slot], d = P.paths.ray_d[slot];
+                s_rays[wib][w][0] = make_float4(o.x, o.y, o.z, __int_as_float(slot));
+                s_rays[wib][w][1] = make_float4(d.x, d.y, d.z, __int_as_float(1 | (lane << 8)));
+            }
+            s_alive[wib][lane] = 0;
+            if (lane == 0) s_cursor[wib] = 0;
+            __syncwarp();
+            n_shade += __popc(__ballot_sync(0xffffffffu, live));
+            n_shadow += n0 + n1; n_extend += n2;
+            TailOps ops{P, &s_rays[wib][0][0], s_alive[wib]};
+            trace_queue(P.scene.geom, n0 + n1 + n2, &s_cursor[wib], ops, 0.f, 1e30f, P.collect_stats ? st : nullptr);
+            __syncwarp();
+            live = s_alive[wib][lane] != 0;
+            __syncwarp();
+        }
+    }
+    if (P.collect_stats) {
+        flush_trav(P.q.trav + 0, st[0]);
+        flush_trav(P.q.trav + 2, st[1]);
+        TraceStats both{st[0].nodes + st[1].nodes, st[0].prims + st[1].prims};
+        flush_trav(P.q.trav + 10, both);
+        if (lane == 0 && (n_shade | n_extend | n_shadow)) {
+            atomicAdd(P.q.trav + 6, n_extend);
+            atomicAdd(P.q.trav + 7, n_shadow);
+            atomicAdd(P.q.trav + 8, n_shade);
+            atomicAdd(P.q.trav + 12, n_extend + n_shadow);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // finalize
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ FrameParams P) {
@@ -391,6 +512,8 @@ __global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ FrameP
                 }
             }
             P.gbuffer[slot] = f4(color, __int_as_float(flags));
+            // the RENDER pass reads the network output of hair hits only (cuda/hair_msnn.cu:325-340)
+            if (P.query_tiles && (flags & 1) && !(flags & 2)) P.query_tiles[slot >> 7] = 1;
         }
     }
 }
@@ -722,13 +845,33 @@ void launch_primary(const FrameParams& P, cudaStream_t stream) {
     k_primary<<<grid, kBlock, 0, stream>>>(P);
     g_launches++;
 }
-void launch_shade(const FrameParams& P, int src, cudaStream_t stream) {
-    if (P.mode == MODE_NRC) k_shade_nrc<<<persistent_grid(8), kBlock, 0, stream>>>(P, src);
-    else k_shade<<<persistent_grid(HM_SHADE_GRID), kBlock, 0, stream>>>(P, src);
+// max_items > 0: the caller knows an upper bound of the queue length (tail pieces carry the few long paths
+// only) — the grid is sized for it instead of for the whole GPU, so these launches do not sweep every SM
+// with CTAs that find no work while other frames' main pieces are running.
+static int bounded_grid(int full, long long max_items, int items_per_cta) {
+    if (max_items <= 0) return full;
+    long long need = (max_items + items_per_cta - 1) / items_per_cta;
+    if (need < 1) need = 1;
+    return need < full ? (int)need : full;
+}
+void launch_shade(const FrameParams& P, int src, cudaStream_t stream, long long max_items) {
+    if (P.mode == MODE_NRC) k_shade_nrc<<<bounded_grid(persistent_grid(8), max_items, kBlock), kBlock, 0, stream>>>(P, src);
+    else k_shade<<<bounded_grid(persistent_grid(HM_SHADE_GRID), max_items, kBlock), kBlock, 0, stream>>>(P, src);
     g_launches++;
 }
-void launch_trace(const FrameParams& P, int dst, cudaStream_t stream) {
-    k_trace<<<persistent_grid(kTraceCtasPerSm), kBlock, 0, stream>>>(P, dst);
+void launch_trace(const FrameParams& P, int dst, cudaStream_t stream, long long max_items) {
+    // a vertex pushes at most 3 rays (2 probes + 1 continuation); 2 x 32 rays per warp keeps the refill loop busy
+    k_trace<<<bounded_grid(persistent_grid(kTraceCtasPerSm), 3 * max_items, 2 * kBlock), kBlock, 0, stream>>>(P, dst);
+    g_launches++;
+}
+#ifndef HM_TAIL_CTAS
+#define HM_TAIL_CTAS 37      // x 4 warps x 32 lanes = 4736 paths in flight per frame
+#endif
+void launch_tail_mega(const FrameParams& P, int src, int max_paths, cudaStream_t stream) {
+    int grid = (max_paths + kBlock - 1) / kBlock;
+    if (grid < 1) grid = 1;
+    if (grid > HM_TAIL_CTAS) grid = HM_TAIL_CTAS;
+    k_tail_mega<<<grid, kBlock, 0, stream>>>(P, src);
     g_launches++;
 }
 void launch_finalize(const FrameParams& P, cudaStream_t stream) {

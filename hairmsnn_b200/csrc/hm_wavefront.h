@@ -62,7 +62,7 @@ struct Queues {
     int* shade[2];       // double-buffered slot lists
     int* extend;
     float4* shadow;      // 2 x float4 per entry: (o.xyz, slot|bit<<31) (d.xyz, -)
-    int* counts;         // [0],[1] shade ; [2] extend ; [3] shadow ; work cursors: [4] trace [6] primary
+    int* counts;         // [0],[1] shade ; [2] extend ; [3] shadow ; work cursors: [4] trace [6] primary [7] tail
     unsigned long long* trav;   // [0],[1] extend nodes/prims ; [2],[3] shadow nodes/prims ; [4],[5] primary ;
                                 // [6] extend rays ; [7] shadow rays ; [8] shade items ; [9] primary rays ;
                                 // tail-piece share of the above: [10] nodes [11] prims [12] rays
@@ -99,6 +99,7 @@ struct FrameParams {
     float* nn_train_in;  // [records][12]
     float* nn_train_out; // [records][3]
     float4* gbuffer;     // rgb = short-path colour (NRC: pathRadiance), w = flags (bit0 hit, bit1 surface)
+    int* query_tiles;    // [W*H / 128] set to 1 when any pixel of the 128-pixel tile reads its cache output
     int in_ch;
     // NRC
     float4* gbuffer_b;   // rgb = throughput at the cache query (GBuffer::beta), w = bounces (int bits)
@@ -132,9 +133,12 @@ struct MsnnComposite {
 
 // All launches are asynchronous on `stream`.
 void launch_primary(const FrameParams& P, cudaStream_t stream);
-void launch_shade(const FrameParams& P, int src_queue, cudaStream_t stream);
+void launch_shade(const FrameParams& P, int src_queue, cudaStream_t stream, long long max_items = 0);
 // occlusion probes + continuation rays of one vertex in one launch
-void launch_trace(const FrameParams& P, int dst_queue, cudaStream_t stream);
+void launch_trace(const FrameParams& P, int dst_queue, cudaStream_t stream, long long max_items = 0);
+// render_hair_msnn: all remaining vertices of the paths in shade queue `src_queue` in one launch;
+// max_paths bounds the queue length (training paths only)
+void launch_tail_mega(const FrameParams& P, int src_queue, int max_paths, cudaStream_t stream);
 void launch_finalize(const FrameParams& P, cudaStream_t stream);
 void launch_msnn_composite(const MsnnComposite& C, cudaStream_t stream);
 void launch_nrc_render(const NrcRender& R, cudaStream_t stream);

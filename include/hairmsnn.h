@@ -233,6 +233,10 @@ int hm_renderer_get_stats(hm_renderer* r, hm_stats* out);
 int hm_renderer_set_profiling(hm_renderer* r, int on);
 /* instrumented traversal + queue-size accounting (polls the queue counters every bounce) */
 int hm_renderer_set_collect_stats(hm_renderer* r, int on);
+/* render_hair_msnn: the RENDER pass reads the network output of hair-hit pixels only (cuda/hair_msnn.cu:325-340).
+ * on (default): inference skips 128-pixel tiles without a hair hit (their HM_BUF_NN_FRAME_OUTPUT rows keep
+ * stale values; images are identical).  off: all W*H rows are evaluated, as the reference does. */
+int hm_renderer_set_skip_unused_queries(hm_renderer* r, int on);
 int hm_renderer_reset_stats(hm_renderer* r);
 /* Sample schedule for spp-sharded rendering: the RNG frame id of this renderer's
  * k-th sample is offset + k * stride (default 0, 1 == the reference's accumId). */

@@ -1,6 +1,6 @@
 source scripts/sweep.sh
-run refill8 HM_X=1
-run refill4 HM_LIB=$V/libhairmsnn_refill4.so
-run refill2 HM_LIB=$V/libhairmsnn_refill2.so
-run refill12 HM_LIB=$V/libhairmsnn_refill12.so
-run refill16 HM_LIB=$V/libhairmsnn_refill16.so
+run tail37 HM_X=1
+run tail8 HM_LIB=$V/libhairmsnn_tail8.so
+run tail16 HM_LIB=$V/libhairmsnn_tail16.so
+run tail24 HM_LIB=$V/libhairmsnn_tail24.so
+run pairs HM_TAIL_MEGA=0

@@ -137,3 +137,33 @@ def test_train_data_gen_pass_matches_reference():
     l1 = r.stats().last_loss
     assert np.isfinite(l0) and np.isfinite(l1) and r.accum_id == 0
     print("pre-training loss", l0, "->", l1)
+
+
+def test_skipping_unread_cache_queries_leaves_the_image_unchanged():
+    W, H = 256, 128
+    kw = small_scene_kwargs(width=W, height=H, strands=1500, segs=16, path_v2=10)
+    sc = api.Scene.from_arrays(**kw)
+    imgs = []
+    for skip in (True, False):
+        r = api.Renderer(sc, api.HAIR_MSNN, beta_cli=1)
+        r.set_skip_unused_queries(skip)
+        r.render_frames(4)
+        imgs.append((r.buffer(api.BUF_FINAL_ACCUM), r.buffer(api.BUF_NN_ACCUM), r.buffer(api.BUF_FB8)))
+    for a, b in zip(*imgs):
+        assert np.array_equal(a, b)
+
+
+def test_tail_megakernel_matches_launch_pairs(monkeypatch):
+    """HM_TAIL_MEGA=1 walks the training paths' tail vertices in one launch: same records, same image."""
+    W, H = 256, 128
+    kw = small_scene_kwargs(width=W, height=H, strands=1500, segs=16, path_v2=12)
+    sc = api.Scene.from_arrays(**kw)
+    out = []
+    for mega in ("0", "1"):
+        monkeypatch.setenv("HM_TAIL_MEGA", mega)
+        r = api.Renderer(sc, api.HAIR_MSNN, beta_cli=1)
+        r.msnn_trace(); r.sync()
+        out.append((r.buffer(api.BUF_NN_TRAIN_INPUT), r.buffer(api.BUF_NN_TRAIN_OUTPUT), r.buffer(api.BUF_GBUFFER)))
+        r.msnn_finish()
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)
