@@ -255,7 +255,11 @@ def main():
 
     # ---- timed region: device-resident -------------------------------------------------
     r.reset_stats()
-    r.set_profiling(True)          # event pairs around each launch; resolved after the region
+    # event pairs around the launches the roofline line is about (main-piece k_trace, 2 per frame) and the
+    # network inference; timing all ~320 launches of a frame costs ~3 % of the frame rate, so the full
+    # per-stage table comes from a second, untimed pass below
+    r.set_profiling_stages((1 << 2) | (1 << 6))
+    r.set_profiling(True)
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = r.stats().kernel_launches
@@ -270,6 +274,15 @@ def main():
     sampler.stop_flag = True
     st = r.stats()
     launches = st.kernel_launches - launches0
+    r.set_profiling(False)
+    # second pass, all stages timed (not part of the headline number)
+    r.reset_stats()
+    r.set_profiling_stages(0xffffffff)
+    r.set_profiling(True)
+    for _ in range(args.steps):
+        step()
+    barrier()
+    st_all = r.stats()
     r.set_profiling(False)
     if world > 1:
         t = torch.tensor([ms], device=f"cuda:{local_rank}")
@@ -320,9 +333,10 @@ def main():
     # launches split into the main piece (vertices 0..BETA of every path: ~97% of the secondary rays, on
     # the main stream) and the tail piece (the few training paths' deeper vertices: dozens of tiny
     # latency-bound launches on a side stream).  The roofline line is about the main-piece launches.
-    stage_ms = {"primary": st.ms_primary, "shade": st.ms_shade, "trace": st.ms_extend, "trace_tail": st.ms_shadow,
-                "train": st.ms_train, "infer": st.ms_infer, "composite": st.ms_composite, "finalize": st.ms_finalize}
-    stage_launches = dict(zip(("primary", "shade", "trace", "trace_tail", "finalize", "train", "infer", "composite"), st.stage_launches))
+    stage_ms = {"primary": st_all.ms_primary, "shade": st_all.ms_shade, "trace": st.ms_extend, "trace_tail": st_all.ms_shadow,
+                "train": st_all.ms_train, "infer": st.ms_infer, "composite": st_all.ms_composite, "finalize": st_all.ms_finalize}
+    stage_launches = dict(zip(("primary", "shade", "trace", "trace_tail", "finalize", "train", "infer", "composite"), st_all.stage_launches))
+    stage_launches["trace"] = st.stage_launches[2]
     dominant = max(("primary", "trace"), key=lambda k: stage_ms[k])
     rays = {"primary": si.rays_primary, "trace": si.rays_extend + si.rays_shadow - si.rays_tail}
     nodes = {"primary": si.trav_nodes_primary, "trace": si.trav_nodes_extend + si.trav_nodes_shadow - si.trav_nodes_tail}
@@ -351,10 +365,16 @@ def main():
                 "note": "main-piece k_trace launches (2 per frame at BETA=1), CUDA events around each launch inside the timed region; "
                         "8 frames are in flight, so a launch shares the GPU with other frames' tail-piece and MLP kernels; the kernel is "
                         "bound by dependent-fetch latency and SIMT divergence, not by bandwidth (profiles/)"}
-    mlp_qps = W * H / (stage_ms["infer"] / args.steps * 1e-3) if stage_ms["infer"] > 0 else None
+    # rows the inference launch evaluates: 128-pixel tiles holding at least one hair hit (the RENDER pass reads no
+    # other row's output; hm_renderer_set_skip_unused_queries).  Counted on the last frame's G-buffer.
+    gflags = r.buffer(api.BUF_GBUFFER).reshape(-1, 4)[:, 3].copy().view(np.int32)
+    hair_hit = ((gflags & 1) != 0) & ((gflags & 2) == 0)
+    rows_evaluated = int(hair_hit.reshape(-1, 128).any(axis=1).sum()) * 128
+    mlp_qps = rows_evaluated / (stage_ms["infer"] / args.steps * 1e-3) if stage_ms["infer"] > 0 else None
     mlp_info = {"queries_per_s": mlp_qps, "tflops": mlp_qps * FLOPS_PER_QUERY / 1e12 if mlp_qps else None,
                 "frac_of_tensor_peak": (mlp_qps * FLOPS_PER_QUERY / 1e12 / peaks["bf16_tflops"]) if mlp_qps else None,
                 "peak_tflops": peaks["bf16_tflops"], "ms_infer_per_step": stage_ms["infer"] / args.steps,
+                "rows_per_step_submitted": W * H, "rows_per_step_evaluated": rows_evaluated,
                 "ms_train_per_step": stage_ms["train"] / args.steps}
 
     cb = None if args.no_cpu_baseline else cpu_baseline(sc, kw)

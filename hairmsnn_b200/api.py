@@ -382,6 +382,9 @@ class Renderer:
     def set_profiling(self, on):
         _check(lib.hm_renderer_set_profiling(self._h, int(on)))
 
+    def set_profiling_stages(self, mask):
+        _check(lib.hm_renderer_set_profiling_stages(self._h, C.c_uint(mask)))
+
     def set_collect_stats(self, on):
         _check(lib.hm_renderer_set_collect_stats(self._h, int(on)))
 

@@ -366,6 +366,9 @@ int hm_renderer_get_stats(hm_renderer* r, hm_stats* out) {
 int hm_renderer_set_collect_stats(hm_renderer* r, int on) {
     return guarded([&] { need(r, "renderer"); r->r->set_collect_stats(on != 0); });
 }
+int hm_renderer_set_profiling_stages(hm_renderer* r, unsigned mask) {
+    return guarded([&] { need(r, "renderer"); r->r->set_profiling_stages(mask); });
+}
 int hm_renderer_set_skip_unused_queries(hm_renderer* r, int on) {
     return guarded([&] { need(r, "renderer"); r->r->set_skip_unused_queries(on != 0); });
 }

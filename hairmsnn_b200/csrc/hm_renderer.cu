@@ -274,7 +274,7 @@ cudaEvent_t Renderer::take_event() {
 template <typename F>
 void Renderer::timed(int stage, cudaStream_t s, F&& f) {
     stats_.launches[stage]++;
-    if (!profiling_) { f(); return; }
+    if (!profiling_ || !((profile_mask_ >> stage) & 1u)) { f(); return; }
     Pending p{stage, take_event(), take_event()};
     HM_CUDA(cudaEventRecord(p.a, s));
     f();
@@ -603,7 +603,7 @@ void Renderer::render_frames(int n) {
     HM_CUDA(cudaSetDevice(device_));
     for (int i = 0; i < n; ++i) {
         Pending whole{8, nullptr, nullptr};
-        if (profiling_) {
+        if (profiling_ && ((profile_mask_ >> 8) & 1u)) {
             // frame span on the order stream: previous frame's completion -> this frame's completion
             whole.a = take_event(); whole.b = take_event();
             HM_CUDA(cudaEventRecord(whole.a, order_stream_));

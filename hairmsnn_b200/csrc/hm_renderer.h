@@ -111,6 +111,8 @@ public:
     // enqueue a device->host copy of an output buffer behind the last enqueued frame
     void readback_async(int which, void* host_dst, size_t bytes);
     void set_profiling(bool on) { profiling_ = on; }
+    // bit s set: stage s (Stats::ms index) gets event pairs while profiling is on; default all
+    void set_profiling_stages(unsigned mask) { profile_mask_ = mask; }
     void set_collect_stats(bool on) { collect_stats_ = on; }
     // off: evaluate the cache for every pixel as the reference does (default: skip 128-pixel tiles without a hair hit)
     void set_skip_unused_queries(bool on) { skip_unused_queries_ = on; }
@@ -173,6 +175,7 @@ private:
     FrameCtx* last_ctx_ = nullptr;
     bool profiling_ = false, collect_stats_ = false, skip_unused_queries_ = true, tail_mega_ = false;
     int frame_offset_ = 0, frame_stride_ = 1;
+    unsigned profile_mask_ = 0xffffffffu;
     Stats stats_;
     struct Pending { int stage; cudaEvent_t a, b; };
     std::vector<Pending> pending_;

@@ -231,6 +231,10 @@ typedef struct {
 int hm_renderer_get_stats(hm_renderer* r, hm_stats* out);
 /* per-stage CUDA-event timing on/off (event pairs around each launch, resolved in hm_renderer_get_stats) */
 int hm_renderer_set_profiling(hm_renderer* r, int on);
+/* which stages get event pairs while profiling is on: bit 0 primary, 1 shade, 2 trace (main piece), 3 trace (tail
+ * piece), 4 finalize, 5 train, 6 infer, 7 composite, 8 whole frame; default all.  A frame has ~320 launches:
+ * timing all of them costs ~3 % of the frame rate. */
+int hm_renderer_set_profiling_stages(hm_renderer* r, unsigned mask);
 /* instrumented traversal + queue-size accounting (polls the queue counters every bounce) */
 int hm_renderer_set_collect_stats(hm_renderer* r, int on);
 /* render_hair_msnn: the RENDER pass reads the network output of hair-hit pixels only (cuda/hair_msnn.cu:325-340).
