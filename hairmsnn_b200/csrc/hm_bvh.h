@@ -75,9 +75,43 @@ HM_D F4 load_f4(const F4* p) {
     return r;
 }
 HM_D int load_i(const int* p) { return __ldg(p); }
+// leaf primitives are touched once per test and there are 2.8 GB of them: HM_LEAF_LOAD picks the cache
+// operator (0 = ld.global.nc like the nodes, 1 = .cs streaming, 2 = .L2::evict_first) so that they displace
+// fewer node lines
+#ifndef HM_LEAF_LOAD
+#define HM_LEAF_LOAD 0
+#endif
+HM_D F4 load_f4_leaf(const F4* p) {
+#if HM_LEAF_LOAD == 1
+    float4 v = __ldcs(reinterpret_cast<const float4*>(p));
+#else
+    float4 v = HM_LDG4(p);
+#endif
+    F4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+    return r;
+}
+// the whole 64-byte primitive; HM_LEAF_LOAD == 2: two 256-bit loads marked evict-first in L2 (sm_100 accepts
+// the L2 eviction hint on the 256-bit forms only)
+HM_D void load_leaf64(const F4* p, F4& a, F4& b, F4& c, F4& e) {
+#if HM_LEAF_LOAD == 2
+    unsigned r[16];
+    asm volatile("ld.global.L2::evict_first.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+    asm volatile("ld.global.L2::evict_first.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "l"(p + 2));
+    a.x = __uint_as_float(r[0]); a.y = __uint_as_float(r[1]); a.z = __uint_as_float(r[2]); a.w = __uint_as_float(r[3]);
+    b.x = __uint_as_float(r[4]); b.y = __uint_as_float(r[5]); b.z = __uint_as_float(r[6]); b.w = __uint_as_float(r[7]);
+    c.x = __uint_as_float(r[8]); c.y = __uint_as_float(r[9]); c.z = __uint_as_float(r[10]); c.w = __uint_as_float(r[11]);
+    e.x = __uint_as_float(r[12]); e.y = __uint_as_float(r[13]); e.z = __uint_as_float(r[14]); e.w = __uint_as_float(r[15]);
+#else
+    a = load_f4_leaf(p + 0); b = load_f4_leaf(p + 1); c = load_f4_leaf(p + 2); e = load_f4_leaf(p + 3);
+#endif
+}
 #else
 inline F4 load_f4(const F4* p) { return *p; }
 inline int load_i(const int* p) { return *p; }
+inline F4 load_f4_leaf(const F4* p) { return *p; }
+inline void load_leaf64(const F4* p, F4& a, F4& b, F4& c, F4& e) { a = p[0]; b = p[1]; c = p[2]; e = p[3]; }
 #endif
 
 HM_HD int f_as_i(float f) {

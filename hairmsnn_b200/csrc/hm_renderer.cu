@@ -135,7 +135,7 @@ Renderer::Renderer(const HostScene& hs, int kind, int beta_cli, int device, int 
     // persistent traversal grids fight over the SMs and the L2, so the default stays 1.
     if (const char* e = getenv("HM_MAIN_STREAMS")) n_work_ = std::max(1, std::min((int)kMaxWorkStreams, atoi(e)));
     for (int i = 0; i < n_work_ && n_work_ > 1; ++i) HM_CUDA(cudaStreamCreateWithPriority(&work_streams_[i], cudaStreamNonBlocking, prio_lo));
-    HM_CUDA(cudaStreamCreateWithPriority(&order_stream_, cudaStreamNonBlocking, prio_hi));
+    HM_CUDA(cudaStreamCreateWithPriority(&order_stream_, cudaStreamNonBlocking, getenv("HM_ORDER_LOW_PRIO") ? prio_lo : prio_hi));
     scene_.reset(new DeviceScene(hs));
     camera_basis(hs, W_, H_, cam_.pos, cam_.d00, cam_.du, cam_.dv);
 
@@ -209,7 +209,7 @@ Renderer::Renderer(const HostScene& hs, int kind, int beta_cli, int device, int 
         c.q.shadow = (float4*)alloc(n * 2 * 32);
         c.q.counts = (int*)alloc(16 * 4);
         c.q.trav = d_trav_;
-        HM_CUDA(cudaStreamCreateWithPriority(&c.tail_stream, cudaStreamNonBlocking, prio_hi));
+        HM_CUDA(cudaStreamCreateWithPriority(&c.tail_stream, cudaStreamNonBlocking, getenv("HM_TAIL_LOW_PRIO") ? prio_lo : prio_hi));
         HM_CUDA(cudaEventCreateWithFlags(&c.ev_main_done, cudaEventDisableTiming));
         HM_CUDA(cudaEventCreateWithFlags(&c.ev_traced, cudaEventDisableTiming));
         HM_CUDA(cudaEventCreateWithFlags(&c.ev_free, cudaEventDisableTiming));

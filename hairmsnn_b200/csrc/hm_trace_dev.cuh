@@ -133,7 +133,8 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
             if (can_solve) {
                 const int ref = s_solve[--nsolve][tx];
                 const F4* p = g.wleaf_data + 4 * (size_t)ref;
-                F4 a = load_f4(p + 0), b = load_f4(p + 1), c = load_f4(p + 2), e = load_f4(p + 3);
+                F4 a, b, c, e;
+                load_leaf64(p, a, b, c, e);
                 FibreCandidate fc;
                 // re-run the rejects: best.t may have shrunk since the span was parked
                 if (f_as_i(a.w) != best.prim &&
@@ -150,7 +151,8 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
             if (can_prim) {
                 const int ref = s_leaf[--nleaf][tx];
                 const F4* p = g.wleaf_data + 4 * (size_t)ref;
-                F4 a = load_f4(p + 0), b = load_f4(p + 1), c = load_f4(p + 2), e = load_f4(p + 3);
+                F4 a, b, c, e;
+                load_leaf64(p, a, b, c, e);
                 if (stats) stats[any ? 1 : 0].prims++;
                 if (e.w < 0.f) {
                     float t, b1, b2;
