@@ -18,6 +18,11 @@ compiled for the host in oracle/_ref) on the box's CPU cores over a bounded band
 same frame.
 """
 import argparse
+import os
+
+# 10+ streams per renderer (main, order, one tail stream per frame in flight): more hardware queues than the
+# default 8 avoid false serialisation between them (+1 % on B200); must be set before CUDA initialises
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import ctypes as C
 import json
 import os
@@ -333,9 +338,9 @@ def main():
     # launches split into the main piece (vertices 0..BETA of every path: ~97% of the secondary rays, on
     # the main stream) and the tail piece (the few training paths' deeper vertices: dozens of tiny
     # latency-bound launches on a side stream).  The roofline line is about the main-piece launches.
-    stage_ms = {"primary": st_all.ms_primary, "shade": st_all.ms_shade, "trace": st.ms_extend, "trace_tail": st_all.ms_shadow,
+    stage_ms = {"primary": st_all.ms_primary, "shade": st_all.ms_shade, "trace": st.ms_extend, "tail_piece": st_all.ms_shadow,
                 "train": st_all.ms_train, "infer": st.ms_infer, "composite": st_all.ms_composite, "finalize": st_all.ms_finalize}
-    stage_launches = dict(zip(("primary", "shade", "trace", "trace_tail", "finalize", "train", "infer", "composite"), st_all.stage_launches))
+    stage_launches = dict(zip(("primary", "shade", "trace", "tail_piece", "finalize", "train", "infer", "composite"), st_all.stage_launches))
     stage_launches["trace"] = st.stage_launches[2]
     dominant = max(("primary", "trace"), key=lambda k: stage_ms[k])
     rays = {"primary": si.rays_primary, "trace": si.rays_extend + si.rays_shadow - si.rays_tail}
@@ -360,8 +365,8 @@ def main():
                 "rays_per_step": rays[dominant] / n_inst, "nodes_per_ray": nodes[dominant] / max(rays[dominant], 1),
                 "prims_per_ray": prims[dominant] / max(rays[dominant], 1), "avg_launch_ms": avg_launch_ms,
                 "launches_per_step": launches_dom,
-                "tail_piece": {"launches_per_step": stage_launches["trace_tail"] / args.steps, "rays_per_step": si.rays_tail / n_inst,
-                               "ms_per_step_sum": stage_ms["trace_tail"] / args.steps},
+                "tail_piece": {"launches_per_step": stage_launches["tail_piece"] / args.steps, "rays_per_step": si.rays_tail / n_inst,
+                               "ms_per_step_sum": stage_ms["tail_piece"] / args.steps},
                 "note": "main-piece k_trace launches (2 per frame at BETA=1), CUDA events around each launch inside the timed region; "
                         "8 frames are in flight, so a launch shares the GPU with other frames' tail-piece and MLP kernels; the kernel is "
                         "bound by dependent-fetch latency and SIMT divergence, not by bandwidth (profiles/)"}

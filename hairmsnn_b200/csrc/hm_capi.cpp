@@ -407,8 +407,8 @@ int hm_write_stats(hm_renderer* r, const char* path) {
         f << "  \"paths\": " << paths << ",\n";
         f << "  \"ms_total\": " << s.ms[8] << ",\n";
         f << "  \"mpaths_per_s\": " << (s.ms[8] > 0 ? paths / (s.ms[8] * 1e-3) / 1e6 : 0.0) << ",\n";
-        f << "  \"ms\": {\"primary\": " << s.ms[0] << ", \"shade\": " << s.ms[1] << ", \"trace_main\": " << s.ms[2]
-          << ", \"trace_tail\": " << s.ms[3] << ", \"finalize\": " << s.ms[4] << ", \"train\": " << s.ms[5]
+        f << "  \"ms\": {\"primary\": " << s.ms[0] << ", \"shade_main\": " << s.ms[1] << ", \"trace_main\": " << s.ms[2]
+          << ", \"tail_piece\": " << s.ms[3] << ", \"finalize\": " << s.ms[4] << ", \"train\": " << s.ms[5]
           << ", \"infer\": " << s.ms[6] << ", \"composite\": " << s.ms[7] << "},\n";
         f << "  \"rays\": {\"primary\": " << s.rays_primary << ", \"extend\": " << s.rays_extend << ", \"shadow\": "
           << s.rays_shadow << "},\n";

@@ -168,6 +168,7 @@ Renderer::Renderer(const HostScene& hs, int kind, int beta_cli, int device, int 
         nn_frame_rows_ = (int)n + nrc_train_pixels_ - nrc_train_pixels_ % 128 + 128;
     }
     if (const char* e = getenv("HM_TAIL_MEGA")) tail_mega_ = atoi(e) != 0;
+    if (const char* e = getenv("HM_TAIL_BOUND")) tail_bound_items_ = atoi(e);
     if (const char* e = getenv("HM_FRAMES_IN_FLIGHT")) frames_in_flight_ = std::max(1, std::min((int)kFramesInFlight, atoi(e)));
     for (int ci = 0; ci < frames_in_flight_; ++ci) {
         FrameCtx& c = ctx_[ci];
@@ -417,7 +418,7 @@ void Renderer::trace_frame(FrameCtx& c) {
             s = c.tail_stream;
             HM_CUDA(cudaStreamWaitEvent(s, c.ev_main_done, 0));
             P.tail = 1;
-            if (kind_ == HM_KIND_MSNN) tail_bound = records_;
+            if (kind_ == HM_KIND_MSNN) tail_bound = tail_bound_items_ > 0 ? tail_bound_items_ : records_;
             if (kind_ == HM_KIND_MSNN && tail_mega_) {
                 // HM_TAIL_MEGA=1: the whole tail piece in one launch (k_tail_mega) instead of a launch pair per vertex.
                 // Measured equal on B200 (profiles/r1k_sweep_tail_mega.txt: 202-205 Mpaths/s either way, 245 instead of
@@ -426,7 +427,7 @@ void Renderer::trace_frame(FrameCtx& c) {
                 break;
             }
         }
-        timed(1, s, [&] { launch_shade(P, src, s, tail_bound); });
+        timed(P.tail ? 3 : 1, s, [&] { launch_shade(P, src, s, tail_bound); });   // stage 1: main piece, stage 3: tail piece
         const int dst = src ^ 1;
         HM_CUDA(cudaMemsetAsync(c.q.counts + dst, 0, 4, s));
         timed(P.tail ? 3 : 2, s, [&] { launch_trace(P, dst, s, tail_bound); });   // stage 2: main piece, stage 3: tail piece

@@ -16,7 +16,7 @@
 namespace hm {
 
 struct Stats {
-    double ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // primary shade trace(main piece) trace(tail piece) finalize train infer composite total
+    double ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // primary shade(main piece) trace(main piece) shade+trace(tail piece) finalize train infer composite total
     uint64_t launches[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t rays_primary = 0, rays_extend = 0, rays_shadow = 0, shade_items = 0;
     uint64_t trav[6] = {0, 0, 0, 0, 0, 0};        // extend nodes/prims, shadow nodes/prims, primary nodes/prims
@@ -176,6 +176,7 @@ private:
     bool profiling_ = false, collect_stats_ = false, skip_unused_queries_ = true, tail_mega_ = false;
     int frame_offset_ = 0, frame_stride_ = 1;
     unsigned profile_mask_ = 0xffffffffu;
+    int tail_bound_items_ = 0;      // HM_TAIL_BOUND: grid bound (in queue items) of tail-piece launches; 0 = training records
     Stats stats_;
     struct Pending { int stage; cudaEvent_t a, b; };
     std::vector<Pending> pending_;

@@ -213,8 +213,9 @@ int hm_save_exr(hm_renderer* r, int which, const char* path);
 /* integrator.stats_output — parsed by the reference (scene.cpp:295) but never written */
 int hm_write_stats(hm_renderer* r, const char* path);
 
-/* ms_extend / ms_shadow: k_trace launches (each traces a vertex's occlusion probes AND continuation
- * rays) of a frame's main piece / of its tail piece (vertices past beta+1, long paths only). */
+/* ms_shade / ms_extend: k_shade / k_trace launches of a frame's main piece (a k_trace launch traces a vertex's
+ * occlusion probes AND continuation rays); ms_shadow: all launches of its tail piece (vertices past beta+1,
+ * long paths only). */
 typedef struct {
     double ms_primary, ms_shade, ms_extend, ms_shadow, ms_finalize, ms_train, ms_infer, ms_composite, ms_total;
     uint64_t rays_primary, rays_extend, rays_shadow, shade_items;
@@ -231,7 +232,7 @@ typedef struct {
 int hm_renderer_get_stats(hm_renderer* r, hm_stats* out);
 /* per-stage CUDA-event timing on/off (event pairs around each launch, resolved in hm_renderer_get_stats) */
 int hm_renderer_set_profiling(hm_renderer* r, int on);
-/* which stages get event pairs while profiling is on: bit 0 primary, 1 shade, 2 trace (main piece), 3 trace (tail
+/* which stages get event pairs while profiling is on: bit 0 primary, 1 shade (main piece), 2 trace (main piece), 3 shade + trace (tail
  * piece), 4 finalize, 5 train, 6 infer, 7 composite, 8 whole frame; default all.  A frame has ~320 launches:
  * timing all of them costs ~3 % of the frame rate. */
 int hm_renderer_set_profiling_stages(hm_renderer* r, unsigned mask);
