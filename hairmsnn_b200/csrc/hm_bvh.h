@@ -307,7 +307,10 @@ HM_HD WideRay make_wide_ray(V3 o, V3 d) {
 }
 
 // Slab test of the 8 child boxes of one wide node; returns the slots hit (bit i = slot i).
-HM_HD unsigned wide_node_hits(F4 w0, F4 w2, F4 w3, F4 w4, const WideRay& r, float tmin, float tmax) {
+// near_key (optional): (bits of the smallest entry distance among the hit children, low 3 bits replaced by
+// that child's slot), 0xffffffff when nothing is hit — entry distances are >= tmin >= 0, so their bit patterns
+// order like unsigned integers.
+HM_HD unsigned wide_node_hits(F4 w0, F4 w2, F4 w3, F4 w4, const WideRay& r, float tmin, float tmax, unsigned* near_key = nullptr) {
     const unsigned em = f_as_u(w0.w);
     // t(q) = (q + bias) * (cell * idir) + (origin * idir - o * idir - bias * cell * idir)
     const float ax = u_as_f((em & 0xffu) << 23) * r.idir.x, bx = fmaf(-kQBias, ax, fmaf(w0.x, r.idir.x, -r.ood.x));
@@ -319,6 +322,7 @@ HM_HD unsigned wide_node_hits(F4 w0, F4 w2, F4 w3, F4 w4, const WideRay& r, floa
     const unsigned loz[2] = {f_as_u(w3.x), f_as_u(w3.y)}, hix[2] = {f_as_u(w3.z), f_as_u(w3.w)};
     const unsigned hiy[2] = {f_as_u(w4.x), f_as_u(w4.y)}, hiz[2] = {f_as_u(w4.z), f_as_u(w4.w)};
     unsigned hits = 0;
+    unsigned nearest = 0xffffffffu;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -335,9 +339,14 @@ HM_HD unsigned wide_node_hits(F4 w0, F4 w2, F4 w3, F4 w4, const WideRay& r, floa
             const float tnz = fmaf(byte_biased(nz, k), az, bz), tfz = fmaf(byte_biased(fz, k), az, bz);
             const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
             const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-            if (tn <= tf) hits |= 1u << (4 * h + k);
+            if (tn <= tf) {
+                hits |= 1u << (4 * h + k);
+                const unsigned key = (f_as_u(tn) & ~7u) | (unsigned)(4 * h + k);
+                nearest = key < nearest ? key : nearest;
+            }
         }
     }
+    if (near_key) *near_key = nearest;
     return hits;
 }
 

@@ -84,13 +84,14 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
     int g_base = 0;
     unsigned g_bits = 0;
     int sp = 0, nleaf = 0, nsolve = 0;
+    int next_node = -1;      // the nearest hit inner child of the node just tested: visited before the rest of its group
     int2 stack[kWideStack];
     bool exhausted = false;
     bool any = false;
 
     while (true) {
         // ---- commit finished rays, refill idle lanes ----
-        const bool finished = id >= 0 && (g_bits >> 8) == 0 && sp == 0 && nleaf == 0 && nsolve == 0;
+        const bool finished = id >= 0 && next_node < 0 && (g_bits >> 8) == 0 && sp == 0 && nleaf == 0 && nsolve == 0;
         if (__any_sync(FULL, finished)) {
             ops.commit(id, best, finished);
             if (finished) id = -1;
@@ -113,14 +114,14 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
                     // pseudo-group whose slot 0 is the root
                     g_base = 0;
                     g_bits = g.num_wnodes > 0 ? (1u | (1u << (8 + wr.octinv))) : 0u;
-                    sp = 0; nleaf = 0; nsolve = 0;
+                    sp = 0; nleaf = 0; nsolve = 0; next_node = -1;
                 }
             }
         }
         if (__all_sync(FULL, id < 0)) break;
 
         // ---- vote on the step kind ----
-        const bool can_node = id >= 0 && ((g_bits >> 8) != 0 || sp > 0) && nleaf <= kLeafCap - 8;   // a node parks at most 8 references
+        const bool can_node = id >= 0 && (next_node >= 0 || (g_bits >> 8) != 0 || sp > 0) && nleaf <= kLeafCap - 8;   // a node parks at most 8 references
         const bool can_prim = nleaf > 0 && nsolve < kSolveCap;
         const bool can_solve = nsolve > 0;
         const int n_node = __popc(__ballot_sync(FULL, can_node));
@@ -142,7 +143,7 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
                     SegHit sh;
                     if (fibre_solve(fc, tmin, best.t, sh)) {
                         best.t = sh.t; best.u = sh.u; best.v = 0.f; best.prim = f_as_i(a.w);
-                        if (any) { g_bits = 0; sp = 0; nleaf = 0; nsolve = 0; }
+                        if (any) { g_bits = 0; sp = 0; nleaf = 0; nsolve = 0; next_node = -1; }
                     }
                 }
             }
@@ -158,7 +159,7 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
                     float t, b1, b2;
                     if (intersect_triangle(o, d, tmin, best.t, V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), V3(c.x, c.y, c.z), t, b1, b2)) {
                         best.t = t; best.u = b1; best.v = b2; best.prim = f_as_i(e.x);
-                        if (any) { g_bits = 0; sp = 0; nleaf = 0; nsolve = 0; }
+                        if (any) { g_bits = 0; sp = 0; nleaf = 0; nsolve = 0; next_node = -1; }
                     }
                 } else if (f_as_i(a.w) != best.prim) {
                     FibreCandidate fc;
@@ -171,22 +172,33 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
             // commit/refill/vote preamble costs about a quarter of a node test.
 #pragma unroll 1
             for (int rep = 0; rep < HM_TRACE_NODE_REPEAT; ++rep) {
-                const bool go = id >= 0 && ((g_bits >> 8) != 0 || sp > 0) && nleaf <= kLeafCap - 8;
+                const bool go = id >= 0 && (next_node >= 0 || (g_bits >> 8) != 0 || sp > 0) && nleaf <= kLeafCap - 8;
                 if (rep > 0 && __popc(__ballot_sync(FULL, go)) < HM_TRACE_NODE_LANES) break;
                 if (go) {
-                    if ((g_bits >> 8) == 0) { const int2 e = stack[--sp]; g_base = e.x; g_bits = (unsigned)e.y; }
-                    const int bit = top_bit(g_bits >> 8);
-                    g_bits &= ~(1u << (8 + bit));
-                    const int slot = bit ^ wr.octinv;
-                    const int ni = g_base + __popc(g_bits & 0xffu & ((1u << slot) - 1u));
+                    int ni = next_node;
+                    next_node = -1;
+                    if (ni < 0) {
+                        if ((g_bits >> 8) == 0) { const int2 e = stack[--sp]; g_base = e.x; g_bits = (unsigned)e.y; }
+                        const int bit = top_bit(g_bits >> 8);
+                        g_bits &= ~(1u << (8 + bit));
+                        const int slot = bit ^ wr.octinv;
+                        ni = g_base + __popc(g_bits & 0xffu & ((1u << slot) - 1u));
+                    }
                     const F4* nd = g.wnodes + 5 * (size_t)ni;
                     F4 w0 = load_f4(nd + 0), w1 = load_f4(nd + 1), w2 = load_f4(nd + 2), w3 = load_f4(nd + 3), w4 = load_f4(nd + 4);
                     if (stats) stats[any ? 1 : 0].nodes++;
                     const unsigned imask = f_as_u(w0.w) >> 24, lmask = f_as_u(w1.z) & 0xffu;
-                    const unsigned h = wide_node_hits(w0, w2, w3, w4, wr, tmin, best.t);
-                    // leaves: park far-to-near, so the nearest is popped first
-                    unsigned pl = xor_permute8(h & lmask, wr.octinv);
+                    unsigned near_key;
+                    const unsigned h = wide_node_hits(w0, w2, w3, w4, wr, tmin, best.t, &near_key);
+                    // The child with the smallest entry distance goes first (an inner one is the next node, a leaf
+                    // is parked last = popped first); the others keep the octant order.  On the host build of the
+                    // same tree this order alone cuts closest-hit node visits by 15 % and primitive tests by 16 %
+                    // (primary rays: 24 % / 36 %; scripts/bvh_stats.py with HM_STATS_SORTED=1).
+                    const int near_slot = h ? (int)(near_key & 7u) : 8;
+                    const unsigned near_bit = (1u << near_slot) & 0xffu;
                     const int leaf_base = f_as_i(w1.y);
+                    // leaves: park far-to-near, so the nearest is popped first
+                    unsigned pl = xor_permute8(h & lmask & ~near_bit, wr.octinv);
                     while (pl) {
                         const int b = __ffs((int)pl) - 1;
                         pl &= pl - 1;
@@ -195,7 +207,9 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
                         s_leaf[nleaf++][tx] = ref;
                         prefetch_line(g.wleaf_data + 4 * (size_t)ref);
                     }
-                    const unsigned hi = h & imask;
+                    if (near_bit & lmask) s_leaf[nleaf++][tx] = leaf_base + __popc(lmask & (near_bit - 1u));
+                    if (near_bit & imask) next_node = f_as_i(w1.x) + __popc(imask & (near_bit - 1u));
+                    const unsigned hi = h & imask & ~near_bit;
                     if (hi) {
                         if (g_bits >> 8) stack[sp++] = make_int2(g_base, (int)g_bits);
                         g_base = f_as_i(w1.x);

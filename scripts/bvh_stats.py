@@ -101,6 +101,14 @@ def main():
     z = rng.uniform(-1, 1, len(ph)); phi = rng.uniform(0, 2 * np.pi, len(ph)); r = np.sqrt(1 - z * z)
     d2 = np.stack([r * np.cos(phi), r * np.sin(phi), z], axis=1).astype(np.float32)
     o2 = (ph + 0.05 * d2).astype(np.float32)
+    if os.environ.get("HM_STATS_SORTED"):
+        for mode, what in ((0, "octant order, no culling"), (2, "octant order + pop-time culling"), (8, "octant order + group-min culling"), (4, "nearest first + octant, no culling"), (6, "nearest first + octant + culling"), (12, "nearest first + octant + group cull"), (3, "distance order + pop-time culling")):
+          for label, oo, dd in (("primary", o, d), ("closest", o2, d2)):
+            nn = len(oo); oo = np.ascontiguousarray(oo, np.float32); dd = np.ascontiguousarray(dd, np.float32)
+            pp = np.zeros(nn, np.int32); nodes = np.zeros(nn, np.int32); prims = np.zeros(nn, np.int32)
+            probe.probe_trace_wide_sorted(h, nn, oo.ctypes.data_as(fp), dd.ctypes.data_as(fp), C.c_float(0), C.c_float(1e30),
+                                          pp.ctypes.data_as(ip), nodes.ctypes.data_as(ip), prims.ctypes.data_as(ip), mode)
+            print(f"{label:8s} {what:36s}: nodes/ray {nodes.mean():7.1f} prims/ray {prims.mean():6.1f}")
     for any_hit in (False, True):
         t0 = time.time()
         t, p, nodes, prims = trace(probe, h, o2, d2, any_hit)

@@ -1,2 +1,3 @@
 source scripts/sweep.sh
-run stage_split HM_X=1
+run nearest_first HM_X=1
+run nearest_first_again HM_X=1

@@ -1,6 +1,7 @@
 // cpu_probe.cpp — test-only host build of the product's shared host/device headers
 // (hm_rng.h, hm_bsdf.h, hm_curve.h, hm_bvh.h).  Lets the CPU test-suite check the
 // arithmetic the CUDA kernels run against the oracle without a GPU.
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -130,6 +131,76 @@ void probe_trace_wide(void* p, int n, const float* org, const float* dir, float 
         Hit h = any ? trace_wide<true>(g, o, d, tmin, tmax, &st) : trace_wide<false>(g, o, d, tmin, tmax, &st);
         out_t[i] = h.t; out_prim[i] = h.prim; out_u[i] = h.u; out_v[i] = h.v;
         if (out_nodes) { out_nodes[i] = st.nodes; out_prims[i] = st.prims; }
+    }
+}
+// experiment: wide-tree traversal visiting hit children in true entry-distance order (upper bound on what
+// a better child order could save over the octant order); statistics only
+struct DistEntry { float t; int code; float tg; };   // code >= 0 inner node, < 0 leaf ref (~ref)
+void probe_trace_wide_sorted(void* p, int n, const float* org, const float* dir, float tmin, float tmax,
+                             int* out_prim, int* out_nodes, int* out_prims, int mode) {
+    // mode bit 0: sort children by entry distance (else octant order); bit 1: cull stale entries when popped;
+    // bit 2: octant order but the nearest hit child first; bit 3: cull by the node's minimum entry distance only
+    ProbeScene* s = (ProbeScene*)p;
+    GeomView g = make_view(s->geo, s->bvh);
+    for (int i = 0; i < n; ++i) {
+        V3 o(org[3 * i], org[3 * i + 1], org[3 * i + 2]), d(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+        WideRay wr = make_wide_ray(o, d);
+        RayFrame rf = make_ray_frame(o, d);
+        Hit best; best.t = tmax; best.prim = -1; best.u = 0; best.v = 0;
+        std::vector<DistEntry> stack;
+        stack.push_back({0.f, 0, 0.f});
+        int nodes = 0, prims = 0;
+        while (!stack.empty()) {
+            DistEntry e = stack.back(); stack.pop_back();
+            if ((mode & 2) && e.t > best.t) continue;
+            if ((mode & 8) && e.tg > best.t) continue;
+            if (e.code < 0) { prims++; test_wide_leaf(g, ~e.code, o, d, rf, tmin, best); continue; }
+            const F4* nd = g.wnodes + 5 * (size_t)e.code;
+            nodes++;
+            unsigned imask = f_as_u(nd[0].w) >> 24, lmask = f_as_u(nd[1].z) & 0xff;
+            unsigned h = wide_node_hits(nd[0], nd[2], nd[3], nd[4], wr, tmin, best.t) & (imask | lmask);
+            // entry distance per hit child (recomputed the slow way)
+            const unsigned em = f_as_u(nd[0].w);
+            float cell[3] = {u_as_f((em & 0xff) << 23), u_as_f(((em >> 8) & 0xff) << 23), u_as_f(((em >> 16) & 0xff) << 23)};
+            float org3[3] = {nd[0].x, nd[0].y, nd[0].z};
+            float oo[3] = {o.x, o.y, o.z}, id[3] = {wr.idir.x, wr.idir.y, wr.idir.z};
+            const unsigned words[12] = {f_as_u(nd[2].x), f_as_u(nd[2].y), f_as_u(nd[2].z), f_as_u(nd[2].w), f_as_u(nd[3].x), f_as_u(nd[3].y),
+                                        f_as_u(nd[3].z), f_as_u(nd[3].w), f_as_u(nd[4].x), f_as_u(nd[4].y), f_as_u(nd[4].z), f_as_u(nd[4].w)};
+            DistEntry found[8]; int nf = 0;
+            for (int sl = 0; sl < 8; ++sl) {
+                if (!((h >> sl) & 1)) continue;
+                float tn = tmin;
+                for (int a = 0; a < 3; ++a) {
+                    unsigned qlo = (words[2 * a + (sl >> 2)] >> (8 * (sl & 3))) & 0xff, qhi = (words[6 + 2 * a + (sl >> 2)] >> (8 * (sl & 3))) & 0xff;
+                    float lo = org3[a] + qlo * cell[a], hi = org3[a] + qhi * cell[a];
+                    float t0 = (lo - oo[a]) * id[a], t1 = (hi - oo[a]) * id[a];
+                    tn = fmaxf(tn, fminf(t0, t1));
+                }
+                unsigned below = (1u << sl) - 1u;
+                int code = ((imask >> sl) & 1) ? f_as_i(nd[1].x) + popc_u(imask & below) : ~(f_as_i(nd[1].y) + popc_u(lmask & below));
+                found[nf++] = {tn, code, 0.f};
+            }
+            if (mode & 1) std::sort(found, found + nf, [](const DistEntry& a, const DistEntry& b) { return a.t > b.t; });   // far first: near popped first
+            else {
+                // octant order: priority of slot sl = sl ^ octinv, highest first -> push lowest priority first
+                DistEntry tmp[8]; int order[8]; int k = 0;
+                int slots[8]; { int q = 0; for (int sl = 0; sl < 8; ++sl) if ((h >> sl) & 1) slots[q++] = sl; }
+                for (int pr = 0; pr < 8; ++pr) for (int q = 0; q < nf; ++q) if ((slots[q] ^ wr.octinv) == pr) order[k++] = q;
+                for (int q = 0; q < nf; ++q) tmp[q] = found[order[q]];
+                for (int q = 0; q < nf; ++q) found[q] = tmp[q];
+            }
+            if ((mode & 4) && nf > 1) {   // nearest to the end of the list (= popped first), the rest keeps its order
+                int best_k = 0;
+                for (int k = 1; k < nf; ++k) if (found[k].t < found[best_k].t) best_k = k;
+                DistEntry near = found[best_k];
+                for (int k = best_k; k + 1 < nf; ++k) found[k] = found[k + 1];
+                found[nf - 1] = near;
+            }
+            float tg = 3e38f;
+            for (int k = 0; k < nf; ++k) tg = fminf(tg, found[k].t);
+            for (int k = 0; k < nf; ++k) { found[k].tg = tg; stack.push_back(found[k]); }
+        }
+        out_prim[i] = best.prim; out_nodes[i] = nodes; out_prims[i] = prims;
     }
 }
 // exhaustive reference: test every primitive, no BVH
