@@ -102,7 +102,7 @@ def main():
     d2 = np.stack([r * np.cos(phi), r * np.sin(phi), z], axis=1).astype(np.float32)
     o2 = (ph + 0.05 * d2).astype(np.float32)
     if os.environ.get("HM_STATS_SORTED"):
-        for mode, what in ((0, "octant order, no culling"), (2, "octant order + pop-time culling"), (8, "octant order + group-min culling"), (4, "nearest first + octant, no culling"), (6, "nearest first + octant + culling"), (12, "nearest first + octant + group cull"), (3, "distance order + pop-time culling")):
+        for mode, what in ((0, "octant order, no culling"), (2, "octant order + pop-time culling"), (8, "octant order + group-min culling"), (4, "nearest first + octant, no culling"), (6, "nearest first + octant + culling"), (28, "nearest first + cull rest-of-group min"), (3, "distance order + pop-time culling")):
           for label, oo, dd in (("primary", o, d), ("closest", o2, d2)):
             nn = len(oo); oo = np.ascontiguousarray(oo, np.float32); dd = np.ascontiguousarray(dd, np.float32)
             pp = np.zeros(nn, np.int32); nodes = np.zeros(nn, np.int32); prims = np.zeros(nn, np.int32)

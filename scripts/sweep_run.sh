@@ -1,3 +1,3 @@
 source scripts/sweep.sh
-run nearest_first HM_X=1
-run nearest_first_again HM_X=1
+run group_cull HM_X=1
+run group_cull_again HM_X=1

@@ -197,8 +197,9 @@ void probe_trace_wide_sorted(void* p, int n, const float* org, const float* dir,
                 found[nf - 1] = near;
             }
             float tg = 3e38f;
-            for (int k = 0; k < nf; ++k) tg = fminf(tg, found[k].t);
-            for (int k = 0; k < nf; ++k) { found[k].tg = tg; stack.push_back(found[k]); }
+            // bit 4: the group minimum excludes the nearest child (which is visited right away)
+            for (int k = 0; k < nf - ((mode & 16) ? 1 : 0); ++k) tg = fminf(tg, found[k].t);
+            for (int k = 0; k < nf; ++k) { found[k].tg = ((mode & 16) && k == nf - 1) ? found[k].t : tg; stack.push_back(found[k]); }
         }
         out_prim[i] = best.prim; out_nodes[i] = nodes; out_prims[i] = prims;
     }
