@@ -46,6 +46,12 @@ constexpr int kRefillLanes = HM_TRACE_REFILL;    // refill when this many lanes 
 #define HM_TRACE_NODE_LANES 10     // below this many node-ready lanes, parked work goes first
 #endif
 
+#ifndef HM_TRACE_ANY_WAIT
+#define HM_TRACE_ANY_WAIT 0
+#endif
+#ifndef HM_TRACE_CLOSEST_WAIT
+#define HM_TRACE_CLOSEST_WAIT 0
+#endif
 #ifndef HM_TRACE_NODE_REPEAT
 #define HM_TRACE_NODE_REPEAT 2     // node steps per vote
 #endif
@@ -121,7 +127,12 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
         if (__all_sync(FULL, id < 0)) break;
 
         // ---- vote on the step kind ----
-        const bool can_node = id >= 0 && (next_node >= 0 || (g_bits >> 8) != 0 || sp > 0) && nleaf <= kLeafCap - 8;   // a node parks at most 8 references
+        // An occlusion ray ends at its first accepted primitive (72 % of them do on the bench scene): once it holds
+        // a parked reference it stops descending and waits for the prim step (HM_TRACE_ANY_WAIT parked references;
+        // 0 = never wait).  Closest-hit rays keep descending (HM_TRACE_CLOSEST_WAIT).
+        const int wait_at = any ? HM_TRACE_ANY_WAIT : HM_TRACE_CLOSEST_WAIT;
+        const bool waits = wait_at > 0 && nleaf >= wait_at;
+        const bool can_node = id >= 0 && !waits && (next_node >= 0 || (g_bits >> 8) != 0 || sp > 0) && nleaf <= kLeafCap - 8;   // a node parks at most 8 references
         const bool can_prim = nleaf > 0 && nsolve < kSolveCap;
         const bool can_solve = nsolve > 0;
         const int n_node = __popc(__ballot_sync(FULL, can_node));
@@ -172,7 +183,8 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
             // commit/refill/vote preamble costs about a quarter of a node test.
 #pragma unroll 1
             for (int rep = 0; rep < HM_TRACE_NODE_REPEAT; ++rep) {
-                const bool go = id >= 0 && (next_node >= 0 || (g_bits >> 8) != 0 || sp > 0) && nleaf <= kLeafCap - 8;
+                const int wait_at2 = any ? HM_TRACE_ANY_WAIT : HM_TRACE_CLOSEST_WAIT;
+                const bool go = id >= 0 && !(wait_at2 > 0 && nleaf >= wait_at2) && (next_node >= 0 || (g_bits >> 8) != 0 || sp > 0) && nleaf <= kLeafCap - 8;
                 if (rep > 0 && __popc(__ballot_sync(FULL, go)) < HM_TRACE_NODE_LANES) break;
                 if (go) {
                     int ni = next_node;
