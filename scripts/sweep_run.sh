@@ -1,7 +1,4 @@
 source scripts/sweep.sh
-run base HM_X=1
-run aw1 HM_LIB=$V/libhairmsnn_aw1.so
-run aw2 HM_LIB=$V/libhairmsnn_aw2.so
-run aw1cw2 HM_LIB=$V/libhairmsnn_aw1cw2.so
-run aw1cw1 HM_LIB=$V/libhairmsnn_aw1cw1.so
-run aw1p12 HM_LIB=$V/libhairmsnn_aw1p12.so
+run greedy_collapse HM_X=1
+run dp_collapse HM_BVH_COLLAPSE=dp
+run dp_collapse_again HM_BVH_COLLAPSE=dp
