@@ -1,4 +1,5 @@
 source scripts/sweep.sh
-run greedy_collapse HM_X=1
-run dp_collapse HM_BVH_COLLAPSE=dp
-run dp_collapse_again HM_BVH_COLLAPSE=dp
+run s16_5 HM_X=1
+run s16_4 HM_BVH_SPAN=4
+run s16_7 HM_BVH_SPAN=7
+run s8_8 HM_BVH_SPLIT=8 HM_BVH_SPAN=8
