@@ -83,6 +83,27 @@ def _worker(rank, port, tmp):
         both = [torch.zeros(2, dtype=torch.float64) for _ in range(WORLD)]
         dist.all_gather(both, digest)
         assert torch.equal(both[0], both[1])
+
+        # ---- acceleration structure: rank 0 builds and publishes, the others restore (bench.py's start-up) ----
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from common import small_scene_kwargs
+        kw = small_scene_kwargs(strands=150, segs=10)
+        cache = os.path.join(tmp, "bvh_cache")
+        os.makedirs(cache, exist_ok=True)
+        if rank == 0:
+            sc = api.Scene.from_arrays(**kw)
+            sc.save_bvh_cache(cache)
+        dist.barrier()
+        if rank != 0:
+            os.environ["HM_BVH_CACHE"] = cache
+            sc = api.Scene.from_arrays(**kw)
+            del os.environ["HM_BVH_CACHE"]
+        i = sc.info()
+        mine = torch.tensor([i.num_wide_nodes, i.num_wide_leaf_refs, i.wide_depth, i.num_bvh_nodes], dtype=torch.int64)
+        allinfo = [torch.zeros(4, dtype=torch.int64) for _ in range(WORLD)]
+        dist.all_gather(allinfo, mine)
+        assert torch.equal(allinfo[0][:3], allinfo[1][:3]) and int(allinfo[0][0]) > 0
+        assert int(allinfo[0][3]) > 0 and int(allinfo[1][3]) == 0      # only the builder holds the binary tree
         open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
