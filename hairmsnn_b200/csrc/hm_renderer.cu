@@ -259,7 +259,7 @@ void Renderer::sync() {
     HM_CUDA(cudaSetDevice(device_));
     HM_CUDA(cudaStreamSynchronize(main_stream_));
     for (int i = 0; i < n_work_; ++i) if (work_streams_[i]) HM_CUDA(cudaStreamSynchronize(work_streams_[i]));
-    for (FrameCtx& c : ctx_) HM_CUDA(cudaStreamSynchronize(c.tail_stream));
+    for (FrameCtx& c : ctx_) if (c.tail_stream) HM_CUDA(cudaStreamSynchronize(c.tail_stream));
     HM_CUDA(cudaStreamSynchronize(order_stream_));
 }
 
