@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <limits>
+#include <sstream>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -394,25 +396,63 @@ int hm_renderer_set_profiling(hm_renderer* r, int on) {
     return guarded([&] { need(r, "renderer"); r->r->set_profiling(on != 0); });
 }
 
+// integrator.stats_output: the reference parses the key (scene.cpp:295) and never writes the file; this is
+// the schema the headless executables write (SURVEY §5 "Metrics"): samples, seconds, Mpaths/s, per-stage
+// milliseconds (event pairs, when profiling is on), ray counts and traversal work per ray (when the
+// instrumented traversal is on), network queries per second, training loss.
+static std::string stats_json(const Stats& s, int kind, int width, int rows, int nn_rows_per_frame) {
+    std::ostringstream f;
+    auto num = [](double v) -> std::string {
+        if (!std::isfinite(v)) return "null";
+        std::ostringstream o; o.precision(9); o << v; return o.str();
+    };
+    const double paths = (double)s.frames * rows * width;
+    const char* kinds[3] = {"render_path_tracing", "render_nrc", "render_hair_msnn"};
+    f << "{\n  \"renderer\": \"" << kinds[kind] << "\",\n";
+    f << "  \"width\": " << width << ", \"rows\": " << rows << ", \"spp\": " << s.frames << ",\n";
+    f << "  \"paths\": " << num(paths) << ",\n";
+    f << "  \"seconds\": " << num(s.ms[8] * 1e-3) << ",\n";
+    f << "  \"mpaths_per_s\": " << num(s.ms[8] > 0 ? paths / (s.ms[8] * 1e-3) / 1e6 : 0.0) << ",\n";
+    f << "  \"ms\": {\"primary\": " << num(s.ms[0]) << ", \"shade_main\": " << num(s.ms[1]) << ", \"trace_main\": " << num(s.ms[2])
+      << ", \"tail_piece\": " << num(s.ms[3]) << ", \"finalize\": " << num(s.ms[4]) << ", \"train\": " << num(s.ms[5])
+      << ", \"infer\": " << num(s.ms[6]) << ", \"composite\": " << num(s.ms[7]) << "},\n";
+    uint64_t launches = 0;
+    for (int i = 0; i < 8; ++i) launches += s.launches[i];
+    f << "  \"kernel_launches\": " << launches << ",\n";
+    f << "  \"rays\": {\"primary\": " << s.rays_primary << ", \"extend\": " << s.rays_extend << ", \"shadow\": "
+      << s.rays_shadow << "},\n";
+    auto per = [&](uint64_t a, uint64_t b) { return b ? num((double)a / (double)b) : std::string("null"); };
+    f << "  \"traversal_per_ray\": {\"primary\": {\"nodes\": " << per(s.trav[4], s.rays_primary) << ", \"primitives\": " << per(s.trav[5], s.rays_primary)
+      << "}, \"extend\": {\"nodes\": " << per(s.trav[0], s.rays_extend) << ", \"primitives\": " << per(s.trav[1], s.rays_extend)
+      << "}, \"shadow\": {\"nodes\": " << per(s.trav[2], s.rays_shadow) << ", \"primitives\": " << per(s.trav[3], s.rays_shadow) << "}},\n";
+    f << "  \"mlp_rows_per_frame\": " << nn_rows_per_frame << ",\n";
+    f << "  \"mlp_queries_per_s\": " << (s.ms[6] > 0 ? num((double)nn_rows_per_frame * s.frames / (s.ms[6] * 1e-3)) : std::string("null")) << ",\n";
+    f << "  \"training_loss\": " << num(s.last_loss) << "\n}\n";
+    return f.str();
+}
+
 int hm_write_stats(hm_renderer* r, const char* path) {
     return guarded([&] {
         need(r, "renderer"); need(path, "path");
         Stats s = r->r->stats();
         std::ofstream f(path);
         if (!f) throw hm::IoError(std::string("cannot write ") + path);
-        const double paths = (double)s.frames * (r->r->row1() - r->r->row0()) * r->r->width();
-        const char* kinds[3] = {"render_path_tracing", "render_nrc", "render_hair_msnn"};
-        f << "{\n  \"renderer\": \"" << kinds[r->r->kind()] << "\",\n";
-        f << "  \"width\": " << r->r->width() << ", \"height\": " << r->r->height() << ", \"spp\": " << s.frames << ",\n";
-        f << "  \"paths\": " << paths << ",\n";
-        f << "  \"ms_total\": " << s.ms[8] << ",\n";
-        f << "  \"mpaths_per_s\": " << (s.ms[8] > 0 ? paths / (s.ms[8] * 1e-3) / 1e6 : 0.0) << ",\n";
-        f << "  \"ms\": {\"primary\": " << s.ms[0] << ", \"shade_main\": " << s.ms[1] << ", \"trace_main\": " << s.ms[2]
-          << ", \"tail_piece\": " << s.ms[3] << ", \"finalize\": " << s.ms[4] << ", \"train\": " << s.ms[5]
-          << ", \"infer\": " << s.ms[6] << ", \"composite\": " << s.ms[7] << "},\n";
-        f << "  \"rays\": {\"primary\": " << s.rays_primary << ", \"extend\": " << s.rays_extend << ", \"shadow\": "
-          << s.rays_shadow << "},\n";
-        f << "  \"training_loss\": " << s.last_loss << "\n}\n";
+        f << stats_json(s, r->r->kind(), r->r->width(), r->r->row1() - r->r->row0(), r->r->mlp() ? r->r->nn_frame_rows() : 0);
+        if (!f) throw hm::IoError(std::string("cannot write ") + path);
+    });
+}
+// test hook (not part of the ABI header): the stats schema on made-up counters, incl. a non-finite loss
+int hm_test_stats_json(char* buf, size_t capacity) {
+    return guarded([&] {
+        need(buf, "buf");
+        Stats s;
+        for (int i = 0; i < 9; ++i) { s.ms[i] = 1.5 * (i + 1); s.launches[i] = 10 + i; }
+        s.frames = 4; s.rays_primary = 1000; s.rays_extend = 400; s.rays_shadow = 0;
+        s.trav[0] = 12000; s.trav[1] = 1600; s.trav[4] = 15000; s.trav[5] = 1900;
+        s.last_loss = std::numeric_limits<float>::quiet_NaN();
+        const std::string j = stats_json(s, HM_RENDER_HAIR_MSNN, 256, 128, 32768);
+        if (j.size() + 1 > capacity) throw std::invalid_argument("buffer too small");
+        memcpy(buf, j.c_str(), j.size() + 1);
     });
 }
 

@@ -217,3 +217,18 @@ def test_fibre_intersector_finds_surface_points(probe):
     assert misses / total < 2e-3, (misses, total)
     assert late / total < 2e-3, (late, total)
     assert worst < 2.5      # an earlier entry can only be on this ~1-unit segment
+
+
+def test_stats_json_schema_is_valid_json():
+    """integrator.stats_output (never written by the reference): schema of the file the executables write."""
+    import json
+    buf = C.create_string_buffer(8192)
+    assert api.lib.hm_test_stats_json(buf, C.c_size_t(len(buf))) == 0
+    j = json.loads(buf.value.decode())
+    assert j["renderer"] == "render_hair_msnn" and j["spp"] == 4 and j["paths"] == 4 * 256 * 128
+    assert j["seconds"] == pytest.approx(13.5e-3) and j["mpaths_per_s"] == pytest.approx(4 * 256 * 128 / 13.5e-3 / 1e6)
+    assert set(j["ms"]) == {"primary", "shade_main", "trace_main", "tail_piece", "finalize", "train", "infer", "composite"}
+    assert j["traversal_per_ray"]["primary"] == {"nodes": 15.0, "primitives": 1.9}
+    assert j["traversal_per_ray"]["shadow"] == {"nodes": None, "primitives": None}      # no such rays: null, not a division by zero
+    assert j["training_loss"] is None                                                   # NaN is not JSON
+    assert j["mlp_queries_per_s"] == pytest.approx(32768 * 4 / 10.5e-3)
