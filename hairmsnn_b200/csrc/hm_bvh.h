@@ -3,7 +3,14 @@
 // Replaces the reference's OptiX IAS{triangle GAS, curve GAS} + RT-core traversal
 // (owl::traceRay call sites cuda/path_tracing.cu:50,
 // cuda/hair_msnn.cu:62,240, cuda_headers/optix_common.cuh:189,257,357).  B200 has no
-// RT cores, so this is a plain binary BVH laid out for 128-bit loads:
+// RT cores.  Two trees over the same primitive references live here:
+//   * the binary SAH tree described next — what the builder produces first, what the host oracle /
+//     CPU baseline traverses (trace<>), and the input of the collapse;
+//   * the 8-wide quantised tree derived from it (second half of this file: wide_node_hits,
+//     trace_wide<>) — what every CUDA kernel traverses (hm_trace_dev.cuh).
+// Both return bit-identical closest hits (same references, same primitive tests).
+//
+// Binary tree, laid out for 128-bit loads:
 //
 //   node = 4 x float4 (64 B, one coalesced 64-byte read per visit)
 //     q0 = (lo0.x lo0.y lo0.z hi0.x)
@@ -29,9 +36,8 @@
 //                 leaf_code[s]  = host-side bookkeeping only (first control-point index,
 //                                 or triangle index | kTriTag)
 //
-// The traversal routine is shared by the CUDA kernels and the host build (the
-// latter only serves the CPU oracle / baseline); it uses only IEEE + - * / sqrt and
-// explicit fmaf so both builds return bit-identical (t, prim, u).
+// The primitive tests and both traversal routines compile for host and device; they use only
+// IEEE + - * / sqrt and explicit fmaf so both builds return bit-identical (t, prim, u).
 #pragma once
 #include "hm_curve.h"
 

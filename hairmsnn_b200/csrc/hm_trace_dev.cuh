@@ -1,6 +1,6 @@
 // hm_trace_dev.cuh — warp-cooperative BVH traversal for the sm_100a kernels.
 //
-// Same per-(ray, primitive) arithmetic as the portable trace<>() in hm_bvh.h (slab test,
+// Same node and primitive arithmetic as the portable trace_wide<>() in hm_bvh.h (wide_node_hits,
 // fibre_candidate + fibre_solve, intersect_triangle), so results are bit-identical to the
 // host build; what differs is the schedule.  ncu on the earlier "descend, then leaf, then
 // solve" loop (profiles/r1c_k_trace) showed the kernel latency-bound on its warp-level
@@ -19,8 +19,11 @@
 //
 // The warp votes each iteration: a prim (solve) step runs once enough lanes hold a parked
 // reference (candidate), or when no lane can take a node step; otherwise a node step runs.
-// Parking defers a leaf by a few node visits, which only costs when that leaf would have
-// shortened the ray — rare (a ray tests ~7 primitives for at most a couple of accepted hits).
+// Parking defers a leaf by a few node visits; measured against the host's test-at-once order it costs
+// 17-23 % more node visits (scripts/trav_split.py vs scripts/bvh_stats.py), but making lanes wait for
+// the prim step instead costs more in idle lanes than it saves (HM_TRACE_*_WAIT,
+// profiles/r1m_sweep_wait_for_prim_step.txt).  Within a node the child with the smallest entry
+// distance goes first, the others in octant order.
 // Persistent warps pull rays from the queue through one atomic cursor and refill idle lanes
 // as soon as a quarter of the warp has finished; commits happen at the top of the loop with
 // the whole warp present, so queue appends stay warp-aggregated (one atomic per warp).
