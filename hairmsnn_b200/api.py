@@ -368,6 +368,16 @@ class Renderer:
     def sync(self):
         _check(lib.hm_renderer_sync(self._h))
 
+    def set_hair_params(self, sigma_a, beta_m, beta_n, alpha_rad, gains=(1, 1, 1, 1)):
+        s, g = _f32(sigma_a), _f32(gains)
+        _check(lib.hm_renderer_set_hair_params(self._h, _ptr(s), C.c_float(beta_m), C.c_float(beta_n), C.c_float(alpha_rad), _ptr(g)))
+
+    def set_environment(self, scale, rotation=0.0):
+        _check(lib.hm_renderer_set_environment(self._h, C.c_float(scale), C.c_float(rotation)))
+
+    def set_sampling(self, mis=True, env_pdf=True):
+        _check(lib.hm_renderer_set_sampling(self._h, int(mis), int(env_pdf)))
+
     def reset_accumulation(self):
         _check(lib.hm_renderer_reset_accumulation(self._h))
 

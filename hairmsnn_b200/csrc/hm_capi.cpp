@@ -263,6 +263,19 @@ int hm_renderer_sync(hm_renderer* r) {
 int hm_renderer_reset_accumulation(hm_renderer* r) {
     return guarded([&] { need(r, "renderer"); r->r->reset_accumulation(); });
 }
+int hm_renderer_set_hair_params(hm_renderer* r, const float* sigma_a3, float beta_m, float beta_n, float alpha_radians,
+                                const float* gains4) {
+    return guarded([&] {
+        need(r, "renderer"); need(sigma_a3, "sigma_a3"); need(gains4, "gains4");
+        r->r->set_hair_params(sigma_a3, beta_m, beta_n, alpha_radians, gains4);
+    });
+}
+int hm_renderer_set_environment(hm_renderer* r, float scale, float rotation) {
+    return guarded([&] { need(r, "renderer"); r->r->set_environment(scale, rotation); });
+}
+int hm_renderer_set_sampling(hm_renderer* r, int mis, int env_pdf) {
+    return guarded([&] { need(r, "renderer"); r->r->set_sampling(mis != 0, env_pdf != 0); });
+}
 int hm_renderer_accum_id(const hm_renderer* r) { return r ? r->r->accum_id() : -1; }
 void* hm_renderer_stream(hm_renderer* r) { return r ? (void*)r->r->stream() : nullptr; }
 

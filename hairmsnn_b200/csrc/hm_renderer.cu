@@ -255,6 +255,29 @@ Renderer::~Renderer() {
     if (order_stream_) cudaStreamDestroy(order_stream_);
 }
 
+void Renderer::set_hair_params(const float sigma_a[3], float beta_m, float beta_n, float alpha_rad, const float gains[4]) {
+    sync();
+    SceneView& v = scene_->view;
+    v.lobes.setup(beta_m, beta_n, alpha_rad);
+    v.lobes.sigma_a = V3(sigma_a[0], sigma_a[1], sigma_a[2]);
+    for (int i = 0; i < 4; ++i) v.lobes.gain[i] = gains[i];
+    accum_id_ = 0;
+}
+
+void Renderer::set_environment(float scale, float rotation) {
+    sync();
+    scene_->view.lights.env.scale = scale;
+    scene_->view.lights.env.rot_phi = rotation;
+    accum_id_ = 0;
+}
+
+void Renderer::set_sampling(bool mis, bool env_pdf) {
+    sync();
+    scene_->view.mis = mis ? 1 : 0;
+    scene_->view.lights.env.pdf_sampling = env_pdf ? 1 : 0;
+    accum_id_ = 0;
+}
+
 void Renderer::sync() {
     HM_CUDA(cudaSetDevice(device_));
     HM_CUDA(cudaStreamSynchronize(main_stream_));

@@ -79,6 +79,12 @@ public:
     void render_frames(int n);          // enqueue n frames (async)
     void sync();
     void reset_accumulation() { sync(); accum_id_ = 0; }
+    // Live edits of the viewer's panels (render_hair_msnn.cu:780-1000 drawUI: hair colour / roughness / tilt /
+    // lobe gains, environment scale and rotation, MIS and ENV_PDF switches).  The values travel in the kernel
+    // parameter block of every launch, so an edit is a host-side store; accumulation restarts as in the viewer.
+    void set_hair_params(const float sigma_a[3], float beta_m, float beta_n, float alpha_rad, const float gains[4]);
+    void set_environment(float scale, float rotation);
+    void set_sampling(bool mis, bool env_pdf);
     int accum_id() const { return accum_id_; }
     cudaStream_t stream() const { return order_stream_; }
 

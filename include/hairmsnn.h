@@ -158,6 +158,14 @@ int hm_renderer_sync(hm_renderer* r);
 /* restart accumulation (cameraChanged(): accumId = 0) */
 int hm_renderer_reset_accumulation(hm_renderer* r);
 int hm_renderer_accum_id(const hm_renderer* r);
+/* Live edits, as the viewer's ImGui panels make them (render_hair_msnn.cu drawUI / render_path_tracing.cu drawUI:
+ * hair sigma_a, beta_m, beta_n, alpha, the four lobe gains; environment scale and rotation; MIS and ENV_PDF).
+ * Each call waits for the frames in flight, stores the values (they travel in every launch's parameter block)
+ * and restarts accumulation (accumId = 0), which is what the panels do.  alpha in radians. */
+int hm_renderer_set_hair_params(hm_renderer* r, const float* sigma_a3, float beta_m, float beta_n, float alpha_radians,
+                                const float* gains4);
+int hm_renderer_set_environment(hm_renderer* r, float scale, float rotation);
+int hm_renderer_set_sampling(hm_renderer* r, int mis, int env_pdf);
 /* CUDA stream the renderer launches on (cudaStream_t as void*), for event timing */
 void* hm_renderer_stream(hm_renderer* r);
 

@@ -171,3 +171,27 @@ def test_scene_restored_from_bvh_cache_renders_identically(tmp_path, monkeypatch
     ra = api.Renderer(a, api.PATH_TRACING); rb = api.Renderer(b, api.PATH_TRACING)
     ra.render_frames(2); rb.render_frames(2)
     assert np.array_equal(ra.buffer(api.BUF_FINAL_ACCUM), rb.buffer(api.BUF_FINAL_ACCUM))
+
+
+def test_live_parameter_edits_equal_a_fresh_renderer():
+    """hm_renderer_set_hair_params / set_environment / set_sampling (the viewer's panels): after an edit the
+    renderer produces exactly what a renderer created on a scene with those values produces."""
+    base = small_scene_kwargs(width=128, height=128, strands=600, segs=12, path_v2=6)
+    edited = dict(base, sigma_a=(0.2, 0.35, 0.6), beta_m=0.22, beta_n=0.41, gains=(1.0, 0.8, 1.2, 0.5),
+                  env_scale=1.7, env_rotation=0.3, mis=False)
+    fresh = api.Renderer(api.Scene.from_arrays(**edited), api.PATH_TRACING)
+    fresh.render_frames(2)
+    want = fresh.buffer(api.BUF_FINAL_ACCUM)
+
+    r = api.Renderer(api.Scene.from_arrays(**base), api.PATH_TRACING)
+    r.render_frames(3)
+    before = r.buffer(api.BUF_FINAL_AVG).copy()
+    alpha = float(np.float32(3.14159) * np.float32(base["alpha_deg"]) / np.float32(180.0))
+    r.set_hair_params(edited["sigma_a"], edited["beta_m"], edited["beta_n"], alpha, edited["gains"])
+    r.set_environment(edited["env_scale"], edited["env_rotation"])
+    r.set_sampling(mis=False, env_pdf=True)
+    assert r.accum_id == 0                       # the panels restart accumulation
+    r.render_frames(2)
+    got = r.buffer(api.BUF_FINAL_ACCUM)
+    assert np.array_equal(got, want)
+    assert not np.allclose(r.buffer(api.BUF_FINAL_AVG), before)
