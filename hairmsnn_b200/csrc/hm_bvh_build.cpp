@@ -543,12 +543,14 @@ void build_bvh(const HostGeometry& geo, HostBvh& out, int threads_hint) {
     {
         const char* e = getenv("HM_BVH_COLLAPSE");
         if (!(e && !strcmp(e, "greedy")) && packed.size() > 1) {
-            // bottom-up over the depth-first array (children have larger indices than their parent)
+            // post-order over the binary tree (children before their parent); subtrees near the top run as
+            // parallel tasks — every node's table depends on its own subtree only, so the result does not
+            // depend on the schedule
             const size_t nb = packed.size();
             std::vector<float> cost(7 * nb);
             cut.assign(8 * nb, 0);
             auto C = [&](int code, int i) -> float { return code < 0 ? 0.f : cost[7 * (size_t)code + (i - 1)]; };   // leaves: constant, dropped
-            for (size_t idx = nb; idx-- > 0;) {
+            auto solve_node = [&](size_t idx) {
                 const NodeRaw& n = packed[idx];
                 Box nbx = WideBuilder::child_box(n, 0);
                 if (!(n.q[6] > n.q[9])) nbx.grow(WideBuilder::child_box(n, 1));
@@ -570,7 +572,43 @@ void build_bvh(const HostGeometry& geo, HostBvh& out, int threads_hint) {
                     if (d < cost[7 * idx + (i - 2)]) { cost[7 * idx + (i - 1)] = d; cut[8 * idx + (i - 1)] = (unsigned char)k; }
                     else { cost[7 * idx + (i - 1)] = cost[7 * idx + (i - 2)]; cut[8 * idx + (i - 1)] = 0; }
                 }
+            };
+            // iterative post-order of one subtree
+            auto solve_subtree = [&](int root_idx) {
+                std::vector<std::pair<int, bool>> st;
+                st.push_back({root_idx, false});
+                while (!st.empty()) {
+                    auto [idx, expanded] = st.back();
+                    if (expanded) { st.pop_back(); solve_node((size_t)idx); continue; }
+                    st.back().second = true;
+                    const NodeRaw& n = packed[idx];
+                    if (n.c1 >= 0 && n.c1 != idx) st.push_back({n.c1, false});
+                    if (n.c0 >= 0) st.push_back({n.c0, false});
+                }
+            };
+            // frontier: inner nodes at depth `par_depth`; everything above is solved afterwards, bottom-up
+            const int par_depth = hw > 1 ? 10 : 0;
+            std::vector<int> frontier, upper;
+            {
+                std::vector<std::pair<int, int>> st;
+                st.push_back({0, 0});
+                while (!st.empty()) {
+                    auto [idx, dep] = st.back(); st.pop_back();
+                    if (dep >= par_depth) { frontier.push_back(idx); continue; }
+                    upper.push_back(idx);     // pre-order: parents before children
+                    const NodeRaw& n = packed[idx];
+                    if (n.c0 >= 0) st.push_back({n.c0, dep + 1});
+                    if (n.c1 >= 0 && !(n.q[6] > n.q[9])) st.push_back({n.c1, dep + 1});
+                }
             }
+            {
+                std::atomic<size_t> next{0};
+                std::vector<std::thread> pool;
+                for (unsigned t = 0; t < hw; ++t)
+                    pool.emplace_back([&]() { for (size_t i; (i = next.fetch_add(1)) < frontier.size();) solve_subtree(frontier[i]); });
+                for (auto& th : pool) th.join();
+            }
+            for (size_t i = upper.size(); i-- > 0;) solve_node((size_t)upper[i]);   // reverse pre-order: children first
             wb.cut = &cut;
         }
     }
