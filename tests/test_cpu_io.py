@@ -81,3 +81,17 @@ def test_bvh_cache_roundtrip(tmp_path, monkeypatch):
     open(path, "r+b").write(b"garbage!")
     d = api.Scene.from_arrays(**kw)
     assert d.info().num_bvh_nodes == ia.num_bvh_nodes
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference scenes are not mounted here")
+@pytest.mark.parametrize("name", ["studio_small_01_4k.exr", "christmas_photo_studio_07_4k.exr"])
+def test_shipped_env_maps_decode_bit_exact(name):
+    cv2 = pytest.importorskip("cv2")
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    path = os.path.join(REF, "envmaps", name)
+    ref = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    if ref is None:
+        pytest.skip("OpenCV build has no OpenEXR")
+    img = api.load_exr(path)
+    assert img.shape == (2048, 4096, 4)
+    assert np.array_equal(img[..., :3], ref[..., ::-1]) and np.all(img[..., 3] == 1.0)
