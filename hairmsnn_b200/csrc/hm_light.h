@@ -131,6 +131,45 @@ HM_HD int cdf_lower_bound(float u, const float* t, int w, int h, float yn, float
     return first - 1 > 0 ? first - 1 : 0;
 }
 
+// Same partition point found four ways at a time: three independent fetches per round and half the dependent
+// round trips (the rows of the conditional CDF are 16 KB each and cold, so every step of the binary search is a
+// DRAM/L2 round trip in k_shade).  The predicate "texel < u" is monotone along the row, so any search order
+// returns the index std::lower_bound returns (tests/test_cpu_oracle.py::test_cdf_search_variants_agree).
+// Not the default: HM_ENV_SEARCH_4ARY=1 selects it — to be A/B-measured on the GPU before it replaces the
+// binary search.
+HM_HD int cdf_lower_bound4(float u, const float* t, int w, int h, float yn, float size) {
+    int first = 0;
+    int count = (int)size;
+    while (count > 0) {
+        if (count < 4) {
+            int step = count >> 1;
+            int middle = first + step;
+            if (table_fetch(t, w, h, middle / size, yn) < u) { first = middle + 1; count -= step + 1; }
+            else count = step;
+        } else {
+            const int s1 = count >> 2, s2 = count >> 1, s3 = s1 + s2;
+            const float g1 = table_fetch(t, w, h, (first + s1) / size, yn);
+            const float g2 = table_fetch(t, w, h, (first + s2) / size, yn);
+            const float g3 = table_fetch(t, w, h, (first + s3) / size, yn);
+            if (!(g1 < u)) count = s1;
+            else if (!(g2 < u)) { first += s1 + 1; count = s2 - s1 - 1; }
+            else if (!(g3 < u)) { first += s2 + 1; count = s3 - s2 - 1; }
+            else { first += s3 + 1; count -= s3 + 1; }
+        }
+    }
+    return first - 1 > 0 ? first - 1 : 0;
+}
+#ifndef HM_ENV_SEARCH_4ARY
+#define HM_ENV_SEARCH_4ARY 0
+#endif
+HM_HD int cdf_search(float u, const float* t, int w, int h, float yn, float size) {
+#if HM_ENV_SEARCH_4ARY
+    return cdf_lower_bound4(u, t, w, h, yn, size);
+#else
+    return cdf_lower_bound(u, t, w, h, yn, size);
+#endif
+}
+
 HM_HD V3 uniform_sample_sphere(float u0, float u1) {
     float z = 1 - 2 * u0;
     float r = sqrtf(fmaxf(0.f, 1.f - z * z));
@@ -149,13 +188,13 @@ static HM_HD_OUTLINE V3 env_sample(const EnvView& e, float u0, float u1, V3& wi,
     const float width = (float)e.W, height = (float)e.H;
     const int cw = e.W + 1, mh = e.H + 1;
 
-    int index_v = cdf_lower_bound(u1, e.mcdf, mh, 1, 0.f, height);
+    int index_v = cdf_search(u1, e.mcdf, mh, 1, 0.f, height);
     float cdf_v = table_fetch(e.mcdf, mh, 1, index_v / height, 0.f);
     float cdf_next_v = table_fetch(e.mcdf, mh, 1, (index_v + 1) / height, 0.f);
     float dv = (cdf_next_v - u1) / (cdf_next_v - cdf_v);
     float v = (index_v + dv) / height;
 
-    int index_u = cdf_lower_bound(u0, e.ccdf, cw, e.H, index_v / height, width);
+    int index_u = cdf_search(u0, e.ccdf, cw, e.H, index_v / height, width);
     float cdf_u = table_fetch(e.ccdf, cw, e.H, index_u / width, index_v / height);
     float cdf_next_u = table_fetch(e.ccdf, cw, e.H, (index_u + 1) / width, index_v / height);
     float du = (cdf_next_u - u0) / (cdf_next_u - cdf_u);

@@ -87,6 +87,15 @@ int probe_intersect_fibre(const float* cps16, const float* org, const float* dir
     return ok ? 1 : 0;
 }
 
+// environment CDF search: binary (std::lower_bound order) and 4-ary variants on the same table
+#include "../hairmsnn_b200/csrc/hm_light.h"
+void probe_cdf_search(const float* table, int w, int h, int n, const float* u, const float* yn, float size, int* out2) {
+    for (int i = 0; i < n; ++i) {
+        out2[2 * i + 0] = cdf_lower_bound(u[i], table, w, h, yn[i], size);
+        out2[2 * i + 1] = cdf_lower_bound4(u[i], table, w, h, yn[i], size);
+    }
+}
+
 // BVH build + trace on the host
 struct ProbeScene { HostGeometry geo; HostBvh bvh; };
 void* probe_scene_create(const float* cps, int ncps, const int* seg_cp, int nseg, const float* tri_verts, int ntri, int threads) {

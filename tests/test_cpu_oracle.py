@@ -138,3 +138,30 @@ def test_curve_hit_geometry_matches_reference(ref, probe):
         probe.probe_curve_geometry(_p(cps), _p(o), _p(d), C.c_float(t), C.c_float(u), _p(b))
         worst = max(worst, float(np.abs(a - b).max()))
     assert worst < 1e-5
+
+
+def test_cdf_search_variants_agree(probe):
+    """The 4-ary search of the environment CDF rows (hm_light.h: cdf_lower_bound4, an A/B switch) returns the
+    index the reference's std::lower_bound order returns — incl. flat stretches, the ends and u outside (0,1)."""
+    rng = np.random.default_rng(11)
+    W, H = 509, 37                                   # w = W + 1 texels per row, like the conditional CDF
+    pdf = rng.random((H, W)).astype(np.float32) ** 4
+    pdf[:, 100:180] = 0.0                            # flat stretch in every row
+    pdf[5] = 0.0; pdf[5, 300] = 1.0                  # a row that is one step
+    cdf = np.concatenate([np.zeros((H, 1), np.float32), np.cumsum(pdf, axis=1, dtype=np.float32)], axis=1)
+    cdf /= cdf[:, -1:]
+    cdf = np.ascontiguousarray(cdf, np.float32)
+    n = 20000
+    u = rng.random(n).astype(np.float32)
+    u[:50] = 0.0; u[50:100] = 1.0; u[100:150] = -0.5; u[150:200] = 1.5
+    u[200:400] = cdf[rng.integers(0, H, 200), rng.integers(0, W + 1, 200)]     # exactly on table values
+    yn = ((rng.integers(0, H, n) + 0.5) / H).astype(np.float32)
+    out = np.zeros((n, 2), np.int32)
+    probe.probe_cdf_search(_p(cdf), W + 1, H, n, _p(u), _p(yn), C.c_float(W), out.ctypes.data_as(C.POINTER(C.c_int)))
+    assert np.array_equal(out[:, 0], out[:, 1])
+    assert out.min() >= 0 and out.max() <= W - 1 and len(np.unique(out[:, 0])) > 200
+    # marginal-CDF shape: one row
+    m = np.ascontiguousarray(cdf[7])
+    out1 = np.zeros((n, 2), np.int32)
+    probe.probe_cdf_search(_p(m), W + 1, 1, n, _p(u), _p(np.zeros(n, np.float32)), C.c_float(W), out1.ctypes.data_as(C.POINTER(C.c_int)))
+    assert np.array_equal(out1[:, 0], out1[:, 1])
