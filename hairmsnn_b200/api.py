@@ -245,6 +245,13 @@ def load_exr(path):
     return out
 
 
+def nrc_layout(width, height):
+    """(numTrainingPixels, everyNth, nnFrameSize, numTrainingRecords) of render_nrc for a frame size."""
+    out = (C.c_int * 4)()
+    _check(lib.hm_nrc_layout(width, height, out))
+    return tuple(out)
+
+
 class Mlp:
     """TINY_MLP stand-in.  `inference` / `train_step` take HOST numpy arrays; the
     `*_device` variants take raw device pointers (ints), e.g. torch tensors' data_ptr()."""

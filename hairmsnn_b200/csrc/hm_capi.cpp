@@ -397,6 +397,16 @@ int hm_renderer_set_frame_schedule(hm_renderer* r, int offset, int stride) {
         r->r->set_frame_schedule(offset, stride);
     });
 }
+int hm_nrc_layout(int width, int height, int* out4) {
+    return guarded([&] {
+        need(out4, "out4");
+        if (width <= 0 || height <= 0) throw std::invalid_argument("bad frame size");
+        const NrcLayout l = nrc_layout(width, height);
+        if (l.every_nth < 1) throw std::invalid_argument("render_nrc needs at least 1638 pixels (everyNth would be 0)");
+        if (((long long)width * height) % 128) throw std::invalid_argument("render_nrc needs W*H to be a multiple of 128 (scene.cpp:302-306)");
+        out4[0] = l.train_pixels; out4[1] = l.every_nth; out4[2] = l.nn_frame_rows; out4[3] = l.records;
+    });
+}
 int hm_band_partition(int width, int height, int records, int rank, int world, int* out5) {
     return guarded([&] {
         if (!out5 || width <= 0 || height <= 0 || records < 0 || world < 1 || rank < 0 || rank >= world)

@@ -117,6 +117,24 @@ inline BandPartition band_partition(int W, int H, int records, int rank, int wor
     return b;
 }
 
+// Buffer sizes of render_nrc (RenderWindowNRC::initialize, render_nrc.cu:116-160; std::ceil of INTEGER
+// divisions throughout): numTrainingRecords = 65536, MAX_BOUNCES = 40 (headers/render_nrc.h:126, nrc.cuh:13).
+struct NrcLayout {
+    int records;          // numTrainingRecords
+    int train_pixels;     // numTrainingPixels = records / MAX_BOUNCES
+    int every_nth;        // frameSize / numTrainingPixels (0: frame too small)
+    int nn_frame_rows;    // nnFrameSize = frameSize + numTrainingPixels - numTrainingPixels % 128 + 128
+};
+inline NrcLayout nrc_layout(int W, int H) {
+    NrcLayout l;
+    const long long n = (long long)W * H;
+    l.records = 65536;
+    l.train_pixels = l.records / 40;
+    l.every_nth = (int)(n / l.train_pixels);
+    l.nn_frame_rows = (int)n + l.train_pixels - l.train_pixels % 128 + 128;
+    return l;
+}
+
 inline GeomView make_view(const HostGeometry& g, const HostBvh& b) {
     GeomView v;
     v.nodes = b.nodes.data();

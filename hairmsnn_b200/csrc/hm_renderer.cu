@@ -160,12 +160,14 @@ Renderer::Renderer(const HostScene& hs, int kind, int beta_cli, int device, int 
         // RenderWindowNRC::initialize (render_nrc.cu:116-160); std::ceil of INTEGER divisions throughout
         if (world != 1) throw std::invalid_argument("render_nrc shards by samples (hm_renderer_set_frame_schedule), not by row bands");
         in_ch_ = 9;
-        records_ = kNrcTrainRecords;
-        nrc_train_pixels_ = records_ / kNrcMaxBounces;
-        every_nth_ = (int)(n / (size_t)nrc_train_pixels_);
+        const NrcLayout nl = nrc_layout(W_, H_);     // shared with hm_nrc_layout (pure host arithmetic)
+        static_assert(kNrcTrainRecords == 65536 && kNrcMaxBounces == 40, "nrc_layout() holds the same constants");
+        records_ = nl.records;
+        nrc_train_pixels_ = nl.train_pixels;
+        every_nth_ = nl.every_nth;
         if (every_nth_ < 1) throw std::invalid_argument("render_nrc needs at least 1638 pixels (everyNth would be 0)");
         if (n % 128) throw std::invalid_argument("render_nrc needs W*H to be a multiple of 128 (scene.cpp:302-306)");
-        nn_frame_rows_ = (int)n + nrc_train_pixels_ - nrc_train_pixels_ % 128 + 128;
+        nn_frame_rows_ = nl.nn_frame_rows;
     }
     if (const char* e = getenv("HM_TAIL_MEGA")) tail_mega_ = atoi(e) != 0;
     if (const char* e = getenv("HM_TAIL_BOUND")) tail_bound_items_ = atoi(e);

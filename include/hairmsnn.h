@@ -259,6 +259,10 @@ int hm_renderer_set_frame_schedule(hm_renderer* r, int offset, int stride);
  * to the backward pass (rounded down to tcnn's 128-row granularity, common.h:280).  `records` is
  * numTrainRecordsX*Y = 16384 for render_hair_msnn (headers/render_hair_msnn.h:127-130). */
 int hm_band_partition(int width, int height, int records, int rank, int world, int* out5);
+/* Buffer sizes of render_nrc for a frame (RenderWindowNRC::initialize, render_nrc.cu:116-160; pure host
+ * arithmetic): out4 = numTrainingPixels (65536 / MAX_BOUNCES), everyNth, nnFrameSize (rows fed to inference:
+ * frame + training suffixes, rounded up to tcnn's 128-row granularity), numTrainingRecords. */
+int hm_nrc_layout(int width, int height, int* out4);
 
 /* ---- stand-alone kernels (parity tests, micro-benchmarks) ----------------------- */
 

@@ -232,3 +232,14 @@ def test_stats_json_schema_is_valid_json():
     assert j["traversal_per_ray"]["shadow"] == {"nodes": None, "primitives": None}      # no such rays: null, not a division by zero
     assert j["training_loss"] is None                                                   # NaN is not JSON
     assert j["mlp_queries_per_s"] == pytest.approx(32768 * 4 / 10.5e-3)
+
+
+def test_nrc_buffer_layout_follows_the_reference_arithmetic():
+    # RenderWindowNRC::initialize (render_nrc.cu:116-160) at the shipped 1024 x 1024: SURVEY §3.3
+    assert api.nrc_layout(1024, 1024) == (1638, 640, 1048576 + 1638 - 102 + 128, 65536)
+    assert api.nrc_layout(1024, 1024)[2] == 1050240 and 1050240 % 128 == 0
+    tp, nth, rows, rec = api.nrc_layout(256, 128)
+    assert (tp, nth, rec) == (1638, 20, 65536) and rows % 128 == 0 and rows >= 256 * 128 + tp
+    for bad in [(32, 32), (100, 3), (0, 128)]:
+        with pytest.raises(api.HairMSNNError):
+            api.nrc_layout(*bad)
