@@ -636,22 +636,39 @@ void build_bvh(const HostGeometry& geo, HostBvh& out, int threads_hint) {
         for (auto& th : pool) th.join();
         auto as_u = [](float f) { unsigned u; memcpy(&u, &f, 4); return u; };
         auto as_f = [](unsigned u) { float f; memcpy(&f, &u, 4); return f; };
-        for (size_t i = 0; i < subtrees.size(); ++i) {
+        // placement: subtree i's nodes 1.. go to node_off[i].., its leaves to leaf_off[i].. (prefix sums in task
+        // order, so the arrays come out the same for any schedule); then every task shifts its base indices
+        // and copies itself into place
+        const size_t ns_ = subtrees.size();
+        std::vector<size_t> node_off(ns_ + 1), leaf_off(ns_ + 1);
+        node_off[0] = out.wnodes.size() / 5; leaf_off[0] = out.wleaf_data.size() / 4;
+        for (size_t i = 0; i < ns_; ++i) {
             max_depth = std::max(max_depth, loc[i].depth);
-            const size_t n_local = loc[i].nodes.size() / 5;
-            const unsigned node_off = (unsigned)(out.wnodes.size() / 5);       // local index k >= 1 -> node_off + k - 1
-            const unsigned leaf_off = (unsigned)(out.wleaf_data.size() / 4);
-            for (size_t k = 0; k < n_local; ++k) {
-                F4* w = loc[i].nodes.data() + 5 * k;
-                w[1].x = as_f(as_u(w[1].x) + node_off - 1u);
-                w[1].y = as_f(as_u(w[1].y) + leaf_off);
-            }
-            memcpy(out.wnodes.data() + 5 * (size_t)subtrees[i].wi, loc[i].nodes.data(), 5 * sizeof(F4));
-            out.wnodes.insert(out.wnodes.end(), loc[i].nodes.begin() + 5, loc[i].nodes.end());
-            out.wleaf_data.insert(out.wleaf_data.end(), loc[i].leaves.begin(), loc[i].leaves.end());
-            std::vector<F4>().swap(loc[i].nodes);
-            std::vector<F4>().swap(loc[i].leaves);
+            node_off[i + 1] = node_off[i] + (loc[i].nodes.size() / 5 - 1);
+            leaf_off[i + 1] = leaf_off[i] + loc[i].leaves.size() / 4;
         }
+        out.wnodes.resize(5 * node_off[ns_]);
+        out.wleaf_data.resize(4 * leaf_off[ns_]);
+        next.store(0);
+        pool.clear();
+        for (unsigned t = 0; t < hw; ++t)
+            pool.emplace_back([&]() {
+                for (size_t i; (i = next.fetch_add(1)) < ns_;) {
+                    const size_t n_local = loc[i].nodes.size() / 5;
+                    const unsigned noff = (unsigned)node_off[i], loff = (unsigned)leaf_off[i];   // local index k >= 1 -> noff + k - 1
+                    for (size_t k = 0; k < n_local; ++k) {
+                        F4* w = loc[i].nodes.data() + 5 * k;
+                        w[1].x = as_f(as_u(w[1].x) + noff - 1u);
+                        w[1].y = as_f(as_u(w[1].y) + loff);
+                    }
+                    memcpy(out.wnodes.data() + 5 * (size_t)subtrees[i].wi, loc[i].nodes.data(), 5 * sizeof(F4));
+                    if (n_local > 1) memcpy(out.wnodes.data() + 5 * node_off[i], loc[i].nodes.data() + 5, (n_local - 1) * 5 * sizeof(F4));
+                    if (!loc[i].leaves.empty()) memcpy(out.wleaf_data.data() + 4 * leaf_off[i], loc[i].leaves.data(), loc[i].leaves.size() * sizeof(F4));
+                    std::vector<F4>().swap(loc[i].nodes);
+                    std::vector<F4>().swap(loc[i].leaves);
+                }
+            });
+        for (auto& th : pool) th.join();
     }
     out.wide_depth = max_depth;
     wb.max_depth = max_depth;
