@@ -78,30 +78,41 @@ struct Builder {
         int best_axis = -1, best_bin = -1;
 
         // beyond depth 36 fall back to median splits: bounds the depth (traversal stack: kStackDepth)
-        for (int axis = 0; axis < 3 && n > 2 && depth < 36; ++axis) {
-            float ext = cb.hi[axis] - cb.lo[axis];
-            if (!(ext > 0.f)) continue;
-            Box bin_box[kBins];
-            int bin_cnt[kBins];
-            for (int k = 0; k < kBins; ++k) { bin_box[k].reset(); bin_cnt[k] = 0; }
-            float scale = kBins / ext;
+        // One pass bins the references on all three axes (the gather through `order` is what costs), and the
+        // winning split's child bounds are the unions of its bins — no separate bounds passes.
+        Box bin_box[3][kBins];
+        int bin_cnt[3][kBins];
+        float scale3[3] = {0.f, 0.f, 0.f};
+        const bool try_sah = n > 2 && depth < 36;
+        if (try_sah) {
+            for (int axis = 0; axis < 3; ++axis) {
+                float ext = cb.hi[axis] - cb.lo[axis];
+                scale3[axis] = ext > 0.f ? kBins / ext : 0.f;
+                for (int k = 0; k < kBins; ++k) { bin_box[axis][k].reset(); bin_cnt[axis][k] = 0; }
+            }
             for (int i = b; i < e; ++i) {
                 const PrimRef& p = prims[order[i]];
-                int k = std::min(kBins - 1, std::max(0, (int)((p.cen[axis] - cb.lo[axis]) * scale)));
-                bin_box[k].grow(p.box);
-                bin_cnt[k]++;
+                for (int axis = 0; axis < 3; ++axis) {
+                    if (!(scale3[axis] > 0.f)) continue;
+                    int k = std::min(kBins - 1, std::max(0, (int)((p.cen[axis] - cb.lo[axis]) * scale3[axis])));
+                    bin_box[axis][k].grow(p.box);
+                    bin_cnt[axis][k]++;
+                }
             }
+        }
+        for (int axis = 0; axis < 3 && try_sah; ++axis) {
+            if (!(scale3[axis] > 0.f)) continue;
             float right_area[kBins];
             int right_cnt[kBins];
             Box acc; acc.reset();
             int cnt = 0;
             for (int k = kBins - 1; k > 0; --k) {
-                acc.grow(bin_box[k]); cnt += bin_cnt[k];
+                acc.grow(bin_box[axis][k]); cnt += bin_cnt[axis][k];
                 right_area[k] = acc.half_area(); right_cnt[k] = cnt;
             }
             acc.reset(); cnt = 0;
             for (int k = 0; k < kBins - 1; ++k) {
-                acc.grow(bin_box[k]); cnt += bin_cnt[k];
+                acc.grow(bin_box[axis][k]); cnt += bin_cnt[axis][k];
                 if (cnt == 0 || right_cnt[k + 1] == 0) continue;
                 float c = acc.half_area() * cnt + right_area[k + 1] * right_cnt[k + 1];
                 if (c < best_cost) { best_cost = c; best_axis = axis; best_bin = k; }
@@ -109,12 +120,12 @@ struct Builder {
         }
 
         int mid;
+        bool bounds_from_bins = false;
         if (best_axis < 0) {
             // two references, or all centroids coincide: split by count
             mid = b + n / 2;
         } else {
-            float ext = cb.hi[best_axis] - cb.lo[best_axis];
-            float scale = kBins / ext;
+            float scale = scale3[best_axis];
             float lo = cb.lo[best_axis];
             int axis = best_axis, bin = best_bin;
             auto it = std::partition(order.begin() + b, order.begin() + e, [&](int pi) {
@@ -123,9 +134,17 @@ struct Builder {
             });
             mid = (int)(it - order.begin());
             if (mid == b || mid == e) mid = b + n / 2;
+            else bounds_from_bins = true;
         }
 
-        Box lb = bounds_of(b, mid), rb = bounds_of(mid, e);
+        Box lb, rb;
+        if (bounds_from_bins) {
+            lb.reset(); rb.reset();
+            for (int k = 0; k <= best_bin; ++k) lb.grow(bin_box[best_axis][k]);
+            for (int k = best_bin + 1; k < kBins; ++k) rb.grow(bin_box[best_axis][k]);
+        } else {
+            lb = bounds_of(b, mid); rb = bounds_of(mid, e);
+        }
         int me = next_node.fetch_add(1);
         int cl, cr;
         if (depth < spawn_depth && n > 4096) {
