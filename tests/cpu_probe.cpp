@@ -7,6 +7,7 @@
 
 #include "../hairmsnn_b200/csrc/hm_bsdf.h"
 #include "../hairmsnn_b200/csrc/hm_host.h"
+#include "../hairmsnn_b200/csrc/hm_light.h"
 #include "../hairmsnn_b200/csrc/hm_rng.h"
 
 using namespace hm;
@@ -88,7 +89,6 @@ int probe_intersect_fibre(const float* cps16, const float* org, const float* dir
 }
 
 // environment CDF search: binary (std::lower_bound order) and 4-ary variants on the same table
-#include "../hairmsnn_b200/csrc/hm_light.h"
 void probe_cdf_search(const float* table, int w, int h, int n, const float* u, const float* yn, float size, int* out2) {
     for (int i = 0; i < n; ++i) {
         out2[2 * i + 0] = cdf_lower_bound(u[i], table, w, h, yn[i], size);
