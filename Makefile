@@ -7,7 +7,12 @@ ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC,-O3,-ffp-contract=off -fmad=false --expt-relaxed-constexpr -Xptxas -v $(EXTRA)
 NVFLAGS_MLP := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC,-O3 --expt-relaxed-constexpr -Xptxas -v
 CXXFLAGS := -O2 -std=c++17 -fPIC -ffp-contract=off -mfma -pthread -I/usr/local/cuda/include
-OBJ := build/hm_wavefront.o build/hm_renderer.o build/hm_mlp.o build/hm_capi.o build/hm_io.o build/hm_piz.o build/hm_scene_util.o build/hm_bvh_build.o
+# NCCL: the copy bundled with the image's PyTorch (2.28.9) when present, so a process that also imports torch
+# (bench.py, the tests) maps ONE libnccl.so.2; else the system library.
+NCCL_HOME ?= $(firstword $(wildcard /opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/nccl) /usr)
+NCCL_INC := $(if $(filter /usr,$(NCCL_HOME)),,-I$(NCCL_HOME)/include)
+NCCL_LIB := $(if $(filter /usr,$(NCCL_HOME)),-lnccl,-L$(NCCL_HOME)/lib -l:libnccl.so.2 -Xlinker -rpath,$(NCCL_HOME)/lib)
+OBJ := build/hm_wavefront.o build/hm_renderer.o build/hm_mlp.o build/hm_capi.o build/hm_io.o build/hm_piz.o build/hm_scene_util.o build/hm_bvh_build.o build/hm_comm.o
 HDRS := $(wildcard $(CSRC)/*.h) include/hairmsnn.h
 
 all: $(LIB) bin
@@ -23,11 +28,11 @@ build/hm_mlp.o: $(CSRC)/hm_mlp.cu $(HDRS)
 	$(NVCC) $(NVFLAGS_MLP) -c $< -o $@ 2> build/hm_mlp.ptxas.log || (cat build/hm_mlp.ptxas.log; false)
 build/%.o: $(CSRC)/%.cpp $(HDRS)
 	@mkdir -p build
-	g++ $(CXXFLAGS) -c $< -o $@
+	g++ $(CXXFLAGS) $(NCCL_INC) -c $< -o $@
 
 $(LIB): $(OBJ)
 	@mkdir -p hairmsnn_b200/lib
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lz -Xlinker -rpath,/usr/local/cuda/lib64
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lz $(NCCL_LIB) -Xlinker -rpath,/usr/local/cuda/lib64
 
 bin: hairmsnn_b200/bin/render_path_tracing hairmsnn_b200/bin/render_nrc hairmsnn_b200/bin/render_hair_msnn
 hairmsnn_b200/bin/%: $(CSRC)/main_%.cpp $(LIB)

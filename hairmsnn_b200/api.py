@@ -86,8 +86,13 @@ for _name in ("hm_renderer_stream", "hm_renderer_mlp", "hm_renderer_destroy", "h
               "hm_msnn_train_backward", "hm_msnn_train_apply", "hm_msnn_finish", "hm_nrc_trace", "hm_nrc_query",
               "hm_nrc_train_backward", "hm_nrc_train_apply", "hm_nrc_end", "hm_mlp_stream", "hm_mlp_n_params",
               "hm_mlp_launch_count", "hm_mlp_destroy", "hm_mlp_optimizer_step", "hm_mlp_reset", "hm_mlp_reinitialize",
-              "hm_scene_free"):
+              "hm_scene_free", "hm_comm_destroy", "hm_comm_barrier", "hm_reduce_framebuffers"):
     getattr(lib, _name).argtypes = [C.c_void_p]
+
+
+lib.hm_renderer_set_comm.argtypes = [C.c_void_p, C.c_void_p]
+lib.hm_comm_all_reduce_max.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+lib.hm_comm_all_reduce_sum.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
 
 
 class HairMSNNError(RuntimeError):
@@ -252,6 +257,42 @@ def nrc_layout(width, height):
     return tuple(out)
 
 
+class Comm:
+    """NCCL communicator of a multi-GPU job (hm_comm_*): one process per GPU.  `unique_id()` on rank 0,
+    the 128 bytes travel to the other ranks by any side channel (bench.py: torchrun's TCP store)."""
+
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(128)
+        _check(lib.hm_comm_get_unique_id(buf))
+        return buf.raw
+
+    def __init__(self, id_bytes, rank, world, device):
+        assert len(id_bytes) == 128
+        h = C.c_void_p()
+        _check(lib.hm_comm_create(C.c_char_p(id_bytes), rank, world, device, C.byref(h)))
+        self._h = h
+        self.rank, self.world, self.device = rank, world, device
+
+    def barrier(self):
+        _check(lib.hm_comm_barrier(self._h))
+
+    def all_reduce_max(self, v):
+        d = C.c_double(v)
+        _check(lib.hm_comm_all_reduce_max(self._h, C.byref(d)))
+        return d.value
+
+    def all_reduce_sum(self, v):
+        d = C.c_double(v)
+        _check(lib.hm_comm_all_reduce_sum(self._h, C.byref(d)))
+        return d.value
+
+    def close(self):
+        if self._h:
+            lib.hm_comm_destroy(self._h)
+            self._h = None
+
+
 class Mlp:
     """TINY_MLP stand-in.  `inference` / `train_step` take HOST numpy arrays; the
     `*_device` variants take raw device pointers (ints), e.g. torch tensors' data_ptr()."""
@@ -411,6 +452,15 @@ class Renderer:
     def reset_stats(self):
         _check(lib.hm_renderer_reset_stats(self._h))
 
+    def set_comm(self, comm):
+        """Attach a Comm: sample schedule by group, gradient all-reduce inside every training step,
+        reduce_framebuffers() (hm_renderer_set_comm)."""
+        _check(lib.hm_renderer_set_comm(self._h, comm._h if comm is not None else None))
+        self._comm = comm
+
+    def reduce_framebuffers(self):
+        _check(lib.hm_reduce_framebuffers(self._h))
+
     def set_frame_schedule(self, offset, stride):
         _check(lib.hm_renderer_set_frame_schedule(self._h, offset, stride))
 
@@ -472,6 +522,8 @@ class Renderer:
             out = np.empty(nbytes // 4, np.int32)
         elif which in (BUF_NN_FRAME_INPUT, BUF_NN_FRAME_OUTPUT, BUF_NN_TRAIN_INPUT, BUF_NN_TRAIN_OUTPUT, BUF_SCENE_POINTS):
             out = np.empty(nbytes // 4, np.float32)
+        elif which == BUF_GBUFFER:
+            out = np.empty((nbytes // (16 * self.W), self.W, 4), np.float32)   # this renderer's row band
         else:
             out = np.empty((self.H, self.W, 4), np.float32)
         _check(lib.hm_get_buffer(self._h, which, out.ctypes.data_as(C.c_void_p), C.c_size_t(out.nbytes)))

@@ -19,8 +19,10 @@
 
 using namespace hm;
 
+// The host scene is shared: a renderer keeps it alive, so hm_scene_free before hm_renderer_destroy is safe.
 struct hm_scene {
-    HostScene hs;
+    std::shared_ptr<HostScene> keep{new HostScene};
+    HostScene& hs = *keep;
 };
 struct hm_mlp {
     std::unique_ptr<Mlp> owned;
@@ -28,7 +30,11 @@ struct hm_mlp {
     cudaStream_t stream = nullptr;
     int device = 0;
 };
+struct hm_comm {
+    std::unique_ptr<hm::Comm> c;
+};
 struct hm_renderer {
+    std::shared_ptr<HostScene> scene_keep;   // declared first: destroyed after the renderer that references it
     std::unique_ptr<Renderer> r;
     hm_mlp mlp_view;
 };
@@ -52,7 +58,7 @@ int guarded(F&& f) {
         return HM_ERR_STATE;
     } catch (const std::exception& e) {
         g_err = e.what();
-        return strncmp(e.what(), "CUDA", 4) == 0 ? HM_ERR_CUDA : HM_ERR_ARG;
+        return (strncmp(e.what(), "CUDA", 4) == 0 || strncmp(e.what(), "NCCL", 4) == 0) ? HM_ERR_CUDA : HM_ERR_ARG;
     } catch (...) {
         g_err = "unknown error";
         return HM_ERR_ARG;
@@ -100,7 +106,6 @@ int hm_scene_create(const hm_scene_desc* d, hm_scene** out) {
         if (d->num_triangles > 0) { need(d->tri_vertices, "tri_vertices"); need(d->tri_normals, "tri_normals"); }
         if (!d->env_rgba && d->num_dlights <= 0)
             throw std::invalid_argument("Either directional or environment light must be defined");
-        if ((int64_t)d->width * d->height > 2048 * 2048 && false) {}
         if (d->width <= 0 || d->height <= 0 || ((int64_t)d->width * d->height) % 128 != 0)
             throw std::invalid_argument("width*height must be a positive multiple of 128 (scene.cpp:302-306)");
         std::unique_ptr<hm_scene> s(new hm_scene);
@@ -239,6 +244,7 @@ int hm_renderer_create(hm_scene* s, int kind, int beta_cli, int device, int rank
         if (kind != HM_RENDER_PATH_TRACING && kind != HM_RENDER_HAIR_MSNN && kind != HM_RENDER_NRC)
             throw std::invalid_argument("unknown renderer kind");
         std::unique_ptr<hm_renderer> h(new hm_renderer);
+        h->scene_keep = s->keep;
         h->r.reset(new Renderer(s->hs, kind, beta_cli, device, rank, world));
         h->mlp_view.m = h->r->mlp();
         h->mlp_view.stream = h->r->stream();
@@ -278,6 +284,32 @@ int hm_renderer_set_sampling(hm_renderer* r, int mis, int env_pdf) {
 }
 int hm_renderer_accum_id(const hm_renderer* r) { return r ? r->r->accum_id() : -1; }
 void* hm_renderer_stream(hm_renderer* r) { return r ? (void*)r->r->stream() : nullptr; }
+
+int hm_comm_get_unique_id(void* out_id128) {
+    return guarded([&] { need(out_id128, "out_id128"); hm::Comm::unique_id(out_id128); });
+}
+int hm_comm_create(const void* id128, int rank, int world, int device, hm_comm** out) {
+    return guarded([&] {
+        need(id128, "id128"); need(out, "out");
+        std::unique_ptr<hm_comm> h(new hm_comm);
+        h->c.reset(new hm::Comm(id128, rank, world, device));
+        *out = h.release();
+    });
+}
+void hm_comm_destroy(hm_comm* c) { delete c; }
+int hm_comm_barrier(hm_comm* c) { return guarded([&] { need(c, "comm"); c->c->barrier(); }); }
+int hm_comm_all_reduce_max(hm_comm* c, double* v) {
+    return guarded([&] { need(c, "comm"); need(v, "inout"); *v = c->c->all_reduce_max(*v); });
+}
+int hm_comm_all_reduce_sum(hm_comm* c, double* v) {
+    return guarded([&] { need(c, "comm"); need(v, "inout"); *v = c->c->all_reduce_sum(*v); });
+}
+int hm_renderer_set_comm(hm_renderer* r, hm_comm* c) {
+    return guarded([&] { need(r, "renderer"); r->r->set_comm(c ? c->c.get() : nullptr); });
+}
+int hm_reduce_framebuffers(hm_renderer* r) {
+    return guarded([&] { need(r, "renderer"); r->r->reduce_framebuffers(); });
+}
 
 int hm_msnn_trace(hm_renderer* r) { return guarded([&] { need(r, "renderer"); r->r->msnn_trace(); }); }
 int hm_msnn_train_backward(hm_renderer* r) { return guarded([&] { need(r, "renderer"); r->r->msnn_train_backward(); }); }

@@ -262,6 +262,7 @@ void load_obj_file(const std::string& path, HostGeometry& geo) {
     std::string line;
     struct Idx { int v, t, n; };
     std::vector<Idx> face;
+    std::vector<std::string> used_mtls;
     while (std::getline(f, line)) {
         const char* s = line.c_str();
         while (*s == ' ' || *s == '\t') ++s;
@@ -278,7 +279,9 @@ void load_obj_file(const std::string& path, HostGeometry& geo) {
                 while (*c == ' ' || *c == '\t' || *c == '\r') ++c;
                 if (!*c) break;
                 Idx id{0, 0, 0};
+                const char* before = c;
                 id.v = (int)strtol(c, (char**)&c, 10);
+                if (c == before) throw std::invalid_argument("malformed face record in " + path + ": " + line);
                 if (*c == '/') {
                     ++c;
                     if (*c != '/') id.t = (int)strtol(c, (char**)&c, 10);
@@ -298,6 +301,11 @@ void load_obj_file(const std::string& path, HostGeometry& geo) {
                     else geo.tri_normals.push_back(F4{0.f, 0.f, 0.f, 0.f});
                 }
             }
+        } else if (strncmp(s, "usemtl", 6) == 0) {
+            std::string nm = s + 6;
+            while (!nm.empty() && (nm.front() == ' ' || nm.front() == '\t')) nm.erase(nm.begin());
+            while (!nm.empty() && (nm.back() == '\r' || nm.back() == ' ')) nm.pop_back();
+            if (std::find(used_mtls.begin(), used_mtls.end(), nm) == used_mtls.end()) used_mtls.push_back(nm);
         } else if (strncmp(s, "mtllib", 6) == 0) {
             mtllib = s + 7;
             while (!mtllib.empty() && (mtllib.back() == '\r' || mtllib.back() == ' ')) mtllib.pop_back();
@@ -313,19 +321,39 @@ void load_obj_file(const std::string& path, HostGeometry& geo) {
             geo.tri_normals[t] = geo.tri_normals[t + 1] = geo.tri_normals[t + 2] = n;
         }
     }
-    // material: Kd of the first material (tinyobj default 0 when absent); alpha fixed at 1 (model.cpp:322)
+    // material: the reference builds one mesh per material id, each with its own Kd (model.cpp:258-330), and
+    // alpha fixed at 1 (model.cpp:322).  Here the surface carries ONE Kd: the materials the faces use must
+    // agree on it (the shipped heads have a single material without Kd -> tinyobj's default 0).
     geo.kd[0] = geo.kd[1] = geo.kd[2] = 0.f;
     geo.surf_alpha = 1.f;
     if (!mtllib.empty()) {
         std::string dir = path.substr(0, path.rfind('/') + 1);
         std::ifstream m(dir + mtllib);
-        bool seen = false;
+        struct Mtl { std::string name; float kd[3]; };
+        std::vector<Mtl> mtls;
         while (m && std::getline(m, line)) {
             const char* s = line.c_str();
             while (*s == ' ' || *s == '\t') ++s;
-            if (strncmp(s, "newmtl", 6) == 0) { if (seen) break; seen = true; }
-            else if (s[0] == 'K' && s[1] == 'd' && s[2] == ' ') sscanf(s + 3, "%f %f %f", &geo.kd[0], &geo.kd[1], &geo.kd[2]);
+            if (strncmp(s, "newmtl", 6) == 0) {
+                std::string nm = s + 6;
+                while (!nm.empty() && (nm.front() == ' ' || nm.front() == '\t')) nm.erase(nm.begin());
+                while (!nm.empty() && (nm.back() == '\r' || nm.back() == ' ')) nm.pop_back();
+                mtls.push_back(Mtl{nm, {0.f, 0.f, 0.f}});
+            } else if (s[0] == 'K' && s[1] == 'd' && s[2] == ' ' && !mtls.empty()) {
+                sscanf(s + 3, "%f %f %f", &mtls.back().kd[0], &mtls.back().kd[1], &mtls.back().kd[2]);
+            }
         }
+        const Mtl* chosen = nullptr;
+        for (const std::string& u : used_mtls)
+            for (const Mtl& mt : mtls) {
+                if (mt.name != u) continue;
+                if (chosen && (chosen->kd[0] != mt.kd[0] || chosen->kd[1] != mt.kd[1] || chosen->kd[2] != mt.kd[2]))
+                    throw std::invalid_argument("OBJ uses several materials with different Kd (" + chosen->name + ", " + mt.name +
+                                                "): per-material surface colours are not supported");
+                if (!chosen) chosen = &mt;
+            }
+        if (!chosen && !mtls.empty()) chosen = &mtls[0];
+        if (chosen) for (int k = 0; k < 3; ++k) geo.kd[k] = chosen->kd[k];
     }
 }
 
@@ -387,28 +415,31 @@ void load_exr_rgba(const std::string& path, std::vector<float>& rgba, int& w, in
         if (p >= n) throw std::invalid_argument("truncated EXR header");
         if (d[p] == 0) { ++p; break; }
         std::string name = rd_str(), type = rd_str();
+        if (p + 4 > n) throw std::invalid_argument("truncated EXR header");
         uint32_t size; memcpy(&size, d + p, 4); p += 4;
-        if (p + size > n) throw std::invalid_argument("truncated EXR header");
+        if (p + (size_t)size > n) throw std::invalid_argument("truncated EXR header");
         if (name == "channels") {
             size_t q = p;
             while (q < p + size && d[q]) {
                 Chan c;
-                while (d[q]) c.name += (char)d[q++];
+                while (q < p + size && d[q]) c.name += (char)d[q++];
                 ++q;
+                if (q + 16 > p + size) throw std::invalid_argument("truncated EXR channel list");
                 int32_t t; memcpy(&t, d + q, 4); c.type = t; q += 8;   // type + pLinear/reserved
                 int32_t xs, ys; memcpy(&xs, d + q, 4); memcpy(&ys, d + q + 4, 4); q += 8;
                 c.xs = xs; c.ys = ys;
                 if (xs != 1 || ys != 1) throw std::invalid_argument("sub-sampled EXR channels are not supported");
                 chans.push_back(c);
             }
-        } else if (name == "compression") compression = d[p];
-        else if (name == "dataWindow") memcpy(dw, d + p, 16);
-        else if (name == "lineOrder") line_order = d[p];
+        } else if (name == "compression" && size >= 1) compression = d[p];
+        else if (name == "dataWindow" && size >= 16) memcpy(dw, d + p, 16);
+        else if (name == "lineOrder" && size >= 1) line_order = d[p];
         p += size;
     }
     (void)line_order;
     w = dw[2] - dw[0] + 1; h = dw[3] - dw[1] + 1;
-    if (w <= 0 || h <= 0 || chans.empty()) throw std::invalid_argument("bad EXR header");
+    if (dw[2] < dw[0] || dw[3] < dw[1] || (long long)dw[2] - dw[0] >= 65536 || (long long)dw[3] - dw[1] >= 65536 || chans.empty())
+        throw std::invalid_argument("bad EXR header");
     int lines_per_block;
     switch (compression) {
         case 0: case 1: case 2: lines_per_block = 1; break;   // NONE, RLE, ZIPS
@@ -448,7 +479,9 @@ void load_exr_rgba(const std::string& path, std::vector<float>& rgba, int& w, in
         int32_t y0, len; memcpy(&y0, d + o, 4); memcpy(&len, d + o + 4, 4);
         o += 8;
         if (len < 0 || o + (size_t)len > n) throw std::invalid_argument("bad EXR block size");
-        const int row0 = y0 - dw[1];
+        const long long row0_ll = (long long)y0 - dw[1];
+        if (row0_ll < 0 || row0_ll >= h) throw std::invalid_argument("EXR block lies outside the data window");
+        const int row0 = (int)row0_ll;
         const int rows = std::min(lines_per_block, h - row0);
         const size_t expect = line_bytes * rows;
         raw.resize(expect);
@@ -658,8 +691,11 @@ void load_scene_file(const std::string& config_path, HostScene& s) {
     s.stats_output = integ->at("stats_output").string();
     s.mis = integ->at("MIS").boolean();
     s.env_pdf = integ->at("ENV_PDF").boolean();
-    if ((int64_t)s.width * s.height > 2048 * 2048 || ((int64_t)s.width * s.height) % 128 != 0)
-        throw std::invalid_argument("Image size has a hard limit of 2K*2K (and must be a multiple of 128 pixels)!");
+    // scene.cpp:302-306 rejects W*H > 2048^2 and W*H % 128 != 0.  The 2K*2K limit is applied PER GPU BAND here
+    // (hm_renderer_create: each band's pixel count), so that a 4096^2 frame renders on >= 4 row bands
+    // (BASELINE config 5); the frame itself is bounded by 8192^2.
+    if (s.width <= 0 || s.height <= 0 || (int64_t)s.width * s.height > (int64_t)8192 * 8192 || ((int64_t)s.width * s.height) % 128 != 0)
+        throw std::invalid_argument("Image size must be a positive multiple of 128 pixels, at most 8K*8K (2K*2K per GPU band)!");
 
     if (const Json* t = cfg.find("tcnn")) {
         if (const Json* c = t->find("config")) {

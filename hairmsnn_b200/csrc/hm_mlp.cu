@@ -819,6 +819,7 @@ MlpConfig mlp_config_from_json(const std::string& path, int in_ch, int out_ch) {
         if (otype(*opt) == "ExponentialDecay") {
             if (opt->has("decay_start")) c.decay_start = (int)opt->at("decay_start").number();
             if (opt->has("decay_interval")) c.decay_interval = (int)opt->at("decay_interval").number();
+            if (c.decay_interval <= 0) throw std::invalid_argument("tcnn optimizer.decay_interval must be positive");
             if (opt->has("decay_base")) c.decay_base = (float)opt->at("decay_base").number();
             adam = &opt->at("nested");
         } else {

@@ -13,32 +13,6 @@
 
 namespace hm {
 
-// Scratch allocator for thrust: its default allocator calls cudaMalloc/cudaFree per algorithm
-// invocation, and cudaFree synchronises the whole device — which would serialise the frames in
-// flight.  Blocks are kept and reused (all uses are ordered on one stream).
-struct ThrustScratch {
-    typedef char value_type;
-    struct Block { char* p; size_t n; bool busy; };
-    std::vector<Block> blocks;
-    char* allocate(std::ptrdiff_t n) {
-        for (auto& b : blocks)
-            if (!b.busy && b.n >= (size_t)n) { b.busy = true; return b.p; }
-        char* p = nullptr;
-        if (cudaMalloc((void**)&p, (size_t)n) != cudaSuccess) throw std::runtime_error("CUDA: scratch allocation failed");
-        blocks.push_back(Block{p, (size_t)n, true});
-        return p;
-    }
-    void deallocate(char* p, size_t) {
-        for (auto& b : blocks)
-            if (b.p == p) { b.busy = false; return; }
-    }
-    ~ThrustScratch() { for (auto& b : blocks) cudaFree(b.p); }
-};
-static ThrustScratch& thrust_scratch() {
-    static thread_local ThrustScratch s;
-    return s;
-}
-
 #define HM_CUDA(call)                                                                          \
     do {                                                                                       \
         cudaError_t e_ = (call);                                                               \
@@ -172,27 +146,36 @@ Renderer::Renderer(const HostScene& hs, int kind, int beta_cli, int device, int 
     if (const char* e = getenv("HM_TAIL_MEGA")) tail_mega_ = atoi(e) != 0;
     if (const char* e = getenv("HM_TAIL_BOUND")) tail_bound_items_ = atoi(e);
     if (const char* e = getenv("HM_FRAMES_IN_FLIGHT")) frames_in_flight_ = std::max(1, std::min((int)kFramesInFlight, atoi(e)));
+    // Per-pixel state is allocated for this rank's row band only.  Slots stay FULL-frame pixel indices (RNG keys,
+    // training-pixel rule), so each array's base pointer is moved back by the band's first pixel:
+    // kernels index it with the global slot and touch [first, first + nb) only.
+    const size_t nb = (size_t)(row1_ - row0_) * W_;        // pixels of the band
+    const size_t first = (size_t)row0_ * W_;
+    if (nb > (size_t)2048 * 2048)
+        throw std::invalid_argument("a renderer's band holds more than 2048 x 2048 pixels (scene.cpp:302-306 limit, applied per GPU band): use more bands");
+    auto alloc_px = [&](size_t bytes_per_px) { return (char*)alloc(nb * bytes_per_px) - first * bytes_per_px; };
     for (int ci = 0; ci < frames_in_flight_; ++ci) {
         FrameCtx& c = ctx_[ci];
-        c.paths.rng = (uint32_t*)alloc(n * 4);
-        c.paths.ray_o = (float4*)alloc(n * 16);
-        c.paths.ray_d = (float4*)alloc(n * 16);
-        c.paths.hit = (float4*)alloc(n * 16);
-        c.paths.beta = (float4*)alloc(n * 16);
-        c.paths.color = (float4*)alloc(n * 16);
-        c.paths.dl_beta = (float4*)alloc(n * 16);
-        c.paths.dl_light = (float4*)alloc(n * 16);
-        c.paths.dl_bsdf = (float4*)alloc(n * 16);
-        c.paths.vis = (uint32_t*)alloc(n * 4);
+        c.paths.rng = (uint32_t*)alloc_px(4);
+        c.paths.ray_o = (float4*)alloc_px(16);
+        c.paths.ray_d = (float4*)alloc_px(16);
+        c.paths.hit = (float4*)alloc_px(16);
+        c.paths.beta = (float4*)alloc_px(16);
+        c.paths.color = (float4*)alloc_px(16);
+        c.paths.dl_beta = (float4*)alloc_px(16);
+        c.paths.dl_light = (float4*)alloc_px(16);
+        c.paths.dl_bsdf = (float4*)alloc_px(16);
+        c.paths.vis = (uint32_t*)alloc_px(4);
         if (kind_ == HM_KIND_MSNN) {
-            c.paths.beta_short = (float4*)alloc(n * 16);
-            c.paths.color_short = (float4*)alloc(n * 16);
-            c.paths.dl_beta_short = (float4*)alloc(n * 16);
+            c.paths.beta_short = (float4*)alloc_px(16);
+            c.paths.color_short = (float4*)alloc_px(16);
+            c.paths.dl_beta_short = (float4*)alloc_px(16);
             c.train_idxs = (int*)alloc((size_t)records_ * 4);
-            c.nn_frame_in = (float*)alloc(n * in_ch_ * 4);
+            c.nn_frame_in = (float*)alloc_px((size_t)in_ch_ * 4);
             c.nn_train_in = (float*)alloc((size_t)records_ * in_ch_ * 4);
             c.nn_train_out = (float*)alloc((size_t)records_ * 3 * 4);
-            c.gbuffer = (float4*)alloc(n * 16);
+            c.gbuffer = (float4*)alloc_px(16);
+            // one flag per 128-pixel tile of the FULL frame (tiny): bands need not start on a tile boundary
             c.query_tiles = (int*)alloc((n / 128 + 1) * 4);
         }
         if (kind_ == HM_KIND_NRC) {
@@ -206,10 +189,10 @@ Renderer::Renderer(const HostScene& hs, int kind, int beta_cli, int device, int 
             c.gbuffer_b = (float4*)alloc(n * 16);
             c.tbuffer = (NrcTrainRec*)alloc((size_t)nrc_train_pixels_ * sizeof(NrcTrainRec));
         }
-        c.q.shade[0] = (int*)alloc(n * 4);
-        c.q.shade[1] = (int*)alloc(n * 4);
-        c.q.extend = (int*)alloc(n * 4);
-        c.q.shadow = (float4*)alloc(n * 2 * 32);
+        c.q.shade[0] = (int*)alloc(nb * 4);
+        c.q.shade[1] = (int*)alloc(nb * 4);
+        c.q.extend = (int*)alloc(nb * 4);
+        c.q.shadow = (float4*)alloc(nb * 2 * 32);
         c.q.counts = (int*)alloc(16 * 4);
         c.q.trav = d_trav_;
         HM_CUDA(cudaStreamCreateWithPriority(&c.tail_stream, cudaStreamNonBlocking, getenv("HM_TAIL_LOW_PRIO") ? prio_lo : prio_hi));
@@ -231,7 +214,7 @@ Renderer::Renderer(const HostScene& hs, int kind, int beta_cli, int device, int 
         for (int i = 0; i < n_idxs_; ++i) seq[i] = i;   // thrust::sequence
         d_train_idxs_ = (int*)alloc((size_t)n_idxs_ * 4);
         HM_CUDA(cudaMemcpy(d_train_idxs_, seq.data(), (size_t)n_idxs_ * 4, cudaMemcpyHostToDevice));
-        nn_frame_out_ = (float*)alloc((size_t)nn_frame_rows_ * 3 * 4);
+        nn_frame_out_ = kind_ == HM_KIND_MSNN ? (float*)alloc_px(3 * 4) : (float*)alloc((size_t)nn_frame_rows_ * 3 * 4);
     }
     last_ctx_ = &ctx_[0];
     HM_CUDA(cudaDeviceSynchronize());
@@ -241,6 +224,7 @@ Renderer::~Renderer() {
     cudaSetDevice(device_);
     cudaDeviceSynchronize();
     mlp_.reset();
+    scratch_.release();
     for (void* p : allocs_) cudaFree(p);
     scene_.reset();
     for (auto& p : pending_) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -345,6 +329,16 @@ FrameParams Renderer::params_for(const FrameCtx& c) {
     P.in_ch = in_ch_;
     P.n_primary = (row1_ - row0_) * W_;
     if (c.pretrain) {
+        // TRAIN_DATA_GEN: slot == record index 0..records-1, whatever the band: undo the band offset of the
+        // per-pixel arrays (the constructor moved their base pointers back by the band's first pixel)
+        const ptrdiff_t first = (ptrdiff_t)row0_ * W_;
+        if (first) {
+            if ((size_t)(row1_ - row0_) * W_ < (size_t)records_) throw std::invalid_argument("TRAIN_DATA_GEN needs a band of at least 16384 pixels");
+            PathBuffers& b = P.paths;
+            b.rng += first; b.ray_o += first; b.ray_d += first; b.hit += first; b.beta += first; b.color += first;
+            b.dl_beta += first; b.dl_light += first; b.dl_bsdf += first; b.vis += first;
+            if (b.beta_short) { b.beta_short += first; b.color_short += first; b.dl_beta_short += first; }
+        }
         P.pretrain = 1;
         P.n_primary = records_;
         P.sampled_points = d_scene_points_;
@@ -358,10 +352,12 @@ FrameParams Renderer::params_for(const FrameCtx& c) {
         const BandPartition bp = band_partition(W_, H_, records_, rank_, world_);
         P.train_slot0 = c.pretrain ? 0 : bp.slot0;
         P.train_slots = c.pretrain ? records_ : bp.slots;
-        P.nn_frame_in = c.nn_frame_in;
+        P.train_records = records_;
+        const size_t unshift = c.pretrain ? (size_t)row0_ * W_ : 0;
+        P.nn_frame_in = c.nn_frame_in + unshift * in_ch_;
         P.nn_train_in = c.nn_train_in;
         P.nn_train_out = c.nn_train_out;
-        P.gbuffer = c.gbuffer;
+        P.gbuffer = c.gbuffer + unshift;
         P.query_tiles = c.pretrain ? nullptr : c.query_tiles;
     } else if (kind_ == HM_KIND_NRC) {
         P.mode = MODE_NRC;
@@ -388,7 +384,7 @@ void Renderer::shuffle_train_idxs(FrameCtx& c) {
     thrust::device_ptr<int> p = thrust::device_pointer_cast(d_train_idxs_);
     // on main_stream_ (frame order); the frame's own stream picks the copy up through ev_shuffled
     if (c.main != main_stream_) HM_CUDA(cudaStreamWaitEvent(main_stream_, c.ev_free, 0));
-    thrust::shuffle(thrust::cuda::par_nosync(thrust_scratch()).on(main_stream_), p, p + n_idxs_, thrust::default_random_engine());
+    thrust::shuffle(thrust::cuda::par_nosync(scratch_).on(main_stream_), p, p + n_idxs_, thrust::default_random_engine());
     HM_CUDA(cudaMemcpyAsync(c.train_idxs, d_train_idxs_, (size_t)n_idxs_ * 4, cudaMemcpyDeviceToDevice, main_stream_));
     if (c.main != main_stream_) {
         HM_CUDA(cudaEventRecord(c.ev_shuffled, main_stream_));
@@ -491,12 +487,52 @@ void Renderer::msnn_train_backward() {
     const int s0 = bp.slot0, n = bp.train_n;
     FrameCtx& c = *current_;
     timed(5, order_stream_, [&] {
-        mlp_->forward_backward(c.nn_train_in + (size_t)s0 * in_ch_, c.nn_train_out + (size_t)s0 * 3, n, world_ == 1 ? n : records_);
+        mlp_->forward_backward(c.nn_train_in + (size_t)s0 * in_ch_, c.nn_train_out + (size_t)s0 * 3, n,
+                               (world_ == 1 ? n : records_) * groups_);
     });
+}
+
+// One NCCL all-reduce of the fp32 gradient buffer (1 000 448 floats, 4 MB) over NVLink, in frame order on the
+// order stream: backward -> all-reduce -> Adam.  Every rank applies the same sum, so the replicas' weights
+// stay bit-identical.
+void Renderer::all_reduce_gradients() {
+    if (!comm_ || comm_->world() == 1) return;
+    timed(5, order_stream_, [&] { comm_->all_reduce_sum(mlp_->gradients(), mlp_->n_params(), order_stream_); });
+}
+
+void Renderer::set_comm(Comm* comm) {
+    sync();
+    if (!comm) { comm_ = nullptr; groups_ = 1; frame_offset_ = 0; frame_stride_ = 1; return; }
+    if (comm->device() != device_) throw std::invalid_argument("communicator and renderer are on different devices");
+    if (comm->world() % world_ != 0 || comm->rank() % world_ != rank_)
+        throw std::invalid_argument("communicator rank must be group * bands + band (comm world a multiple of the band count)");
+    comm_ = comm;
+    groups_ = comm->world() / world_;
+    frame_offset_ = comm->rank() / world_;
+    frame_stride_ = groups_;
+}
+
+void Renderer::reduce_framebuffers() {
+    if (!comm_) throw std::logic_error("reduce_framebuffers: no communicator attached (hm_renderer_set_comm)");
+    if (current_) throw std::logic_error("reduce_framebuffers: a frame is in flight");
+    HM_CUDA(cudaSetDevice(device_));
+    const size_t n = (size_t)W_ * H_;
+    const double total = comm_->all_reduce_sum((double)accum_id_) / world_;   // samples per pixel over all groups
+    if (total <= 0) throw std::logic_error("reduce_framebuffers: nothing rendered yet");
+    const int pairs = kind_ == HM_KIND_MSNN ? 3 : 1;
+    for (int i = 0; i < pairs; ++i) {
+        float4* avg = bufs_[2 * i];
+        float4* accum = bufs_[2 * i + 1];
+        HM_CUDA(cudaMemcpyAsync(avg, accum, n * 16, cudaMemcpyDeviceToDevice, order_stream_));
+        comm_->all_reduce_sum((float*)avg, n * 4, order_stream_);
+        launch_resolve_sum(avg, i == 0 ? fb_ : nullptr, 1.f / (float)total, (int)n, order_stream_);
+    }
+    HM_CUDA(cudaStreamSynchronize(order_stream_));
 }
 
 void Renderer::msnn_train_apply() {
     if (kind_ != HM_KIND_MSNN) throw std::logic_error("not a HairMSNN renderer");
+    all_reduce_gradients();
     timed(5, order_stream_, [&] { mlp_->optimizer_step(); });
 }
 
@@ -551,11 +587,12 @@ void Renderer::nrc_train_backward() {
     if (kind_ != HM_KIND_NRC) throw std::logic_error("not an NRC renderer");
     if (!current_) throw std::logic_error("nrc_train_backward: call nrc_trace first");
     FrameCtx& c = *current_;
-    timed(5, order_stream_, [&] { mlp_->forward_backward(c.nn_train_in, c.nn_train_out, records_, records_); });
+    timed(5, order_stream_, [&] { mlp_->forward_backward(c.nn_train_in, c.nn_train_out, records_, records_ * groups_); });
 }
 
 void Renderer::nrc_train_apply() {
     if (kind_ != HM_KIND_NRC) throw std::logic_error("not an NRC renderer");
+    all_reduce_gradients();
     timed(5, order_stream_, [&] { mlp_->optimizer_step(); });
 }
 
@@ -582,7 +619,7 @@ void Renderer::ensure_scene_samples() {
     HM_CUDA(cudaMemcpy(d_scene_indices_, seq.data(), (size_t)n_scene_samples_ * 4, cudaMemcpyHostToDevice));
     // the initial shuffle of sceneIndices (render_hair_msnn.cu:395-400)
     thrust::device_ptr<int> p = thrust::device_pointer_cast(d_scene_indices_);
-    thrust::shuffle(thrust::cuda::par_nosync(thrust_scratch()).on(main_stream_), p, p + n_scene_samples_, thrust::default_random_engine());
+    thrust::shuffle(thrust::cuda::par_nosync(scratch_).on(main_stream_), p, p + n_scene_samples_, thrust::default_random_engine());
 }
 
 void Renderer::msnn_train_data_gen() {
@@ -614,8 +651,11 @@ void Renderer::msnn_pretrain(int steps) {
         trace_frame(c);
         current_ = &c;
         thrust::device_ptr<int> p = thrust::device_pointer_cast(d_scene_indices_);
-        thrust::shuffle(thrust::cuda::par_nosync(thrust_scratch()).on(main_stream_), p, p + n_scene_samples_, thrust::default_random_engine());
-        timed(5, order_stream_, [&] { mlp_->forward_backward(c.nn_train_in, c.nn_train_out, records_, records_); });
+        thrust::shuffle(thrust::cuda::par_nosync(scratch_).on(main_stream_), p, p + n_scene_samples_, thrust::default_random_engine());
+        // with a communicator every rank contributes a full batch (groups render different sample ids, the bands
+        // of a group the same one): global batch = records x comm world
+        timed(5, order_stream_, [&] { mlp_->forward_backward(c.nn_train_in, c.nn_train_out, records_, records_ * (comm_ ? comm_->world() : 1)); });
+        all_reduce_gradients();
         timed(5, order_stream_, [&] { mlp_->optimizer_step(); });
         end_frame(c);
         current_ = nullptr;
@@ -676,15 +716,17 @@ Stats Renderer::stats() {
 
 void* Renderer::device_buffer(int which, size_t* bytes) {
     const size_t n = (size_t)W_ * H_;
+    const size_t nb = (size_t)(row1_ - row0_) * W_, first = (size_t)row0_ * W_;
     FrameCtx& c = *last_ctx_;
     switch (which) {
         case 0: case 1: case 2: case 3: case 4: case 5: *bytes = n * 16; return bufs_[which];
         case 6: *bytes = n * 4; return fb_;
-        case 7: *bytes = (kind_ == HM_KIND_NRC ? (size_t)nn_frame_rows_ : n) * in_ch_ * 4; return c.nn_frame_in;
-        case 8: *bytes = (kind_ == HM_KIND_NRC ? (size_t)nn_frame_rows_ : n) * 3 * 4; return nn_frame_out_;
+        // per-pixel working buffers hold this renderer's row band only: [rows of the band][W] (the whole frame when world = 1)
+        case 7: *bytes = (kind_ == HM_KIND_NRC ? (size_t)nn_frame_rows_ : nb) * in_ch_ * 4; return c.nn_frame_in + first * in_ch_;
+        case 8: *bytes = (kind_ == HM_KIND_NRC ? (size_t)nn_frame_rows_ : nb) * 3 * 4; return nn_frame_out_ + first * 3;
         case 9: *bytes = (size_t)records_ * in_ch_ * 4; return c.nn_train_in;
         case 10: *bytes = (size_t)records_ * 3 * 4; return c.nn_train_out;
-        case 11: *bytes = n * 16; return c.gbuffer;
+        case 11: *bytes = nb * 16; return c.gbuffer + first;
         case 12: *bytes = (size_t)n_idxs_ * 4; return c.train_idxs;
         case 13: *bytes = n * 16; return c.gbuffer_b;
         case 14: *bytes = (size_t)nrc_train_pixels_ * sizeof(NrcTrainRec); return c.tbuffer;

@@ -6,9 +6,11 @@
 // render_hair_msnn.cu) minus the GLFW/ImGui shell.
 #pragma once
 #include <memory>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
+#include "hm_comm.h"
 #include "hm_host.h"
 #include "hm_mlp.h"
 #include "hm_wavefront.h"
@@ -23,6 +25,28 @@ struct Stats {
     uint64_t tail_nodes = 0, tail_prims = 0, tail_rays = 0;   // share of extend+shadow traced by tail-piece launches
     float last_loss = 0.f;
     int frames = 0;
+};
+
+// Scratch allocator for thrust: its default allocator calls cudaMalloc/cudaFree per algorithm invocation, and
+// cudaFree synchronises the whole device — which would serialise the frames in flight.  Blocks are kept and
+// reused.  One instance per Renderer: every use is ordered on that renderer's main stream, on its device.
+struct ThrustScratch {
+    typedef char value_type;
+    struct Block { char* p; size_t n; bool busy; };
+    std::vector<Block> blocks;
+    char* allocate(std::ptrdiff_t n) {
+        for (auto& b : blocks)
+            if (!b.busy && b.n >= (size_t)n) { b.busy = true; return b.p; }
+        char* p = nullptr;
+        if (cudaMalloc((void**)&p, (size_t)n) != cudaSuccess) throw std::runtime_error("CUDA: scratch allocation failed");
+        blocks.push_back(Block{p, (size_t)n, true});
+        return p;
+    }
+    void deallocate(char* p, size_t) {
+        for (auto& b : blocks)
+            if (b.p == p) { b.busy = false; return; }
+    }
+    void release() { for (auto& b : blocks) cudaFree(b.p); blocks.clear(); }   // called by ~Renderer after a device sync
 };
 
 class DeviceScene {
@@ -122,6 +146,19 @@ public:
     void set_collect_stats(bool on) { collect_stats_ = on; }
     // off: evaluate the cache for every pixel as the reference does (default: skip 128-pixel tiles without a hair hit)
     void set_skip_unused_queries(bool on) { skip_unused_queries_ = on; }
+    // Multi-GPU.  The communicator's ranks form `groups` sample groups of `world` row bands each
+    // (comm world = groups * band world, comm rank = group * band world + band rank).  Attaching it
+    //  * sets the sample schedule: group g renders sample ids g, g + groups, ... (weak scaling by samples);
+    //  * makes every training step all-reduce the network's gradients over ALL ranks on the order stream,
+    //    between backward and Adam, with the loss normalised by the global batch — replicas stay bit-identical;
+    //  * enables reduce_framebuffers().
+    void set_comm(Comm* comm);
+    // Sum of all ranks' accumulation buffers -> average over the global sample count + 8-bit frame, left in the
+    // average / fb8 buffers of EVERY rank (rows a rank does not own are zero in its accumulation buffers, so one
+    // all-reduce serves sample groups and row bands alike).  The accumulation buffers stay local: rendering can
+    // continue afterwards.
+    void reduce_framebuffers();
+    int sample_groups() const { return groups_; }
     // spp sharding: RNG frame id = offset + accum_id * stride (accum_id counts this renderer's own samples)
     void set_frame_schedule(int offset, int stride) { frame_offset_ = offset; frame_stride_ = stride; }
     void reset_stats();
@@ -159,6 +196,7 @@ private:
     Camera cam_;
     FrameCtx ctx_[kFramesInFlight];
     std::vector<void*> allocs_;
+    ThrustScratch scratch_;
     // outputs
     float4* bufs_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // final avg/accum, pt avg/accum, nn avg/accum
     uint32_t* fb_ = nullptr;
@@ -179,6 +217,9 @@ private:
     bool nrc_all_unbiased_ = false;
     float nrc_c_ = 0.01f;           // headers/render_nrc.h:132
     FrameCtx* last_ctx_ = nullptr;
+    Comm* comm_ = nullptr;          // not owned
+    int groups_ = 1;                // sample groups of the communicator (comm world / band world)
+    void all_reduce_gradients();
     bool profiling_ = false, collect_stats_ = false, skip_unused_queries_ = true, tail_mega_ = false;
     int frame_offset_ = 0, frame_stride_ = 1;
     unsigned profile_mask_ = 0xffffffffu;

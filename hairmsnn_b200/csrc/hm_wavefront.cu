@@ -60,6 +60,9 @@ __device__ __forceinline__ int queue_reserve(int* counter, bool want) {
 __device__ __forceinline__ bool is_training_pixel(const FrameParams& P, int fb_ofs, int& tr_ofs) {
     if (P.pretrain) { tr_ofs = fb_ofs; return true; }   // TRAIN_DATA_GEN: every work item is a training record
     tr_ofs = fb_ofs / P.every_nth;
+    // W*H need not be a multiple of numTrainRecords (everyNth = floor(W*H / 16384)): the reference reads past
+    // trainIdxs for the trailing groups (cuda/hair_msnn.cu:208); they have no training pixel here
+    if (tr_ofs >= P.train_records) return false;
     int train_idx = __ldg(P.train_idxs + tr_ofs) % P.every_nth;
     return fb_ofs % P.every_nth == train_idx;
 }
@@ -801,6 +804,18 @@ __global__ void __launch_bounds__(256) k_msnn_composite(const MsnnComposite C) {
     }
 }
 
+// Multi-GPU output resolve: `img` holds the all-reduced SUM of the ranks' accumulation buffers;
+// turns it into the average over `total` samples in place and, for the final image, the 8-bit sRGB frame
+// (writePixel's tail, utils.cuh:27-34).
+__global__ void __launch_bounds__(256) k_resolve_sum(float4* img, uint32_t* fb, float inv_total, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 a = img[i];
+        V3 c = inv_total * V3(a.x, a.y, a.z);
+        img[i] = f4(c, 1.f);
+        if (fb) fb[i] = pack_rgba8(V3(linear_to_srgb(c.x), linear_to_srgb(c.y), linear_to_srgb(c.z)));
+    }
+}
+
 struct HookOps {
     const float* org; const float* dir; float4* out_hit; int any;
     __device__ __forceinline__ bool fetch(int w, V3& o, V3& d) const {
@@ -881,6 +896,10 @@ void launch_finalize(const FrameParams& P, cudaStream_t stream) {
 }
 void launch_msnn_composite(const MsnnComposite& C, cudaStream_t stream) {
     k_msnn_composite<<<persistent_grid(8), 256, 0, stream>>>(C);
+    g_launches++;
+}
+void launch_resolve_sum(float4* img, uint32_t* fb, float inv_total, int n, cudaStream_t stream) {
+    k_resolve_sum<<<persistent_grid(8), 256, 0, stream>>>(img, fb, inv_total, n);
     g_launches++;
 }
 void launch_nrc_render(const NrcRender& R, cudaStream_t stream) {

@@ -95,6 +95,7 @@ struct FrameParams {
     int every_nth;
     const int* train_idxs;
     int train_slot0, train_slots;    // this rank's range of training records
+    int train_records;   // length of train_idxs (numTrainRecords); groups past it have no training pixel
     float* nn_frame_in;  // [W*H][12]
     float* nn_train_in;  // [records][12]
     float* nn_train_out; // [records][3]
@@ -142,6 +143,8 @@ void launch_tail_mega(const FrameParams& P, int src_queue, int max_paths, cudaSt
 void launch_finalize(const FrameParams& P, cudaStream_t stream);
 void launch_msnn_composite(const MsnnComposite& C, cudaStream_t stream);
 void launch_nrc_render(const NrcRender& R, cudaStream_t stream);
+// multi-GPU: summed accumulation buffer -> average (in place) + optional 8-bit frame
+void launch_resolve_sum(float4* img, uint32_t* fb, float inv_total, int n, cudaStream_t stream);
 // test hook: closest-hit / any-hit for caller-supplied rays (device pointers)
 void launch_trace_rays(const SceneView& S, const float* org, const float* dir, int n, int any,
                        float tmin, float tmax, float4* out_hit, int* out_stats, int* cursor, cudaStream_t stream);

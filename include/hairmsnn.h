@@ -25,12 +25,13 @@ extern "C" {
 typedef struct hm_scene hm_scene;
 typedef struct hm_renderer hm_renderer;
 typedef struct hm_mlp hm_mlp;
+typedef struct hm_comm hm_comm;
 
 typedef enum {
     HM_OK = 0,
     HM_ERR_ARG = -1,      /* bad argument / malformed scene                          */
     HM_ERR_IO = -2,       /* file missing or unreadable                               */
-    HM_ERR_CUDA = -3,     /* CUDA runtime error, or no usable device                  */
+    HM_ERR_CUDA = -3,     /* CUDA / NCCL runtime error, or no usable device           */
     HM_ERR_STATE = -4,    /* call not valid for this handle (e.g. wrong renderer kind) */
     HM_ERR_UNSUPPORTED = -5
 } hm_status;
@@ -146,6 +147,7 @@ int hm_scene_get_env_tables(const hm_scene* scene, const float** env_rgba, const
  * beta_cli is the [BETA] argument (render_hair_msnn.cu:1146-1170: internal beta = BETA-1).
  * The frame is split into `world` contiguous row bands; this handle renders band
  * `rank` on CUDA device `device`.  world = 1 renders everything. */
+/* The renderer shares ownership of the host scene: hm_scene_free may be called before hm_renderer_destroy. */
 int hm_renderer_create(hm_scene* scene, int kind, int beta_cli, int device, int rank, int world, hm_renderer** out);
 void hm_renderer_destroy(hm_renderer* r);
 
@@ -263,6 +265,32 @@ int hm_band_partition(int width, int height, int records, int rank, int world, i
  * arithmetic): out4 = numTrainingPixels (65536 / MAX_BOUNCES), everyNth, nnFrameSize (rows fed to inference:
  * frame + training suffixes, rounded up to tcnn's 128-row granularity), numTrainingRecords. */
 int hm_nrc_layout(int width, int height, int* out4);
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink / NVSwitch ----------
+ * The reference is single-GPU (render_hair_msnn.cu:1056: owlContextCreate(nullptr, 1)); these calls are the
+ * new partitioning of its render()/train() loop.  Rank 0 obtains a 128-byte id and hands it to the other
+ * processes by any means (file, pipe, TCP store); every process then creates its communicator on its device. */
+#define HM_COMM_ID_BYTES 128
+int hm_comm_get_unique_id(void* out_id128);
+int hm_comm_create(const void* id128, int rank, int world, int device, hm_comm** out);
+void hm_comm_destroy(hm_comm* c);
+int hm_comm_barrier(hm_comm* c);
+/* max / sum of one double over all ranks (timing: max over ranks of a device-measured duration) */
+int hm_comm_all_reduce_max(hm_comm* c, double* inout);
+int hm_comm_all_reduce_sum(hm_comm* c, double* inout);
+/* Attaches the communicator to a renderer (NULL detaches).  comm world = G sample groups x B row bands, where
+ * B is the renderer's own `world` (hm_renderer_create) and comm rank = group * B + band.  From then on
+ *  - group g renders sample ids g, g + G, g + 2G, ... (hm_renderer_set_frame_schedule is set accordingly);
+ *  - every training step inside hm_render_frames / hm_msnn_train_apply / hm_nrc_train_apply / hm_msnn_pretrain
+ *    all-reduces the network's gradients over all ranks between backward and Adam (ncclAllReduce on the
+ *    renderer's stream, loss normalised by the global batch), so the replicas' weights stay bit-identical;
+ *  - hm_reduce_framebuffers is available.
+ * Every rank must make the same sequence of rendering calls.  The communicator must outlive the attachment. */
+int hm_renderer_set_comm(hm_renderer* r, hm_comm* c);
+/* Sums the ranks' accumulation buffers (row bands a rank does not own are zero in its buffers, so one
+ * all-reduce serves sample groups and bands alike) and leaves the average over the GLOBAL sample count and
+ * the 8-bit frame in HM_BUF_*_AVG / HM_BUF_FB8 of every rank.  Accumulation buffers stay local. */
+int hm_reduce_framebuffers(hm_renderer* r);
 
 /* ---- stand-alone kernels (parity tests, micro-benchmarks) ----------------------- */
 
