@@ -190,9 +190,22 @@ __device__ __forceinline__ void encode_row(const NetShape& S, const __half2* __r
             left = right;
         }
     }
+    const int blob0 = c0;
     c0 += S.blob_dims * nb;
     for (int j = 0; j < S.identity_dims; ++j) *at(c0 + j) = __float2half_rn(x[3 + S.blob_dims + j]);
-    for (int c = c0 + S.identity_dims; c < kW; ++c) *at(c) = __float2half_rn(1.0f);
+    if (S.identity_dims > 0) {
+        // Identity is the last nested encoding and pads the network input with ones (identity.h:46-66)
+        for (int c = c0 + S.identity_dims; c < kW; ++c) *at(c) = __float2half_rn(1.0f);
+    } else {
+        // render_nrc (9 inputs): the Identity encoding is dropped (composite.h:181) and OneBlob pads.  Its SoA
+        // padding writes the ones at element offset N * n_dims_to_encode of its own slice (oneblob.h:221-225),
+        // i.e. over its rows blob_dims .. blob_dims + n_pad - 1 (network inputs 38..45), and never writes the real
+        // padding rows, which keep the allocation's contents — zero in a fresh one.  Pinned by the reference's
+        // own tiny-cuda-nn: tests/golden/tcnn_9.npz.
+        const int n_pad = kW - c0;
+        for (int c = 0; c < n_pad; ++c) *at(blob0 + S.blob_dims + c) = __float2half_rn(1.0f);
+        for (int c = c0; c < kW; ++c) *at(c) = __float2half_rn(0.0f);
+    }
 }
 
 struct FwdArgs {
@@ -909,7 +922,8 @@ void Mlp::initial_params(const MlpConfig& c, std::vector<float>& out, size_t& n_
         for (size_t j = 0; j < 4; ++j) {
             const size_t idx = i + T * j;
             if (idx >= n_grid) break;
-            out[n_matrix + idx] = stream[4 * i + j] * (1e-4f - -1e-4f) + -1e-4f;
+            // val * (upper - lower) + lower: one FMA in tcnn's device code (nvcc contracts it), pinned by tests/golden/tcnn_*.npz
+            out[n_matrix + idx] = std::fmaf(stream[4 * i + j], 1e-4f - -1e-4f, -1e-4f);
         }
 }
 

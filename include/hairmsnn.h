@@ -195,9 +195,10 @@ hm_mlp* hm_renderer_mlp(hm_renderer* r);
  * (nrcGenerateTrainingData + composite, cuda/nrc.cu:69-133,367-381); train_backward / train_apply =
  * trainer->training_step over the 65536 records (a multi-GPU caller all-reduces hm_mlp_gradients()
  * in between); end = accumId++ (the buffer clears and the RESET pass happen at the next trace).
- * For render_nrc BUF_GBUFFER holds rgb = GBuffer::pathRadiance, w = hit; with the 9 input channels the
- * tcnn composite encoding has no identity part and the 8 padding inputs of the 64-wide network are 1
- * (the reference leaves them uninitialised). */
+ * For render_nrc BUF_GBUFFER holds rgb = GBuffer::pathRadiance, w = hit.  With the 9 input channels the
+ * tcnn composite encoding has no identity part and OneBlob pads: as tiny-cuda-nn does (oneblob.h:221-225,
+ * pinned by tests/golden/tcnn_9.npz), network inputs 38..45 are overwritten with 1 and the padding inputs
+ * 56..63 — left unwritten by the reference — are 0. */
 int hm_nrc_trace(hm_renderer* r);
 int hm_nrc_query(hm_renderer* r);
 int hm_nrc_train_backward(hm_renderer* r);

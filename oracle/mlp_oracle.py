@@ -3,10 +3,14 @@ instantiates for render_hair_msnn / render_nrc.
 tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module;
 the product never does.
 
-PARITY UNPINNED BY REFERENCE TESTS: tiny-cuda-nn ships no golden vectors for this
-configuration and its kernels need a tensor-core GPU, so they cannot run in the build
-container.  Each function restates the cited source; the PRNG is pinned against the
-published PCG32 reference stream and std::seed_seq (C++ standard [rand.util.seedseq]).
+PINNED against the reference's own tiny-cuda-nn: oracle/Makefile.tcnn compiles the vendored
+library for sm_100, oracle/tcnn_golden.cu drives it the way TINY_MLP does on seeded inputs, and the
+outputs of one run on a B200 are committed as tests/golden/tcnn_{12,9}.npz
+(tests/test_cpu_mlp_oracle.py checks every function below against them).  Two things only the
+golden vectors revealed: the grid initialisation is an FMA (nvcc contracts val * scale + lower), and
+with 9 inputs (render_nrc) OneBlob's SoA padding overwrites network inputs 38-45 with 1.0 and
+leaves 56-63 unwritten (0 in a fresh allocation).  The PRNG is also pinned against the published
+PCG32 reference stream and std::seed_seq (C++ standard [rand.util.seedseq]).
 
 All paths are relative to /root/reference/extern/tiny-cuda-nn.
 Two arithmetic modes:
@@ -180,7 +184,8 @@ def initial_params(cfg):
         ok = idx < n_grid
         src = 4 * i[ok] + j
         ok2 = src < len(f)
-        grid[idx[ok][ok2]] = f[src[ok2]] * np.float32(2e-4) + np.float32(-1e-4)
+        # val * (upper - lower) + lower is contracted to one FMA by nvcc (random.h:66-94): a single rounding
+        grid[idx[ok][ok2]] = (f[src[ok2]].astype(np.float64) * np.float64(np.float32(2e-4)) + np.float64(np.float32(-1e-4))).astype(np.float32)
     out[n_matrix:] = grid
     return out
 
@@ -275,6 +280,15 @@ def encode(cfg, params, x, half=True, half_accumulate=False):
     c1 = c0 + cfg.blob_dims * nb
     for j in range(cfg.identity_dims):
         out[:, c1 + j] = _h(x[:, 3 + cfg.blob_dims + j], half)
+    if cfg.identity_dims == 0:
+        # render_nrc (9 inputs): the Identity encoding is dropped (composite.h:181), OneBlob is last and pads.
+        # Its SoA padding writes the ones at offset N * n_dims_to_encode of its own slice (oneblob.h:221-225)
+        # — rows 6..13 of the slice = network inputs 38..45, overwriting those OneBlob outputs — and never
+        # touches the real padding rows 56..63, which stay whatever the allocation held (0 when fresh; pinned
+        # by tests/golden/tcnn_9.npz).
+        n_pad = cfg.width - c1
+        out[:, c0 + cfg.blob_dims:c0 + cfg.blob_dims + n_pad] = 1.0
+        out[:, c1:] = 0.0
     return out
 
 

@@ -119,3 +119,124 @@ def test_adam_first_step_is_sign_step():
     untouched = np.ones(p.size, bool); untouched[:9216] = False; untouched[20000:20010] = False
     assert np.array_equal(new[untouched], p[untouched])          # sparse skip for zero-gradient grid entries
     assert opt.steps[20000] == 1 and opt.steps[30000] == 0
+
+
+# ---- pinned against the reference's own tiny-cuda-nn --------------------------------------------------------
+# tests/golden/tcnn_{12,9}.npz: outputs of /root/reference/extern/tiny-cuda-nn compiled for sm_100
+# (oracle/Makefile.tcnn) and driven as TINY_MLP does (oracle/tcnn_golden.cu) on a B200, reduced by
+# oracle/make_tcnn_golden.py.  Tolerances: tcnn accumulates in fp16 inside wmma and scatters grid gradients
+# with half2 atomics; the oracle rounds to fp16 only where tcnn STORES fp16.
+import tcnn_inputs  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _rl2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+@pytest.fixture(scope="module", params=[12, 9])
+def golden(request):
+    ch = request.param
+    g = np.load(os.path.join(GOLD, f"tcnn_{ch}.npz"))
+    x = tcnn_inputs.make_inputs(int(g["n_rows"]), ch, int(g["input_seed"]))
+    y = tcnn_inputs.make_targets(int(g["n_rows"]), int(g["target_seed"]))
+    return ch, g, x, y
+
+
+def test_golden_initial_parameters_bit_exact(golden):
+    ch, g, _, _ = golden
+    cfg = mo.Config(ch)
+    p = mo.initial_params(cfg)
+    assert p.size == int(g["n_params"])
+    stride = int(g["grid_stride"])
+    assert np.array_equal(p[:9216].view(np.uint32), g["params0_f32.mlp"].view(np.uint32))
+    assert np.array_equal(p[9216::stride].view(np.uint32), g["params0_f32.grid_sample"].view(np.uint32))
+    assert abs(p.astype(np.float64).sum() - float(g["params0_f32.sum"])) < 1e-12
+    assert abs(np.abs(p.astype(np.float64)).sum() - float(g["params0_f32.abs_sum"])) < 1e-12
+    # the fp16 copy tcnn trains with is the round-to-nearest cast
+    assert np.array_equal(p[:9216].astype(np.float16), g["params0_f16.mlp"])
+
+
+def test_golden_inference(golden):
+    """TINY_MLP::inference with the initial weights: fp16-storage oracle within 1e-3 (1 fp16 ulp at |y| <= 1)."""
+    ch, g, x, _ = golden
+    cfg = mo.Config(ch)
+    rows = int(g["rows_kept"])
+    y = mo.forward(cfg, mo.initial_params(cfg), x[:rows], half=True)
+    assert np.abs(g["infer0"]).max() > 0.2
+    assert np.abs(y - g["infer0"]).max() <= 1e-3
+    assert _rl2(y, g["infer0"]) < 2e-3
+    # the training forward computes the same output (fp16) as inference
+    assert np.array_equal(g["fwd1_out_f16"].astype(np.float32), g["infer0"])
+
+
+def test_golden_training_steps(golden):
+    """Trainer::training_step x4 on one batch: loss, dL/dy, gradients, Adam updates, and the network after 4 steps."""
+    ch, g, x, y = golden
+    cfg = mo.Config(ch)
+    stride, rows = int(g["grid_stride"]), int(g["rows_kept"])
+    opt = mo.Adam(cfg, mo.initial_params(cfg))
+    for s in range(4):
+        loss, gr = mo.backward(cfg, opt.master, x, y, half=True)
+        assert abs(loss - float(g["losses"][s])) <= 5e-4 * float(g["losses"][s]), (s, loss, g["losses"][s])
+        if s == 0:
+            yy = mo.forward(cfg, opt.master, x[:rows], True, keep=True)[0]
+            _, dy = mo.loss_and_grad(cfg, yy, y[:rows], x.shape[0], True)
+            assert _rl2(dy[:, :3], g["dLdo1_f16"].astype(np.float32)) < 2e-3
+            assert _rl2(gr[:9216], g["grad1_f16.mlp"].astype(np.float32)) < 5e-3
+            assert _rl2(gr[9216::stride], g["grad1_f16.grid_sample"].astype(np.float32)) < 3e-2      # half2 atomics
+            nz = np.count_nonzero(gr.astype(np.float16))
+            assert abs(nz - int(g["grad1_f16.nonzero"])) < 1e-3 * nz
+        opt.step(gr, half=True)
+        if s == 0:
+            # first Adam step: every touched parameter moves by lr * sign(g); only near-zero gradients may flip
+            d = np.abs(opt.master[:9216] - g["params1_f32.mlp"])
+            assert (d > 1e-4).mean() < 0.01 and _rl2(opt.master[:9216], g["params1_f32.mlp"]) < 2e-2
+            moved_ref = g["params1_f32.grid_sample"] != g["params0_f32.grid_sample"]
+            moved = opt.master[9216::stride] != mo.initial_params(cfg)[9216::stride]
+            assert (moved == moved_ref).mean() > 0.999          # sparse skip of zero-gradient grid entries
+    assert _rl2(opt.master[:9216], g["params4_f32.mlp"]) < 2e-2
+    assert _rl2(opt.master[9216::stride], g["params4_f32.grid_sample"]) < 0.1
+    out = mo.forward(cfg, opt.master, x[:rows], True)
+    assert _rl2(out, g["infer4"]) < 5e-3
+
+
+def _scalar_lib():
+    import ctypes as C
+    out_dir = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libmlp_scalar.so")
+    src = os.path.join(ROOT, "oracle", "mlp_scalar.c")
+    if not os.path.exists(so) or os.path.getmtime(src) > os.path.getmtime(so):
+        subprocess.check_call(["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-pthread", src, "-lm", "-o", so])
+    lib = C.CDLL(so)
+    lib.mlps_n_params.restype = C.c_size_t
+    lib.mlps_gradients.restype = C.c_double
+    return lib
+
+
+def test_scalar_c_port_matches_golden():
+    """oracle/mlp_scalar.c (the CPU baseline's network, 12 inputs = render_hair_msnn): same answers as tiny-cuda-nn."""
+    import ctypes as C
+    ch = 12
+    g = np.load(os.path.join(GOLD, f"tcnn_{ch}.npz"))
+    x = tcnn_inputs.make_inputs(int(g["n_rows"]), ch, int(g["input_seed"]))
+    y = tcnn_inputs.make_targets(int(g["n_rows"]), int(g["target_seed"]))
+    lib = _scalar_lib()
+    cfg = mo.Config(ch)
+    p = mo.initial_params(cfg)
+    assert lib.mlps_n_params() == p.size
+    fp = C.POINTER(C.c_float)
+    ph = p.astype(np.float16).astype(np.float32)       # the weights tcnn computes with
+    rows = int(g["rows_kept"])
+    out = np.zeros((rows, 3), np.float32)
+    lib.mlps_inference(ph.ctypes.data_as(fp), np.ascontiguousarray(x[:rows]).ctypes.data_as(fp), rows, ch, out.ctypes.data_as(fp), 4)
+    assert np.abs(out - g["infer0"]).max() <= 2e-3
+    grads = np.zeros(p.size, np.float32)
+    n = x.shape[0]
+    loss = lib.mlps_gradients(ph.ctypes.data_as(fp), x.ctypes.data_as(fp), y.ctypes.data_as(fp), n, ch, n, grads.ctypes.data_as(fp), 4)
+    assert abs(loss - float(g["losses"][0])) <= 2e-3 * float(g["losses"][0])
+    assert _rl2(grads[:9216], g["grad1_f16.mlp"].astype(np.float32)) < 1e-2
+    assert _rl2(grads[9216::int(g["grid_stride"])], g["grad1_f16.grid_sample"].astype(np.float32)) < 3e-2

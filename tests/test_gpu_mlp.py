@@ -202,3 +202,66 @@ def test_tcnn_snapshot_roundtrip_and_half_snapshots(tmp_path):
     json.dump(j2, open(p2, "w"))
     with pytest.raises(api.HairMSNNError):
         c.load(p2)
+
+
+# ---- pinned against the reference's own tiny-cuda-nn (tests/golden/tcnn_{12,9}.npz) -----------------------------
+# The vectors are outputs of /root/reference/extern/tiny-cuda-nn built for sm_100 and driven as TINY_MLP does
+# (oracle/tcnn_golden.cu), one run on a B200.  Tolerances are the fp16-accumulation ones SURVEY §7 suggests:
+# tcnn accumulates in fp16 inside wmma and scatters grid gradients with half2 atomics; these kernels accumulate
+# in fp32 and round where tcnn stores fp16.
+import tcnn_inputs  # noqa: E402
+
+
+def _rl2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+@pytest.mark.parametrize("in_ch", [12, 9])
+def test_against_tiny_cuda_nn_golden_vectors(in_ch):
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"tcnn_{in_ch}.npz"))
+    n, rows, stride = int(g["n_rows"]), int(g["rows_kept"]), int(g["grid_stride"])
+    x = tcnn_inputs.make_inputs(n, in_ch, int(g["input_seed"]))
+    y = tcnn_inputs.make_targets(n, int(g["target_seed"]))
+    m = api.Mlp.create(in_ch=in_ch)
+    # initial parameters: bit-exact (Trainer::initialize_params incl. the FMA of the grid initialisation)
+    p0 = m.get_params()
+    assert p0.size == int(g["n_params"])
+    assert np.array_equal(p0[:9216].view(np.uint32), g["params0_f32.mlp"].view(np.uint32))
+    assert np.array_equal(p0[9216::stride].view(np.uint32), g["params0_f32.grid_sample"].view(np.uint32))
+    assert abs(p0.astype(np.float64).sum() - float(g["params0_f32.sum"])) < 1e-12
+    # TINY_MLP::inference
+    out = m.inference(x)
+    assert np.abs(out[:rows] - g["infer0"]).max() <= 1e-3, np.abs(out[:rows] - g["infer0"]).max()
+    assert np.allclose(out.astype(np.float64).sum(axis=0), g["infer0.sum"], rtol=2e-3, atol=0.5)
+    # Trainer::training_step x 4 on one batch
+    rt = _cudart()
+    d_x, d_y = C.c_void_p(), C.c_void_p()
+    rt.cudaMalloc(C.byref(d_x), x.nbytes); rt.cudaMalloc(C.byref(d_y), y.nbytes)
+    rt.cudaMemcpy(d_x, x.ctypes.data_as(C.c_void_p), C.c_size_t(x.nbytes), 1)
+    rt.cudaMemcpy(d_y, y.ctypes.data_as(C.c_void_p), C.c_size_t(y.nbytes), 1)
+    for s in range(4):
+        m.forward_backward_device(d_x.value, d_y.value, n)
+        loss = m.loss()
+        assert abs(loss - float(g["losses"][s])) <= 1e-3 * float(g["losses"][s]), (s, loss, float(g["losses"][s]))
+        if s == 0:
+            gptr, gcount = m.gradients_device()
+            gr = _d2h(gptr, gcount * 4).view(np.float32)
+            assert _rl2(gr[:9216], g["grad1_f16.mlp"].astype(np.float32)) < 5e-3
+            assert _rl2(gr[9216::stride], g["grad1_f16.grid_sample"].astype(np.float32)) < 3e-2
+        m.optimizer_step()
+        if s == 0:
+            p1 = m.get_params()
+            assert _rl2(p1[:9216], g["params1_f32.mlp"]) < 2e-2
+            moved_ref = g["params1_f32.grid_sample"] != g["params0_f32.grid_sample"]
+            assert ((p1[9216::stride] != p0[9216::stride]) == moved_ref).mean() > 0.999
+    p4 = m.get_params()
+    assert _rl2(p4[:9216], g["params4_f32.mlp"]) < 2e-2
+    assert _rl2(p4[9216::stride], g["params4_f32.grid_sample"]) < 0.1
+    out4 = m.inference(x)
+    assert _rl2(out4[:rows], g["infer4"]) < 5e-3
+    # TINY_MLP::reset(): weights zeroed, optimiser state kept; one more step from there
+    m.reset()
+    m.forward_backward_device(d_x.value, d_y.value, n)
+    assert abs(m.loss() - float(g["loss_reset"][0])) <= 1e-3 * float(g["loss_reset"][0])
+    rt.cudaFree(d_x); rt.cudaFree(d_y)
