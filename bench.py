@@ -1,21 +1,27 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200-native HairMSNN per-path rendering loop.
 
-Workload (BASELINE.json metric / configs[3]): synthetic stand-in for scenes/curly
-(50 000 strands, 3.4 M Catmull-Rom segments, ~78 k head triangles, 4096x2048 RGBA32F
-environment + 1 directional light), render_hair_msnn at 1024x1024, BETA=1, MIS + ENV_PDF.
-One "step" = one sample per pixel through the whole frame loop: wavefront trace (G_BUFFER
-pass) -> online training step (16 384 records) -> MLP inference (1 048 576 queries) ->
-composite (RENDER pass).  Metric: Mpaths/s = W*H*steps*n_gpus / seconds / 1e6.
+Default workload (BASELINE.json metric / configs[3]): the reference's shipped scene `scenes/curly`
+(50 000 strands, 3 391 580 Catmull-Rom segments, 78 520 head triangles, 4096x2048 RGBA32F environment +
+1 directional light), loaded through hm_scene_load from assets/scenes/ (staged by scripts/stage_assets.py;
+a procedural stand-in of the same size is used — and labelled — only when the staged files are missing),
+render_hair_msnn at 1024x1024, BETA=1, MIS + ENV_PDF.  One "step" = one sample per pixel through the whole
+frame loop: wavefront trace (G_BUFFER pass) -> online training step (16 384 records) -> MLP inference
+(1 048 576 queries) -> composite (RENDER pass).  Metric: Mpaths/s = W*H*steps*n_gpus / seconds / 1e6.
 
-Multi-GPU (--gpus N under torchrun): samples are sharded (rank r renders sample indices
-r, r+N, ...: weak scaling, per-GPU work fixed), MLP gradients are all-reduced over NCCL
-every step so all replicas hold identical weights; framebuffers would be summed once at the
-end of a job (not part of a step).
+--workload {msnn_b1 (default), msnn_b10, pt, nrc, straight4096} selects the other BASELINE configs; the
+default single-GPU run also measures pt / nrc / msnn_b10 briefly (`other_workloads`) and the image gate
+(relMSE of render_hair_msnn against a 500-spp render_path_tracing image, `image_gate`).
 
-`--impl reference` times the REFERENCE's own per-path code (cuda/hair_msnn.cu + headers,
-compiled for the host in oracle/_ref) on the box's CPU cores over a bounded band of the
-same frame.
+Multi-GPU (--gpus N under torchrun): one process per GPU.  The NCCL communicator lives in libhairmsnn.so
+(hm_comm_*): attached to the renderer it shards samples (rank r renders sample ids r, r+N, ...: weak
+scaling, per-GPU work fixed; straight4096: row bands), all-reduces the network's gradients inside every
+training step and reduces framebuffers at the end of a job.  bench.py makes no collective of its own; the
+128-byte communicator id travels through a file in /dev/shm.
+
+`--impl reference` times the REFERENCE's own per-path code (cuda/hair_msnn.cu + headers compiled for the
+host, oracle/_ref) plus the scalar network (oracle/mlp_scalar.c) on the box's CPU cores over a bounded,
+frame-stratified sample of the same workload.
 """
 import argparse
 import os
@@ -25,7 +31,6 @@ import os
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import ctypes as C
 import json
-import os
 import subprocess
 import sys
 import threading
@@ -37,11 +42,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-W = H = 1024
-BETA_CLI = 1
 RECORDS = 16384
 NODE_BYTES = 80          # 8-wide quantised BVH node (hm_bvh.h)
 FLOPS_PER_QUERY = 16768           # 2*(64*64 + 64*64 + 64*3)
+FLOPS_PER_RECORD = 50304          # forward + dgrad + wgrad
+RELMSE_TOLERANCE = {"msnn_b1": 0.05, "msnn_b10": 0.01}   # gate against the 500-spp path-traced image
+
+WORKLOADS = {
+    # name: (scene, renderer kind, BETA, frame size or None = the scene file's)
+    "msnn_b1": ("curly", "msnn", 1, None),
+    "msnn_b10": ("curly", "msnn", 10, None),
+    "pt": ("curly", "pt", 1, None),
+    "nrc": ("curly", "nrc", 1, None),
+    "straight4096": ("straight", "msnn", 1, 4096),
+}
 
 
 def log(*a):
@@ -52,8 +66,9 @@ def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "bf16_tflops": d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0)), "src": "measured"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "src": "fallback"}
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "bf16_tflops": d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0)),
+                "bf16_tflops_burst": d.get("bf16_tflops", 1590.0), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "bf16_tflops_burst": 1590.0, "src": "fallback"}
 
 
 class ClockSampler(threading.Thread):
@@ -83,73 +98,173 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons)}
 
 
-def make_scene(num_strands):
+# ---- scenes -------------------------------------------------------------------------------------------------
+def scene_config_path(scene, size=None):
+    """Staged reference scene (assets/scenes/<scene>/config.json); a copy with another frame size is written
+    next to it when `size` is given (paths inside resolve relative to the config's directory)."""
+    base = os.path.join(ROOT, "assets", "scenes", scene, "config.json")
+    if not os.path.exists(base) or not os.path.exists(os.path.join(ROOT, "assets", "scenes", "envmaps")):
+        return None
+    if size is None:
+        return base
+    cfg = json.load(open(base))
+    cfg["integrator"]["width"] = cfg["integrator"]["height"] = int(size)
+    out = os.path.join(os.path.dirname(base), f"config_{size}.json")
+    tmp = out + f".{os.getpid()}.tmp"
+    json.dump(cfg, open(tmp, "w"))
+    os.replace(tmp, out)
+    return out
+
+
+def kw_from_config(path):
+    """The reference-side parameters tests/refhost.py needs, read from a scene file (scene.cpp:119-339 keys)."""
+    cfg = json.load(open(path))
+    hair, integ, lights = cfg.get("hair", {}), cfg["integrator"], cfg.get("lights", {})
+    dls = lights.get("directional", [])
+    return dict(sigma_a=tuple(hair.get("sigma_a", (0.06, 0.1, 0.2))), beta_m=hair.get("beta_m", 0.3), beta_n=hair.get("beta_n", 0.3),
+                alpha_deg=hair.get("alpha", 2.0), env_scale=lights.get("environment", {}).get("scale", 1.0), env_rotation=0.0,
+                dl_from=[d["from"] for d in dls], dl_emit=[d["emit"] for d in dls], mis=integ.get("MIS", True),
+                env_pdf=integ.get("ENV_PDF", True), path_v1=integ.get("path_v1", 1), path_v2=integ.get("path_v2", 40))
+
+
+def make_scene(workload, strands=50000):
+    """-> (api.Scene, reference-side kw, data label, W, H)"""
     from hairmsnn_b200 import api, synth
-    kw = synth.scene_kwargs("curly", W, H, num_strands=num_strands)
-    sc = api.Scene.from_arrays(**kw)
-    return sc, kw
+    scene, _, _, size = WORKLOADS[workload]
+    cfgp = scene_config_path(scene, size)
+    if cfgp:
+        sc = api.Scene.load(cfgp)
+        i = sc.info()
+        return sc, kw_from_config(cfgp), f"reference-scene (scenes/{scene} of the reference, staged under assets/)", i.width, i.height
+    W = H = size or 1024
+    kw = synth.scene_kwargs(scene, W, H, num_strands=strands)
+    return api.Scene.from_arrays(**kw), kw, f"synthetic (procedural stand-in for scenes/{scene}: staged assets missing)", W, H
 
 
-CONFIG = {"workload": "render_hair_msnn synthetic-curly 1024x1024 BETA=1 (50k strands, 3.4M segments, env 4096x2048 + 1 directional, MIS+ENV_PDF, online training 16384 records/step, 1048576 MLP queries/step)",
-          "l2": "working set (wide BVH nodes 1.1 GB + leaf primitive copies 2.8 GB + control points 57 MB + env tables 200 MB + path state 180 MB per frame in flight) exceeds the 126 MB L2; no flush needed",
-          "sharding": "spp"}
+def workload_text(workload, W, H, info):
+    scene, kind, beta, _ = WORKLOADS[workload]
+    what = {"msnn": f"render_hair_msnn BETA={beta} (online training 16384 records/step, {W * H} MLP queries/step)",
+            "pt": "render_path_tracing (path_v2=40)", "nrc": "render_nrc (65536 training records/step, cache queries + training suffixes)"}[kind]
+    return (f"{what} scenes/{scene} {W}x{H} ({info.num_strands} strands, {info.num_segments} segments, {info.num_triangles} triangles, "
+            f"env {info.env_w}x{info.env_h} + {info.num_dlights} directional, MIS+ENV_PDF)")
 
 
-def reference_band():
-    """Rows of the frame the CPU arm renders per step: a band through the hair volume."""
-    return H // 2 - 4, H // 2 + 4
+# ---- CPU arm: the reference's per-path code + scalar network on the host cores --------------------------------
+def scalar_mlp_lib():
+    so = os.path.join(ROOT, "oracle", "_ref", "libmlp_scalar.so")
+    src = os.path.join(ROOT, "oracle", "mlp_scalar.c")
+    if not os.path.exists(so) or os.path.getmtime(src) > os.path.getmtime(so):
+        os.makedirs(os.path.dirname(so), exist_ok=True)
+        subprocess.check_call(["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-pthread", src, "-lm", "-o", so])
+    lib = C.CDLL(so)
+    lib.mlps_n_params.restype = C.c_size_t
+    lib.mlps_gradients.restype = C.c_double
+    return lib
+
+
+class CpuArm:
+    """One bounded sample of the msnn_b1 step on the host: 1/128 of everything a frame does.
+    Rows y = 64 + 128 k (k = 0..H/128-1) — stratified over the whole frame, so the hair-hit fraction matches the
+    GPU frame's — go through the reference's G_BUFFER pass (cuda/hair_msnn.cu compiled for the host); the rows'
+    pixels are queried through the scalar network (inference of every pixel, as the reference does), their
+    training records (W*rows/everyNth of the 16384) train it (forward + backward), and Adam updates 1/128 of the
+    parameters.  Weights = the seeded initial weights, the same the GPU run starts from."""
+
+    def __init__(self, sc, kw, W, H, beta_cli):
+        from refhost import RefHost
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import mlp_oracle as mo
+        self.ref = RefHost("msnn")
+        self.ref.bind_all(sc, kw)
+        self.W, self.H, self.beta = W, H, beta_cli - 1
+        self.rows = list(range(64 % H, H, 128)) if H >= 128 else [H // 2]
+        self.idxs = np.arange(RECORDS, dtype=np.int32)
+        self.every_nth = W * H // RECORDS
+        self.cores = os.cpu_count()
+        self.lib = scalar_mlp_lib()
+        self.params = mo.initial_params(mo.Config(12)).astype(np.float16).astype(np.float32)
+        n = self.params.size
+        self.master = self.params.copy()
+        self.m1, self.m2, self.steps = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.uint32)
+        self.grads = np.zeros(n, np.float32)
+        self.paths_per_step = len(self.rows) * W
+        self.slice = n // 128
+        self.bufs = None
+
+    def step(self, k):
+        fp = C.POINTER(C.c_float)
+        W = self.W
+        self.bufs = self.ref.render_msnn_rows(k, W, self.H, self.beta, self.every_nth, self.idxs, self.rows, self.bufs, threads=self.cores)
+        nn_in, tr_in, tr_out, _ = self.bufs
+        # the sample's pixels and training records, gathered so that each network call spawns its threads once
+        x = np.concatenate([nn_in[y * W:(y + 1) * W] for y in self.rows])
+        out = np.empty((x.shape[0], 3), np.float32)
+        self.lib.mlps_inference(self.params.ctypes.data_as(fp), x.ctypes.data_as(fp), x.shape[0], 12, out.ctypes.data_as(fp), self.cores)
+        recs = np.concatenate([np.arange(y * W // self.every_nth, (y + 1) * W // self.every_nth) for y in self.rows])
+        n_rec = len(recs)
+        if n_rec:
+            ti, to = np.ascontiguousarray(tr_in[recs]), np.ascontiguousarray(tr_out[recs])
+            self.lib.mlps_gradients(self.params.ctypes.data_as(fp), ti.ctypes.data_as(fp), to.ctypes.data_as(fp), n_rec, 12, RECORDS,
+                                    self.grads.ctypes.data_as(fp), min(self.cores, n_rec))
+        first = (k % 128) * self.slice
+        self.lib.mlps_adam(self.master.ctypes.data_as(fp), self.m1.ctypes.data_as(fp), self.m2.ctypes.data_as(fp),
+                           self.steps.ctypes.data_as(C.POINTER(C.c_uint32)), self.grads.ctypes.data_as(fp), C.c_size_t(first), C.c_size_t(self.slice),
+                           C.c_float(1e-2), C.c_float(0.9), C.c_float(0.99), C.c_float(1e-15), C.c_float(1e-6))
+        return n_rec
+
+    def sample_text(self, n_steps, secs):
+        return (f"{n_steps} samples of rows {self.rows[0]}, {self.rows[0] + 128}, ... ({len(self.rows)} rows stratified over the frame, "
+                f"{self.paths_per_step} paths each, {secs:.1f} s): G_BUFFER pass of the reference's cuda/hair_msnn.cu compiled for the host "
+                f"(oracle/_ref; traversal = this repo's BVH + intersector on the host, OptiX being closed) + scalar network with the "
+                f"seeded weights (oracle/mlp_scalar.c): inference of the rows' pixels, forward+backward of their {self.paths_per_step // self.every_nth} "
+                f"training records, Adam on 1/128 of the parameters; {self.cores} threads")
+
+
+def cpu_baseline(sc, kw, W, H, beta_cli, seconds_target=12.0):
+    arm = CpuArm(sc, kw, W, H, beta_cli)
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        arm.step(n)
+        n += 1
+        if time.perf_counter() - t0 > seconds_target or n >= 4096:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": arm.paths_per_step * n / dt / 1e6, "unit": "Mpaths/s", "cores": arm.cores, "kind": "reference", "sample": arm.sample_text(n, dt)}
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    from refhost import RefHost
-    sc, kw = make_scene(args.strands)
-    ref = RefHost("msnn")
-    ref.bind_all(sc, kw)
-    y0, y1 = reference_band()
-    idxs = np.arange(RECORDS, dtype=np.int32)
-    cores = os.cpu_count()
-    every_nth = W * H // RECORDS
+    if args.workload not in ("msnn_b1", "msnn_b10"):
+        emit(json.dumps({"impl": "reference", "unavailable": f"the CPU arm implements the render_hair_msnn workloads, not {args.workload}"}))
+        return
+    sc, kw, data, W, H = make_scene(args.workload, args.strands)
+    info = sc.info()
+    arm = CpuArm(sc, kw, W, H, WORKLOADS[args.workload][2])
     times = []
     for step in range(args.warmup + args.steps):
         t = time.perf_counter()
-        ref.render_msnn_gbuffer(step, W, H, BETA_CLI - 1, every_nth, idxs, y0=y0, y1=y1, threads=cores)
+        arm.step(step)
         dt = time.perf_counter() - t
         if step >= args.warmup:
             times.append(dt)
-    paths = (y1 - y0) * W
     total = sum(times)
-    value = paths * len(times) / total / 1e6
+    value = arm.paths_per_step * len(times) / total / 1e6
     line = {"metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "impl": "reference", "config": CONFIG,
-            "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": cores, "kind": "reference",
-                             "sample": f"rows {y0}..{y1 - 1} of the 1024x1024 frame ({paths} paths) per step: G_BUFFER pass of cuda/hair_msnn.cu compiled for the host, all host threads"},
+            "dtype": "f32", "data": data, "impl": "reference", "config": bench_config(args.workload, W, H, info, "spp"),
+            "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": arm.cores, "kind": "reference", "sample": arm.sample_text(len(times), total)},
             "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(json.dumps(line))
 
 
-def cpu_baseline(sc, kw, seconds_target=12.0):
-    from refhost import RefHost
-    ref = RefHost("msnn")
-    ref.bind_all(sc, kw)
-    y0, y1 = reference_band()
-    idxs = np.arange(RECORDS, dtype=np.int32)
-    cores = os.cpu_count()
-    every_nth = W * H // RECORDS
-    t0 = time.perf_counter()
-    n = 0
-    while True:
-        ref.render_msnn_gbuffer(n, W, H, BETA_CLI - 1, every_nth, idxs, y0=y0, y1=y1, threads=cores)
-        n += 1
-        if time.perf_counter() - t0 > seconds_target or n >= 4096:
-            break
-    dt = time.perf_counter() - t0
-    paths = (y1 - y0) * W * n
-    return {"value": paths / dt / 1e6, "unit": "Mpaths/s", "cores": cores, "kind": "reference",
-            "sample": f"{n} samples of rows {y0}..{y1 - 1} ({paths} paths, {dt:.1f} s): the reference's hair_msnn.cu G_BUFFER pass compiled for the host (oracle/_ref), {cores} threads"}
+def bench_config(workload, W, H, info, sharding):
+    return {"workload": workload_text(workload, W, H, info), "name": workload,
+            "l2": "working set (wide BVH nodes + leaf primitive copies ~3.5 GB, env tables 200 MB, path state ~200 MB per frame in flight) "
+                  "exceeds the 126 MB L2; no flush needed",
+            "sharding": sharding}
 
 
 _REAL_STDOUT = None
@@ -170,14 +285,220 @@ def emit(text):
         os.write(_REAL_STDOUT, (text + "\n").encode())
 
 
+# ---- multi-GPU plumbing: communicator id through /dev/shm ---------------------------------------------------------
+def exchange_comm_id(rank):
+    from hairmsnn_b200 import api
+    tag = f"{os.environ.get('MASTER_PORT', '0')}_{os.environ.get('TORCHELASTIC_RUN_ID', 'none')}_{os.getppid()}"
+    path = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp", f"hm_bench_comm_{tag}.id")
+    if rank == 0:
+        ident = api.Comm.unique_id()
+        with open(path + ".tmp", "wb") as f:
+            f.write(ident)
+        os.replace(path + ".tmp", path)
+        return ident, path
+    for _ in range(3000):
+        if os.path.exists(path):
+            b = open(path, "rb").read()
+            if len(b) == 128:
+                return b, path
+        time.sleep(0.1)
+    raise RuntimeError("rank 0 never published the communicator id")
+
+
+# ---- measurement of one renderer ------------------------------------------------------------------------------
+def measure(r, api, torch, local_rank, comm, W, H, steps, warmup, peaks, kind, want_e2e=True, sampler=None):
+    """Times `steps` frames of renderer `r` (device events on its stream, max over ranks), then the end-to-end
+    leg, the per-stage table and the instrumented pass.  Returns a dict of raw results."""
+    world = comm.world if comm else 1
+    stream = torch.cuda.ExternalStream(r.stream, device=local_rank)
+
+    def step():
+        r.render_frames_async(1)
+
+    def barrier():
+        r.sync()
+        torch.cuda.synchronize()
+        if comm:
+            comm.barrier()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    r.reset_stats()
+    # event pairs around the launches the roofline line is about (main-piece k_trace) and the network's kernels;
+    # timing all ~320 launches of a frame costs ~3 % of the frame rate, so the full per-stage table comes from a
+    # second, untimed pass below
+    r.set_profiling_stages((1 << 2) | (1 << 5) | (1 << 6))
+    r.set_profiling(True)
+    if sampler:
+        sampler.start()
+    launches0 = r.stats().kernel_launches
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if sampler:
+        sampler.stop_flag = True
+    st = r.stats()
+    launches = st.kernel_launches - launches0
+    r.set_profiling(False)
+    if comm:
+        ms = comm.all_reduce_max(ms)
+    out = {"ms": ms, "value": W * H * steps * world / (ms * 1e-3) / 1e6, "launches": int(launches), "loss": st.last_loss}
+
+    # second pass, all stages timed (not part of the headline number)
+    r.reset_stats()
+    r.set_profiling_stages(0xffffffff)
+    r.set_profiling(True)
+    for _ in range(steps):
+        step()
+    barrier()
+    st_all = r.stats()
+    r.set_profiling(False)
+
+    if want_e2e:
+        # end to end through the C ABI with host buffers: every step's results (8-bit framebuffer + fp32 average)
+        # are streamed to pinned host memory behind that step's composite; two host buffer sets alternate
+        fb_host = [torch.empty((H, W), dtype=torch.int32).pin_memory() for _ in range(2)]
+        avg_host = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            step()
+            r.readback_async(api.BUF_FB8, fb_host[i & 1].data_ptr(), fb_host[0].numel() * 4)
+            r.readback_async(api.BUF_FINAL_AVG, avg_host[i & 1].data_ptr(), avg_host[0].numel() * 4)
+        r.sync()
+        e2e_s = time.perf_counter() - t0
+        assert np.isfinite(avg_host[(steps - 1) & 1].numpy()).all()
+        if comm:
+            e2e_s = comm.all_reduce_max(e2e_s)
+        out["e2e"] = {"value": W * H * steps * world / e2e_s / 1e6, "unit": "Mpaths/s",
+                      "h2d_bytes_per_step": int(api.lib.hm_frame_param_bytes() * launches / max(steps, 1)),
+                      "d2h_bytes_per_step": int(fb_host[0].numel() * 4 + avg_host[0].numel() * 4),
+                      "note": "per step: one frame through the C ABI (hm_render_frames_async; with N GPUs the gradient all-reduce is inside the call) "
+                              "followed by hm_readback_async of the 8-bit framebuffer and the fp32 average buffer into pinned host memory, host clock "
+                              "around the whole loop incl. the final sync; host->device traffic of a frame is its kernel parameter blocks"}
+
+    # instrumented pass: nodes visited / primitives tested per stage (SURVEY §8d per-ray bytes); every rank takes part
+    r.reset_stats()
+    r.set_collect_stats(True)
+    n_inst = 2
+    for _ in range(n_inst):
+        step()
+        r.sync()
+    si = r.stats()
+    r.set_collect_stats(False)
+    barrier()
+
+    stage_ms = {"primary": st_all.ms_primary, "shade": st_all.ms_shade, "trace": st.ms_extend, "tail_piece": st_all.ms_shadow,
+                "train": st.ms_train, "infer": st.ms_infer, "composite": st_all.ms_composite, "finalize": st_all.ms_finalize}
+    stage_launches = dict(zip(("primary", "shade", "trace", "tail_piece", "finalize", "train", "infer", "composite"), st_all.stage_launches))
+    stage_launches["trace"] = st.stage_launches[2]
+    dominant = max(("primary", "trace"), key=lambda k: stage_ms[k])
+    rays = {"primary": si.rays_primary, "trace": si.rays_extend + si.rays_shadow - si.rays_tail}
+    nodes = {"primary": si.trav_nodes_primary, "trace": si.trav_nodes_extend + si.trav_nodes_shadow - si.trav_nodes_tail}
+    prims = {"primary": si.trav_prims_primary, "trace": si.trav_prims_extend + si.trav_prims_shadow - si.trav_prims_tail}
+    # algorithmic bytes per ray (SURVEY §8d): 32 B ray + 16 B hit + 80 B per wide node visited + 64 B per primitive tested
+    alg_bytes_per_step = (rays[dominant] * 48 + nodes[dominant] * NODE_BYTES + prims[dominant] * 64) / n_inst
+    launches_dom = stage_launches[dominant] / steps
+    avg_launch_ms = stage_ms[dominant] / max(stage_launches[dominant], 1)
+    achieved = alg_bytes_per_step / max(launches_dom, 1) / max(avg_launch_ms * 1e-3, 1e-12) / 1e9
+    traffic, traffic_note = None, None
+    tp = os.path.join(ROOT, "profiles", f"k_{dominant}_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        traffic, traffic_note = tj["traffic_bytes_per_launch"], tj["source"]
+    out["roofline"] = {"kernel": f"k_{dominant}", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                       "frac": achieved / peaks["hbm_gbs"], "peak_source": peaks["src"], "traffic": traffic, "traffic_note": traffic_note,
+                       "algorithmic_bytes_per_step": alg_bytes_per_step,
+                       "algorithmic_bytes_per_launch": alg_bytes_per_step / max(launches_dom, 1),
+                       "rays_per_step": rays[dominant] / n_inst, "nodes_per_ray": nodes[dominant] / max(rays[dominant], 1),
+                       "prims_per_ray": prims[dominant] / max(rays[dominant], 1), "avg_launch_ms": avg_launch_ms,
+                       "launches_per_step": launches_dom,
+                       "tail_piece": {"launches_per_step": stage_launches["tail_piece"] / steps, "rays_per_step": si.rays_tail / n_inst,
+                                      "ms_per_step_sum": stage_ms["tail_piece"] / steps},
+                       "note": "main-piece k_trace launches, CUDA events around each launch inside the timed region; several frames are in flight, "
+                               "so a launch shares the GPU with other frames' tail-piece and MLP kernels"}
+    out["stage_ms_per_step"] = {k: v / steps for k, v in stage_ms.items()}
+    out["rays_per_step"] = (si.rays_primary + si.rays_extend + si.rays_shadow) / n_inst
+    if kind != "pt":
+        in_ch, rows_submitted, records, _ = r.layout()
+        rows_evaluated = rows_submitted
+        if kind == "msnn":
+            # rows the inference launch evaluates: 128-pixel tiles holding at least one hair hit (the RENDER pass reads no
+            # other row's output; hm_renderer_set_skip_unused_queries).  Counted on the last frame's G-buffer.
+            gflags = r.buffer(api.BUF_GBUFFER).reshape(-1, 4)[:, 3].copy().view(np.int32)
+            hair_hit = ((gflags & 1) != 0) & ((gflags & 2) == 0)
+            rows_evaluated = int(hair_hit.reshape(-1, 128).any(axis=1).sum()) * 128
+        ms_infer = stage_ms["infer"] / steps
+        ms_train = stage_ms["train"] / steps
+        qps = rows_evaluated / (ms_infer * 1e-3) if ms_infer > 0 else None
+        train_tflops = records * FLOPS_PER_RECORD / (ms_train * 1e-3) / 1e12 if ms_train > 0 else None
+        out["mlp"] = {"queries_per_s": qps, "tflops": qps * FLOPS_PER_QUERY / 1e12 if qps else None,
+                      "frac_of_tensor_peak": (qps * FLOPS_PER_QUERY / 1e12 / peaks["bf16_tflops"]) if qps else None,
+                      "peak_tflops": peaks["bf16_tflops"], "ms_infer_per_step": ms_infer,
+                      "rows_per_step_submitted": rows_submitted, "rows_per_step_evaluated": rows_evaluated,
+                      "ms_train_per_step": ms_train, "train_records_per_step": records, "train_tflops": train_tflops,
+                      "note": "in-frame numbers (the launches share the GPU with the next frames' traversal); the kernels timed alone: scripts/mlp_bench.py, profiles/"}
+    return out
+
+
+def image_gate(sc, api, W, H, pt_spp, spp, pretrain):
+    """relMSE of render_hair_msnn (BETA 1 and 10) against a render_path_tracing image of pt_spp samples."""
+    def rel_mse(img, ref):
+        img, ref = np.asarray(img, np.float64)[..., :3], np.asarray(ref, np.float64)[..., :3]
+        return float(np.mean((img - ref) ** 2 / (ref ** 2 + 1e-2)))
+
+    def render(kind, beta, n, offset=0):
+        r = api.Renderer(sc, kind, beta_cli=beta, device=0)
+        if offset:
+            r.set_frame_schedule(offset, 1)
+        if kind == api.HAIR_MSNN and pretrain:
+            r.msnn_pretrain(pretrain)
+        r.sync()
+        t = time.perf_counter()
+        done = 0
+        while done < n:
+            k = min(32, n - done)
+            r.render_frames_async(k)
+            done += k
+        r.sync()
+        dt = time.perf_counter() - t
+        img = r.buffer(api.BUF_FINAL_AVG)
+        r.close()
+        return img, W * H * n / dt / 1e6
+
+    gt, pt_rate = render(api.PATH_TRACING, 1, pt_spp)
+    other, _ = render(api.PATH_TRACING, 1, spp, offset=100000)
+    out = {"definition": "relMSE = mean over pixels and RGB of (I-R)^2/(R^2+0.01); R = render_path_tracing with pt_spp samples per pixel",
+           "pt_spp": pt_spp, "spp": spp, "pretrain_steps": pretrain, "pt_mpaths_per_s": pt_rate,
+           "relmse_pt_other_samples": rel_mse(other, gt), "tolerance": RELMSE_TOLERANCE}
+    ok = True
+    for name, beta in (("msnn_b1", 1), ("msnn_b10", 10)):
+        img, rate = render(api.HAIR_MSNN, beta, spp)
+        out[f"relmse_{name}"] = rel_mse(img, gt)
+        out[f"mpaths_per_s_{name}"] = rate
+        ok = ok and out[f"relmse_{name}"] <= RELMSE_TOLERANCE[name]
+    out["pass"] = bool(ok)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--strands", type=int, default=50000)
+    ap.add_argument("--workload", default="msnn_b1", choices=sorted(WORKLOADS))
+    ap.add_argument("--strands", type=int, default=50000, help="synthetic fallback only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the brief pt / nrc / msnn_b10 measurements of the default run")
+    ap.add_argument("--no-gate", action="store_true", help="skip the image gate of the default run")
+    ap.add_argument("--gate-spp", type=int, default=500)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -192,212 +513,98 @@ def main():
         return
 
     import torch
-    import torch.distributed as dist
     from hairmsnn_b200 import api
 
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        import datetime
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
     peaks = load_peaks()
+    scene_name, kind, beta_cli, size = WORKLOADS[args.workload]
+    bands = args.workload == "straight4096"
+    if bands and world < 4:
+        raise SystemExit("straight4096 renders 4096x4096 on row bands of at most 2048x2048 pixels: needs --gpus 4 or 8")
+
+    comm, id_path = None, None
+    if world > 1:
+        ident, id_path = exchange_comm_id(rank)
+        comm = api.Comm(ident, rank, world, local_rank)
 
     t0 = time.time()
     if world == 1:
-        sc, kw = make_scene(args.strands)
+        sc, kw, data, W, H = make_scene(args.workload, args.strands)
     else:
         # one rank builds the acceleration structure (and keeps the binary tree the CPU arm needs), the others
-        # restore the GPU-side tree from a RAM-backed cache instead of N concurrent 40-second builds
-        cache = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp", f"hm_bvh_cache_{os.environ.get('MASTER_PORT', '0')}")
+        # restore the GPU-side tree from a RAM-backed cache instead of N concurrent builds
+        cache = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp", f"hm_bvh_cache_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}")
         os.makedirs(cache, exist_ok=True)
         if rank == 0:
-            sc, kw = make_scene(args.strands)
+            sc, kw, data, W, H = make_scene(args.workload, args.strands)
             sc.save_bvh_cache(cache)
-        dist.barrier()
+        comm.barrier()
         if rank != 0:
             os.environ["HM_BVH_CACHE"] = cache
-            sc, kw = make_scene(args.strands)
+            sc, kw, data, W, H = make_scene(args.workload, args.strands)
             del os.environ["HM_BVH_CACHE"]
-        dist.barrier()
+        comm.barrier()
         if rank == 0:
             import shutil
             shutil.rmtree(cache, ignore_errors=True)
-    r = api.Renderer(sc, api.HAIR_MSNN, beta_cli=BETA_CLI, device=local_rank)
-    r.set_frame_schedule(rank, world)
-    mlp = r.mlp()
-    log(f"[rank {rank}] scene + renderer ready in {time.time() - t0:.1f}s")
-    stream = torch.cuda.ExternalStream(r.stream, device=local_rank)
+            try:
+                os.remove(id_path)
+            except OSError:
+                pass
+    info = sc.info()
+    KIND = {"msnn": api.HAIR_MSNN, "pt": api.PATH_TRACING, "nrc": api.NRC}
+    r = api.Renderer(sc, KIND[kind], beta_cli=beta_cli, device=local_rank, rank=rank if bands else 0, world=world if bands else 1)
+    if comm:
+        r.set_comm(comm)      # sample groups (or row bands) + gradient all-reduce inside every training step
+    log(f"[rank {rank}] scene + renderer ready in {time.time() - t0:.1f}s ({data})")
 
-    class DevBuf:
-        def __init__(self, ptr, nbytes, dtype, shape):
-            self.__cuda_array_interface__ = {"shape": shape, "typestr": dtype, "data": (ptr, False), "version": 3}
-    gptr, gcount = mlp.gradients_device()
-    grads = torch.as_tensor(DevBuf(gptr, gcount * 4, "<f4", (gcount,)), device=f"cuda:{local_rank}")
-    tin_ptr, _ = r.device_buffer(api.BUF_NN_TRAIN_INPUT)
-    tout_ptr, _ = r.device_buffer(api.BUF_NN_TRAIN_OUTPUT)
-
-    def step():
-        if world == 1:
-            r.render_frames_async(1)
-            return
-        # split frame: trace -> backward -> gradient all-reduce over NVLink -> Adam -> inference + composite
-        r.msnn_trace()
-        mlp.forward_backward_device(tin_ptr, tout_ptr, RECORDS, RECORDS * world)
-        with torch.cuda.stream(stream):
-            dist.all_reduce(grads)
-        r.msnn_train_apply()
-        r.msnn_finish()
-
-    def barrier():
-        r.sync()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        r.sync()
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-
-    # ---- timed region: device-resident -------------------------------------------------
-    r.reset_stats()
-    # event pairs around the launches the roofline line is about (main-piece k_trace, 2 per frame) and the
-    # network inference; timing all ~320 launches of a frame costs ~3 % of the frame rate, so the full
-    # per-stage table comes from a second, untimed pass below
-    r.set_profiling_stages((1 << 2) | (1 << 6))
-    r.set_profiling(True)
     sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = r.stats().kernel_launches
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for _ in range(args.steps):
-        step()
-    ev1.record(stream)
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    sampler.stop_flag = True
-    st = r.stats()
-    launches = st.kernel_launches - launches0
-    r.set_profiling(False)
-    # second pass, all stages timed (not part of the headline number)
-    r.reset_stats()
-    r.set_profiling_stages(0xffffffff)
-    r.set_profiling(True)
-    for _ in range(args.steps):
-        step()
-    barrier()
-    st_all = r.stats()
-    r.set_profiling(False)
-    if world > 1:
-        t = torch.tensor([ms], device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    value = W * H * args.steps * world / (ms * 1e-3) / 1e6
-
-    # ---- end to end through the C ABI with host buffers ---------------------------------
-    # every step's results (8-bit framebuffer + fp32 average) are streamed to pinned host memory
-    # behind that step's composite; two host buffer sets alternate
-    fb_host = [torch.empty((H, W), dtype=torch.int32).pin_memory() for _ in range(2)]
-    avg_host = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        step()
-        r.readback_async(api.BUF_FB8, fb_host[i & 1].data_ptr(), fb_host[0].numel() * 4)
-        r.readback_async(api.BUF_FINAL_AVG, avg_host[i & 1].data_ptr(), avg_host[0].numel() * 4)
-    r.sync()
-    e2e_s = time.perf_counter() - t0
-    assert np.isfinite(avg_host[(args.steps - 1) & 1].numpy()).all()
-    if world > 1:
-        t = torch.tensor([e2e_s], device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = W * H * args.steps * world / e2e_s / 1e6
-    frame_param_bytes = int(api.lib.hm_frame_param_bytes())
-    launches_per_step = launches / max(args.steps, 1)
-
-    # ---- roofline of the dominant kernel -------------------------------------------------
-    # instrumented pass: nodes visited / primitives tested per stage (SURVEY §8d per-ray bytes).
-    # Every rank takes part (the step holds a collective when world > 1); rank 0 reports.
-    r.reset_stats()
-    r.set_collect_stats(True)
-    n_inst = 2
-    for _ in range(n_inst):
-        step()
-        r.sync()
-    si = r.stats()
-    r.set_collect_stats(False)
+    # row bands split ONE frame over the ranks: a step is one frame of the job (strong scaling in N)
+    res = measure(r, api, torch, local_rank, comm, W, H, args.steps, args.warmup, peaks, kind, sampler=sampler)
+    if bands:
+        res["value"] /= world
+        res["e2e"]["value"] /= world
+    if comm:
+        r.reduce_framebuffers()     # the job's one framebuffer reduction (not part of a step)
     if rank != 0:
-        barrier()
-        dist.destroy_process_group()
+        r.close()
+        comm.barrier()
+        comm.close()
         return
-    if world > 1:
-        barrier()
-    # k_trace: one launch per path vertex tracing its occlusion probes and continuation rays.  A frame's
-    # launches split into the main piece (vertices 0..BETA of every path: ~97% of the secondary rays, on
-    # the main stream) and the tail piece (the few training paths' deeper vertices: dozens of tiny
-    # latency-bound launches on a side stream).  The roofline line is about the main-piece launches.
-    stage_ms = {"primary": st_all.ms_primary, "shade": st_all.ms_shade, "trace": st.ms_extend, "tail_piece": st_all.ms_shadow,
-                "train": st_all.ms_train, "infer": st.ms_infer, "composite": st_all.ms_composite, "finalize": st_all.ms_finalize}
-    stage_launches = dict(zip(("primary", "shade", "trace", "tail_piece", "finalize", "train", "infer", "composite"), st_all.stage_launches))
-    stage_launches["trace"] = st.stage_launches[2]
-    dominant = max(("primary", "trace"), key=lambda k: stage_ms[k])
-    rays = {"primary": si.rays_primary, "trace": si.rays_extend + si.rays_shadow - si.rays_tail}
-    nodes = {"primary": si.trav_nodes_primary, "trace": si.trav_nodes_extend + si.trav_nodes_shadow - si.trav_nodes_tail}
-    prims = {"primary": si.trav_prims_primary, "trace": si.trav_prims_extend + si.trav_prims_shadow - si.trav_prims_tail}
-    # algorithmic bytes per ray: 32 B ray + 16 B hit + 80 B per wide node visited + 64 B per primitive tested
-    alg_bytes_per_step = (rays[dominant] * 48 + nodes[dominant] * NODE_BYTES + prims[dominant] * 64) / n_inst
-    launches_dom = stage_launches[dominant] / args.steps
-    avg_launch_ms = stage_ms[dominant] / max(stage_launches[dominant], 1)
-    achieved = alg_bytes_per_step / max(launches_dom, 1) / (avg_launch_ms * 1e-3) / 1e9
-    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/)
-    traffic, traffic_note = None, None
-    tp = os.path.join(ROOT, "profiles", f"k_{dominant}_traffic.json")
-    if os.path.exists(tp):
-        tj = json.load(open(tp))
-        traffic = tj["traffic_bytes_per_launch"]
-        traffic_note = tj["source"]
-    roofline = {"kernel": f"k_{dominant}", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "peak_source": peaks["src"], "traffic": traffic, "traffic_note": traffic_note,
-                "algorithmic_bytes_per_step": alg_bytes_per_step,
-                "algorithmic_bytes_per_launch": alg_bytes_per_step / max(launches_dom, 1),
-                "rays_per_step": rays[dominant] / n_inst, "nodes_per_ray": nodes[dominant] / max(rays[dominant], 1),
-                "prims_per_ray": prims[dominant] / max(rays[dominant], 1), "avg_launch_ms": avg_launch_ms,
-                "launches_per_step": launches_dom,
-                "tail_piece": {"launches_per_step": stage_launches["tail_piece"] / args.steps, "rays_per_step": si.rays_tail / n_inst,
-                               "ms_per_step_sum": stage_ms["tail_piece"] / args.steps},
-                "note": "main-piece k_trace launches (2 per frame at BETA=1), CUDA events around each launch inside the timed region; "
-                        "8 frames are in flight, so a launch shares the GPU with other frames' tail-piece and MLP kernels; the kernel is "
-                        "bound by dependent-fetch latency and SIMT divergence, not by bandwidth (profiles/)"}
-    # rows the inference launch evaluates: 128-pixel tiles holding at least one hair hit (the RENDER pass reads no
-    # other row's output; hm_renderer_set_skip_unused_queries).  Counted on the last frame's G-buffer.
-    gflags = r.buffer(api.BUF_GBUFFER).reshape(-1, 4)[:, 3].copy().view(np.int32)
-    hair_hit = ((gflags & 1) != 0) & ((gflags & 2) == 0)
-    rows_evaluated = int(hair_hit.reshape(-1, 128).any(axis=1).sum()) * 128
-    mlp_qps = rows_evaluated / (stage_ms["infer"] / args.steps * 1e-3) if stage_ms["infer"] > 0 else None
-    mlp_info = {"queries_per_s": mlp_qps, "tflops": mlp_qps * FLOPS_PER_QUERY / 1e12 if mlp_qps else None,
-                "frac_of_tensor_peak": (mlp_qps * FLOPS_PER_QUERY / 1e12 / peaks["bf16_tflops"]) if mlp_qps else None,
-                "peak_tflops": peaks["bf16_tflops"], "ms_infer_per_step": stage_ms["infer"] / args.steps,
-                "rows_per_step_submitted": W * H, "rows_per_step_evaluated": rows_evaluated,
-                "ms_train_per_step": stage_ms["train"] / args.steps}
 
-    cb = None if args.no_cpu_baseline else cpu_baseline(sc, kw)
+    others, gate, cb = None, None, None
+    default_single = args.workload == "msnn_b1" and world == 1
+    r.close()
+    if default_single and not args.no_others:
+        others = {}
+        for name in ("pt", "nrc", "msnn_b10"):
+            _, k2, b2, _ = WORKLOADS[name]
+            r2 = api.Renderer(sc, KIND[k2], beta_cli=b2, device=local_rank)
+            m = measure(r2, api, torch, local_rank, None, W, H, 8, 3, peaks, k2, want_e2e=False)
+            r2.close()
+            others[name] = {"workload": workload_text(name, W, H, info), "value": m["value"], "unit": "Mpaths/s", "ms_per_step": m["ms"] / 8, "steps": 8,
+                            "warmup": 3, "gpu_launches": m["launches"], "rays_per_step": m["rays_per_step"], "roofline": m["roofline"],
+                            "mlp": m.get("mlp"), "stage_ms_per_step": m["stage_ms_per_step"]}
+            log(f"[other workload] {name}: {m['value']:.1f} Mpaths/s")
+    if default_single and not args.no_gate and data.startswith("reference-scene"):
+        gate = image_gate(sc, api, W, H, args.gate_spp, args.gate_spp, 200)
+        log(f"[image gate] {gate}")
+    if not args.no_cpu_baseline and kind == "msnn":
+        cb = cpu_baseline(sc, kw, W, H, beta_cli)
 
-    line = {"metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": CONFIG,
-            "clocks": sampler.summary(),
-            "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": int(frame_param_bytes * launches_per_step),
-                    "d2h_bytes_per_step": int(fb_host[0].numel() * 4 + avg_host[0].numel() * 4),
-                    "note": "per step: one frame through the C ABI (hm_render_frames_async / split-frame calls) followed by hm_readback_async of the 8-bit framebuffer and the fp32 average buffer into pinned host memory, host clock around the whole loop incl. the final sync; host->device traffic of a frame is its kernel parameter blocks"},
-            "gpu_launches": int(launches),
-            "roofline": roofline, "mlp": mlp_info, "cpu_baseline": cb,
-            "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
-            "training_loss": st.last_loss}
+    line = {"metric": "Mpaths/s", "value": res["value"], "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": res["ms"] / args.steps, "higher_is_better": True, "scaling": "strong" if bands else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": data, "config": bench_config(args.workload, W, H, info, "row bands" if bands else "spp"),
+            "clocks": sampler.summary(), "e2e": res["e2e"], "gpu_launches": res["launches"],
+            "roofline": res["roofline"], "mlp": res.get("mlp"), "cpu_baseline": cb,
+            "stage_ms_per_step": res["stage_ms_per_step"], "training_loss": res["loss"],
+            "collectives": ("ncclAllReduce of 1000448 fp32 gradients per training step inside hm_render_frames (libhairmsnn.so); "
+                            "bench.py issues none") if world > 1 else None,
+            "image_gate": gate, "other_workloads": others}
     emit(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if comm:
+        comm.barrier()
+        comm.close()
 
 
 if __name__ == "__main__":

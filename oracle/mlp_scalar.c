@@ -114,9 +114,21 @@ static void layers(const float* params, const float* e, float* h1, float* h2, fl
 }
 
 typedef struct {
-    const Layout* L; const float* params; const float* x; const float* target; float* out; float* grads;
+    const Layout* L; const float* params; const float* x; const float* target; float* out;
+    float* grads;       /* private [N_MATRIX] accumulator of the matrix gradients */
+    float* grid_grads;  /* shared grid gradient buffer, updated with atomic adds */
     int in_ch, r0, r1, n_total; double loss;
 } Job;
+
+static inline void atomic_addf(float* p, float v) {
+    uint32_t* u = (uint32_t*)p;
+    uint32_t old = __atomic_load_n(u, __ATOMIC_RELAXED), neu;
+    do {
+        float f; memcpy(&f, &old, 4);
+        f += v;
+        memcpy(&neu, &f, 4);
+    } while (!__atomic_compare_exchange_n(u, &old, neu, 1, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+}
 
 static void* infer_job(void* p) {
     Job* j = (Job*)p;
@@ -129,7 +141,8 @@ static void* infer_job(void* p) {
     return NULL;
 }
 
-/* forward + loss + backward of rows [r0,r1) into this job's private gradient buffer (loss-scaled by 128) */
+/* forward + loss + backward of rows [r0,r1): matrix gradients into this job's private buffer, grid gradients
+ * scattered into the shared buffer (all loss-scaled by 128) */
 static void* train_job(void* p) {
     Job* j = (Job*)p;
     const float* W0 = j->params; const float* W1 = j->params + WIDTH * WIDTH; const float* Wo = j->params + 2 * WIDTH * WIDTH;
@@ -157,8 +170,8 @@ static void* train_job(void* p) {
         for (int o = 0; o < OUT_PAD; ++o) for (int i = 0; i < WIDTH; ++i) g[2 * WIDTH * WIDTH + o * WIDTH + i] += dy[o] * h2[i];
         for (int l = 0; l < LEVELS; ++l)
             for (int c = 0; c < 8; ++c) {
-                float* t = g + N_MATRIX + 2 * (size_t)cn.idx[l][c];
-                t[0] += cn.w[l][c] * de[2 * l]; t[1] += cn.w[l][c] * de[2 * l + 1];
+                float* t = j->grid_grads + 2 * (size_t)cn.idx[l][c];
+                atomic_addf(t, cn.w[l][c] * de[2 * l]); atomic_addf(t + 1, cn.w[l][c] * de[2 * l + 1]);
             }
     }
     j->loss = loss;
@@ -189,24 +202,24 @@ void mlps_inference(const float* params, const float* x, int n, int in_ch, float
     free(jobs);
 }
 
-/* forward + loss + backward: grads [n_params] (loss-scaled by 128) is overwritten; returns the loss */
+/* forward + loss + backward: ACCUMULATES the gradients (loss-scaled by 128) into grads [n_params] — the caller
+ * zeroes it (mlps_adam clears what it consumes, as the optimiser kernel does); returns the loss */
 double mlps_gradients(const float* params, const float* x, const float* target, int n, int in_ch, int n_total_records, float* grads, int threads) {
     Layout L; make_layout(&L);
-    const size_t np = mlps_n_params();
     if (threads < 1) threads = 1;
     if (threads > n) threads = n > 0 ? n : 1;
     Job* jobs = (Job*)calloc(threads, sizeof(Job));
     for (int t = 0; t < threads; ++t) {
         jobs[t].L = &L; jobs[t].params = params; jobs[t].x = x; jobs[t].target = target; jobs[t].in_ch = in_ch;
         jobs[t].n_total = n_total_records > 0 ? n_total_records : n;
-        jobs[t].grads = t == 0 ? grads : (float*)malloc(np * sizeof(float));
-        memset(jobs[t].grads, 0, np * sizeof(float));
+        jobs[t].grads = (float*)calloc(N_MATRIX, sizeof(float));
+        jobs[t].grid_grads = grads + N_MATRIX;
         jobs[t].r0 = (int)((long long)n * t / threads); jobs[t].r1 = (int)((long long)n * (t + 1) / threads);
     }
     run_jobs(train_job, jobs, threads);
-    double loss = jobs[0].loss;
-    for (int t = 1; t < threads; ++t) {
-        for (size_t i = 0; i < np; ++i) grads[i] += jobs[t].grads[i];
+    double loss = 0.0;
+    for (int t = 0; t < threads; ++t) {
+        for (size_t i = 0; i < (size_t)N_MATRIX; ++i) grads[i] += jobs[t].grads[i];
         loss += jobs[t].loss;
         free(jobs[t].grads);
     }
@@ -215,11 +228,12 @@ double mlps_gradients(const float* params, const float* x, const float* target, 
 }
 
 /* adam_step (adam.h:48-120) on parameters [first, first+count): fp32 master/m1/m2 + per-parameter step counts;
- * L2 regularisation on the matrices only, grid entries with a zero gradient are skipped. */
-void mlps_adam(float* master, float* m1, float* m2, uint32_t* steps, const float* grads_scaled, size_t first, size_t count,
+ * L2 regularisation on the matrices only, grid entries with a zero gradient are skipped; consumed gradients are cleared. */
+void mlps_adam(float* master, float* m1, float* m2, uint32_t* steps, float* grads_scaled, size_t first, size_t count,
                float lr, float beta1, float beta2, float eps, float l2_reg) {
     for (size_t i = first; i < first + count; ++i) {
         float g = grads_scaled[i] / 128.f;
+        grads_scaled[i] = 0.f;
         const int is_matrix = i < (size_t)N_MATRIX;
         if (!is_matrix && g == 0.f) continue;
         if (is_matrix) g += l2_reg * master[i];

@@ -3,6 +3,8 @@
 // where they lie) for the host.  See ref_optix_emul.h.
 #include "ref_optix_emul.h"
 
+#include <atomic>
+
 #define __CUDA_ARCH__ 860
 #include "hair_msnn.cuh"
 #undef __CUDA_ARCH__
@@ -59,6 +61,53 @@ void ref_render_msnn_gbuffer(int accum_id, int y0, int y1, int W, int H, int bet
         for (int x = 0; x < W; ++x) {
             size_t i = (size_t)y * W + x;
             float* o = gbuf_out + 8 * i;
+            o[0] = gb[i].hit; o[1] = gb[i].isSurface;
+            o[2] = gb[i].p.x; o[3] = gb[i].p.y; o[4] = gb[i].p.z;
+            o[5] = gb[i].shortPathColor.x; o[6] = gb[i].shortPathColor.y; o[7] = gb[i].shortPathColor.z;
+        }
+}
+
+// Same pass for a LIST of rows (bench.py's CPU arm: rows stratified over the frame).  Pixels are handed to the
+// threads in chunks of 32 through an atomic cursor (path lengths vary a lot between hair and background);
+// the G-buffer is kept between calls.  gbuf_out: float[n_rows*W*8], compact in list order.
+void ref_render_msnn_gbuffer_rows(int accum_id, const int* rows, int n_rows, int W, int H, int beta, int every_nth, const int* train_idxs,
+                                  int in_ch, float* nn_frame_in, float* nn_train_in, float* nn_train_out, float* gbuf_out, int threads) {
+    LaunchParams& P = optixLaunchParams;
+    P.accumId = accum_id;
+    P.pass = G_BUFFER;
+    P.beta = beta;
+    P.everyNth = every_nth;
+    P.trainIdxs = (int*)train_idxs;
+    P.mlpInputCh = in_ch; P.mlpOutputCh = 3;
+    P.nnFrameInput = nn_frame_in;
+    P.nnTrainInput = nn_train_in; P.nnTrainOutput = nn_train_out;
+    static std::vector<GBuffer> gb;
+    if (gb.size() != (size_t)W * H) gb.assign((size_t)W * H, GBuffer());
+    P.gBuffer = gb.data();
+    g_raygen_data.frameBuffer = nullptr;
+    g_raygen_data.frameBufferSize = vec2i(W, H);
+    if (threads < 1) threads = 1;
+    const int total = n_rows * W;
+    std::atomic<int> cursor{0};
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) {
+        pool.emplace_back([&]() {
+            for (;;) {
+                const int k0 = cursor.fetch_add(32);
+                if (k0 >= total) break;
+                for (int k = k0; k < k0 + 32 && k < total; ++k) {
+                    refemu::g_ctx.launch_x = k % W; refemu::g_ctx.launch_y = rows[k / W];
+                    refemu::g_ctx.program_data = &g_raygen_data;
+                    ref_raygen_rayGenCam();
+                }
+            }
+        });
+    }
+    for (auto& th : pool) th.join();
+    if (gbuf_out)
+        for (int k = 0; k < total; ++k) {
+            const size_t i = (size_t)rows[k / W] * W + (k % W);
+            float* o = gbuf_out + 8 * (size_t)k;
             o[0] = gb[i].hit; o[1] = gb[i].isSurface;
             o[2] = gb[i].p.x; o[3] = gb[i].p.y; o[4] = gb[i].p.z;
             o[5] = gb[i].shortPathColor.x; o[6] = gb[i].shortPathColor.y; o[7] = gb[i].shortPathColor.z;

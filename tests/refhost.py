@@ -130,6 +130,21 @@ class RefHost:
                                          _p(tr_in), _p(tr_out), _p(gb), threads or os.cpu_count())
         return nn_in, tr_in, tr_out, gb
 
+    def render_msnn_rows(self, accum_id, W, H, beta, every_nth, train_idxs, rows, bufs=None, in_ch=12, threads=0):
+        """G_BUFFER pass for a list of rows, all host threads sharing the rows' pixels.  `bufs` = (nn_in [W*H][in_ch],
+        tr_in, tr_out, gb [len(rows)*W][8]) from a previous call are reused."""
+        assert self.which == "msnn"
+        train_idxs = np.ascontiguousarray(train_idxs, dtype=np.int32)
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        rec = train_idxs.shape[0]
+        if bufs is None:
+            bufs = (np.zeros((W * H, in_ch), np.float32), np.zeros((rec, in_ch), np.float32), np.zeros((rec, 3), np.float32),
+                    np.zeros((len(rows) * W, 8), np.float32))
+        nn_in, tr_in, tr_out, gb = bufs
+        self.lib.ref_render_msnn_gbuffer_rows(accum_id, _p(rows, _ip), len(rows), W, H, beta, every_nth, _p(train_idxs, _ip), in_ch,
+                                              _p(nn_in), _p(tr_in), _p(tr_out), _p(gb), threads or os.cpu_count())
+        return bufs
+
     def render_msnn_train_data_gen(self, accum_id, W, H, beta, scene_indices, sampled_points, in_ch=12, threads=0):
         assert self.which == "msnn"
         idx = np.ascontiguousarray(scene_indices, dtype=np.int32)
