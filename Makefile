@@ -1,7 +1,9 @@
 # Builds the C-ABI shared library (sm_100a only) and the three headless executables.
 NVCC ?= /usr/local/cuda/bin/nvcc
 CSRC := hairmsnn_b200/csrc
-LIB := hairmsnn_b200/lib/libhairmsnn.so
+# A/B builds: `make lib BUILD=build_v1 LIB=hairmsnn_b200/lib/libhairmsnn_v1.so EXTRA=-DHM_TRACE_CTAS=8`, then HM_LIB=<that .so>
+BUILD ?= build
+LIB ?= hairmsnn_b200/lib/libhairmsnn.so
 ARCH := -gencode arch=compute_100a,code=sm_100a
 # -fmad=false: the traversal/intersection code must round like its host build (hit-id parity)
 NVFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC,-O3,-ffp-contract=off -fmad=false --expt-relaxed-constexpr -Xptxas -v $(EXTRA)
@@ -12,22 +14,23 @@ CXXFLAGS := -O2 -std=c++17 -fPIC -ffp-contract=off -mfma -pthread -I/usr/local/c
 NCCL_HOME ?= $(firstword $(wildcard /opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/nccl) /usr)
 NCCL_INC := $(if $(filter /usr,$(NCCL_HOME)),,-I$(NCCL_HOME)/include)
 NCCL_LIB := $(if $(filter /usr,$(NCCL_HOME)),-lnccl,-L$(NCCL_HOME)/lib -l:libnccl.so.2 -Xlinker -rpath,$(NCCL_HOME)/lib)
-OBJ := build/hm_wavefront.o build/hm_renderer.o build/hm_mlp.o build/hm_capi.o build/hm_io.o build/hm_piz.o build/hm_scene_util.o build/hm_bvh_build.o build/hm_comm.o
+OBJ := $(BUILD)/hm_wavefront.o $(BUILD)/hm_renderer.o $(BUILD)/hm_mlp.o $(BUILD)/hm_capi.o $(BUILD)/hm_io.o $(BUILD)/hm_piz.o $(BUILD)/hm_scene_util.o $(BUILD)/hm_bvh_build.o $(BUILD)/hm_comm.o
 HDRS := $(wildcard $(CSRC)/*.h) include/hairmsnn.h
 
 all: $(LIB) bin
+lib: $(LIB)
 
-build/hm_wavefront.o: $(CSRC)/hm_wavefront.cu $(HDRS)
-	@mkdir -p build
-	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/hm_wavefront.ptxas.log || (cat build/hm_wavefront.ptxas.log; false)
-build/hm_renderer.o: $(CSRC)/hm_renderer.cu $(HDRS)
-	@mkdir -p build
-	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/hm_renderer.ptxas.log || (cat build/hm_renderer.ptxas.log; false)
-build/hm_mlp.o: $(CSRC)/hm_mlp.cu $(HDRS)
-	@mkdir -p build
-	$(NVCC) $(NVFLAGS_MLP) -c $< -o $@ 2> build/hm_mlp.ptxas.log || (cat build/hm_mlp.ptxas.log; false)
-build/%.o: $(CSRC)/%.cpp $(HDRS)
-	@mkdir -p build
+$(BUILD)/hm_wavefront.o: $(CSRC)/hm_wavefront.cu $(HDRS)
+	@mkdir -p $(BUILD)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(BUILD)/hm_wavefront.ptxas.log || (cat $(BUILD)/hm_wavefront.ptxas.log; false)
+$(BUILD)/hm_renderer.o: $(CSRC)/hm_renderer.cu $(HDRS)
+	@mkdir -p $(BUILD)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(BUILD)/hm_renderer.ptxas.log || (cat $(BUILD)/hm_renderer.ptxas.log; false)
+$(BUILD)/hm_mlp.o: $(CSRC)/hm_mlp.cu $(HDRS)
+	@mkdir -p $(BUILD)
+	$(NVCC) $(NVFLAGS_MLP) -c $< -o $@ 2> $(BUILD)/hm_mlp.ptxas.log || (cat $(BUILD)/hm_mlp.ptxas.log; false)
+$(BUILD)/%.o: $(CSRC)/%.cpp $(HDRS)
+	@mkdir -p $(BUILD)
 	g++ $(CXXFLAGS) $(NCCL_INC) -c $< -o $@
 
 $(LIB): $(OBJ)

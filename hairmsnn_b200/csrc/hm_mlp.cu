@@ -54,6 +54,7 @@ struct NetShape {
     int blob_dims, blob_bins, identity_dims;
     int feats;
     uint32_t hashed_mask;       // bit l set: level l is hashed
+    uint32_t pow2_mask;         // bit l set: level l's size is a power of two (index % size == index & (size - 1))
 };
 
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -146,54 +147,73 @@ __device__ __forceinline__ float quartic_cdf(float x, float inv_radius) {
     return fmaxf(0.0f, fminf(1.0f, (15.f / 16.f) * u * (1 - (2.f / 3.f) * u2 + (1.f / 5.f) * u4) + 0.5f));
 }
 
-// Encodes one input row into 64 halves; `at(col)` gives the address of column `col` (even
-// columns are 4-byte aligned and followed by their odd neighbour).
-template <class At>
-__device__ __forceinline__ void encode_row(const NetShape& S, const __half2* __restrict__ table, const float* x, At at) {
-    const int nl = S.grid.n_levels;
-    for (int l = 0; l < nl; ++l) {
-        const float scale = S.grid.scale[l];
-        const uint32_t res = S.grid.resolution[l];
-        const uint32_t size = S.grid.offset[l + 1] - S.grid.offset[l];
-        const bool hashed = (S.hashed_mask >> l) & 1u;
-        const __half2* tl = table + S.grid.offset[l];
-        float fr[3];
-        uint32_t pg[3];
+// One level of the hash grid for one row (kernel_grid, encodings/grid.h:221-351): the 8 corner values are
+// fetched first (8 independent loads), then accumulated exactly as tiny-cuda-nn does — fp32 product, rounded to
+// fp16, added in fp16 (grid.h:337-341) — so the encoded features are bit-identical to the reference's.
+template <bool POW2>
+__device__ __forceinline__ uint32_t encode_level(const NetShape& S, const __half2* __restrict__ table, float x0, float x1, float x2, int l) {
+    const float scale = S.grid.scale[l];
+    const uint32_t res = S.grid.resolution[l];
+    const uint32_t size = S.grid.offset[l + 1] - S.grid.offset[l];
+    const bool hashed = (S.hashed_mask >> l) & 1u;
+    const __half2* tl = table + S.grid.offset[l];
+    float p0 = x0 * scale + 0.5f, p1 = x1 * scale + 0.5f, p2 = x2 * scale + 0.5f;      // pos_fract, common_device.h:434-445
+    const float f0 = floorf(p0), f1 = floorf(p1), f2 = floorf(p2);
+    const uint32_t q0 = (uint32_t)(int)f0, q1 = (uint32_t)(int)f1, q2 = (uint32_t)(int)f2;
+    p0 -= f0; p1 -= f1; p2 -= f2;
+    // per-axis index terms: dense = x + y*res + z*res^2, hashed = x ^ y*2654435761 ^ z*805459861 (grid.h:171-187)
+    uint32_t ix[2], iy[2], iz[2];
+    ix[0] = q0; ix[1] = q0 + 1u;
+    if (hashed) { iy[0] = q1 * 2654435761u; iy[1] = iy[0] + 2654435761u; iz[0] = q2 * 805459861u; iz[1] = iz[0] + 805459861u; }
+    else { iy[0] = q1 * res; iy[1] = iy[0] + res; iz[0] = q2 * res * res; iz[1] = iz[0] + res * res; }
+    __half2 v[8];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            float pos = x[d] * scale + 0.5f;
-            float fl = floorf(pos);
-            pg[d] = (uint32_t)(int)fl;
-            fr[d] = pos - fl;
-        }
-        float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float w = ((c & 1) ? fr[0] : 1 - fr[0]) * ((c & 2) ? fr[1] : 1 - fr[1]);
-            w *= (c & 4) ? fr[2] : 1 - fr[2];
-            uint32_t idx = grid_cell_index(pg[0] + (c & 1), pg[1] + ((c >> 1) & 1), pg[2] + ((c >> 2) & 1), res, size, hashed);
-            float2 v = __half22float2(__ldg(tl + idx));
-            acc.x += w * v.x; acc.y += w * v.y;
-        }
-        *reinterpret_cast<uint32_t*>(at(2 * l)) = pack2(acc.x, acc.y);
+    for (int c = 0; c < 8; ++c) {
+        uint32_t idx = hashed ? (ix[c & 1] ^ iy[(c >> 1) & 1] ^ iz[(c >> 2) & 1]) : (ix[c & 1] + iy[(c >> 1) & 1] + iz[(c >> 2) & 1]);
+        idx = (POW2 || ((S.pow2_mask >> l) & 1u)) ? (idx & (size - 1u)) : (idx % size);
+        v[c] = __ldg(tl + idx);
     }
+    const float wx[2] = {1 - p0, p0}, wy[2] = {1 - p1, p1}, wz[2] = {1 - p2, p2};
+    __half2 acc = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float w = (wx[c & 1] * wy[(c >> 1) & 1]) * wz[(c >> 2) & 1];
+        const float2 f = __half22float2(v[c]);
+        acc = __hadd2(acc, __floats2half2_rn(w * f.x, w * f.y));
+    }
+    return *reinterpret_cast<uint32_t*>(&acc);
+}
+
+// Encodes (part `part` of `parts` of) one input row into 64 halves; `at(col)` gives the address of column `col`
+// (even columns are 4-byte aligned and followed by their odd neighbour).  With parts = 2 two threads share a row:
+// part p takes the grid levels and OneBlob dimensions of parity p, part parts-1 the identity columns and the padding.
+template <bool POW2, class At>
+__device__ __forceinline__ void encode_row(const NetShape& S, const __half2* __restrict__ table, const float* x, At at, int part = 0, int parts = 1) {
+    const int nl = S.grid.n_levels;
+#pragma unroll 2
+    for (int l = part; l < nl; l += parts) *reinterpret_cast<uint32_t*>(at(2 * l)) = encode_level<POW2>(S, table, x[0], x[1], x[2], l);
     int c0 = nl * 2;
     const int nb = S.blob_bins;
     const float inv_r = (float)nb;
-    for (int j = 0; j < S.blob_dims; ++j) {
+    const bool last = part == parts - 1;
+    const bool nrc_pad = S.identity_dims == 0;
+    for (int j = part; j < S.blob_dims; j += parts) {
         const float xv = x[3 + j];
         float left = quartic_cdf(-xv, inv_r) + quartic_cdf(-xv - 1.0f, inv_r) + quartic_cdf(-xv + 1.0f, inv_r);
         for (int k = 0; k < nb; ++k) {
             const float rb = (float)(k + 1) / (float)nb;
             const float right = quartic_cdf(rb - xv, inv_r) + quartic_cdf(rb - xv - 1.0f, inv_r) + quartic_cdf(rb - xv + 1.0f, inv_r);
-            *at(c0 + j * nb + k) = __float2half_rn(right - left);
+            const int col = c0 + j * nb + k;
+            // render_nrc: columns blob_dims .. blob_dims + n_pad - 1 of the OneBlob slice are overwritten with ones (below)
+            if (!(nrc_pad && col >= c0 + S.blob_dims && col < c0 + S.blob_dims + (kW - c0 - S.blob_dims * nb))) *at(col) = __float2half_rn(right - left);
             left = right;
         }
     }
+    if (!last) return;
     const int blob0 = c0;
     c0 += S.blob_dims * nb;
     for (int j = 0; j < S.identity_dims; ++j) *at(c0 + j) = __float2half_rn(x[3 + S.blob_dims + j]);
-    if (S.identity_dims > 0) {
+    if (!nrc_pad) {
         // Identity is the last nested encoding and pads the network input with ones (identity.h:46-66)
         for (int c = c0 + S.identity_dims; c < kW; ++c) *at(c) = __float2half_rn(1.0f);
     } else {
@@ -250,7 +270,7 @@ __global__ void __launch_bounds__(kTile) k_mlp_forward(const NetShape S, const _
                 for (int i = 0; i < 12; ++i) x[i] = i < S.in_ch ? __ldg(src + i) : 0.f;
             }
             __half* rowp = sAct + threadIdx.x * kStride;
-            encode_row(S, table, x, [rowp](int col) { return rowp + col; });
+            encode_row<false>(S, table, x, [rowp](int col) { return rowp + col; });
         }
         __syncwarp();
         if (TRAIN) {
@@ -413,8 +433,14 @@ __device__ __forceinline__ void load_weights_sw(unsigned char* dst, const __half
 
 }  // namespace tc
 
-template <bool TRAIN>
-__global__ void __launch_bounds__(kTile) k_mlp_forward_tc(const NetShape S, const __half* __restrict__ params, FwdArgs A) {
+// 256 threads per CTA, two per row of the 128-row tile: thread (row, part) encodes the grid levels / OneBlob
+// dimensions of parity `part` (the 32 lanes of a warp are 32 adjacent rows working on the SAME level, so their
+// gathers stay as coherent as the rows are), and in the hidden-layer epilogues drains columns [32 part, 32 part + 32)
+// of its row's accumulator.  Warps w and w + 4 share TMEM lanes 32 (w & 3) .. + 31.
+constexpr int kFwdThreads = 256;
+
+template <bool TRAIN, bool POW2>
+__global__ void __launch_bounds__(kFwdThreads, 3) k_mlp_forward_tc(const NetShape S, const __half* __restrict__ params, FwdArgs A) {
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t raw = tc::smem_u32(smem_dyn);
     unsigned char* base = smem_dyn + ((1024u - (raw & 1023u)) & 1023u);
@@ -426,6 +452,8 @@ __global__ void __launch_bounds__(kTile) k_mlp_forward_tc(const NetShape S, cons
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_ptr + 1);
     const uint32_t bar = tc::smem_u32(bar_ptr);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int part = warp >> 2;
+    const uint32_t row = (uint32_t)((warp & 3) * 32 + lane);
 
     tc::load_weights_sw(sW0, params, kW);
     tc::load_weights_sw(sW1, params + kW * kW, kW);
@@ -443,7 +471,7 @@ __global__ void __launch_bounds__(kTile) k_mlp_forward_tc(const NetShape S, cons
     __syncthreads();
     tc::fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tmem_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint64_t dA = tc::make_desc(tc::smem_u32(sA));
     const uint64_t dW0 = tc::make_desc(tc::smem_u32(sW0));
     const uint64_t dW1 = tc::make_desc(tc::smem_u32(sW1));
@@ -451,7 +479,6 @@ __global__ void __launch_bounds__(kTile) k_mlp_forward_tc(const NetShape S, cons
     const uint32_t idesc64 = tc::make_idesc(64), idesc16 = tc::make_idesc(16);
     const __half2* table = reinterpret_cast<const __half2*>(params + 2 * kW * kW + kOutPad * kW);
     uint32_t parity = 0;
-    const uint32_t row = threadIdx.x;
 
     // one layer on the tensor core: D[128 x n] = A[128 x 64] * W[n x 64]^T, K in 4 steps of 16
     auto layer = [&](uint64_t dW, uint32_t idesc) {
@@ -468,29 +495,26 @@ __global__ void __launch_bounds__(kTile) k_mlp_forward_tc(const NetShape S, cons
         parity ^= 1u;
         tc::fence_after();
     };
-    // TMEM row -> ReLU -> fp16 -> A tile (and optionally global)
+    // this thread's 32 accumulator columns of its row -> ReLU -> fp16 -> A tile (and optionally global)
     auto epilogue_hidden = [&](__half* gdst) {
         uint32_t v[32];
-        uint4 packed[8];
+        tc::ld32(tmem_lane + (uint32_t)part * 32u, v);
+        tc::wait_ld();
+        uint4 packed[4];
 #pragma unroll
-        for (int half_i = 0; half_i < 2; ++half_i) {
-            tc::ld32(tmem_lane + half_i * 32, v);
-            tc::wait_ld();
+        for (int c = 0; c < 4; ++c) {
+            uint32_t w[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t w[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    w[j] = pack2(fmaxf(__uint_as_float(v[c * 8 + 2 * j]), 0.f), fmaxf(__uint_as_float(v[c * 8 + 2 * j + 1]), 0.f));
-                packed[half_i * 4 + c] = make_uint4(w[0], w[1], w[2], w[3]);
-            }
+            for (int j = 0; j < 4; ++j)
+                w[j] = pack2(fmaxf(__uint_as_float(v[c * 8 + 2 * j]), 0.f), fmaxf(__uint_as_float(v[c * 8 + 2 * j + 1]), 0.f));
+            packed[c] = make_uint4(w[0], w[1], w[2], w[3]);
         }
 #pragma unroll
-        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(sA + tc::sw128(row, c)) = packed[c];
+        for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(sA + tc::sw128(row, (uint32_t)(4 * part + c))) = packed[c];
         if (gdst) {
-            uint4* d = reinterpret_cast<uint4*>(gdst);
+            uint4* d = reinterpret_cast<uint4*>(gdst) + 4 * part;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) d[c] = packed[c];
+            for (int c = 0; c < 4; ++c) d[c] = packed[c];
         }
     };
 
@@ -508,21 +532,24 @@ __global__ void __launch_bounds__(kTile) k_mlp_forward_tc(const NetShape S, cons
             } else {
                 for (int i = 0; i < 12; ++i) x[i] = i < S.in_ch ? __ldg(src + i) : 0.f;
             }
-            encode_row(S, table, x, [sA, row](int col) {
+            encode_row<POW2>(S, table, x, [sA, row](int col) {
                 return reinterpret_cast<__half*>(sA + tc::sw128(row, (uint32_t)col >> 3) + ((uint32_t)col & 7u) * 2u);
-            });
-            if (TRAIN) {
-                uint4* d = reinterpret_cast<uint4*>(A.e + grow * kW);
+            }, part, 2);
+        }
+        if (TRAIN) {
+            // the encoded row goes to global memory for the backward pass: each thread copies its half once both
+            // parts are in shared memory
+            __syncthreads();
+            uint4* d = reinterpret_cast<uint4*>(A.e + grow * kW) + 4 * part;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) d[c] = *reinterpret_cast<const uint4*>(sA + tc::sw128(row, c));
-            }
+            for (int c = 0; c < 4; ++c) d[c] = *reinterpret_cast<const uint4*>(sA + tc::sw128(row, (uint32_t)(4 * part + c)));
         }
         layer(dW0, idesc64);
         epilogue_hidden(TRAIN ? A.h1 + grow * kW : nullptr);
         layer(dW1, idesc64);
         epilogue_hidden(TRAIN ? A.h2 + grow * kW : nullptr);
         layer(dWo, idesc16);
-        {
+        if (part == 0) {
             uint32_t v[16];
             tc::ld16(tmem_lane, v);
             tc::wait_ld();
@@ -807,12 +834,14 @@ NetShape make_shape(const MlpConfig& c, const GridLayout& g) {
     s.identity_dims = c.in_ch - c.grid_dims - c.blob_dims;
     s.feats = c.feats;
     s.hashed_mask = 0;
+    s.pow2_mask = 0;
     for (int l = 0; l < g.n_levels; ++l) {
         // grid_index (encodings/grid.h:171-187): dense while the running stride fits the level
         uint64_t stride = 1;
         const uint32_t size = g.offset[l + 1] - g.offset[l];
         for (int d = 0; d < 3 && stride <= size; ++d) stride *= g.resolution[l];
         if (size < stride) s.hashed_mask |= 1u << l;
+        if ((size & (size - 1)) == 0) s.pow2_mask |= 1u << l;
     }
     return s;
 }
@@ -949,8 +978,10 @@ Mlp::Mlp(const MlpConfig& cfg, cudaStream_t stream) : cfg_(cfg), stream_(stream)
     HM_CUDA(cudaFuncSetAttribute(k_mlp_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
     HM_CUDA(cudaFuncSetAttribute(k_mlp_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
     HM_CUDA(cudaFuncSetAttribute(k_mlp_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
-    HM_CUDA(cudaFuncSetAttribute(k_mlp_forward_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
-    HM_CUDA(cudaFuncSetAttribute(k_mlp_forward_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
+    HM_CUDA(cudaFuncSetAttribute(k_mlp_forward_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
+    HM_CUDA(cudaFuncSetAttribute(k_mlp_forward_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
+    HM_CUDA(cudaFuncSetAttribute(k_mlp_forward_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
+    HM_CUDA(cudaFuncSetAttribute(k_mlp_forward_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
     // forward implementation: tcgen05/TMEM by default; HM_MLP_IMPL=mma selects the mma.sync kernel
     const char* impl = getenv("HM_MLP_IMPL");
     use_tc_ = !(impl && std::string(impl) == "mma");
@@ -1019,7 +1050,7 @@ void Mlp::ensure_train_buffers(int n) {
 static int fwd_ctas_per_sm() {
     static int v = 0;
     if (!v) {
-        v = 4;
+        v = 3;
         if (const char* e = getenv("HM_MLP_CTAS")) v = std::max(1, std::min(16, atoi(e)));
     }
     return v;
@@ -1033,7 +1064,9 @@ void Mlp::inference(const float* d_in, float* d_out, int n, const int* d_tile_ma
     A.in = d_in; A.out = d_out; A.n_tiles = n / kTile;
     A.tile_mask = d_tile_mask;
     int grid = std::min(A.n_tiles, sm_count() * fwd_ctas_per_sm());
-    if (use_tc_) k_mlp_forward_tc<false><<<grid, kTile, tc::kSmemBytes, stream_>>>(S, (const __half*)d_half_, A);
+    const bool pow2 = S.pow2_mask == (S.grid.n_levels >= 32 ? 0xffffffffu : (1u << S.grid.n_levels) - 1u);
+    if (use_tc_ && pow2) k_mlp_forward_tc<false, true><<<grid, kFwdThreads, tc::kSmemBytes, stream_>>>(S, (const __half*)d_half_, A);
+    else if (use_tc_) k_mlp_forward_tc<false, false><<<grid, kFwdThreads, tc::kSmemBytes, stream_>>>(S, (const __half*)d_half_, A);
     else k_mlp_forward<false><<<grid, kTile, kFwdSmem, stream_>>>(S, (const __half*)d_half_, A);
     launches_++;
     HM_CUDA(cudaGetLastError());
@@ -1053,7 +1086,9 @@ void Mlp::forward_backward(const float* d_in, const float* d_target, int n, int 
     A.inv_n_total = 1.f / (float)((size_t)n_total_records * cfg_.out_ch);
     A.n_tiles = n / kTile;
     int grid = std::min(A.n_tiles, sm_count() * 4);
-    if (use_tc_) k_mlp_forward_tc<true><<<grid, kTile, tc::kSmemBytes, stream_>>>(S, (const __half*)d_half_, A);
+    const bool pow2 = S.pow2_mask == (S.grid.n_levels >= 32 ? 0xffffffffu : (1u << S.grid.n_levels) - 1u);
+    if (use_tc_ && pow2) k_mlp_forward_tc<true, true><<<grid, kFwdThreads, tc::kSmemBytes, stream_>>>(S, (const __half*)d_half_, A);
+    else if (use_tc_) k_mlp_forward_tc<true, false><<<grid, kFwdThreads, tc::kSmemBytes, stream_>>>(S, (const __half*)d_half_, A);
     else k_mlp_forward<true><<<grid, kTile, kFwdSmem, stream_>>>(S, (const __half*)d_half_, A);
     BwdArgs B;
     B.in = d_in; B.dy = (const __half*)d_dy_; B.h1 = h1; B.h2 = h2; B.dh1 = dh1; B.dh2 = dh2;

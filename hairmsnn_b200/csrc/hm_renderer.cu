@@ -6,6 +6,7 @@
 #include <thrust/random.h>
 #include <thrust/shuffle.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <stdexcept>
@@ -153,7 +154,10 @@ Renderer::Renderer(const HostScene& hs, int kind, int beta_cli, int device, int 
     const size_t first = (size_t)row0_ * W_;
     if (nb > (size_t)2048 * 2048)
         throw std::invalid_argument("a renderer's band holds more than 2048 x 2048 pixels (scene.cpp:302-306 limit, applied per GPU band): use more bands");
-    auto alloc_px = [&](size_t bytes_per_px) { return (char*)alloc(nb * bytes_per_px) - first * bytes_per_px; };
+    // the TRAIN_DATA_GEN pass uses slots 0 .. records-1 of the same arrays (band offset undone, params_for): a band
+    // smaller than the record count still allocates that many elements
+    const size_t n_alloc = kind_ == HM_KIND_MSNN ? std::max(nb, (size_t)(128 * 128)) : nb;
+    auto alloc_px = [&](size_t bytes_per_px) { return (char*)alloc(n_alloc * bytes_per_px) - first * bytes_per_px; };
     for (int ci = 0; ci < frames_in_flight_; ++ci) {
         FrameCtx& c = ctx_[ci];
         c.paths.rng = (uint32_t*)alloc_px(4);
@@ -189,10 +193,10 @@ Renderer::Renderer(const HostScene& hs, int kind, int beta_cli, int device, int 
             c.gbuffer_b = (float4*)alloc(n * 16);
             c.tbuffer = (NrcTrainRec*)alloc((size_t)nrc_train_pixels_ * sizeof(NrcTrainRec));
         }
-        c.q.shade[0] = (int*)alloc(nb * 4);
-        c.q.shade[1] = (int*)alloc(nb * 4);
-        c.q.extend = (int*)alloc(nb * 4);
-        c.q.shadow = (float4*)alloc(nb * 2 * 32);
+        c.q.shade[0] = (int*)alloc(n_alloc * 4);
+        c.q.shade[1] = (int*)alloc(n_alloc * 4);
+        c.q.extend = (int*)alloc(n_alloc * 4);
+        c.q.shadow = (float4*)alloc(n_alloc * 2 * 32);
         c.q.counts = (int*)alloc(16 * 4);
         c.q.trav = d_trav_;
         HM_CUDA(cudaStreamCreateWithPriority(&c.tail_stream, cudaStreamNonBlocking, getenv("HM_TAIL_LOW_PRIO") ? prio_lo : prio_hi));
@@ -333,7 +337,6 @@ FrameParams Renderer::params_for(const FrameCtx& c) {
         // per-pixel arrays (the constructor moved their base pointers back by the band's first pixel)
         const ptrdiff_t first = (ptrdiff_t)row0_ * W_;
         if (first) {
-            if ((size_t)(row1_ - row0_) * W_ < (size_t)records_) throw std::invalid_argument("TRAIN_DATA_GEN needs a band of at least 16384 pixels");
             PathBuffers& b = P.paths;
             b.rng += first; b.ray_o += first; b.ray_d += first; b.hit += first; b.beta += first; b.color += first;
             b.dl_beta += first; b.dl_light += first; b.dl_bsdf += first; b.vis += first;

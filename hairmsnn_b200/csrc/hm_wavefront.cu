@@ -85,11 +85,24 @@ __device__ __forceinline__ void write_nn_input(float* dst, V3 p, V3 wo, V3 t, fl
 // ---------------------------------------------------------------------------------
 // primary
 // ---------------------------------------------------------------------------------
+#ifndef HM_PRIMARY_TILES
+#define HM_PRIMARY_TILES 1
+#endif
 struct PrimaryOps {
     const FrameParams& P;
     int first;
+    bool tiled;
+    // Work item -> pixel slot.  With HM_PRIMARY_TILES the 32 consecutive work items a warp pulls are an 8 x 4 pixel
+    // tile instead of 32 pixels of a scanline: camera rays of a tile stay together deeper into the tree.  The slot
+    // (= full-frame pixel index) keys the RNG and all path state, so results do not depend on the mapping.
+    __device__ __forceinline__ int slot_of(int w) const {
+        if (!tiled) return first + w;
+        const int t = w >> 5, i = w & 31, tiles_x = P.W >> 3;
+        const int tx = t % tiles_x, ty = t / tiles_x;
+        return first + (ty * 4 + (i >> 3)) * P.W + tx * 8 + (i & 7);
+    }
     __device__ __forceinline__ bool fetch(int w, V3& o, V3& d) const {
-        const int slot = first + w;
+        const int slot = slot_of(w);
         o = V3(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]);
         Rng rng;
         if (P.pretrain) {
@@ -114,7 +127,7 @@ struct PrimaryOps {
         return false;
     }
     __device__ __forceinline__ void commit(int w, const Hit& h, bool finished) const {
-        const int slot = first + (finished ? w : 0);
+        const int slot = finished ? slot_of(w) : first;
         const bool hit_any = finished && h.prim >= 0;
         if (finished) {
             P.paths.hit[slot] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
@@ -147,7 +160,8 @@ struct PrimaryOps {
 __global__ void __launch_bounds__(kBlock, kTraceCtasPerSm) k_primary(const __grid_constant__ FrameParams P) {
     const int n = P.n_primary;
     TraceStats st[2] = {{0, 0}, {0, 0}};
-    PrimaryOps ops{P, P.pretrain ? 0 : P.row0 * P.W};
+    const bool tiled = HM_PRIMARY_TILES && !P.pretrain && (P.W & 7) == 0 && ((P.row1 - P.row0) & 3) == 0;
+    PrimaryOps ops{P, P.pretrain ? 0 : P.row0 * P.W, tiled};
     trace_queue(P.scene.geom, n, P.q.counts + 6, ops, 0.f, 1e30f, P.collect_stats ? st : nullptr);
     if (P.collect_stats) {
         flush_trav(P.q.trav + 4, st[0]);

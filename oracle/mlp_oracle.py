@@ -14,9 +14,9 @@ PCG32 reference stream and std::seed_seq (C++ standard [rand.util.seedseq]).
 
 All paths are relative to /root/reference/extern/tiny-cuda-nn.
 Two arithmetic modes:
-  half=True  : round where tcnn holds __half (parameters, encoded features, activations
-               between layers, network output, loss gradients) — what tcnn computes, up to
-               its fp16 ACCUMULATION inside wmma (emulated only at tile boundaries);
+  half=True  : round where tcnn holds __half (parameters, encoded features incl. the fp16 accumulation of
+               the 8 grid corners (grid.h:337-341), activations between layers, network output, loss
+               gradients) — what tcnn computes, up to its fp16 ACCUMULATION inside wmma;
   half=False : everything in fp32 — the mathematical ground truth.
 """
 import numpy as np
@@ -246,7 +246,7 @@ def quartic_cdf(x, inv_radius):
     return np.maximum(np.float32(0), np.minimum(np.float32(1), v)).astype(np.float32)
 
 
-def encode(cfg, params, x, half=True, half_accumulate=False):
+def encode(cfg, params, x, half=True, half_accumulate=True):
     """Composite[HashGrid | OneBlob | Identity] -> [N, 64] (encodings/composite.h:136-215,
     grid.h:221-351, oneblob.h:99-127, identity.h:46-66).  Unused trailing network inputs are
     filled with 1.0 by the last nested encoding."""
