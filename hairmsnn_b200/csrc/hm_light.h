@@ -131,44 +131,10 @@ HM_HD int cdf_lower_bound(float u, const float* t, int w, int h, float yn, float
     return first - 1 > 0 ? first - 1 : 0;
 }
 
-// Same partition point found four ways at a time: three independent fetches per round and half the dependent
-// round trips (the rows of the conditional CDF are 16 KB each and cold, so every step of the binary search is a
-// DRAM/L2 round trip in k_shade).  The predicate "texel < u" is monotone along the row, so any search order
-// returns the index std::lower_bound returns (tests/test_cpu_oracle.py::test_cdf_search_variants_agree).
-// Not the default: HM_ENV_SEARCH_4ARY=1 selects it — to be A/B-measured on the GPU before it replaces the
-// binary search.
-HM_HD int cdf_lower_bound4(float u, const float* t, int w, int h, float yn, float size) {
-    int first = 0;
-    int count = (int)size;
-    while (count > 0) {
-        if (count < 4) {
-            int step = count >> 1;
-            int middle = first + step;
-            if (table_fetch(t, w, h, middle / size, yn) < u) { first = middle + 1; count -= step + 1; }
-            else count = step;
-        } else {
-            const int s1 = count >> 2, s2 = count >> 1, s3 = s1 + s2;
-            const float g1 = table_fetch(t, w, h, (first + s1) / size, yn);
-            const float g2 = table_fetch(t, w, h, (first + s2) / size, yn);
-            const float g3 = table_fetch(t, w, h, (first + s3) / size, yn);
-            if (!(g1 < u)) count = s1;
-            else if (!(g2 < u)) { first += s1 + 1; count = s2 - s1 - 1; }
-            else if (!(g3 < u)) { first += s2 + 1; count = s3 - s2 - 1; }
-            else { first += s3 + 1; count -= s3 + 1; }
-        }
-    }
-    return first - 1 > 0 ? first - 1 : 0;
-}
-#ifndef HM_ENV_SEARCH_4ARY
-#define HM_ENV_SEARCH_4ARY 0
-#endif
-HM_HD int cdf_search(float u, const float* t, int w, int h, float yn, float size) {
-#if HM_ENV_SEARCH_4ARY
-    return cdf_lower_bound4(u, t, w, h, yn, size);
-#else
-    return cdf_lower_bound(u, t, w, h, yn, size);
-#endif
-}
+// (A 4-ary variant of this search — half the dependent round trips, three probes each — was measured on the B200
+// against the real scenes/curly frame: k_shade 1.77 vs 1.59 ms per frame, profiles/r2d_sweep_knobs.txt `env4`.
+// The extra probes cost more than the saved round trips; it was removed.)
+HM_HD int cdf_search(float u, const float* t, int w, int h, float yn, float size) { return cdf_lower_bound(u, t, w, h, yn, size); }
 
 HM_HD V3 uniform_sample_sphere(float u0, float u1) {
     float z = 1 - 2 * u0;

@@ -379,9 +379,25 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-    // c_format F32 (bit 4), A/B F16 K-major, N >> 3 at bit 17, M >> 4 at bit 24
-    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(int n, uint32_t a_mn = 0, uint32_t b_mn = 0) {
+    // c_format F32 (bit 4), A/B F16, a_major (bit 15) / b_major (bit 16): 0 = K-major, 1 = MN-major,
+    // N >> 3 at bit 17, M >> 4 at bit 24
+    return (1u << 4) | (a_mn << 15) | (b_mn << 16) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+// The SAME bytes read MN-major: a [rows][64] fp16 tile in the K-major SWIZZLE_128B layout above (128-byte rows,
+// 8-row groups of 1024 B, 16-byte chunk c of row r at c ^ (r & 7)) is also the canonical MN-major SWIZZLE_128B
+// layout of its transpose — MN = the 64 contiguous elements of a row, K = the rows: SBO = 1024 B between 8-row
+// (K) groups, LBO = distance between 64-element blocks along MN (two tiles stacked for M or N = 128).  This is
+// what lets the backward pass reuse the forward pass's weight tiles (dX = dY * W) and the activation tiles as
+// both operands of the weight-gradient products (dW = dY^T * X) without any transposed copy.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+    d |= (uint64_t)64 << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
 }
 __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -583,6 +599,273 @@ __global__ void __launch_bounds__(kFwdThreads, 3) k_mlp_forward_tc(const NetShap
     __syncthreads();
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(tc::kTmemCols) : "memory");
+    }
+}
+
+// ---- fused training step (forward + loss + backward + weight gradients), all on tcgen05 -----------------------
+// tiny-cuda-nn runs kernel_mlp_fused (forward, src/fully_fused_mlp.cu:499-557), the loss kernel, kernel_mlp_fused_backward
+// (:150-259), three split-K CUTLASS GEMMs for the weight gradients (:784-836) and kernel_grid_backward
+// (encodings/grid.h:395-516).  Here one persistent CTA per SM takes a 128-row tile through all of it without the
+// activations ever leaving shared memory:
+//   e  --W0-->  h1  --W1-->  h2  --Wout-->  y  -> loss, dy
+//   dy --Wout(MN-major)--> dh2 (masked by h2 > 0) --W1(MN-major)--> dh1 (masked by h1 > 0) --W0(MN-major)--> de -> grid scatter
+//   G1[128 x 128] += [dh2 | dh1]^T * [h1 | e]   (both operands MN-major views of the activation tiles; the diagonal
+//                                                64 x 64 blocks are dW1 and dW0, the off-diagonal blocks are not used)
+//   G2[128 x 64]  += [dy | dy]^T * h2           (rows 0..2 are dWout)
+// Nine tcgen05.mma groups per tile, every one M = 128; G1 / G2 stay in TMEM (fp32) for the CTA's lifetime and are
+// added to the global gradient buffer once at the end.
+namespace tc {
+constexpr uint32_t kTile16K = 128 * 128;
+constexpr uint32_t kTrainSmem = 6 * kTile16K + 2 * kWBytes + kWoBytes + 64 + 1024;
+constexpr uint32_t kTrainTmemCols = 256;   // acc 64 | G1 128 | G2 64
+}
+
+template <bool POW2>
+__global__ void __launch_bounds__(kFwdThreads, 1) k_mlp_train_fused(const NetShape S, const __half* __restrict__ params, FwdArgs A,
+                                                                     float* __restrict__ grads, float* __restrict__ grid_grads) {
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t raw = tc::smem_u32(smem_dyn);
+    unsigned char* base = smem_dyn + ((1024u - (raw & 1023u)) & 1023u);
+    unsigned char* sH1 = base;                          // [h1 | e] : B operand of G1 (blocks 16 KB apart)
+    unsigned char* sE = sH1 + tc::kTile16K;
+    unsigned char* sDH2 = sE + tc::kTile16K;            // [dh2 | dh1] : A operand of G1
+    unsigned char* sDH1 = sDH2 + tc::kTile16K;
+    unsigned char* sH2 = sDH1 + tc::kTile16K;
+    unsigned char* sDY = sH2 + tc::kTile16K;
+    unsigned char* sW0 = sDY + tc::kTile16K;
+    unsigned char* sW1 = sW0 + tc::kWBytes;
+    unsigned char* sWo = sW1 + tc::kWBytes;
+    uint64_t* bar_ptr = reinterpret_cast<uint64_t*>(sWo + tc::kWoBytes);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_ptr + 1);
+    const uint32_t bar = tc::smem_u32(bar_ptr);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int part = warp >> 2;
+    const uint32_t row = (uint32_t)((warp & 3) * 32 + lane);
+
+    tc::load_weights_sw(sW0, params, kW);
+    tc::load_weights_sw(sW1, params + kW * kW, kW);
+    tc::load_weights_sw(sWo, params + 2 * kW * kW, kOutPad);
+    // dy tile: only columns 0..15 are ever written; the rest must read as zero (it is an operand of G2)
+    for (uint32_t i = threadIdx.x; i < tc::kTile16K / 16; i += blockDim.x) reinterpret_cast<uint4*>(sDY)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tc::smem_u32(tmem_slot)), "r"(tc::kTrainTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc::fence_async_smem();
+    tc::fence_before();
+    __syncthreads();
+    tc::fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t tG1 = tmem + 64, tG2 = tmem + 192;
+    // K-major views (forward operands, and the A operands of the dgrad products)
+    const uint64_t kE = tc::make_desc(tc::smem_u32(sE)), kH1 = tc::make_desc(tc::smem_u32(sH1)), kH2 = tc::make_desc(tc::smem_u32(sH2));
+    const uint64_t kDY = tc::make_desc(tc::smem_u32(sDY)), kDH2 = tc::make_desc(tc::smem_u32(sDH2)), kDH1 = tc::make_desc(tc::smem_u32(sDH1));
+    const uint64_t kW0 = tc::make_desc(tc::smem_u32(sW0)), kW1 = tc::make_desc(tc::smem_u32(sW1)), kWo = tc::make_desc(tc::smem_u32(sWo));
+    // MN-major views: weights as B of the dgrad products, activation tiles as both operands of the weight gradients
+    const uint64_t mW0 = tc::make_desc_mn(tc::smem_u32(sW0), 0), mW1 = tc::make_desc_mn(tc::smem_u32(sW1), 0), mWo = tc::make_desc_mn(tc::smem_u32(sWo), 0);
+    const uint64_t mD = tc::make_desc_mn(tc::smem_u32(sDH2), tc::kTile16K);     // [dh2 | dh1], M = 128
+    const uint64_t mX = tc::make_desc_mn(tc::smem_u32(sH1), tc::kTile16K);      // [h1 | e],   N = 128
+    const uint64_t mDY = tc::make_desc_mn(tc::smem_u32(sDY), 0);                // [dy | dy],  M = 128 (both blocks the same tile)
+    const uint64_t mH2 = tc::make_desc_mn(tc::smem_u32(sH2), 0);
+    const uint32_t i64 = tc::make_idesc(64), i16 = tc::make_idesc(16);
+    const uint32_t i64_bmn = tc::make_idesc(64, 0, 1);
+    const uint32_t i128_mn = tc::make_idesc(128, 1, 1), i64_mn = tc::make_idesc(64, 1, 1);
+    const __half2* table = reinterpret_cast<const __half2*>(params + 2 * kW * kW + kOutPad * kW);
+    uint32_t parity = 0;
+    int tiles_done = 0;
+
+    // publish this thread's shared-memory writes to the async proxy, meet, let one thread issue, wait for the commit
+    auto run = [&](auto&& issue) {
+        tc::fence_async_smem();
+        tc::fence_before();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tc::fence_after();
+            issue();
+            tc::commit(bar);
+        }
+        tc::wait_bar(bar, parity);
+        parity ^= 1u;
+        tc::fence_after();
+    };
+    auto pack_row = [&](unsigned char* dst, const uint32_t (&v)[32], const unsigned char* mask_tile, bool relu) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t chunk = (uint32_t)(4 * part + c);
+            uint32_t w[4];
+            uint4 m = make_uint4(0, 0, 0, 0);
+            if (mask_tile) m = *reinterpret_cast<const uint4*>(mask_tile + tc::sw128(row, chunk));
+            const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float lo = __uint_as_float(v[c * 8 + 2 * j]), hi = __uint_as_float(v[c * 8 + 2 * j + 1]);
+                if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+                if (mask_tile) {
+                    const __half2 h = *reinterpret_cast<const __half2*>(&mw[j]);
+                    if (!(__low2float(h) > 0.f)) lo = 0.f;
+                    if (!(__high2float(h) > 0.f)) hi = 0.f;
+                }
+                w[j] = pack2(lo, hi);
+            }
+            *reinterpret_cast<uint4*>(dst + tc::sw128(row, chunk)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    };
+    auto drain_to = [&](unsigned char* dst, const unsigned char* mask_tile, bool relu) {
+        uint32_t v[32];
+        tc::ld32(tmem_lane + (uint32_t)part * 32u, v);
+        tc::wait_ld();
+        pack_row(dst, v, mask_tile, relu);
+    };
+
+    for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tiles_done) {
+        const size_t grow = (size_t)tile * kTile + row;
+        float x[12];
+        {
+            const float* src = A.in + grow * S.in_ch;
+            if (S.in_ch == 12) {
+                const float4* s4 = reinterpret_cast<const float4*>(src);
+                float4 a = __ldg(s4), b = __ldg(s4 + 1), c = __ldg(s4 + 2);
+                x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+                x[8] = c.x; x[9] = c.y; x[10] = c.z; x[11] = c.w;
+            } else {
+                for (int i = 0; i < 12; ++i) x[i] = i < S.in_ch ? __ldg(src + i) : 0.f;
+            }
+            encode_row<POW2>(S, table, x, [sE, row](int col) {
+                return reinterpret_cast<__half*>(sE + tc::sw128(row, (uint32_t)col >> 3) + ((uint32_t)col & 7u) * 2u);
+            }, part, 2);
+        }
+        // ---- forward ----
+        run([&] {
+#pragma unroll
+            for (uint32_t kk = 0; kk < 4; ++kk) tc::mma_f16(tmem, kE + 2 * kk, kW0 + 2 * kk, i64, kk);
+        });
+        drain_to(sH1, nullptr, true);
+        run([&] {
+#pragma unroll
+            for (uint32_t kk = 0; kk < 4; ++kk) tc::mma_f16(tmem, kH1 + 2 * kk, kW1 + 2 * kk, i64, kk);
+        });
+        drain_to(sH2, nullptr, true);
+        run([&] {
+#pragma unroll
+            for (uint32_t kk = 0; kk < 4; ++kk) tc::mma_f16(tmem, kH2 + 2 * kk, kWo + 2 * kk, i16, kk);
+        });
+        // ---- loss (relative_l2_luminance.h:40-87) and dL/dy ----
+        if (part == 0) {
+            uint32_t v[16];
+            tc::ld16(tmem_lane, v);
+            tc::wait_ld();
+            const float pr = __half2float(__float2half_rn(__uint_as_float(v[0])));
+            const float pg = __half2float(__float2half_rn(__uint_as_float(v[1])));
+            const float pb = __half2float(__float2half_rn(__uint_as_float(v[2])));
+            const float lum = 0.299f * pr + 0.587f * pg + 0.114f * pb;
+            const float denom = lum * lum + 0.01f;
+            const float df0 = pr - __ldg(A.target + grow * 3 + 0);
+            const float df1 = pg - __ldg(A.target + grow * 3 + 1);
+            const float df2 = pb - __ldg(A.target + grow * 3 + 2);
+            float lsum = df0 * df0 / denom * A.inv_n_total + df1 * df1 / denom * A.inv_n_total + df2 * df2 / denom * A.inv_n_total;
+            uint4 d0;
+            d0.x = pack2(kLossScale * (2 * df0 / denom) * A.inv_n_total, kLossScale * (2 * df1 / denom) * A.inv_n_total);
+            d0.y = pack2(kLossScale * (2 * df2 / denom) * A.inv_n_total, 0.f);
+            d0.z = 0u; d0.w = 0u;
+            *reinterpret_cast<uint4*>(sDY + tc::sw128(row, 0)) = d0;      // columns 0..7; columns 8..63 stay zero
+#pragma unroll
+            for (int ofs = 16; ofs > 0; ofs >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, ofs);
+            if (lane == 0) atomicAdd(A.loss, lsum);
+        }
+        // ---- backward: dh2 = (dy * Wout) . [h2 > 0] ----
+        run([&] { tc::mma_f16(tmem, kDY, mWo, i64_bmn, 0); });           // K = 16: the 16 rows of the Wout tile
+        drain_to(sDH2, sH2, false);
+        // dh1 = (dh2 * W1) . [h1 > 0]
+        run([&] {
+#pragma unroll
+            for (uint32_t kk = 0; kk < 4; ++kk) tc::mma_f16(tmem, kDH2 + 2 * kk, mW1 + 128 * kk, i64_bmn, kk);   // B: 16 rows = 2048 B per K step
+        });
+        drain_to(sDH1, sH1, false);
+        // de = dh1 * W0, and the weight gradients of this tile (all operands are complete now)
+        const uint32_t acc_first = tiles_done > 0 ? 1u : 0u;
+        run([&] {
+#pragma unroll
+            for (uint32_t kk = 0; kk < 4; ++kk) tc::mma_f16(tmem, kDH1 + 2 * kk, mW0 + 128 * kk, i64_bmn, kk);
+#pragma unroll
+            for (uint32_t kk = 0; kk < 8; ++kk) tc::mma_f16(tG1, mD + 128 * kk, mX + 128 * kk, i128_mn, kk ? 1u : acc_first);
+#pragma unroll
+            for (uint32_t kk = 0; kk < 8; ++kk) tc::mma_f16(tG2, mDY + 128 * kk, mH2 + 128 * kk, i64_mn, kk ? 1u : acc_first);
+        });
+        // ---- hash-grid scatter (kernel_grid_backward, grid.h:395-516): this thread's levels of its row ----
+        {
+            uint32_t v[32];
+            tc::ld32(tmem_lane, v);          // columns 0..31 = the 16 levels x 2 features
+            tc::wait_ld();
+            const int nl = S.grid.n_levels;
+#pragma unroll
+            for (int l2 = 0; l2 < kMlpMaxLevels / 2; ++l2) {
+                const int l = 2 * l2 + part;
+                if (l >= nl) continue;
+                // the reference holds dL/d(encoded) in fp16 (fc_multiply output)
+                const float g0 = __half2float(__float2half_rn(__uint_as_float(v[2 * l])));
+                const float g1 = __half2float(__float2half_rn(__uint_as_float(v[2 * l + 1])));
+                if (g0 == 0.f && g1 == 0.f) continue;
+                const float scale = S.grid.scale[l];
+                const uint32_t res = S.grid.resolution[l];
+                const uint32_t size = S.grid.offset[l + 1] - S.grid.offset[l];
+                const bool hashed = (S.hashed_mask >> l) & 1u;
+                float* gl = grid_grads + 2 * (size_t)S.grid.offset[l];
+                float p0 = x[0] * scale + 0.5f, p1 = x[1] * scale + 0.5f, p2 = x[2] * scale + 0.5f;
+                const float f0 = floorf(p0), f1 = floorf(p1), f2 = floorf(p2);
+                const uint32_t q0 = (uint32_t)(int)f0, q1 = (uint32_t)(int)f1, q2 = (uint32_t)(int)f2;
+                p0 -= f0; p1 -= f1; p2 -= f2;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float w = ((c & 1) ? p0 : 1 - p0) * ((c & 2) ? p1 : 1 - p1);
+                    w *= (c & 4) ? p2 : 1 - p2;
+                    const uint32_t idx = grid_cell_index(q0 + (c & 1), q1 + ((c >> 1) & 1), q2 + ((c >> 2) & 1), res, size, hashed);
+                    // per-contribution fp16 rounding as in kernel_grid_backward's half2 atomics
+                    atomicAdd(gl + 2 * (size_t)idx + 0, __half2float(__float2half_rn(g0 * w)));
+                    atomicAdd(gl + 2 * (size_t)idx + 1, __half2float(__float2half_rn(g1 * w)));
+                }
+            }
+        }
+        // the next tile's encode overwrites e and its MMAs the accumulator: order them after every thread's TMEM reads
+        tc::fence_before();
+        __syncthreads();
+    }
+    // ---- weight gradients: TMEM -> global (fp32 atomics; one add per CTA and element) ----
+    if (tiles_done > 0) {
+        tc::fence_after();
+        // G1 row m, columns n: m < 64, n < 64 -> dW1[m][n];  m >= 64, n >= 64 -> dW0[m - 64][n - 64]
+        const bool want = (row < 64u) == (part == 0);
+        if (want) {
+            float* dst = row < 64u ? grads + kW * kW + (size_t)row * kW : grads + (size_t)(row - 64u) * kW;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t v[32];
+                tc::ld32(tG1 + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)part * 64u + (uint32_t)h * 32u, v);
+                tc::wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) atomicAdd(dst + h * 32 + j, __uint_as_float(v[j]));
+            }
+        }
+        // G2 rows 0..2 = dWout (rows 3..15 of the padded matrix get no gradient: their dy columns are zero)
+        if (warp == 0 || warp == 4) {
+            uint32_t v[32];
+            tc::ld32(tG2 + (uint32_t)part * 32u, v);      // warps 0 and 4 both own lanes 0..31; columns by part
+            tc::wait_ld();
+            if (lane < 3) {
+                float* dst = grads + 2 * kW * kW + (size_t)lane * kW + part * 32;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+            }
+        }
+    }
+    tc::fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(tc::kTrainTmemCols) : "memory");
     }
 }
 
@@ -978,6 +1261,8 @@ Mlp::Mlp(const MlpConfig& cfg, cudaStream_t stream) : cfg_(cfg), stream_(stream)
     HM_CUDA(cudaFuncSetAttribute(k_mlp_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
     HM_CUDA(cudaFuncSetAttribute(k_mlp_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
     HM_CUDA(cudaFuncSetAttribute(k_mlp_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
+    HM_CUDA(cudaFuncSetAttribute(k_mlp_train_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kTrainSmem));
+    HM_CUDA(cudaFuncSetAttribute(k_mlp_train_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kTrainSmem));
     HM_CUDA(cudaFuncSetAttribute(k_mlp_forward_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
     HM_CUDA(cudaFuncSetAttribute(k_mlp_forward_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
     HM_CUDA(cudaFuncSetAttribute(k_mlp_forward_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
@@ -985,6 +1270,10 @@ Mlp::Mlp(const MlpConfig& cfg, cudaStream_t stream) : cfg_(cfg), stream_(stream)
     // forward implementation: tcgen05/TMEM by default; HM_MLP_IMPL=mma selects the mma.sync kernel
     const char* impl = getenv("HM_MLP_IMPL");
     use_tc_ = !(impl && std::string(impl) == "mma");
+    // training step: one fused tcgen05 kernel by default; HM_MLP_TRAIN=split selects the forward + mma.sync backward +
+    // CUDA-core weight-gradient kernels it replaced (kept for A/B and as the reference point of profiles/)
+    const char* tr = getenv("HM_MLP_TRAIN");
+    fused_train_ = use_tc_ && !(tr && std::string(tr) == "split");
     reinitialize();
 }
 
@@ -1074,8 +1363,23 @@ void Mlp::inference(const float* d_in, float* d_out, int n, const int* d_tile_ma
 
 void Mlp::forward_backward(const float* d_in, const float* d_target, int n, int n_total_records) {
     if (n % kTile != 0) throw std::invalid_argument("batch size must be a multiple of 128");
-    ensure_train_buffers(n);
     NetShape S = make_shape(cfg_, layout_);
+    if (fused_train_) {
+        HM_CUDA(cudaMemsetAsync(d_loss_, 0, 4, stream_));
+        FwdArgs A;
+        memset(&A, 0, sizeof(A));
+        A.in = d_in; A.target = d_target; A.loss = d_loss_;
+        A.inv_n_total = 1.f / (float)((size_t)n_total_records * cfg_.out_ch);
+        A.n_tiles = n / kTile;
+        const int grid = std::min(A.n_tiles, sm_count());
+        const bool pow2 = S.pow2_mask == (S.grid.n_levels >= 32 ? 0xffffffffu : (1u << S.grid.n_levels) - 1u);
+        if (pow2) k_mlp_train_fused<true><<<grid, kFwdThreads, tc::kTrainSmem, stream_>>>(S, (const __half*)d_half_, A, d_grads_, d_grads_ + n_matrix_);
+        else k_mlp_train_fused<false><<<grid, kFwdThreads, tc::kTrainSmem, stream_>>>(S, (const __half*)d_half_, A, d_grads_, d_grads_ + n_matrix_);
+        launches_++;
+        HM_CUDA(cudaGetLastError());
+        return;
+    }
+    ensure_train_buffers(n);
     __half* e = (__half*)d_x_;
     __half* h1 = (__half*)d_h1_; __half* dh1 = h1 + (size_t)train_cap_ * kW;
     __half* h2 = (__half*)d_h2_; __half* dh2 = h2 + (size_t)train_cap_ * kW;

@@ -94,6 +94,7 @@ private:
     int step_ = 0;
     uint64_t launches_ = 0;
     bool use_tc_ = true;
+    bool fused_train_ = true;
 };
 
 }  // namespace hm

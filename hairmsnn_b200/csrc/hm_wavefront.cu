@@ -85,8 +85,9 @@ __device__ __forceinline__ void write_nn_input(float* dst, V3 p, V3 wo, V3 t, fl
 // ---------------------------------------------------------------------------------
 // primary
 // ---------------------------------------------------------------------------------
+// measured on the real scenes/curly frame (profiles/r2d_sweep_knobs.txt): scanlines 1.27 ms, 8 x 4 tiles 1.35 ms
 #ifndef HM_PRIMARY_TILES
-#define HM_PRIMARY_TILES 1
+#define HM_PRIMARY_TILES 0
 #endif
 struct PrimaryOps {
     const FrameParams& P;
@@ -192,8 +193,10 @@ __device__ __forceinline__ void fold_pending(const FrameParams& P, int slot, boo
 #ifndef HM_SHADE_GRID
 #define HM_SHADE_GRID 8
 #endif
+// resident CTAs per SM = register cap of k_shade: 4 -> 128 regs 1.59 ms per frame, 6 -> 80 regs 1.48, 8 -> 64 regs 1.45
+// (profiles/r2d_sweep_knobs.txt: the kernel stalls on instruction fetch, more warps hide it better than fewer spills)
 #ifndef HM_SHADE_CTAS
-#define HM_SHADE_CTAS 4
+#define HM_SHADE_CTAS 8
 #endif
 // One path vertex of render_path_tracing / render_hair_msnn: everything k_shade does for a live queue
 // item except the queue pushes.  Reads and writes the slot's path state in HBM; the caller gets the two

@@ -92,7 +92,7 @@ int probe_intersect_fibre(const float* cps16, const float* org, const float* dir
 void probe_cdf_search(const float* table, int w, int h, int n, const float* u, const float* yn, float size, int* out2) {
     for (int i = 0; i < n; ++i) {
         out2[2 * i + 0] = cdf_lower_bound(u[i], table, w, h, yn[i], size);
-        out2[2 * i + 1] = cdf_lower_bound4(u[i], table, w, h, yn[i], size);
+        out2[2 * i + 1] = cdf_search(u[i], table, w, h, yn[i], size);
     }
 }
 

@@ -140,9 +140,9 @@ def test_curve_hit_geometry_matches_reference(ref, probe):
     assert worst < 1e-5
 
 
-def test_cdf_search_variants_agree(probe):
-    """The 4-ary search of the environment CDF rows (hm_light.h: cdf_lower_bound4, an A/B switch) returns the
-    index the reference's std::lower_bound order returns — incl. flat stretches, the ends and u outside (0,1)."""
+def test_cdf_search_is_lower_bound(probe):
+    """The search of the environment CDF rows (hm_light.h: cdf_search) returns the index the reference's
+    std::lower_bound order returns (optix_common.cuh:95-149) — incl. flat stretches, the ends and u outside (0,1)."""
     rng = np.random.default_rng(11)
     W, H = 509, 37                                   # w = W + 1 texels per row, like the conditional CDF
     pdf = rng.random((H, W)).astype(np.float32) ** 4
@@ -159,6 +159,9 @@ def test_cdf_search_variants_agree(probe):
     out = np.zeros((n, 2), np.int32)
     probe.probe_cdf_search(_p(cdf), W + 1, H, n, _p(u), _p(yn), C.c_float(W), out.ctypes.data_as(C.POINTER(C.c_int)))
     assert np.array_equal(out[:, 0], out[:, 1])
+    rows = np.floor(yn * H).astype(int)
+    want = np.array([max(int(np.searchsorted(cdf[r, :W], uu, side="left")) - 1, 0) for r, uu in zip(rows, u)])
+    assert np.array_equal(out[:, 0], want)
     assert out.min() >= 0 and out.max() <= W - 1 and len(np.unique(out[:, 0])) > 200
     # marginal-CDF shape: one row
     m = np.ascontiguousarray(cdf[7])
