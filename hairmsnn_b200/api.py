@@ -241,6 +241,28 @@ class Scene:
             pass
 
 
+def bsdf_eval(wo_local, wi_local, h, sigma_a=(0.06, 0.1, 0.2), beta_m=0.3, beta_n=0.3, alpha_rad=0.0349065, gains=(1, 1, 1, 1), device=0):
+    """disney_hair on the device for HOST arrays (hm_bsdf_eval): returns (f*cos [n][3], pdf [n])."""
+    wo, wi, h = _f32(wo_local).reshape(-1, 3), _f32(wi_local).reshape(-1, 3), _f32(h).reshape(-1)
+    n = wo.shape[0]
+    s, g = _f32(sigma_a), _f32(gains)
+    f = np.empty((n, 3), np.float32); pdf = np.empty(n, np.float32)
+    _check(lib.hm_bsdf_eval(device, _ptr(s), C.c_float(beta_m), C.c_float(beta_n), C.c_float(alpha_rad), _ptr(g), _ptr(wo), _ptr(wi), _ptr(h), n,
+                            _ptr(f), _ptr(pdf)))
+    return f, pdf
+
+
+def bsdf_sample(wo_local, h, rand4, sigma_a=(0.06, 0.1, 0.2), beta_m=0.3, beta_n=0.3, alpha_rad=0.0349065, gains=(1, 1, 1, 1), device=0):
+    """sample_disney_hair on the device (hm_bsdf_sample): returns (wi_local [n][3], f*cos [n][3], pdf [n])."""
+    wo, h, u = _f32(wo_local).reshape(-1, 3), _f32(h).reshape(-1), _f32(rand4).reshape(-1, 4)
+    n = wo.shape[0]
+    s, g = _f32(sigma_a), _f32(gains)
+    wi = np.empty((n, 3), np.float32); f = np.empty((n, 3), np.float32); pdf = np.empty(n, np.float32)
+    _check(lib.hm_bsdf_sample(device, _ptr(s), C.c_float(beta_m), C.c_float(beta_n), C.c_float(alpha_rad), _ptr(g), _ptr(wo), _ptr(h), _ptr(u), n,
+                              _ptr(wi), _ptr(f), _ptr(pdf)))
+    return wi, f, pdf
+
+
 def load_exr(path):
     """RGBA32F image [h][w][4] through the library's OpenEXR reader (hm_image_load_exr)."""
     w, h = C.c_int(), C.c_int()

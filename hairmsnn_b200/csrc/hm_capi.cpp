@@ -311,6 +311,60 @@ int hm_reduce_framebuffers(hm_renderer* r) {
     return guarded([&] { need(r, "renderer"); r->r->reduce_framebuffers(); });
 }
 
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    DevBuf(const void* host, size_t bytes) {
+        cuda_ok(cudaMalloc(&p, bytes ? bytes : 1), "cudaMalloc");
+        if (host) cuda_ok(cudaMemcpy(p, host, bytes, cudaMemcpyHostToDevice), "cudaMemcpy");
+    }
+    ~DevBuf() { cudaFree(p); }
+    float* f() const { return (float*)p; }
+};
+hm::HairLobes bsdf_lobes(int device, const float* sigma_a3, float beta_m, float beta_n, float alpha, const float* gains4) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw std::runtime_error("CUDA: no usable device (this library has no CPU path)");
+    if (device < 0 || device >= ndev) throw std::runtime_error("CUDA: device index out of range");
+    cuda_ok(cudaSetDevice(device), "cudaSetDevice");
+    hm::HairLobes L;
+    L.setup(beta_m, beta_n, alpha);
+    L.sigma_a = hm::V3(sigma_a3[0], sigma_a3[1], sigma_a3[2]);
+    for (int i = 0; i < 4; ++i) L.gain[i] = gains4[i];
+    return L;
+}
+}  // namespace
+
+int hm_bsdf_eval(int device, const float* sigma_a3, float beta_m, float beta_n, float alpha, const float* gains4,
+                 const float* wo, const float* wi, const float* h, int n, float* out_f, float* out_pdf) {
+    return guarded([&] {
+        need(sigma_a3, "sigma_a3"); need(gains4, "gains4"); need(wo, "wo_local3"); need(wi, "wi_local3"); need(h, "h");
+        need(out_f, "out_f3"); need(out_pdf, "out_pdf");
+        if (n <= 0) throw std::invalid_argument("n must be positive");
+        const hm::HairLobes L = bsdf_lobes(device, sigma_a3, beta_m, beta_n, alpha, gains4);
+        DevBuf dwo(wo, (size_t)n * 12), dwi(wi, (size_t)n * 12), dh(h, (size_t)n * 4), df(nullptr, (size_t)n * 12), dp(nullptr, (size_t)n * 4);
+        hm::launch_bsdf_eval(L, dwo.f(), dwi.f(), dh.f(), n, df.f(), dp.f(), nullptr);
+        cuda_ok(cudaDeviceSynchronize(), "hm_bsdf_eval");
+        cuda_ok(cudaMemcpy(out_f, df.p, (size_t)n * 12, cudaMemcpyDeviceToHost), "hm_bsdf_eval");
+        cuda_ok(cudaMemcpy(out_pdf, dp.p, (size_t)n * 4, cudaMemcpyDeviceToHost), "hm_bsdf_eval");
+    });
+}
+int hm_bsdf_sample(int device, const float* sigma_a3, float beta_m, float beta_n, float alpha, const float* gains4,
+                   const float* wo, const float* h, const float* rand4, int n, float* out_wi, float* out_f, float* out_pdf) {
+    return guarded([&] {
+        need(sigma_a3, "sigma_a3"); need(gains4, "gains4"); need(wo, "wo_local3"); need(h, "h"); need(rand4, "rand4");
+        need(out_wi, "out_wi_local3"); need(out_f, "out_f3"); need(out_pdf, "out_pdf");
+        if (n <= 0) throw std::invalid_argument("n must be positive");
+        const hm::HairLobes L = bsdf_lobes(device, sigma_a3, beta_m, beta_n, alpha, gains4);
+        DevBuf dwo(wo, (size_t)n * 12), dh(h, (size_t)n * 4), du(rand4, (size_t)n * 16);
+        DevBuf dw(nullptr, (size_t)n * 12), df(nullptr, (size_t)n * 12), dp(nullptr, (size_t)n * 4);
+        hm::launch_bsdf_sample(L, dwo.f(), dh.f(), du.f(), n, dw.f(), df.f(), dp.f(), nullptr);
+        cuda_ok(cudaDeviceSynchronize(), "hm_bsdf_sample");
+        cuda_ok(cudaMemcpy(out_wi, dw.p, (size_t)n * 12, cudaMemcpyDeviceToHost), "hm_bsdf_sample");
+        cuda_ok(cudaMemcpy(out_f, df.p, (size_t)n * 12, cudaMemcpyDeviceToHost), "hm_bsdf_sample");
+        cuda_ok(cudaMemcpy(out_pdf, dp.p, (size_t)n * 4, cudaMemcpyDeviceToHost), "hm_bsdf_sample");
+    });
+}
+
 int hm_msnn_trace(hm_renderer* r) { return guarded([&] { need(r, "renderer"); r->r->msnn_trace(); }); }
 int hm_msnn_train_backward(hm_renderer* r) { return guarded([&] { need(r, "renderer"); r->r->msnn_train_backward(); }); }
 int hm_msnn_train_apply(hm_renderer* r) { return guarded([&] { need(r, "renderer"); r->r->msnn_train_apply(); }); }

@@ -923,6 +923,35 @@ void launch_nrc_render(const NrcRender& R, cudaStream_t stream) {
     k_nrc_render<<<persistent_grid(8), 256, 0, stream>>>(R);
     g_launches++;
 }
+// Test hooks: the fibre scattering model for caller-supplied local directions (device pointers).
+__global__ void __launch_bounds__(256) k_bsdf_eval(const HairLobes L, const float* wo, const float* wi, const float* h, int n,
+                                                   float* out_f, float* out_pdf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float pdf;
+    const V3 f = hair_eval(L, V3(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]), V3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), h[i], &pdf);
+    out_f[3 * i] = f.x; out_f[3 * i + 1] = f.y; out_f[3 * i + 2] = f.z; out_pdf[i] = pdf;
+}
+__global__ void __launch_bounds__(256) k_bsdf_sample(const HairLobes L, const float* wo, const float* h, const float* u, int n,
+                                                     float* out_wi, float* out_f, float* out_pdf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const V3 o(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]);
+    const V3 w = hair_sample_dir(L, o, h[i], u[4 * i], u[4 * i + 1], u[4 * i + 2], u[4 * i + 3]);
+    float pdf;
+    const V3 f = hair_eval(L, o, w, h[i], &pdf);
+    out_wi[3 * i] = w.x; out_wi[3 * i + 1] = w.y; out_wi[3 * i + 2] = w.z;
+    out_f[3 * i] = f.x; out_f[3 * i + 1] = f.y; out_f[3 * i + 2] = f.z; out_pdf[i] = pdf;
+}
+void launch_bsdf_eval(const HairLobes& L, const float* wo, const float* wi, const float* h, int n, float* out_f, float* out_pdf, cudaStream_t stream) {
+    k_bsdf_eval<<<(n + 255) / 256, 256, 0, stream>>>(L, wo, wi, h, n, out_f, out_pdf);
+    g_launches++;
+}
+void launch_bsdf_sample(const HairLobes& L, const float* wo, const float* h, const float* u, int n, float* out_wi, float* out_f, float* out_pdf,
+                        cudaStream_t stream) {
+    k_bsdf_sample<<<(n + 255) / 256, 256, 0, stream>>>(L, wo, h, u, n, out_wi, out_f, out_pdf);
+    g_launches++;
+}
 void launch_trace_rays(const SceneView& S, const float* org, const float* dir, int n, int any, float tmin, float tmax,
                        float4* out_hit, int* out_stats, int* cursor, cudaStream_t stream) {
     int blocks = (n + kBlock - 1) / kBlock;

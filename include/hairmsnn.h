@@ -305,6 +305,17 @@ int hm_trace_rays(hm_renderer* r, const float* org3, const float* dir3, int n, i
 int hm_trace_rays_device(hm_renderer* r, const float* d_org3, const float* d_dir3, int n, int any_hit, float tmin,
                          float tmax, float* d_out_hit4);
 
+/* disney_hair(si, pdf) (cuda_headers/disney_hair.cuh:185-266): f * cos and pdf of the fibre scattering model for n
+ * HOST (wo_local, wi_local, h) triples, evaluated by the sm_100a build on `device`.  Local frame: x = fibre tangent;
+ * h = dot(to_local[1], n).  alpha in radians; gains4 = R, TT, TRT, TRRT.  NaNs come back as NaNs (the renderer's
+ * callers scrub them as the reference does). */
+int hm_bsdf_eval(int device, const float* sigma_a3, float beta_m, float beta_n, float alpha_radians, const float* gains4,
+                 const float* wo_local3, const float* wi_local3, const float* h, int n, float* out_f3, float* out_pdf);
+/* sample_disney_hair (disney_hair.cuh:276-386): rand4 = the four draws in the reference's order (lobe, theta,
+ * phi-of-theta, dphi); returns the sampled LOCAL direction and disney_hair evaluated on it. */
+int hm_bsdf_sample(int device, const float* sigma_a3, float beta_m, float beta_n, float alpha_radians, const float* gains4,
+                   const float* wo_local3, const float* h, const float* rand4, int n, float* out_wi_local3, float* out_f3, float* out_pdf);
+
 /* ---- MLP: TINY_MLP (cuda_headers/neural_network.cuh:33-50, cuda/neural_network.cu) ---- */
 
 /* TINY_MLP(configPath, inCh, outCh): config_path = tiny-cuda-nn JSON (NULL = the shipped

@@ -145,6 +145,21 @@ class RefHost:
                                               _p(nn_in), _p(tr_in), _p(tr_out), _p(gb), threads or os.cpu_count())
         return bufs
 
+    def render_msnn_composite(self, accum_id, W, H, hit, is_surface, short_color, nn_out, pt_accum, nn_accum, final_accum):
+        """RENDER pass of cuda/hair_msnn.cu:314-356 over all pixels.  hit / is_surface: bool [H*W]; short_color [H*W][3];
+        nn_out [H*W][3]; the three accumulation buffers float4 [H][W][4] are updated in place.
+        Returns (pt_avg, nn_avg, final_avg, fb8)."""
+        assert self.which == "msnn"
+        gb = np.zeros((W * H, 8), np.float32)
+        gb[:, 0] = np.asarray(hit, np.float32).reshape(-1); gb[:, 1] = np.asarray(is_surface, np.float32).reshape(-1)
+        gb[:, 5:8] = _f(short_color).reshape(-1, 3)
+        nn = _f(nn_out).reshape(-1, 3)
+        pt_avg = np.zeros((H, W, 4), np.float32); nn_avg = np.zeros((H, W, 4), np.float32); final_avg = np.zeros((H, W, 4), np.float32)
+        fb = np.zeros((H, W), np.uint32)
+        self.lib.ref_render_msnn_composite(accum_id, W, H, _p(gb), _p(nn), _p(pt_accum), _p(nn_accum), _p(final_accum),
+                                           _p(pt_avg), _p(nn_avg), _p(final_avg), _p(fb, _up))
+        return pt_avg, nn_avg, final_avg, fb
+
     def render_msnn_train_data_gen(self, accum_id, W, H, beta, scene_indices, sampled_points, in_ch=12, threads=0):
         assert self.which == "msnn"
         idx = np.ascontiguousarray(scene_indices, dtype=np.int32)

@@ -83,6 +83,35 @@ def test_frame_loop_composites_and_trains():
     assert np.isfinite(p).all()
 
 
+def test_render_pass_matches_reference_composite():
+    """RENDER pass (cuda/hair_msnn.cu:314-356, compiled for the host): the three accumulation / average buffer pairs
+    and the 8-bit frame from the frame's G-buffer and network output, for the first frame (accumId 0: buffers are
+    overwritten) and the second (accumulated)."""
+    W, H = 256, 128
+    kw = small_scene_kwargs(width=W, height=H, strands=1500, segs=16, path_v2=10)
+    sc = api.Scene.from_arrays(**kw)
+    r = api.Renderer(sc, api.HAIR_MSNN, beta_cli=1)
+    r.set_skip_unused_queries(False)     # every pixel's network output is defined, as in the reference
+    ref = RefHost("msnn")
+    ref.bind_all(sc, kw)
+    acc = [np.zeros((H, W, 4), np.float32) for _ in range(3)]        # pt, nn, final accumulation (oracle side)
+    for frame in range(2):
+        r.render_frames(1)
+        gb = r.buffer(api.BUF_GBUFFER).reshape(-1, 4)
+        flags = gb[:, 3].copy().view(np.int32)
+        nn_out = r.buffer(api.BUF_NN_FRAME_OUTPUT).reshape(-1, 3)
+        pt_avg, nn_avg, final_avg, fb = ref.render_msnn_composite(frame, W, H, (flags & 1) != 0, (flags & 2) != 0, gb[:, :3], nn_out,
+                                                                   acc[0], acc[1], acc[2])
+        for which, want in ((api.BUF_PT_ACCUM, acc[0]), (api.BUF_NN_ACCUM, acc[1]), (api.BUF_FINAL_ACCUM, acc[2]),
+                            (api.BUF_PT_AVG, pt_avg), (api.BUF_NN_AVG, nn_avg), (api.BUF_FINAL_AVG, final_avg)):
+            got = r.buffer(which)
+            assert np.allclose(got[..., :3], want[..., :3], rtol=1e-6, atol=1e-7), (frame, which, np.abs(got[..., :3] - want[..., :3]).max())
+        g_fb = r.buffer(api.BUF_FB8)
+        assert (np.abs(g_fb.view(np.uint8).astype(int) - fb.view(np.uint8).astype(int)) <= 1).all()
+        assert (g_fb == fb).mean() > 0.99
+    assert (flags & 1).any() and acc[1].any()
+
+
 def test_cache_learns_the_residual():
     """With training on, nn + short-path converges towards the long-path estimate."""
     W, H = 256, 128
