@@ -263,6 +263,15 @@ def bsdf_sample(wo_local, h, rand4, sigma_a=(0.06, 0.1, 0.2), beta_m=0.3, beta_n
     return wi, f, pdf
 
 
+def load_hair_file(path):
+    """The .hair reader alone (hm_hair_file_load): dict(cps [n][4], seg_cp [m], strands, bounds (min, max))."""
+    counts = (C.c_int * 3)()
+    _check(lib.hm_hair_file_load(os.fsencode(path), counts, None, None, None))
+    cps = np.empty((counts[0], 4), np.float32); seg = np.empty(counts[1], np.int32); b = np.empty(6, np.float32)
+    _check(lib.hm_hair_file_load(os.fsencode(path), counts, _ptr(cps), _ptr(seg, _ip), _ptr(b)))
+    return {"cps": cps, "seg_cp": seg, "strands": counts[2], "bounds": (b[:3].copy(), b[3:].copy())}
+
+
 def load_exr(path):
     """RGBA32F image [h][w][4] through the library's OpenEXR reader (hm_image_load_exr)."""
     w, h = C.c_int(), C.c_int()

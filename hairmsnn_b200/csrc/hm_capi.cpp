@@ -159,6 +159,18 @@ int hm_scene_create(const hm_scene_desc* d, hm_scene** out) {
 
 void hm_scene_free(hm_scene* s) { delete s; }
 
+int hm_hair_file_load(const char* path, int* counts3, float* cps4, int* segment_first_cp, float* bounds6) {
+    return guarded([&] {
+        need(path, "path"); need(counts3, "counts3");
+        hm::HostGeometry g;
+        hm::load_hair_file(path, g);
+        counts3[0] = (int)g.cps.size(); counts3[1] = (int)g.seg_cp.size(); counts3[2] = g.num_strands;
+        if (cps4) memcpy(cps4, g.cps.data(), g.cps.size() * sizeof(hm::F4));
+        if (segment_first_cp) memcpy(segment_first_cp, g.seg_cp.data(), g.seg_cp.size() * sizeof(int));
+        if (bounds6) for (int k = 0; k < 3; ++k) { bounds6[k] = g.hair_min[k]; bounds6[3 + k] = g.hair_max[k]; }
+    });
+}
+
 int hm_scene_save_bvh_cache(const hm_scene* s, const char* dir) {
     return guarded([&] {
         need(s, "scene"); need(dir, "dir");

@@ -115,6 +115,12 @@ int hm_scene_create(const hm_scene_desc* desc, hm_scene** out);
  * the file has none.  Call with rgba = NULL to get the size, then with a buffer of
  * capacity_floats >= 4*w*h. */
 int hm_image_load_exr(const char* path, float* rgba, size_t capacity_floats, int* width, int* height);
+/* LoadCemYuksel + Scene::extractHairData (scene.cpp:75-117, 10-73) alone — the .hair reader without the rest of the
+ * scene or the acceleration structure.  counts3 = control points (phantom end points included), segments, strands.
+ * Call with NULL arrays for the counts, then with cps4 [control points][4] (xyz + radius = 0.2 x file thickness),
+ * segment_first_cp [segments] and bounds6 (min xyz, max xyz of the file's points, grown from the origin as
+ * headers/model.h:93-94 does); any of the three may stay NULL. */
+int hm_hair_file_load(const char* path, int* counts3, float* cps4, int* segment_first_cp, float* bounds6);
 /* stores the scene's wide tree in `dir` under the name HM_BVH_CACHE lookups use (no-op if it came from there) */
 int hm_scene_save_bvh_cache(const hm_scene* scene, const char* dir);
 void hm_scene_free(hm_scene* scene);

@@ -206,6 +206,14 @@ class RefHost:
                                        _p(tr_gt), _p(accum), _p(average), _p(fb, _up))
         return tr_in, tr_gt, accum, average, fb
 
+    def trace_ids(self, org, dir, any_hit=False):
+        """(t, prim, u) of the host traversal (binary tree + the product's intersector compiled for the host)."""
+        org, dir = _f(org).reshape(-1, 3), _f(dir).reshape(-1, 3)
+        n = org.shape[0]
+        t = np.zeros(n, np.float32); p = np.zeros(n, np.int32); u = np.zeros(n, np.float32)
+        self.lib.ref_trace_ids(n, _p(org), _p(dir), int(any_hit), _p(t), _p(p, _ip), _p(u))
+        return t, p, u
+
     def trace_radiance(self, org, dir):
         org, dir = _f(org).reshape(-1, 3), _f(dir).reshape(-1, 3)
         out = np.zeros((org.shape[0], 24), np.float32)

@@ -95,3 +95,39 @@ def test_shipped_env_maps_decode_bit_exact(name):
     img = api.load_exr(path)
     assert img.shape == (2048, 4096, 4)
     assert np.array_equal(img[..., :3], ref[..., ::-1]) and np.all(img[..., 3] == 1.0)
+
+
+def _scene_dir():
+    for d in (REF, os.path.join(os.path.dirname(GOLD), "..", "assets", "scenes")):
+        if os.path.isdir(d):
+            return os.path.abspath(d)
+    return None
+
+
+@pytest.mark.skipif(_scene_dir() is None or not os.path.exists(os.path.join(os.path.dirname(GOLD), "..", "oracle", "_ref", "libref_scene.so")),
+                    reason="needs the shipped scenes and oracle/_ref/libref_scene.so (the reference's scene.cpp compiled for the host)")
+@pytest.mark.parametrize("scene,hair", [("curly", "wCurly.hair"), ("straight", "wStraight.hair")])
+def test_hair_reader_matches_reference_extract_hair_data(scene, hair):
+    """SURVEY §8 row a27: Scene::extractHairData (scene.cpp:10-73, the REFERENCE's own source compiled for the host) vs
+    the product's .hair reader, array by array, for both shipped files: control points incl. the mirrored phantom end
+    points, radii (0.2 x thickness), first-control-point index of every segment, bounds grown from the origin."""
+    import ctypes as C
+    path = os.path.join(_scene_dir(), scene, hair)
+    lib = C.CDLL(os.path.join(os.path.dirname(GOLD), "..", "oracle", "_ref", "libref_scene.so"))
+    counts = (C.c_int * 3)()
+    assert lib.ref_extract_hair(os.fsencode(path), counts) == 0
+    ncp, nseg, nstrands = counts[0], counts[1], counts[2]
+    cps = np.zeros((ncp, 3), np.float32); w = np.zeros(ncp, np.float32); seg = np.zeros(nseg, np.int32)
+    b = np.zeros(6, np.float32); scale = C.c_float()
+    fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
+    lib.ref_hair_arrays(cps.ctypes.data_as(fp), w.ctypes.data_as(fp), seg.ctypes.data_as(ip), b.ctypes.data_as(fp), C.byref(scale))
+    got = api.load_hair_file(path)
+    want_counts = {"curly": (3541580, 3391580, 50000), "straight": (1350000, 1200000, 50000)}[scene]     # SURVEY §8
+    assert (ncp, nseg, nstrands) == want_counts
+    assert (got["cps"].shape[0], got["seg_cp"].shape[0], got["strands"]) == want_counts
+    assert np.array_equal(got["cps"][:, :3].view(np.uint32), cps.view(np.uint32))
+    assert np.array_equal(got["cps"][:, 3].view(np.uint32), w.view(np.uint32))
+    assert np.array_equal(got["seg_cp"], seg)
+    assert np.array_equal(got["bounds"][0], b[:3]) and np.array_equal(got["bounds"][1], b[3:])
+    d = got["bounds"][1] - got["bounds"][0]
+    assert abs(float(np.sqrt((d * d).sum(dtype=np.float32))) - scale.value) < 1e-3
