@@ -499,6 +499,7 @@ def main():
     ap.add_argument("--no-others", action="store_true", help="skip the brief pt / nrc / msnn_b10 measurements of the default run")
     ap.add_argument("--no-gate", action="store_true", help="skip the image gate of the default run")
     ap.add_argument("--gate-spp", type=int, default=500)
+    ap.add_argument("--size", type=int, default=0, help="override the frame size of the workload (testing the band path on fewer GPUs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -517,9 +518,12 @@ def main():
 
     torch.cuda.set_device(local_rank)
     peaks = load_peaks()
+    if args.size:
+        w = WORKLOADS[args.workload]
+        WORKLOADS[args.workload] = (w[0], w[1], w[2], args.size)
     scene_name, kind, beta_cli, size = WORKLOADS[args.workload]
     bands = args.workload == "straight4096"
-    if bands and world < 4:
+    if bands and (size * size) // world > 2048 * 2048:
         raise SystemExit("straight4096 renders 4096x4096 on row bands of at most 2048x2048 pixels: needs --gpus 4 or 8")
 
     comm, id_path = None, None
