@@ -361,27 +361,34 @@ def measure(r, api, torch, local_rank, comm, W, H, steps, warmup, peaks, kind, w
     r.set_profiling(False)
 
     if want_e2e:
-        # end to end through the C ABI with host buffers: every step's results (8-bit framebuffer + fp32 average)
-        # are streamed to pinned host memory behind that step's composite; two host buffer sets alternate
-        fb_host = [torch.empty((H, W), dtype=torch.int32).pin_memory() for _ in range(2)]
-        avg_host = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+        # End to end through the C ABI with host buffers, as a headless job runs: every step's 8-bit frame (the rows this
+        # rank renders) is streamed to pinned host memory behind that step's composite — what the reference's viewer blits
+        # per frame — and the job ends with the framebuffer reduction over the ranks (N > 1) and the read-back of the
+        # fp32 average image (what saveEXR writes).  All of it is inside the timed region; two host buffer sets alternate.
+        r0, r1 = r.rows()
+        fb_host = [torch.empty((r1 - r0, W), dtype=torch.int32).pin_memory() for _ in range(2)]
+        avg_host = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
         barrier()
         t0 = time.perf_counter()
         for i in range(steps):
             step()
-            r.readback_async(api.BUF_FB8, fb_host[i & 1].data_ptr(), fb_host[0].numel() * 4)
-            r.readback_async(api.BUF_FINAL_AVG, avg_host[i & 1].data_ptr(), avg_host[0].numel() * 4)
+            r.readback_rows_async(api.BUF_FB8, r0, r1 - r0, fb_host[i & 1].data_ptr())
+        if comm:
+            r.reduce_framebuffers()
+        r.readback_async(api.BUF_FINAL_AVG, avg_host.data_ptr(), avg_host.numel() * 4)
         r.sync()
         e2e_s = time.perf_counter() - t0
-        assert np.isfinite(avg_host[(steps - 1) & 1].numpy()).all()
+        assert np.isfinite(avg_host.numpy()).all()
         if comm:
             e2e_s = comm.all_reduce_max(e2e_s)
         out["e2e"] = {"value": W * H * steps * world / e2e_s / 1e6, "unit": "Mpaths/s",
                       "h2d_bytes_per_step": int(api.lib.hm_frame_param_bytes() * launches / max(steps, 1)),
-                      "d2h_bytes_per_step": int(fb_host[0].numel() * 4 + avg_host[0].numel() * 4),
+                      "d2h_bytes_per_step": int(fb_host[0].numel() * 4 + avg_host.numel() * 4 / max(steps, 1)),
                       "note": "per step: one frame through the C ABI (hm_render_frames_async; with N GPUs the gradient all-reduce is inside the call) "
-                              "followed by hm_readback_async of the 8-bit framebuffer and the fp32 average buffer into pinned host memory, host clock "
-                              "around the whole loop incl. the final sync; host->device traffic of a frame is its kernel parameter blocks"}
+                              "followed by hm_readback_rows_async of this rank's rows of the 8-bit frame into pinned host memory; once per job "
+                              "(amortised over the steps in d2h_bytes_per_step): hm_reduce_framebuffers over the ranks and hm_readback_async of the "
+                              "fp32 average image; host clock around the whole loop incl. the final sync; host->device traffic of a frame is its "
+                              "kernel parameter blocks"}
 
     # instrumented pass: nodes visited / primitives tested per stage (SURVEY §8d per-ray bytes); every rank takes part
     r.reset_stats()

@@ -563,6 +563,14 @@ class Renderer:
     def readback_async(self, which, host_ptr, nbytes):
         _check(lib.hm_readback_async(self._h, which, C.c_void_p(host_ptr), C.c_size_t(nbytes)))
 
+    def readback_rows_async(self, which, row0, rows, host_ptr):
+        _check(lib.hm_readback_rows_async(self._h, which, row0, rows, C.c_void_p(host_ptr)))
+
+    def rows(self):
+        out = (C.c_int * 2)()
+        _check(lib.hm_renderer_get_rows(self._h, out))
+        return out[0], out[1]
+
     def trace_rays(self, org, dir, any_hit=False, tmin=0.0, tmax=1e30, stats=False):
         org, dir = _f32(org).reshape(-1, 3), _f32(dir).reshape(-1, 3)
         n = org.shape[0]

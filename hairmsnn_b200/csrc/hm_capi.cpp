@@ -428,6 +428,20 @@ int hm_readback_async(hm_renderer* r, int which, void* dst, size_t bytes) {
     return guarded([&] { need(r, "renderer"); need(dst, "host_dst"); r->r->readback_async(which, dst, bytes); });
 }
 
+int hm_readback_rows_async(hm_renderer* r, int which, int row0, int rows, void* dst) {
+    return guarded([&] {
+        need(r, "renderer"); need(dst, "host_dst");
+        if (which < 0 || which > HM_BUF_FB8) throw std::invalid_argument("hm_readback_rows_async: not an image buffer");
+        const int W = r->r->width(), H = r->r->height();
+        if (row0 < 0 || rows < 0 || row0 + rows > H) throw std::invalid_argument("row range outside the frame");
+        r->r->readback_rows_async(which, row0, rows, dst);
+        (void)W;
+    });
+}
+int hm_renderer_get_rows(const hm_renderer* r, int* out2) {
+    return guarded([&] { need(r, "renderer"); need(out2, "out2"); out2[0] = r->r->row0(); out2[1] = r->r->row1(); });
+}
+
 int hm_save_png(hm_renderer* r, const char* path) {
     return guarded([&] {
         need(r, "renderer"); need(path, "path");

@@ -152,9 +152,11 @@ static int hm_main(int argc, char** argv, int kind, const char* name) {
     t0 = std::chrono::steady_clock::now();
     for (int done = 0; done < my_spp;) {
         int n = my_spp - done < 16 ? my_spp - done : 16;
-        if (hm_render_frames(r, n) != HM_OK) { fprintf(stderr, "%s: %s\n", name, hm_last_error()); return -1; }
+        // enqueue only: the frames in flight overlap across the chunks; one synchronisation at the end
+        if (hm_render_frames_async(r, n) != HM_OK) { fprintf(stderr, "%s: %s\n", name, hm_last_error()); return -1; }
         done += n;
     }
+    if (hm_renderer_sync(r) != HM_OK) { fprintf(stderr, "%s: %s\n", name, hm_last_error()); return -1; }
     if (comm && hm_reduce_framebuffers(r) != HM_OK) { fprintf(stderr, "%s: %s\n", name, hm_last_error()); return -1; }
     double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     const int total_spp = (multi && !bands) ? my_spp * world : spp;

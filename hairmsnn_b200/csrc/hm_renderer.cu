@@ -747,6 +747,14 @@ void Renderer::readback_async(int which, void* host_dst, size_t bytes) {
     HM_CUDA(cudaMemcpyAsync(host_dst, p, bytes, cudaMemcpyDeviceToHost, order_stream_));
 }
 
+void Renderer::readback_rows_async(int which, int row0, int rows, void* host_dst) {
+    size_t have = 0;
+    char* p = (char*)device_buffer(which, &have);
+    if (!p) throw std::logic_error("buffer not available for this renderer kind");
+    const size_t px = which == 6 ? 4 : 16;
+    HM_CUDA(cudaMemcpyAsync(host_dst, p + (size_t)row0 * W_ * px, (size_t)rows * W_ * px, cudaMemcpyDeviceToHost, order_stream_));
+}
+
 void Renderer::trace_rays_device(const float* d_org, const float* d_dir, int n, int any, float tmin, float tmax,
                                  float* d_out_hit, int* d_out_stats) {
     HM_CUDA(cudaSetDevice(device_));

@@ -140,6 +140,7 @@ public:
                            float* d_out_hit, int* d_out_stats);
     // enqueue a device->host copy of an output buffer behind the last enqueued frame
     void readback_async(int which, void* host_dst, size_t bytes);
+    void readback_rows_async(int which, int row0, int rows, void* host_dst);   // image buffers 0..6 only
     void set_profiling(bool on) { profiling_ = on; }
     // bit s set: stage s (Stats::ms index) gets event pairs while profiling is on; default all
     void set_profiling_stages(unsigned mask) { profile_mask_ = mask; }

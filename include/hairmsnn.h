@@ -221,6 +221,11 @@ int hm_get_buffer(hm_renderer* r, int which, void* host_dst, size_t bytes);
  * pinned) is valid after hm_renderer_sync().  Lets a caller stream every frame's result to the
  * host without stalling the frames in flight. */
 int hm_readback_async(hm_renderer* r, int which, void* host_dst, size_t bytes);
+/* same for rows [row0, row0 + rows) of an image buffer (HM_BUF_FINAL_AVG .. HM_BUF_FB8): what a row-band rank owns.
+ * host_dst receives rows * W pixels. */
+int hm_readback_rows_async(hm_renderer* r, int which, int row0, int rows, void* host_dst);
+/* the rows this renderer renders: out2 = row0, row1 (hm_band_partition of its rank / world) */
+int hm_renderer_get_rows(const hm_renderer* r, int* out2);
 /* device pointer of the same buffers (for in-place NCCL gathers) */
 int hm_get_device_buffer(hm_renderer* r, int which, void** dev_ptr, size_t* bytes);
 

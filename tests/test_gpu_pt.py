@@ -145,6 +145,38 @@ def test_primary_misses_match_tightly():
     assert accum[miss][:, :3].sum() > 0
 
 
+def test_deep_path_criterion_would_catch_a_two_percent_energy_bug():
+    """The deep-path criterion above is statistical (>= 96 % of pixels within 2e-3): this shows it is still sharp.  Take
+    the GPU frame, keep its camera-vertex part (path_v2 = 1 render, pinned to 1e-3 on 100 % of pixels) and scale only the
+    contribution of bounces >= 1 by 1.02 — what a systematic 2 % energy error in the deeper vertices would produce.  The
+    fraction of pixels within tolerance of the reference must collapse."""
+    kw = small_scene_kwargs(width=128, height=128, strands=1500, segs=16, path_v2=12)
+    sc = api.Scene.from_arrays(**kw)
+    r = api.Renderer(sc, api.PATH_TRACING)
+    r.render_frames(1)
+    full = r.buffer(api.BUF_FINAL_ACCUM)[..., :3]
+    kw1 = dict(kw); kw1["path_v2"] = 1
+    sc1 = api.Scene.from_arrays(**kw1)
+    r1 = api.Renderer(sc1, api.PATH_TRACING)
+    r1.render_frames(1)
+    direct = r1.buffer(api.BUF_FINAL_ACCUM)[..., :3]
+    ref = RefHost("pt")
+    info = ref.bind_all(sc, kw)
+    accum, _, _ = ref.render_pt(0, info.width, info.height)
+    want = accum[..., :3]
+
+    def frac_close(img):
+        err = np.abs(img - want).max(axis=2) / np.maximum(np.abs(want).max(axis=2), 1e-2)
+        return (err < 2e-3).mean()
+    hit = np.abs(full - direct).max(axis=2) > 0           # pixels with any deeper contribution
+    assert hit.mean() > 0.2
+    good = frac_close(full)
+    bugged = frac_close(direct + 1.02 * (full - direct))
+    assert good >= 0.96
+    # every pixel whose deeper part carries more than 10 % of its value moves out of tolerance
+    assert bugged < good - 0.5 * hit.mean(), (good, bugged, hit.mean())
+
+
 def test_direct_only_frames_match_tightly():
     """path_v2 = 1: camera vertex + its direct lighting only -> no room for path divergence."""
     kw = small_scene_kwargs(width=128, height=128, strands=1500, segs=16, path_v2=1)
