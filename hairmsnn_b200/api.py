@@ -24,6 +24,7 @@ PATH_TRACING, NRC, HAIR_MSNN = 0, 1, 2
 BUF_FINAL_AVG, BUF_FINAL_ACCUM, BUF_PT_AVG, BUF_PT_ACCUM, BUF_NN_AVG, BUF_NN_ACCUM, BUF_FB8 = range(7)
 BUF_NN_FRAME_INPUT, BUF_NN_FRAME_OUTPUT, BUF_NN_TRAIN_INPUT, BUF_NN_TRAIN_OUTPUT, BUF_GBUFFER, BUF_TRAIN_IDXS = range(7, 13)
 BUF_GBUFFER_B, BUF_NRC_TRAIN_RECORDS, BUF_SCENE_INDICES, BUF_SCENE_POINTS = 13, 14, 15, 16
+BUF_ENV_CPDF, BUF_ENV_CCDF, BUF_ENV_MPDF, BUF_ENV_MCDF = 17, 18, 19, 20
 NRC_MAX_BOUNCES = 40
 
 _fp = C.POINTER(C.c_float)
@@ -72,6 +73,7 @@ class Stats(C.Structure):
         ("trav_prims_shadow", C.c_uint64), ("trav_nodes_primary", C.c_uint64), ("trav_prims_primary", C.c_uint64),
         ("trav_nodes_tail", C.c_uint64), ("trav_prims_tail", C.c_uint64), ("rays_tail", C.c_uint64),
         ("last_loss", C.c_float), ("frames", C.c_int),
+        ("timed_launches", C.c_uint64 * 8),
     ]
 
 
@@ -474,6 +476,9 @@ class Renderer:
     def set_profiling_stages(self, mask):
         _check(lib.hm_renderer_set_profiling_stages(self._h, C.c_uint(mask)))
 
+    def set_profiling_period(self, n):
+        _check(lib.hm_renderer_set_profiling_period(self._h, int(n)))
+
     def set_collect_stats(self, on):
         _check(lib.hm_renderer_set_collect_stats(self._h, int(on)))
 
@@ -551,7 +556,8 @@ class Renderer:
             out = np.empty((self.H, self.W), np.uint32)
         elif which in (BUF_TRAIN_IDXS, BUF_SCENE_INDICES):
             out = np.empty(nbytes // 4, np.int32)
-        elif which in (BUF_NN_FRAME_INPUT, BUF_NN_FRAME_OUTPUT, BUF_NN_TRAIN_INPUT, BUF_NN_TRAIN_OUTPUT, BUF_SCENE_POINTS):
+        elif which in (BUF_NN_FRAME_INPUT, BUF_NN_FRAME_OUTPUT, BUF_NN_TRAIN_INPUT, BUF_NN_TRAIN_OUTPUT, BUF_SCENE_POINTS,
+                       BUF_ENV_CPDF, BUF_ENV_CCDF, BUF_ENV_MPDF, BUF_ENV_MCDF):
             out = np.empty(nbytes // 4, np.float32)
         elif which == BUF_GBUFFER:
             out = np.empty((nbytes // (16 * self.W), self.W, 4), np.float32)   # this renderer's row band

@@ -91,7 +91,6 @@ int hm_scene_load(const char* path, hm_scene** out) {
         std::unique_ptr<hm_scene> s(new hm_scene);
         load_scene_file(path, s->hs);
         finalize_geometry(s->hs);
-        if (s->hs.has_env) build_env_tables(s->hs);
         build_bvh_cached(s->hs.geo, s->hs.bvh);
         *out = s.release();
     });
@@ -151,7 +150,6 @@ int hm_scene_create(const hm_scene_desc* d, hm_scene** out) {
         hs.mis = d->mis != 0; hs.env_pdf = d->env_pdf != 0;
         if (d->tcnn_config_path) hs.tcnn_config = d->tcnn_config_path;
         finalize_geometry(hs);
-        if (hs.has_env) build_env_tables(hs);
         build_bvh_cached(hs.geo, hs.bvh);
         *out = s.release();
     });
@@ -225,6 +223,7 @@ int hm_scene_get_env_tables(const hm_scene* s, const float** env, const float** 
         need(s, "scene");
         const HostScene& hs = s->hs;
         if (!hs.has_env) throw std::logic_error("scene has no environment light");
+        hm::ensure_env_tables(hs);      // the host copy is built on first use; the renderers build theirs on the device
         if (env) *env = hs.env.data();
         if (cpdf) *cpdf = hs.cpdf.data();
         if (ccdf) *ccdf = hs.ccdf.data();
@@ -482,6 +481,7 @@ int hm_renderer_get_stats(hm_renderer* r, hm_stats* out) {
         out->shade_items = s.shade_items;
         out->kernel_launches = wavefront_launch_count() + (r->r->mlp() ? r->r->mlp()->launch_count() : 0);
         for (int i = 0; i < 8; ++i) out->stage_launches[i] = s.launches[i];
+        for (int i = 0; i < 8; ++i) out->timed_launches[i] = s.timed_launches[i];
         out->trav_nodes_extend = s.trav[0]; out->trav_prims_extend = s.trav[1];
         out->trav_nodes_shadow = s.trav[2]; out->trav_prims_shadow = s.trav[3];
         out->trav_nodes_primary = s.trav[4]; out->trav_prims_primary = s.trav[5];
@@ -495,6 +495,9 @@ int hm_renderer_set_collect_stats(hm_renderer* r, int on) {
 }
 int hm_renderer_set_profiling_stages(hm_renderer* r, unsigned mask) {
     return guarded([&] { need(r, "renderer"); r->r->set_profiling_stages(mask); });
+}
+int hm_renderer_set_profiling_period(hm_renderer* r, int n) {
+    return guarded([&] { need(r, "renderer"); r->r->set_profiling_period(n); });
 }
 int hm_renderer_set_skip_unused_queries(hm_renderer* r, int on) {
     return guarded([&] { need(r, "renderer"); r->r->set_skip_unused_queries(on != 0); });

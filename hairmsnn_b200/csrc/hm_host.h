@@ -81,6 +81,12 @@ struct HostScene {
 
 // scene.cpp:349-425
 void build_env_tables(HostScene& s);
+// The host copy of the tables is built on first use (oracle hooks, HM_ENV_TABLES=host): the renderers build theirs on the
+// device from the uploaded map (hm_wavefront.cu: launch_env_tables).  Thread-safe.
+void ensure_env_tables(const HostScene& s);
+// sin(theta) of every row's centre exactly as the host recipe computes it (scene.cpp:358): the device build takes
+// these from the host so that libdevice's sinf cannot move a table entry by an ulp
+void env_row_sines(int H, std::vector<float>& out);
 // fetchSceneSamples (render_hair_msnn.cu:34-97): points on the strands for the TRAIN_DATA_GEN pass
 void build_scene_samples(const HostGeometry& g, int num_samples, unsigned seed, std::vector<float>& points3);
 // bounds / scales as the frame drivers compute them (render_hair_msnn.cu:414-430)

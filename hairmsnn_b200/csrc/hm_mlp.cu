@@ -456,7 +456,7 @@ __device__ __forceinline__ void load_weights_sw(unsigned char* dst, const __half
 constexpr int kFwdThreads = 256;
 
 template <bool TRAIN, bool POW2>
-__global__ void __launch_bounds__(kFwdThreads, 3) k_mlp_forward_tc(const NetShape S, const __half* __restrict__ params, FwdArgs A) {
+__global__ void __launch_bounds__(kFwdThreads, 4) k_mlp_forward_tc(const NetShape S, const __half* __restrict__ params, FwdArgs A) {
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t raw = tc::smem_u32(smem_dyn);
     unsigned char* base = smem_dyn + ((1024u - (raw & 1023u)) & 1023u);
@@ -1339,7 +1339,7 @@ void Mlp::ensure_train_buffers(int n) {
 static int fwd_ctas_per_sm() {
     static int v = 0;
     if (!v) {
-        v = 3;
+        v = 4;
         if (const char* e = getenv("HM_MLP_CTAS")) v = std::max(1, std::min(16, atoi(e)));
     }
     return v;

@@ -62,10 +62,28 @@ DeviceScene::DeviceScene(const HostScene& hs) {
     L.env.scale = hs.env_scale; L.env.rot_phi = hs.env_rot;
     if (hs.has_env) {
         L.env.env = upload(hs.env.data(), hs.env.size());
-        L.env.cpdf = upload(hs.cpdf.data(), hs.cpdf.size());
-        L.env.ccdf = upload(hs.ccdf.data(), hs.ccdf.size());
-        L.env.mpdf = upload(hs.mpdf.data(), hs.mpdf.size());
-        L.env.mcdf = upload(hs.mcdf.data(), hs.mcdf.size());
+        const char* where = getenv("HM_ENV_TABLES");
+        if (where && std::string(where) == "host") {
+            // A/B and test path: the host recipe's tables, uploaded
+            ensure_env_tables(hs);
+            L.env.cpdf = upload(hs.cpdf.data(), hs.cpdf.size());
+            L.env.ccdf = upload(hs.ccdf.data(), hs.ccdf.size());
+            L.env.mpdf = upload(hs.mpdf.data(), hs.mpdf.size());
+            L.env.mcdf = upload(hs.mcdf.data(), hs.mcdf.size());
+        } else {
+            // default: built on the device from the uploaded map (bit-identical, tests/test_gpu_pt.py)
+            const size_t cw = (size_t)hs.env_w + 1;
+            L.env.cpdf = upload<float>(nullptr, cw * hs.env_h);
+            L.env.ccdf = upload<float>(nullptr, cw * hs.env_h);
+            L.env.mpdf = upload<float>(nullptr, (size_t)hs.env_h + 1);
+            L.env.mcdf = upload<float>(nullptr, (size_t)hs.env_h + 1);
+            std::vector<float> sines;
+            env_row_sines(hs.env_h, sines);
+            float* d_sin = upload(sines.data(), sines.size());
+            launch_env_tables(L.env.env, d_sin, hs.env_w, hs.env_h, const_cast<float*>(L.env.cpdf), const_cast<float*>(L.env.ccdf),
+                              const_cast<float*>(L.env.mpdf), const_cast<float*>(L.env.mcdf), nullptr);
+            HM_CUDA(cudaDeviceSynchronize());
+        }
     }
     L.num_dlights = (int)(hs.dl_from.size() / 3);
     if (L.num_dlights > kMaxDirLights) throw std::runtime_error("too many directional lights (max 8)");
@@ -288,7 +306,8 @@ cudaEvent_t Renderer::take_event() {
 template <typename F>
 void Renderer::timed(int stage, cudaStream_t s, F&& f) {
     stats_.launches[stage]++;
-    if (!profiling_ || !((profile_mask_ >> stage) & 1u)) { f(); return; }
+    if (!profiling_ || !((profile_mask_ >> stage) & 1u) || (frames_issued_ % (uint64_t)profile_period_) != 0) { f(); return; }
+    stats_.timed_launches[stage]++;
     Pending p{stage, take_event(), take_event()};
     HM_CUDA(cudaEventRecord(p.a, s));
     f();
@@ -735,6 +754,10 @@ void* Renderer::device_buffer(int which, size_t* bytes) {
         case 14: *bytes = (size_t)nrc_train_pixels_ * sizeof(NrcTrainRec); return c.tbuffer;
         case 15: *bytes = (size_t)n_scene_samples_ * 4; return d_scene_indices_;
         case 16: *bytes = (size_t)n_scene_samples_ * 12; return d_scene_points_;
+        case 17: *bytes = ((size_t)hs_.env_w + 1) * hs_.env_h * 4; return (void*)scene_->view.lights.env.cpdf;
+        case 18: *bytes = ((size_t)hs_.env_w + 1) * hs_.env_h * 4; return (void*)scene_->view.lights.env.ccdf;
+        case 19: *bytes = ((size_t)hs_.env_h + 1) * 4; return (void*)scene_->view.lights.env.mpdf;
+        case 20: *bytes = ((size_t)hs_.env_h + 1) * 4; return (void*)scene_->view.lights.env.mcdf;
         default: *bytes = 0; return nullptr;
     }
 }

@@ -20,6 +20,7 @@ namespace hm {
 struct Stats {
     double ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // primary shade(main piece) trace(main piece) shade+trace(tail piece) finalize train infer composite total
     uint64_t launches[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t timed_launches[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // launches that carried an event pair (ms[] sums over these)
     uint64_t rays_primary = 0, rays_extend = 0, rays_shadow = 0, shade_items = 0;
     uint64_t trav[6] = {0, 0, 0, 0, 0, 0};        // extend nodes/prims, shadow nodes/prims, primary nodes/prims
     uint64_t tail_nodes = 0, tail_prims = 0, tail_rays = 0;   // share of extend+shadow traced by tail-piece launches
@@ -144,6 +145,9 @@ public:
     void set_profiling(bool on) { profiling_ = on; }
     // bit s set: stage s (Stats::ms index) gets event pairs while profiling is on; default all
     void set_profiling_stages(unsigned mask) { profile_mask_ = mask; }
+    // event pairs only around the launches of every n-th frame (default 1 = every frame): an event record between two
+    // kernels of a stream costs a few microseconds of launch gap, ~5 % of the frame rate when every frame is timed
+    void set_profiling_period(int n) { profile_period_ = n < 1 ? 1 : n; }
     void set_collect_stats(bool on) { collect_stats_ = on; }
     // off: evaluate the cache for every pixel as the reference does (default: skip 128-pixel tiles without a hair hit)
     void set_skip_unused_queries(bool on) { skip_unused_queries_ = on; }
@@ -224,6 +228,7 @@ private:
     bool profiling_ = false, collect_stats_ = false, skip_unused_queries_ = true, tail_mega_ = false;
     int frame_offset_ = 0, frame_stride_ = 1;
     unsigned profile_mask_ = 0xffffffffu;
+    int profile_period_ = 1;
     int tail_bound_items_ = 0;      // HM_TAIL_BOUND: grid bound (in queue items) of tail-piece launches; 0 = training records
     Stats stats_;
     struct Pending { int stage; cudaEvent_t a, b; };

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <limits>
 #include <random>
+#include <mutex>
 #include <thread>
 
 #include "hm_host.h"
@@ -23,7 +24,7 @@ void build_env_tables(HostScene& s) {
     if (W <= 0 || H <= 0) return;
     const float* env = s.env.data();
     auto row = [&](int y) {
-        float sin_theta = sinf(3.14159f * (y + 0.5f) / H);
+        const float sin_theta = sinf(3.14159f * (y + 0.5f) / H);     // == env_row_sines()[y]
         float* pdf = s.cpdf.data() + (size_t)y * cw;
         float* cdf = s.ccdf.data() + (size_t)y * cw;
         auto avg = [&](int x) {
@@ -61,6 +62,18 @@ void build_env_tables(HostScene& s) {
     if (total > 0.f)
         for (int i = 1; i < H; ++i) s.mcdf[i] /= total;
     s.mcdf[H] = 1.0f;
+}
+
+void env_row_sines(int H, std::vector<float>& out) {
+    out.resize(H > 0 ? H : 0);
+    for (int y = 0; y < H; ++y) out[y] = sinf(3.14159f * (y + 0.5f) / H);
+}
+
+void ensure_env_tables(const HostScene& cs) {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    HostScene& s = const_cast<HostScene&>(cs);      // a cache: the tables are a pure function of the map
+    if (s.has_env && s.mcdf.empty()) build_env_tables(s);
 }
 
 // RenderWindow_HairMSNN::fetchSceneSamples (render_hair_msnn.cu:34-97), the part the TRAIN_DATA_GEN

@@ -923,6 +923,58 @@ void launch_nrc_render(const NrcRender& R, cudaStream_t stream) {
     k_nrc_render<<<persistent_grid(8), 256, 0, stream>>>(R);
     g_launches++;
 }
+// Environment importance tables on the device (generateEnvSamplingTables, scene.cpp:349-425): one thread per row
+// keeps the reference's sequential float accumulation (bit-identical to the host recipe; this translation unit is
+// compiled with -fmad=false), rows are independent; the marginal is one short sequential pass.  sin_theta comes
+// from the host so that libdevice's sinf cannot move an entry by an ulp.
+__global__ void __launch_bounds__(64) k_env_table_rows(const float4* __restrict__ env, const float* __restrict__ sin_theta, int W, int H,
+                                                        float* __restrict__ cpdf, float* __restrict__ ccdf) {
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= H) return;
+    const int cw = W + 1;
+    const float st = sin_theta[y];
+    const float4* row = env + (size_t)y * W;
+    float* pdf = cpdf + (size_t)y * cw;
+    float* cdf = ccdf + (size_t)y * cw;
+    auto avg = [&](int x) { const float4 p = __ldg(row + x); return (p.x + p.y + p.z) * (1.0f / 3.0f); };
+    float prev_pdf = avg(0) * st, prev_cdf = 0.f;
+    pdf[0] = prev_pdf; cdf[0] = 0.f;
+    for (int x = 1; x < W; ++x) {
+        const float p = avg(x) * st;
+        const float c = prev_cdf + prev_pdf / W;
+        pdf[x] = p; cdf[x] = c;
+        prev_pdf = p; prev_cdf = c;
+    }
+    const float total = prev_cdf + prev_pdf / W;
+    pdf[W] = total;
+    if (total > 0.f) {
+        const float inv = 1.0f / total;
+        for (int x = 1; x < W; ++x) cdf[x] *= inv;
+    }
+    cdf[W] = 1.0f;
+}
+__global__ void k_env_table_marginal(const float* __restrict__ cpdf, int W, int H, float* __restrict__ mpdf, float* __restrict__ mcdf) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const int cw = W + 1;
+    mpdf[0] = cpdf[W];
+    mcdf[0] = 0.f;
+    for (int i = 1; i < H; ++i) {
+        mpdf[i] = cpdf[(size_t)i * cw + W];
+        mcdf[i] = mcdf[i - 1] + mpdf[i - 1] / H;
+    }
+    const float total = mcdf[H - 1] + mpdf[H - 1] / H;
+    mpdf[H] = total;
+    if (total > 0.f)
+        for (int i = 1; i < H; ++i) mcdf[i] /= total;
+    mcdf[H] = 1.0f;
+}
+void launch_env_tables(const float* env_rgba, const float* sin_theta, int W, int H, float* cpdf, float* ccdf, float* mpdf, float* mcdf,
+                       cudaStream_t stream) {
+    k_env_table_rows<<<(H + 63) / 64, 64, 0, stream>>>((const float4*)env_rgba, sin_theta, W, H, cpdf, ccdf);
+    k_env_table_marginal<<<1, 32, 0, stream>>>(cpdf, W, H, mpdf, mcdf);
+    g_launches += 2;
+}
+
 // Test hooks: the fibre scattering model for caller-supplied local directions (device pointers).
 __global__ void __launch_bounds__(256) k_bsdf_eval(const HairLobes L, const float* wo, const float* wi, const float* h, int n,
                                                    float* out_f, float* out_pdf) {

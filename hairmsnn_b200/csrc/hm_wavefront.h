@@ -148,6 +148,9 @@ void launch_resolve_sum(float4* img, uint32_t* fb, float inv_total, int n, cudaS
 // test hook: closest-hit / any-hit for caller-supplied rays (device pointers)
 void launch_trace_rays(const SceneView& S, const float* org, const float* dir, int n, int any,
                        float tmin, float tmax, float4* out_hit, int* out_stats, int* cursor, cudaStream_t stream);
+// generateEnvSamplingTables (scene.cpp:349-425) on the device: env RGBA32F [H][W] -> cPdf/cCdf [H][W+1], mPdf/mCdf [H+1]
+void launch_env_tables(const float* env_rgba, const float* sin_theta, int W, int H, float* cpdf, float* ccdf, float* mpdf, float* mcdf,
+                       cudaStream_t stream);
 // test hooks: hair_eval / hair_sample_dir + hair_eval (hm_bsdf.h) for caller-supplied local directions (device pointers)
 void launch_bsdf_eval(const HairLobes& L, const float* wo, const float* wi, const float* h, int n, float* out_f, float* out_pdf, cudaStream_t stream);
 void launch_bsdf_sample(const HairLobes& L, const float* wo, const float* h, const float* u, int n, float* out_wi, float* out_f, float* out_pdf,

@@ -57,7 +57,10 @@ enum {
     HM_BUF_NRC_TRAIN_RECORDS = 14,/* render_nrc: TrainBuffer[training pixels] as 5 x float[40][3] (vert wo n
                                     vertRadiance vertBeta) + int bounces + int hit = 2408 bytes each */
     HM_BUF_SCENE_INDICES = 15,   /* render_hair_msnn: int[numSamples] sceneIndices (after the first pre-training call) */
-    HM_BUF_SCENE_POINTS = 16     /* render_hair_msnn: float[numSamples][3] sampledPoints */
+    HM_BUF_SCENE_POINTS = 16,    /* render_hair_msnn: float[numSamples][3] sampledPoints */
+    /* the environment importance tables as the device holds them (built there from the uploaded map):
+     * cPdf / cCdf float[env_h][env_w + 1], mPdf / mCdf float[env_h + 1] (generateEnvSamplingTables, scene.cpp:349-425) */
+    HM_BUF_ENV_CPDF = 17, HM_BUF_ENV_CCDF = 18, HM_BUF_ENV_MPDF = 19, HM_BUF_ENV_MCDF = 20
 };
 
 const char* hm_last_error(void);
@@ -250,6 +253,8 @@ typedef struct {
     uint64_t trav_nodes_tail, trav_prims_tail, rays_tail;
     float last_loss;
     int frames;
+    /* launches per stage that carried an event pair: the ms_* sums cover these (hm_renderer_set_profiling_period) */
+    uint64_t timed_launches[8];
 } hm_stats;
 int hm_renderer_get_stats(hm_renderer* r, hm_stats* out);
 /* per-stage CUDA-event timing on/off (event pairs around each launch, resolved in hm_renderer_get_stats) */
@@ -258,6 +263,9 @@ int hm_renderer_set_profiling(hm_renderer* r, int on);
  * piece), 4 finalize, 5 train, 6 infer, 7 composite, 8 whole frame; default all.  A frame has ~320 launches:
  * timing all of them costs ~3 % of the frame rate. */
 int hm_renderer_set_profiling_stages(hm_renderer* r, unsigned mask);
+/* event pairs around the launches of every n-th frame only (default 1).  An event record between two kernels of a stream
+ * costs a few microseconds of launch gap: timing every frame's traversal and network launches costs ~5 % of the frame rate. */
+int hm_renderer_set_profiling_period(hm_renderer* r, int every_nth_frame);
 /* instrumented traversal + queue-size accounting (polls the queue counters every bounce) */
 int hm_renderer_set_collect_stats(hm_renderer* r, int on);
 /* render_hair_msnn: the RENDER pass reads the network output of hair-hit pixels only (cuda/hair_msnn.cu:325-340).

@@ -52,6 +52,16 @@ def test_shipped_curly_scene_loads(curly):
     assert abs(i.scene_scale - 187.85) < 0.5
 
 
+def test_env_tables_of_the_shipped_map_built_on_device(curly):
+    """The 4096 x 2048 studio map: the device-built importance tables equal the host recipe's, entry for entry."""
+    sc, _, _ = curly
+    r = api.Renderer(sc, api.PATH_TRACING)
+    t = sc.env_tables()
+    for which, name in ((api.BUF_ENV_CPDF, "cpdf"), (api.BUF_ENV_CCDF, "ccdf"), (api.BUF_ENV_MPDF, "mpdf"), (api.BUF_ENV_MCDF, "mcdf")):
+        got = r.buffer(which)
+        assert np.array_equal(got.view(np.uint32), np.ascontiguousarray(t[name]).reshape(-1).view(np.uint32)), name
+
+
 def test_hit_ids_bit_exact_on_real_hair(curly):
     """Primary-hit curve / segment ids, t and u on the real geometry: the sm_100a traversal of the 8-wide tree == the host
     traversal of the binary tree it is derived from (same intersector source), for camera rays and for incoherent rays."""
