@@ -32,6 +32,19 @@ struct HairLobes {
     float sin2k[3], cos2k[3];
     float v_sample[4];  // v[0..2], s  (see header note)
     float radius_unused;
+    // Scene-uniform subexpressions of Mp / Np / the lobe sampler, evaluated once here with the reference's own
+    // operations instead of at every evaluation (a vertex evaluates the model up to three times, each with four Mp and
+    // three Np).  What the kernels gain: an IEEE division is ~10 instructions plus a slow-path branch, and k_shade was
+    // spending 44 % of its instructions in them (profiles/r2b_main.summary.txt: 6.2 M FCHK per launch).  Products with
+    // these reciprocals differ from the reference's quotients by at most one ulp per operation.
+    float inv_v[3];        // 1 / v[p]
+    float mp_log_term[3];  // logf(1 / (2 v[p]))                       (Mp, v <= 0.1 branch)
+    float mp_inv_den[3];   // 1 / (sinhf(1 / v[p]) * 2 * v[p])         (Mp, v > 0.1 branch)
+    float inv_s;           // 1 / s
+    float az_inv_norm;     // 1 / (logistic_cdf(pi, s) - logistic_cdf(-pi, s))
+    float az_cdf_lo;       // logistic_cdf(-pi, s)
+    float az_cdf_span;     // logistic_cdf(pi, s) - logistic_cdf(-pi, s)
+    float smp_exp[4];      // expf(-2 / v_sample[p])
 
     void setup(float beta_m, float beta_n, float alpha_rad) {
         v[0] = sqr(0.726f * beta_m + 0.812f * sqr(beta_m) + 3.7f * powf(beta_m, 20.f));
@@ -46,6 +59,18 @@ struct HairLobes {
         }
         v_sample[0] = v[0]; v_sample[1] = v[1]; v_sample[2] = v[2]; v_sample[3] = s;
         radius_unused = 0.f;
+        const float pi = 3.1415926f;   // kPi (utils.cuh:10)
+        for (int i = 0; i < 3; ++i) {
+            inv_v[i] = 1 / v[i];
+            mp_log_term[i] = logf(1 / (2 * v[i]));
+            mp_inv_den[i] = 1 / (sinhf(1 / v[i]) * 2 * v[i]);
+        }
+        inv_s = 1 / s;
+        const float hi = 1 / (1 + expf(-pi / s)), lo = 1 / (1 + expf(pi / s));
+        az_cdf_lo = lo;
+        az_cdf_span = hi - lo;
+        az_inv_norm = 1 / (hi - lo);
+        for (int i = 0; i < 4; ++i) smp_exp[i] = expf(-2.f / v_sample[i]);
     }
 };
 
@@ -59,25 +84,27 @@ HM_HD float schlick(float cos_theta) {
     return f0 + (1 - f0) * xd * xd * xd * xd * xd;
 }
 
-// 10-term power series of the modified Bessel function; the denominators are
-// 4^i * (i!)^2 evaluated the way the reference's mixed int/float expression does.
+// 10-term power series of the modified Bessel function (disney_hair.cuh:53-67); the denominators are
+// 4^i * (i!)^2 evaluated the way the reference's mixed int/float expression does.  The reference divides by them;
+// here each term is multiplied by the correctly rounded reciprocal (exact for the first three, a power of two each;
+// at most one ulp per term otherwise) — ten IEEE divisions per call, twelve calls per vertex, were a third of k_shade.
 HM_HD float bessel_i0(float x) {
-    const float den[10] = {
-        1.f * (1.f * 1.f),
-        4.f * (1.f * 1.f),
-        16.f * (2.f * 2.f),
-        64.f * (6.f * 6.f),
-        256.f * (24.f * 24.f),
-        1024.f * (120.f * 120.f),
-        4096.f * (720.f * 720.f),
-        16384.f * (5040.f * 5040.f),
-        65536.f * (40320.f * 40320.f),
-        262144.f * (362880.f * 362880.f)};
+    const float rden[10] = {
+        1.f / (1.f * (1.f * 1.f)),
+        1.f / (4.f * (1.f * 1.f)),
+        1.f / (16.f * (2.f * 2.f)),
+        1.f / (64.f * (6.f * 6.f)),
+        1.f / (256.f * (24.f * 24.f)),
+        1.f / (1024.f * (120.f * 120.f)),
+        1.f / (4096.f * (720.f * 720.f)),
+        1.f / (16384.f * (5040.f * 5040.f)),
+        1.f / (65536.f * (40320.f * 40320.f)),
+        1.f / (262144.f * (362880.f * 362880.f))};
     float val = 0.f, x2i = 1.f;
     const float xx = x * x;
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
-        val += x2i / den[i];
+        val += x2i * rden[i];
         x2i *= xx;
     }
     return val;
@@ -90,17 +117,22 @@ HM_HD float log_bessel_i0(float x) {
 }
 
 // longitudinal scattering M_p
-static HM_HD_OUTLINE float longitudinal(float cos_i, float cos_o, float sin_i, float sin_o, float v) {
-    float a = cos_i * cos_o / v;
-    float b = sin_i * sin_o / v;
-    if (v <= 0.1f)
-        return expf(log_bessel_i0(a) - b - 1 / v + 0.6931f + logf(1 / (2 * v)));
-    return (expf(-b) * bessel_i0(a)) / (sinhf(1 / v) * 2 * v);
+// L.v[k] is the variance; the quotients by it use the reciprocals of HairLobes::setup (same operation order as
+// disney_hair.cuh:77-88).
+static HM_HD_OUTLINE float longitudinal(const HairLobes& L, int k, float cos_i, float cos_o, float sin_i, float sin_o) {
+    // a and b stay true quotients: for small v they reach several hundred and sit inside an exponential, where one ulp
+    // of them is 1e-4 of the result
+    float a = cos_i * cos_o / L.v[k];
+    float b = sin_i * sin_o / L.v[k];
+    if (L.v[k] <= 0.1f)
+        return expf(log_bessel_i0(a) - b - L.inv_v[k] + 0.6931f + L.mp_log_term[k]);
+    return (expf(-b) * bessel_i0(a)) * L.mp_inv_den[k];
 }
 
-HM_HD float logistic(float x, float s) {
+HM_HD float logistic(float x, float s, float inv_s) {
     x = fabsf(x);
-    return expf(-x / s) / (s * sqr(1 + expf(-x / s)));
+    const float e = expf(-x * inv_s);
+    return e / (s * sqr(1 + e));
 }
 HM_HD float logistic_cdf(float x, float s) { return 1 / (1 + expf(-x / s)); }
 
@@ -109,17 +141,17 @@ HM_HD float net_phi(int p, float gamma_o, float gamma_t) {
 }
 
 // azimuthal scattering N_p (trimmed logistic on [-pi, pi])
-HM_HD float azimuthal(float phi, int p, float s, float gamma_o, float gamma_t) {
+HM_HD float azimuthal(const HairLobes& L, float phi, int p, float gamma_o, float gamma_t) {
     float dphi = phi - net_phi(p, gamma_o, gamma_t);
     while (dphi > kPi) dphi -= kTwoPi;
     while (dphi < -kPi) dphi += kTwoPi;
-    return logistic(dphi, s) / (logistic_cdf(kPi, s) - logistic_cdf(-kPi, s));
+    return logistic(dphi, L.s, L.inv_s) * L.az_inv_norm;      // trimmed to [-pi, pi]: the norm is scene-uniform
 }
 
-HM_HD float sample_trimmed_logistic(float u, float s, float a, float b) {
-    float k = logistic_cdf(b, s) - logistic_cdf(a, s);
-    float x = -s * logf(1 / (u * k + logistic_cdf(a, s)) - 1);
-    return clampf(x, a, b);
+// SampleTrimmedLogistic on [-pi, pi] (disney_hair.cuh:131-139) with the two cdf values from HairLobes::setup
+HM_HD float sample_trimmed_logistic(const HairLobes& L, float u) {
+    float x = -L.s * logf(1 / (u * L.az_cdf_span + L.az_cdf_lo) - 1);
+    return clampf(x, -kPi, kPi);
 }
 
 // Everything that depends only on the outgoing direction and the azimuthal offset h.
@@ -200,12 +232,12 @@ static HM_HD_OUTLINE V3 eval_with_geom(const HairLobes& L, const FibreGeom& g, V
         float sin_op, cos_op;
         tilt(L, p, g.sin_o, g.cos_o, sin_op, cos_op);
         cos_op = fabsf(cos_op);
-        float mp = longitudinal(cos_i, cos_op, sin_i, sin_op, L.v[p]);
-        float np = azimuthal(phi, p, L.s, g.gamma_o, g.gamma_t);
+        float mp = longitudinal(L, p, cos_i, cos_op, sin_i, sin_op);
+        float np = azimuthal(L, phi, p, g.gamma_o, g.gamma_t);
         f += ((L.gain[p] * mp) * g.ap[p]) * np;
         p_acc = p_acc + mp * g.ap_pdf[p] * np;
     }
-    float mp_res = longitudinal(cos_i, g.cos_o, sin_i, g.sin_o, L.v[2]);
+    float mp_res = longitudinal(L, 2, cos_i, g.cos_o, sin_i, g.sin_o);
     float np_res = 1.f / (2.f * kPi);
     f += ((L.gain[3] * mp_res) * g.ap[3]) * np_res;
     p_acc = p_acc + mp_res * g.ap_pdf[3] * np_res;
@@ -253,7 +285,7 @@ static HM_HD_OUTLINE V3 hair_sample_dir_geom(const HairLobes& L, const hairdetai
 
     float vs = L.v_sample[p];
     float eps2 = fmaxf(u1, 1e-5f);
-    float cos_theta = 1.f + vs * logf(eps2 + (1.f - eps2) * expf(-2.f / vs));
+    float cos_theta = 1.f + vs * logf(eps2 + (1.f - eps2) * L.smp_exp[p]);
     float sin_theta = safe_sqrt(1 - sqr(cos_theta));
     float cos_phi = cosf(kTwoPi * u2);
     float sin_i = -cos_theta * sin_op + sin_theta * cos_phi * cos_op;
@@ -261,7 +293,7 @@ static HM_HD_OUTLINE V3 hair_sample_dir_geom(const HairLobes& L, const hairdetai
 
     float dphi;
     if (p < 3)
-        dphi = net_phi(p, g.gamma_o, g.gamma_t) + sample_trimmed_logistic(u3, L.s, -kPi, kPi);
+        dphi = net_phi(p, g.gamma_o, g.gamma_t) + sample_trimmed_logistic(L, u3);
     else
         dphi = kTwoPi * u3;
 
