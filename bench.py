@@ -461,6 +461,57 @@ def measure(r, api, torch, local_rank, comm, W, H, steps, warmup, peaks, kind, w
     return out
 
 
+def mlp_alone(api, torch, local_rank, peaks):
+    """The network's kernels timed alone (nothing else on the GPU), CUDA events on the network's stream: inference of 2^20
+    queries on the synthetic inputs of SURVEY §8d (uniformly random positions: every gather is a distinct 32-byte L2 sector)
+    and on pixel-coherent positions, and training steps of 16384 / 65536 records."""
+    N = 1 << 20
+    rng = np.random.default_rng(0)
+    x = np.zeros((N, 12), np.float32)
+    x[:, :3] = rng.uniform(-0.5, 0.5, (N, 3))
+    d = rng.normal(size=(N, 6)).astype(np.float32)
+    d[:, :3] /= np.linalg.norm(d[:, :3], axis=1, keepdims=True); d[:, 3:] /= np.linalg.norm(d[:, 3:], axis=1, keepdims=True)
+    x[:, 3:9] = d
+    xc = x.copy()
+    g = np.arange(N)
+    xc[:, 0] = ((g % 1024) / 1024.0 - 0.5) * 0.8; xc[:, 1] = ((g // 1024) / 1024.0 - 0.5) * 0.8
+    xc[:, 2] = 0.1 * np.sin(xc[:, 0] * 9) * np.cos(xc[:, 1] * 7)
+    dev = f"cuda:{local_rank}"
+    m = api.Mlp.create(device=local_rank)
+    xr, xco = torch.from_numpy(x).to(dev), torch.from_numpy(xc).to(dev)
+    yo = torch.empty((N, 3), device=dev)
+    st = torch.cuda.ExternalStream(m.stream, device=local_rank)
+    torch.cuda.synchronize()
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(reps):
+            fn()
+        e1.record(st); e1.synchronize()
+        return e0.elapsed_time(e1) / reps
+    ms_r = timed(lambda: m.inference_device(xr.data_ptr(), yo.data_ptr(), N), 20)
+    ms_c = timed(lambda: m.inference_device(xco.data_ptr(), yo.data_ptr(), N), 20)
+    out = {"inference_ms_2p20_random_positions": ms_r, "inference_ms_2p20_pixel_coherent": ms_c,
+           "queries_per_s_random": N / ms_r * 1e3, "queries_per_s_coherent": N / ms_c * 1e3,
+           # 16 levels x 8 corners = 128 gathers per query, one 32-byte L2 sector each when positions are random
+           "l2_gather_TBps_random": N * 128 * 32 / (ms_r * 1e-3) / 1e12,
+           "l2_peak_TBps": 6300 * 1.965e9 / 1e12, "l2_peak_note": "LTS throughput cap ~6300 B/clk (B300_MICROARCH.md) x 1965 MHz",
+           "tflops_random": N * FLOPS_PER_QUERY / (ms_r * 1e-3) / 1e12, "tensor_peak_tflops": peaks["bf16_tflops_burst"]}
+    out["frac_of_l2_gather_peak_random"] = out["l2_gather_TBps_random"] / out["l2_peak_TBps"]
+    out["frac_of_tensor_peak_random"] = out["tflops_random"] / peaks["bf16_tflops_burst"]
+    for nrec in (16384, 65536):
+        tx = xr[:nrec].contiguous(); ty = torch.rand((nrec, 3), device=dev)
+        out[f"training_step_ms_{nrec}"] = timed(lambda: m.train_step_device(tx.data_ptr(), ty.data_ptr(), nrec), 30)
+        fb = timed(lambda: m.forward_backward_device(tx.data_ptr(), ty.data_ptr(), nrec), 30)
+        out[f"forward_backward_ms_{nrec}"] = fb
+        out[f"forward_backward_tflops_{nrec}"] = nrec * FLOPS_PER_RECORD / (fb * 1e-3) / 1e12
+    m.close()
+    return out
+
+
 def image_gate(sc, api, W, H, pt_spp, spp, pretrain):
     """relMSE of render_hair_msnn (BETA 1 and 10) against a render_path_tracing image of pt_spp samples."""
     def rel_mse(img, ref):
@@ -609,6 +660,8 @@ def main():
         log(f"[image gate] {gate}")
     if not args.no_cpu_baseline and kind == "msnn":
         cb = cpu_baseline(sc, kw, W, H, beta_cli)
+    if default_single and res.get("mlp") is not None:
+        res["mlp"]["alone"] = mlp_alone(api, torch, local_rank, peaks)
 
     line = {"metric": "Mpaths/s", "value": res["value"], "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": res["ms"] / args.steps, "higher_is_better": True, "scaling": "strong" if bands else "weak", "vs_baseline": None,

@@ -105,3 +105,35 @@ def test_training_replicas_stay_identical(tmp_path, mode):
         # the composite differs only through the network (training order of atomics, batch split)
         d = np.abs(res[0]["final_avg"][..., :3] - ref["final_avg"][..., :3])
         assert d.mean() < 0.05 * max(ref["final_avg"][..., :3].mean(), 1e-3)
+
+
+def test_executables_with_gpus_flag(tmp_path):
+    """`render_path_tracing <config> --gpus 2 --shard bands` writes the image a single GPU writes, bit for bit; `render_hair_msnn
+    <config> 1 --gpus 2` (sample groups, gradients all-reduced inside the loop) writes a finite image of the same scene."""
+    _need_two_gpus()
+    import json
+    from hairmsnn_b200 import api
+    root = os.path.dirname(HERE)
+    curly = os.path.join(root, "assets", "scenes", "curly", "config.json")
+    if not os.path.exists(curly):
+        pytest.skip("assets/scenes is not staged")
+    cfg = json.load(open(curly))
+    cfg["integrator"]["width"] = cfg["integrator"]["height"] = 256
+    path = os.path.join(os.path.dirname(curly), "config_test_256.json")
+    json.dump(cfg, open(path, "w"))
+    env = dict(os.environ, HM_BVH_CACHE=str(tmp_path))
+    exe = os.path.join(root, "hairmsnn_b200", "bin")
+
+    def run(name, *args):
+        out = str(tmp_path / (name + ".png"))
+        p = subprocess.run(list(args) + ["--out", out], capture_output=True, text=True, timeout=900, env=env)
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+        return api.load_exr(out.replace(".png", ".exr")), p.stdout
+    one, _ = run("pt1", os.path.join(exe, "render_path_tracing"), path, "--spp", "4")
+    two, log = run("pt2", os.path.join(exe, "render_path_tracing"), path, "--spp", "4", "--gpus", "2", "--shard", "bands")
+    assert "on 2 GPU(s) (row bands)" in log
+    assert np.array_equal(one, two)
+    img, log = run("msnn2", os.path.join(exe, "render_hair_msnn"), path, "1", "--spp", "8", "--gpus", "2", "--pretrain-steps", "20")
+    assert "on 2 GPU(s) (sample groups)" in log
+    assert img.shape == (256, 256, 4) and np.isfinite(img).all() and img[..., :3].mean() > 0.01
+    assert np.abs(img[..., :3].mean() - one[..., :3].mean()) < 0.2 * one[..., :3].mean()
