@@ -26,6 +26,9 @@ struct EnvView {
     const float* ccdf;  // (W+1)*H
     const float* mpdf;  // H+1
     const float* mcdf;  // H+1
+    // every 64th entry of each conditional-cdf row, [H][W / 64] (device only, power-of-two W <= 4096; else null): the
+    // first level of the two-level search below
+    const float* ccoarse;
     int W, H;
     float scale, rot_phi;
     int has_env;
@@ -131,6 +134,38 @@ HM_HD int cdf_lower_bound(float u, const float* t, int w, int h, float yn, float
     return first - 1 > 0 ? first - 1 : 0;
 }
 
+// The same index for tables whose `size` is a power of two <= 4096 (every shipped map): there middle / size is exact and
+// (middle / size) * (size + 1) = middle + middle / size needs at most 24 bits, so table_fetch's floor() returns exactly
+// `middle` — the normalised-coordinate arithmetic can be dropped.  Two levels: lower_bound over every 64th entry
+// (`coarse`, 256 contiguous bytes per row), then over the 63 entries of the bracket it names.  A lower_bound of a sorted
+// row is unique, so the result equals cdf_lower_bound's whatever the probe order; what changes is the memory behaviour —
+// the one-level search makes ~7 dependent L2 round trips per row (its first probes are 8 KB, 4 KB, 2 KB ... apart), this
+// one ~3.  (k_shade: long-scoreboard 14 of 27 stall cycles per issue, this loop its hottest line; profiles/r2m_shade.*)
+HM_HD int cdf_lower_bound_two_level(float u, const float* row, const float* coarse, int size) {
+    // first coarse entry k in [0, K) with !(row[64 k] < u); K if none
+    const int K = size >> 6;
+    int first = 0, count = K;
+    while (count > 0) {
+        const int step = count >> 1, middle = first + step;
+        if (ldf(coarse + middle) < u) { first = middle + 1; count -= step + 1; }
+        else count = step;
+    }
+    int F = 0;
+    if (first > 0) {
+        // row[64 (first - 1)] < u and (first == K or row[64 first] >= u): the answer lies in (64 (first - 1), 64 first]
+        int lo = 64 * (first - 1) + 1;
+        int cnt = (first < K ? 64 * first : size) - lo;
+        while (cnt > 0) {
+            const int step = cnt >> 1, middle = lo + step;
+            if (ldf(row + middle) < u) { lo = middle + 1; cnt -= step + 1; }
+            else cnt = step;
+        }
+        F = lo;
+    }
+    return F - 1 > 0 ? F - 1 : 0;
+}
+HM_HD bool cdf_direct_ok(int size) { return size >= 64 && size <= 4096 && (size & (size - 1)) == 0; }
+
 // (A 4-ary variant of this search — half the dependent round trips, three probes each — was measured on the B200
 // against the real scenes/curly frame: k_shade 1.77 vs 1.59 ms per frame, profiles/r2d_sweep_knobs.txt `env4`.
 // The extra probes cost more than the saved round trips; it was removed.)
@@ -160,7 +195,14 @@ static HM_HD_OUTLINE V3 env_sample(const EnvView& e, float u0, float u1, V3& wi,
     float dv = (cdf_next_v - u1) / (cdf_next_v - cdf_v);
     float v = (index_v + dv) / height;
 
-    int index_u = cdf_search(u0, e.ccdf, cw, e.H, index_v / height, width);
+    int index_u;
+    if (e.ccoarse && cdf_direct_ok(e.W)) {
+        // row index exactly as table_fetch derives it from index_v / height
+        const int j = clamp_idx((int)floorf((index_v / height) * (float)e.H), e.H);
+        index_u = cdf_lower_bound_two_level(u0, e.ccdf + (size_t)j * cw, e.ccoarse + (size_t)j * (e.W >> 6), e.W);
+    } else {
+        index_u = cdf_search(u0, e.ccdf, cw, e.H, index_v / height, width);
+    }
     float cdf_u = table_fetch(e.ccdf, cw, e.H, index_u / width, index_v / height);
     float cdf_next_u = table_fetch(e.ccdf, cw, e.H, (index_u + 1) / width, index_v / height);
     float du = (cdf_next_u - u0) / (cdf_next_u - cdf_u);

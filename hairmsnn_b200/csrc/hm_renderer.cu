@@ -84,6 +84,13 @@ DeviceScene::DeviceScene(const HostScene& hs) {
                               const_cast<float*>(L.env.mpdf), const_cast<float*>(L.env.mcdf), nullptr);
             HM_CUDA(cudaDeviceSynchronize());
         }
+        L.env.ccoarse = nullptr;
+        if (cdf_direct_ok(hs.env_w) && !getenv("HM_ENV_ONE_LEVEL")) {
+            float* coarse = upload<float>(nullptr, (size_t)(hs.env_w >> 6) * hs.env_h);
+            launch_env_coarse(L.env.ccdf, hs.env_w, hs.env_h, coarse, nullptr);
+            HM_CUDA(cudaDeviceSynchronize());
+            L.env.ccoarse = coarse;
+        }
     }
     L.num_dlights = (int)(hs.dl_from.size() / 3);
     if (L.num_dlights > kMaxDirLights) throw std::runtime_error("too many directional lights (max 8)");

@@ -968,6 +968,19 @@ __global__ void k_env_table_marginal(const float* __restrict__ cpdf, int W, int 
         for (int i = 1; i < H; ++i) mcdf[i] /= total;
     mcdf[H] = 1.0f;
 }
+// every 64th entry of each conditional-cdf row (first level of cdf_lower_bound_two_level, hm_light.h)
+__global__ void __launch_bounds__(256) k_env_table_coarse(const float* __restrict__ ccdf, int W, int H, float* __restrict__ coarse) {
+    const int K = W >> 6;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * H) return;
+    const int y = i / K, k = i % K;
+    coarse[i] = ccdf[(size_t)y * (W + 1) + 64 * k];
+}
+void launch_env_coarse(const float* ccdf, int W, int H, float* coarse, cudaStream_t stream) {
+    const int n = (W >> 6) * H;
+    k_env_table_coarse<<<(n + 255) / 256, 256, 0, stream>>>(ccdf, W, H, coarse);
+    g_launches++;
+}
 void launch_env_tables(const float* env_rgba, const float* sin_theta, int W, int H, float* cpdf, float* ccdf, float* mpdf, float* mcdf,
                        cudaStream_t stream) {
     k_env_table_rows<<<(H + 63) / 64, 64, 0, stream>>>((const float4*)env_rgba, sin_theta, W, H, cpdf, ccdf);

@@ -151,6 +151,8 @@ void launch_trace_rays(const SceneView& S, const float* org, const float* dir, i
 // generateEnvSamplingTables (scene.cpp:349-425) on the device: env RGBA32F [H][W] -> cPdf/cCdf [H][W+1], mPdf/mCdf [H+1]
 void launch_env_tables(const float* env_rgba, const float* sin_theta, int W, int H, float* cpdf, float* ccdf, float* mpdf, float* mcdf,
                        cudaStream_t stream);
+// every 64th entry of each conditional-cdf row -> coarse [H][W / 64]
+void launch_env_coarse(const float* ccdf, int W, int H, float* coarse, cudaStream_t stream);
 // test hooks: hair_eval / hair_sample_dir + hair_eval (hm_bsdf.h) for caller-supplied local directions (device pointers)
 void launch_bsdf_eval(const HairLobes& L, const float* wo, const float* wi, const float* h, int n, float* out_f, float* out_pdf, cudaStream_t stream);
 void launch_bsdf_sample(const HairLobes& L, const float* wo, const float* h, const float* u, int n, float* out_wi, float* out_f, float* out_pdf,

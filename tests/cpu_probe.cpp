@@ -96,6 +96,19 @@ void probe_cdf_search(const float* table, int w, int h, int n, const float* u, c
     }
 }
 
+// two-level search (power-of-two rows) vs the reference-order search, row by row
+void probe_cdf_two_level(const float* table, int W, int H, int n, const float* u, const int* rows, int* out2) {
+    const int cw = W + 1, K = W >> 6;
+    std::vector<float> coarse((size_t)K * H);
+    for (int y = 0; y < H; ++y)
+        for (int k = 0; k < K; ++k) coarse[(size_t)y * K + k] = table[(size_t)y * cw + 64 * k];
+    for (int i = 0; i < n; ++i) {
+        const int y = rows[i];
+        out2[2 * i + 0] = cdf_lower_bound(u[i], table, cw, H, (y + 0.5f) / H, (float)W);
+        out2[2 * i + 1] = cdf_lower_bound_two_level(u[i], table + (size_t)y * cw, coarse.data() + (size_t)y * K, W);
+    }
+}
+
 // BVH build + trace on the host
 struct ProbeScene { HostGeometry geo; HostBvh bvh; };
 void* probe_scene_create(const float* cps, int ncps, const int* seg_cp, int nseg, const float* tri_verts, int ntri, int threads) {

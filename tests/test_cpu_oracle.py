@@ -168,3 +168,27 @@ def test_cdf_search_is_lower_bound(probe):
     out1 = np.zeros((n, 2), np.int32)
     probe.probe_cdf_search(_p(m), W + 1, 1, n, _p(u), _p(np.zeros(n, np.float32)), C.c_float(W), out1.ctypes.data_as(C.POINTER(C.c_int)))
     assert np.array_equal(out1[:, 0], out1[:, 1])
+
+
+@pytest.mark.parametrize("W", [64, 256, 4096])
+def test_two_level_cdf_search_equals_reference_order_search(probe, W):
+    """hm_light.h: cdf_lower_bound_two_level (what the device uses on power-of-two maps) returns the index of the
+    reference-order search (normalised-coordinate table fetches, std::lower_bound probe order) for every u — flat
+    stretches, single-step rows, values exactly on table entries, u outside (0, 1)."""
+    rng = np.random.default_rng(W)
+    H = 9
+    pdf = rng.random((H, W)).astype(np.float32) ** 4
+    pdf[:, W // 4:W // 2] = 0.0
+    pdf[3] = 0.0; pdf[3, W - 3] = 1.0
+    pdf[4] = 0.0; pdf[4, 0] = 1.0
+    cdf = np.concatenate([np.zeros((H, 1), np.float32), np.cumsum(pdf, axis=1, dtype=np.float32)], axis=1)
+    cdf = np.ascontiguousarray(cdf / cdf[:, -1:], np.float32)
+    n = 30000
+    u = rng.random(n).astype(np.float32)
+    u[:50] = 0.0; u[50:100] = 1.0; u[100:150] = -0.5; u[150:200] = 1.5
+    rows = rng.integers(0, H, n).astype(np.int32)
+    u[200:2200] = cdf[rows[200:2200], rng.integers(0, W + 1, 2000)]
+    out = np.zeros((n, 2), np.int32)
+    probe.probe_cdf_two_level(_p(cdf), W, H, n, _p(u), rows.ctypes.data_as(C.POINTER(C.c_int)), out.ctypes.data_as(C.POINTER(C.c_int)))
+    assert np.array_equal(out[:, 0], out[:, 1])
+    assert len(np.unique(out[:, 0])) > min(W // 2, 200)
