@@ -64,6 +64,7 @@ struct GeomView {
     const F4* wnodes;     // 5 per wide node (80 B)
     const F4* wleaf_data; // 4 per wide leaf reference (64 B, same content as a leaf slot)
     int num_wnodes;
+    unsigned k47;         // 0x47000000 as a RUN-TIME value (see byte_biased_t): set by whoever fills the view
 };
 
 struct Hit {
@@ -274,6 +275,22 @@ HM_HD float byte_biased(unsigned w, int k) {
     return kQBias + (float)((w >> (8 * k)) & 0xffu);
 #endif
 }
+// Same value with the byte index as a template constant and the 0x47000000 operand in a REGISTER (k47, a runtime value
+// the caller reads from GeomView): ptxas then encodes the selector as PRMT's immediate.  With the literal __byte_perm
+// above it makes 0x47000000 the immediate and re-materialises the selector in a register before every PRMT (the
+// destination overwrites it): 48 extra MOVs per node test, a tenth of the traversal's instructions
+// (profiles/r2b_k_trace_lines.txt: 80.8 instructions per warp-visit on the byte_biased line instead of 48).
+template <int K>
+HM_HD float byte_biased_t(unsigned w, unsigned k47) {
+#if defined(__CUDA_ARCH__)
+    unsigned r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(k47), "n"(0x7504 | (K << 4)));
+    return __uint_as_float(r);
+#else
+    (void)k47;
+    return kQBias + (float)((w >> (8 * K)) & 0xffu);
+#endif
+}
 HM_HD int popc_u(unsigned v) {
 #if defined(__CUDA_ARCH__)
     return __popc(v);
@@ -316,7 +333,8 @@ HM_HD WideRay make_wide_ray(V3 o, V3 d) {
 // near_key (optional): (bits of the smallest entry distance among the hit children, low 3 bits replaced by
 // that child's slot), 0xffffffff when nothing is hit — entry distances are >= tmin >= 0, so their bit patterns
 // order like unsigned integers.
-HM_HD unsigned wide_node_hits(F4 w0, F4 w2, F4 w3, F4 w4, const WideRay& r, float tmin, float tmax, unsigned* near_key = nullptr) {
+HM_HD unsigned wide_node_hits(F4 w0, F4 w2, F4 w3, F4 w4, const WideRay& r, float tmin, float tmax, unsigned* near_key = nullptr,
+                              unsigned k47 = 0x47000000u) {
     const unsigned em = f_as_u(w0.w);
     // t(q) = (q + bias) * (cell * idir) + (origin * idir - o * idir - bias * cell * idir)
     const float ax = u_as_f((em & 0xffu) << 23) * r.idir.x, bx = fmaf(-kQBias, ax, fmaf(w0.x, r.idir.x, -r.ood.x));
@@ -329,6 +347,19 @@ HM_HD unsigned wide_node_hits(F4 w0, F4 w2, F4 w3, F4 w4, const WideRay& r, floa
     const unsigned hiy[2] = {f_as_u(w4.x), f_as_u(w4.y)}, hiz[2] = {f_as_u(w4.z), f_as_u(w4.w)};
     unsigned hits = 0;
     unsigned nearest = 0xffffffffu;
+#define HM_WIDE_CHILD(K)                                                                                                  \
+    {                                                                                                                     \
+        const float tnx = fmaf(byte_biased_t<K>(nx, k47), ax, bx), tfx = fmaf(byte_biased_t<K>(fx, k47), ax, bx);         \
+        const float tny = fmaf(byte_biased_t<K>(ny, k47), ay, by), tfy = fmaf(byte_biased_t<K>(fy, k47), ay, by);         \
+        const float tnz = fmaf(byte_biased_t<K>(nz, k47), az, bz), tfz = fmaf(byte_biased_t<K>(fz, k47), az, bz);         \
+        const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));                                                        \
+        const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));                                                        \
+        if (tn <= tf) {                                                                                                   \
+            hits |= 1u << (4 * h + K);                                                                                    \
+            const unsigned key = (f_as_u(tn) & ~7u) | (unsigned)(4 * h + K);                                              \
+            nearest = key < nearest ? key : nearest;                                                                      \
+        }                                                                                                                 \
+    }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -336,22 +367,9 @@ HM_HD unsigned wide_node_hits(F4 w0, F4 w2, F4 w3, F4 w4, const WideRay& r, floa
         const unsigned nx = px ? lox[h] : hix[h], fx = px ? hix[h] : lox[h];
         const unsigned ny = py ? loy[h] : hiy[h], fy = py ? hiy[h] : loy[h];
         const unsigned nz = pz ? loz[h] : hiz[h], fz = pz ? hiz[h] : loz[h];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int k = 0; k < 4; ++k) {
-            const float tnx = fmaf(byte_biased(nx, k), ax, bx), tfx = fmaf(byte_biased(fx, k), ax, bx);
-            const float tny = fmaf(byte_biased(ny, k), ay, by), tfy = fmaf(byte_biased(fy, k), ay, by);
-            const float tnz = fmaf(byte_biased(nz, k), az, bz), tfz = fmaf(byte_biased(fz, k), az, bz);
-            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
-            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-            if (tn <= tf) {
-                hits |= 1u << (4 * h + k);
-                const unsigned key = (f_as_u(tn) & ~7u) | (unsigned)(4 * h + k);
-                nearest = key < nearest ? key : nearest;
-            }
-        }
+        HM_WIDE_CHILD(0) HM_WIDE_CHILD(1) HM_WIDE_CHILD(2) HM_WIDE_CHILD(3)
     }
+#undef HM_WIDE_CHILD
     if (near_key) *near_key = nearest;
     return hits;
 }

@@ -45,6 +45,7 @@ DeviceScene::DeviceScene(const HostScene& hs) {
     view.geom.wnodes = upload(b.wnodes.data(), b.wnodes.size());
     view.geom.wleaf_data = upload(b.wleaf_data.data(), b.wleaf_data.size());
     view.geom.num_wnodes = (int)(b.wnodes.size() / 5);
+    view.geom.k47 = 0x47000000u;
     view.geom.leaf_code = nullptr;   // host-side only
     view.geom.leaf_prim = nullptr;
     view.geom.cps = upload(g.cps.data(), g.cps.size());

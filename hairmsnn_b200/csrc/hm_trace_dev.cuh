@@ -204,7 +204,7 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
                     if (stats) stats[any ? 1 : 0].nodes++;
                     const unsigned imask = f_as_u(w0.w) >> 24, lmask = f_as_u(w1.z) & 0xffu;
                     unsigned near_key;
-                    const unsigned h = wide_node_hits(w0, w2, w3, w4, wr, tmin, best.t, &near_key);
+                    const unsigned h = wide_node_hits(w0, w2, w3, w4, wr, tmin, best.t, &near_key, g.k47);
                     // The child with the smallest entry distance goes first (an inner one is the next node, a leaf
                     // is parked last = popped first); the others keep the octant order.  On the host build of the
                     // same tree this order alone cuts closest-hit node visits by 15 % and primitive tests by 16 %
