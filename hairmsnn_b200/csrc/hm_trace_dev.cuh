@@ -62,8 +62,16 @@ constexpr int kRefillLanes = HM_TRACE_REFILL;    // refill when this many lanes 
 #define HM_TRACE_PREFETCH 0        // 1: prefetch parked primitives and pushed far children into L2/L1
 #endif
 __device__ __forceinline__ void prefetch_line(const void* p) {
-#if HM_TRACE_PREFETCH
+#if HM_TRACE_PREFETCH == 1
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
+// HM_TRACE_PREFETCH == 2: the first two 128-byte lines of a pushed group's child nodes, into L2 (they are visited a few
+// steps later, if at all)
+__device__ __forceinline__ void prefetch_group(const void* p) {
+#if HM_TRACE_PREFETCH == 2
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)p + 128));
 #endif
 }
 
@@ -229,6 +237,7 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
                         if (g_bits >> 8) stack[sp++] = make_int2(g_base, (int)g_bits);
                         g_base = f_as_i(w1.x);
                         g_bits = imask | (xor_permute8(hi, wr.octinv) << 8);
+                        prefetch_group(g.wnodes + 5 * (size_t)g_base);
                     }
                 }
             }
