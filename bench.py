@@ -564,6 +564,7 @@ def main():
     ap.add_argument("--no-others", action="store_true", help="skip the brief pt / nrc / msnn_b10 measurements of the default run")
     ap.add_argument("--no-gate", action="store_true", help="skip the image gate of the default run")
     ap.add_argument("--gate-spp", type=int, default=500)
+    ap.add_argument("--beta-sweep", default="", help="comma-separated BETA values measured after the main run (render_hair_msnn workloads; BASELINE config 5)")
     ap.add_argument("--size", type=int, default=0, help="override the frame size of the workload (testing the band path on fewer GPUs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -635,6 +636,21 @@ def main():
         res["e2e"]["value"] /= world
     if comm:
         r.reduce_framebuffers()     # the job's one framebuffer reduction (not part of a step)
+    sweep = None
+    if args.beta_sweep and kind == "msnn":
+        # BASELINE config 5: the same frame at other BETA values (every rank takes part: the steps hold collectives)
+        sweep = {}
+        r.close()
+        for b in [int(x) for x in args.beta_sweep.split(",") if x]:
+            rb = api.Renderer(sc, KIND[kind], beta_cli=b, device=local_rank, rank=rank if bands else 0, world=world if bands else 1)
+            if comm:
+                rb.set_comm(comm)
+            m = measure(rb, api, torch, local_rank, comm, W, H, args.steps, args.warmup, peaks, kind, want_e2e=False)
+            rb.close()
+            v = m["value"] / world if bands else m["value"]
+            sweep[str(b)] = {"value": v, "unit": "Mpaths/s", "ms_per_step": m["ms"] / args.steps, "rays_per_step": m["rays_per_step"]}
+            if rank == 0:
+                log(f"[beta sweep] BETA={b}: {v:.1f} Mpaths/s")
     if rank != 0:
         r.close()
         comm.barrier()
@@ -671,7 +687,7 @@ def main():
             "stage_ms_per_step": res["stage_ms_per_step"], "training_loss": res["loss"],
             "collectives": ("ncclAllReduce of 1000448 fp32 gradients per training step inside hm_render_frames (libhairmsnn.so); "
                             "bench.py issues none") if world > 1 else None,
-            "image_gate": gate, "other_workloads": others}
+            "image_gate": gate, "other_workloads": others, "beta_sweep": sweep}
     emit(json.dumps(line))
     if comm:
         comm.barrier()
