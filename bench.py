@@ -339,6 +339,7 @@ def measure(r, api, torch, local_rank, comm, W, H, steps, warmup, peaks, kind, w
     ev0.record(stream)
     for _ in range(steps):
         step()
+    r.flush()            # the last frames' merged tail piece + order-stream work (held back until their group is full)
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)

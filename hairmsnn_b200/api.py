@@ -83,7 +83,7 @@ lib.hm_renderer_mlp.restype = C.c_void_p
 lib.hm_mlp_stream.restype = C.c_void_p
 lib.hm_mlp_n_params.restype = C.c_size_t
 lib.hm_mlp_launch_count.restype = C.c_uint64
-for _name in ("hm_renderer_stream", "hm_renderer_mlp", "hm_renderer_destroy", "hm_render_frames", "hm_render_frames_async",
+for _name in ("hm_renderer_stream", "hm_renderer_mlp", "hm_renderer_destroy", "hm_render_frames", "hm_render_frames_async", "hm_render_flush",
               "hm_renderer_sync", "hm_renderer_reset_accumulation", "hm_renderer_accum_id", "hm_msnn_trace",
               "hm_msnn_train_backward", "hm_msnn_train_apply", "hm_msnn_finish", "hm_nrc_trace", "hm_nrc_query",
               "hm_nrc_train_backward", "hm_nrc_train_apply", "hm_nrc_end", "hm_mlp_stream", "hm_mlp_n_params",
@@ -445,6 +445,10 @@ class Renderer:
 
     def render_frames_async(self, n=1):
         _check(lib.hm_render_frames_async(self._h, n))
+
+    def flush(self):
+        """Enqueue whatever render_frames_async() held back (merged tail pieces), without waiting."""
+        _check(lib.hm_render_flush(self._h))
 
     def sync(self):
         _check(lib.hm_renderer_sync(self._h))

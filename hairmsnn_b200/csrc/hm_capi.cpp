@@ -29,7 +29,9 @@ struct hm_mlp {
     Mlp* m = nullptr;
     cudaStream_t stream = nullptr;
     int device = 0;
+    Renderer* owner = nullptr;   // a renderer's network: calls on it come after the frames the renderer holds back
 };
+static void flush_owner(hm_mlp* m) { if (m && m->owner) m->owner->flush(); }
 struct hm_comm {
     std::unique_ptr<hm::Comm> c;
 };
@@ -259,6 +261,7 @@ int hm_renderer_create(hm_scene* s, int kind, int beta_cli, int device, int rank
         h->r.reset(new Renderer(s->hs, kind, beta_cli, device, rank, world));
         h->mlp_view.m = h->r->mlp();
         h->mlp_view.stream = h->r->stream();
+        h->mlp_view.owner = h->r.get();
         h->mlp_view.device = device;
         // tcnn.init_weights (scene.cpp:318-322; loaded right after the TINY_MLP ctor, render_nrc.cu:148-150)
         if (h->r->mlp() && !s->hs.tcnn_weights.empty())
@@ -273,6 +276,9 @@ int hm_render_frames(hm_renderer* r, int n) {
 }
 int hm_render_frames_async(hm_renderer* r, int n) {
     return guarded([&] { need(r, "renderer"); r->r->render_frames(n); });
+}
+int hm_render_flush(hm_renderer* r) {
+    return guarded([&] { need(r, "renderer"); r->r->flush(); });
 }
 int hm_renderer_sync(hm_renderer* r) {
     return guarded([&] { need(r, "renderer"); r->r->sync(); });
@@ -657,11 +663,11 @@ static void check_batch(int n) {
 }
 
 int hm_mlp_inference(hm_mlp* m, const float* d_in, float* d_out, int n) {
-    return guarded([&] { need(m, "mlp"); need(d_in, "d_in"); need(d_out, "d_out"); check_batch(n); m->m->inference(d_in, d_out, n); });
+    return guarded([&] { need(m, "mlp"); flush_owner(m); need(d_in, "d_in"); need(d_out, "d_out"); check_batch(n); m->m->inference(d_in, d_out, n); });
 }
 int hm_mlp_inference_host(hm_mlp* m, const float* in, float* out, int n) {
     return guarded([&] {
-        need(m, "mlp"); need(in, "in"); need(out, "out"); check_batch(n);
+        need(m, "mlp"); flush_owner(m); need(in, "in"); need(out, "out"); check_batch(n);
         cuda_ok(cudaSetDevice(m->device), "set device");
         const int ic = m->m->config().in_ch, oc = m->m->config().out_ch;
         float *d_i = nullptr, *d_o = nullptr;
@@ -676,18 +682,18 @@ int hm_mlp_inference_host(hm_mlp* m, const float* in, float* out, int n) {
 }
 int hm_mlp_forward_backward(hm_mlp* m, const float* d_in, const float* d_target, int n, int n_total) {
     return guarded([&] {
-        need(m, "mlp"); need(d_in, "d_in"); need(d_target, "d_target"); check_batch(n);
+        need(m, "mlp"); flush_owner(m); need(d_in, "d_in"); need(d_target, "d_target"); check_batch(n);
         m->m->forward_backward(d_in, d_target, n, n_total > 0 ? n_total : n);
     });
 }
 int hm_mlp_gradients(hm_mlp* m, float** d_grads, size_t* count) {
-    return guarded([&] { need(m, "mlp"); need(d_grads, "d_grads"); need(count, "count"); *d_grads = m->m->gradients(); *count = m->m->n_params(); });
+    return guarded([&] { need(m, "mlp"); flush_owner(m); need(d_grads, "d_grads"); need(count, "count"); *d_grads = m->m->gradients(); *count = m->m->n_params(); });
 }
-int hm_mlp_optimizer_step(hm_mlp* m) { return guarded([&] { need(m, "mlp"); m->m->optimizer_step(); }); }
-int hm_mlp_loss(hm_mlp* m, float* loss) { return guarded([&] { need(m, "mlp"); need(loss, "loss"); *loss = m->m->loss(); }); }
+int hm_mlp_optimizer_step(hm_mlp* m) { return guarded([&] { need(m, "mlp"); flush_owner(m); m->m->optimizer_step(); }); }
+int hm_mlp_loss(hm_mlp* m, float* loss) { return guarded([&] { need(m, "mlp"); flush_owner(m); need(loss, "loss"); *loss = m->m->loss(); }); }
 int hm_mlp_train_step(hm_mlp* m, const float* d_in, const float* d_target, int n, float* loss) {
     return guarded([&] {
-        need(m, "mlp"); need(d_in, "d_in"); need(d_target, "d_target"); check_batch(n);
+        need(m, "mlp"); flush_owner(m); need(d_in, "d_in"); need(d_target, "d_target"); check_batch(n);
         m->m->forward_backward(d_in, d_target, n, n);
         m->m->optimizer_step();
         if (loss) *loss = m->m->loss();
@@ -695,7 +701,7 @@ int hm_mlp_train_step(hm_mlp* m, const float* d_in, const float* d_target, int n
 }
 int hm_mlp_train_step_host(hm_mlp* m, const float* in, const float* target, int n, float* loss) {
     return guarded([&] {
-        need(m, "mlp"); need(in, "in"); need(target, "target"); check_batch(n);
+        need(m, "mlp"); flush_owner(m); need(in, "in"); need(target, "target"); check_batch(n);
         cuda_ok(cudaSetDevice(m->device), "set device");
         const int ic = m->m->config().in_ch, oc = m->m->config().out_ch;
         float *d_i = nullptr, *d_t = nullptr;
@@ -710,18 +716,18 @@ int hm_mlp_train_step_host(hm_mlp* m, const float* in, const float* target, int 
         cudaFree(d_i); cudaFree(d_t);
     });
 }
-int hm_mlp_reset(hm_mlp* m) { return guarded([&] { need(m, "mlp"); m->m->reset_weights(); }); }
-int hm_mlp_reinitialize(hm_mlp* m) { return guarded([&] { need(m, "mlp"); m->m->reinitialize(); }); }
+int hm_mlp_reset(hm_mlp* m) { return guarded([&] { need(m, "mlp"); flush_owner(m); m->m->reset_weights(); }); }
+int hm_mlp_reinitialize(hm_mlp* m) { return guarded([&] { need(m, "mlp"); flush_owner(m); m->m->reinitialize(); }); }
 size_t hm_mlp_n_params(const hm_mlp* m) { return m ? m->m->n_params() : 0; }
 int hm_mlp_get_params(hm_mlp* m, float* dst, size_t count) {
-    return guarded([&] { need(m, "mlp"); need(dst, "host_dst"); m->m->get_params(dst, count); });
+    return guarded([&] { need(m, "mlp"); flush_owner(m); need(dst, "host_dst"); m->m->get_params(dst, count); });
 }
 int hm_mlp_set_params(hm_mlp* m, const float* src, size_t count) {
-    return guarded([&] { need(m, "mlp"); need(src, "host_src"); m->m->set_params(src, count); });
+    return guarded([&] { need(m, "mlp"); flush_owner(m); need(src, "host_src"); m->m->set_params(src, count); });
 }
 int hm_mlp_save(hm_mlp* m, const char* path) {
     return guarded([&] {
-        need(m, "mlp"); need(path, "path");
+        need(m, "mlp"); flush_owner(m); need(path, "path");
         std::vector<float> p(m->m->n_params());
         m->m->get_params(p.data(), p.size());
         std::ofstream f(path, std::ios::binary);
@@ -780,7 +786,7 @@ static void load_tcnn_snapshot(hm::Mlp& mlp, const std::string& path) {
 
 int hm_mlp_load(hm_mlp* m, const char* path) {
     return guarded([&] {
-        need(m, "mlp"); need(path, "path");
+        need(m, "mlp"); flush_owner(m); need(path, "path");
         std::ifstream f(path, std::ios::binary);
         if (!f) throw hm::IoError(std::string("cannot read ") + path);
         char magic[8]; uint64_t n = 0;
@@ -802,7 +808,7 @@ int hm_mlp_load(hm_mlp* m, const char* path) {
 // Trainer::serialize (trainer.h:270-283) as text JSON, params_type "float"
 int hm_mlp_save_snapshot(hm_mlp* m, const char* path) {
     return guarded([&] {
-        need(m, "mlp"); need(path, "path");
+        need(m, "mlp"); flush_owner(m); need(path, "path");
         std::vector<float> p(m->m->n_params());
         m->m->get_params(p.data(), p.size());
         std::ofstream f(path, std::ios::binary);

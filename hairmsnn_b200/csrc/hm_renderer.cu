@@ -173,6 +173,16 @@ Renderer::Renderer(const HostScene& hs, int kind, int beta_cli, int device, int 
     if (const char* e = getenv("HM_TAIL_MEGA")) tail_mega_ = atoi(e) != 0;
     if (const char* e = getenv("HM_TAIL_BOUND")) tail_bound_items_ = atoi(e);
     if (const char* e = getenv("HM_FRAMES_IN_FLIGHT")) frames_in_flight_ = std::max(1, std::min((int)kFramesInFlight, atoi(e)));
+    if (kind_ == HM_KIND_MSNN) {
+        tail_group_ = 4;
+        if (const char* e = getenv("HM_TAIL_GROUP")) tail_group_ = std::max(1, std::min((int)kTailGroupMax, atoi(e)));
+        if (tail_mega_) tail_group_ = 1;
+        if (tail_group_ > 1) {
+            // a group being filled + two groups' tails and order-stream work in flight, unless told otherwise
+            if (!getenv("HM_FRAMES_IN_FLIGHT")) frames_in_flight_ = std::min((int)kFramesInFlight, 3 * tail_group_);
+            frames_in_flight_ = std::max(tail_group_, frames_in_flight_ / tail_group_ * tail_group_);
+        }
+    }
     // Per-pixel state is allocated for this rank's row band only.  Slots stay FULL-frame pixel indices (RNG keys,
     // training-pixel rule), so each array's base pointer is moved back by the band's first pixel:
     // kernels index it with the global slot and touch [first, first + nb) only.
@@ -184,22 +194,45 @@ Renderer::Renderer(const HostScene& hs, int kind, int beta_cli, int device, int 
     // smaller than the record count still allocates that many elements
     const size_t n_alloc = kind_ == HM_KIND_MSNN ? std::max(nb, (size_t)(128 * 128)) : nb;
     auto alloc_px = [&](size_t bytes_per_px) { return (char*)alloc(n_alloc * bytes_per_px) - first * bytes_per_px; };
+    // Path state the tail kernels touch: the contexts of one tail group are slices, n_alloc elements apart, of one
+    // block per array, so a merged tail addresses frame k's slot s as element s + k * n_alloc of frame 0's arrays.
+    std::vector<char*> group_blocks;
+    size_t group_next = 0;
+    auto alloc_state = [&](int ci, size_t bytes_per_px) {
+        const int K = tail_group_;
+        if (K == 1) return alloc_px(bytes_per_px);
+        if (ci % K == 0) group_blocks.push_back((char*)alloc((size_t)K * n_alloc * bytes_per_px));
+        char* base = group_blocks[group_next++];
+        return base + (size_t)(ci % K) * n_alloc * bytes_per_px - first * bytes_per_px;
+    };
     for (int ci = 0; ci < frames_in_flight_; ++ci) {
         FrameCtx& c = ctx_[ci];
-        c.paths.rng = (uint32_t*)alloc_px(4);
-        c.paths.ray_o = (float4*)alloc_px(16);
-        c.paths.ray_d = (float4*)alloc_px(16);
-        c.paths.hit = (float4*)alloc_px(16);
-        c.paths.beta = (float4*)alloc_px(16);
-        c.paths.color = (float4*)alloc_px(16);
-        c.paths.dl_beta = (float4*)alloc_px(16);
-        c.paths.dl_light = (float4*)alloc_px(16);
-        c.paths.dl_bsdf = (float4*)alloc_px(16);
-        c.paths.vis = (uint32_t*)alloc_px(4);
+        if (ci % tail_group_ == 0) group_blocks.clear();
+        group_next = 0;
+        c.paths.rng = (uint32_t*)alloc_state(ci, 4);
+        c.paths.ray_o = (float4*)alloc_state(ci, 16);
+        c.paths.ray_d = (float4*)alloc_state(ci, 16);
+        c.paths.hit = (float4*)alloc_state(ci, 16);
+        c.paths.beta = (float4*)alloc_state(ci, 16);
+        c.paths.color = (float4*)alloc_state(ci, 16);
+        c.paths.dl_beta = (float4*)alloc_state(ci, 16);
+        c.paths.dl_light = (float4*)alloc_state(ci, 16);
+        c.paths.dl_bsdf = (float4*)alloc_state(ci, 16);
+        c.paths.vis = (uint32_t*)alloc_state(ci, 4);
         if (kind_ == HM_KIND_MSNN) {
-            c.paths.beta_short = (float4*)alloc_px(16);
-            c.paths.color_short = (float4*)alloc_px(16);
-            c.paths.dl_beta_short = (float4*)alloc_px(16);
+            c.paths.beta_short = (float4*)alloc_state(ci, 16);
+            c.paths.color_short = (float4*)alloc_state(ci, 16);
+            c.paths.dl_beta_short = (float4*)alloc_state(ci, 16);
+            if (tail_group_ > 1 && ci % tail_group_ == 0) {
+                Queues& gq = group_q_[ci / tail_group_];
+                const size_t cap = (size_t)tail_group_ * records_;   // a frame has at most `records` training paths
+                gq.shade[0] = (int*)alloc(cap * 4);
+                gq.shade[1] = (int*)alloc(cap * 4);
+                gq.extend = (int*)alloc(cap * 4);
+                gq.shadow = (float4*)alloc(cap * 2 * 32);
+                gq.counts = (int*)alloc(16 * 4);
+                gq.trav = d_trav_;
+            }
             c.train_idxs = (int*)alloc((size_t)records_ * 4);
             c.nn_frame_in = (float*)alloc_px((size_t)in_ch_ * 4);
             c.nn_train_in = (float*)alloc((size_t)records_ * in_ch_ * 4);
@@ -296,6 +329,7 @@ void Renderer::set_sampling(bool mis, bool env_pdf) {
 
 void Renderer::sync() {
     HM_CUDA(cudaSetDevice(device_));
+    flush_deferred();
     HM_CUDA(cudaStreamSynchronize(main_stream_));
     for (int i = 0; i < n_work_; ++i) if (work_streams_[i]) HM_CUDA(cudaStreamSynchronize(work_streams_[i]));
     for (FrameCtx& c : ctx_) if (c.tail_stream) HM_CUDA(cudaStreamSynchronize(c.tail_stream));
@@ -436,10 +470,10 @@ FrameCtx& Renderer::begin_frame(bool pretrain) {
 }
 
 // Wavefront loop: primary, then (shade -> shadow + extend) per path vertex.  The first
-// `main_vertices` vertices run on the main stream, the rest on the frame's tail stream.
+// `main_vertices` vertices run on the main stream (trace_main), the rest on a tail stream (trace_tail).
 // No host synchronisation: every stage reads its queue length from device memory, and the
 // tail always issues the full vertex budget (empty launches cost a few microseconds).
-void Renderer::trace_frame(FrameCtx& c) {
+void Renderer::trace_main(FrameCtx& c) {
     if ((kind_ == HM_KIND_MSNN || kind_ == HM_KIND_NRC) && !c.pretrain) shuffle_train_idxs(c);
     FrameParams P = params_for(c);
     int max_vertices = P.v2_stop + 1;   // the primary hit plus up to v2_stop bounces
@@ -461,34 +495,80 @@ void Renderer::trace_frame(FrameCtx& c) {
     if (c.query_tiles && !c.pretrain) HM_CUDA(cudaMemsetAsync(c.query_tiles, 0, ((size_t)W_ * H_ / 128 + 1) * 4, s));
     timed(0, s, [&] { launch_primary(P, s); });
     int src = 0;
-    // HairMSNN: past the main piece only training paths are alive (16384 at most; all records in a pre-training pass)
-    long long tail_bound = 0;
-    for (int vertex = 0; vertex < max_vertices; ++vertex) {
-        if (vertex == main_vertices) {
-            HM_CUDA(cudaEventRecord(c.ev_main_done, c.main));
-            s = c.tail_stream;
-            HM_CUDA(cudaStreamWaitEvent(s, c.ev_main_done, 0));
-            P.tail = 1;
-            if (kind_ == HM_KIND_MSNN) tail_bound = tail_bound_items_ > 0 ? tail_bound_items_ : records_;
-            if (kind_ == HM_KIND_MSNN && tail_mega_) {
-                // HM_TAIL_MEGA=1: the whole tail piece in one launch (k_tail_mega) instead of a launch pair per vertex.
-                // Measured equal on B200 (profiles/r1k_sweep_tail_mega.txt: 202-205 Mpaths/s either way, 245 instead of
-                // 320 launches per frame), so the launch-pair form every parity test was written against stays the default.
-                timed(3, s, [&] { launch_tail_mega(P, src, records_, s); });
-                break;
-            }
-        }
-        timed(P.tail ? 3 : 1, s, [&] { launch_shade(P, src, s, tail_bound); });   // stage 1: main piece, stage 3: tail piece
+    for (int vertex = 0; vertex < main_vertices; ++vertex) {
+        timed(1, s, [&] { launch_shade(P, src, s, 0); });
         const int dst = src ^ 1;
         HM_CUDA(cudaMemsetAsync(c.q.counts + dst, 0, 4, s));
-        timed(P.tail ? 3 : 2, s, [&] { launch_trace(P, dst, s, tail_bound); });   // stage 2: main piece, stage 3: tail piece
+        timed(2, s, [&] { launch_trace(P, dst, s, 0); });
         HM_CUDA(cudaMemsetAsync(c.q.counts + 2, 0, 16, s));   // extend + shadow counters and their work cursors
         src = dst;
     }
-    if (kind_ != HM_KIND_PT) timed(4, s, [&] { launch_finalize(P, s); });   // frame-local outputs only
-    HM_CUDA(cudaEventRecord(c.ev_traced, s));
-    HM_CUDA(cudaStreamWaitEvent(order_stream_, c.ev_traced, 0));
-    last_ctx_ = &c;
+    c.mp_src = src; c.mp_vertex = main_vertices; c.mp_max = max_vertices;
+    if (main_vertices < max_vertices) HM_CUDA(cudaEventRecord(c.ev_main_done, c.main));
+}
+
+// Tail piece of m frames whose main pieces stopped at the same vertex (m > 1: HairMSNN frames of one tail group,
+// consecutive contexts): the remaining vertices, then each frame's finalize pass; the order stream waits for it.
+void Renderer::trace_tail(FrameCtx* const* cs, int m) {
+    FrameCtx& c0 = *cs[0];
+    cudaStream_t s = c0.main;
+    FrameParams P = params_for(c0);
+    int src = c0.mp_src;
+    const bool has_tail = c0.mp_vertex < c0.mp_max;
+    if (has_tail) {
+        // a merged tail runs on its group's stream: the group's queues have one user at a time
+        s = m > 1 ? ctx_[(int)(cs[0] - ctx_) / tail_group_ * tail_group_].tail_stream : c0.tail_stream;
+        for (int k = 0; k < m; ++k) HM_CUDA(cudaStreamWaitEvent(s, cs[k]->ev_main_done, 0));
+        P.tail = 1;
+        // HairMSNN: past the main piece only training paths are alive (16384 per frame at most; all records in a pre-training pass)
+        long long tail_bound = 0;
+        if (kind_ == HM_KIND_MSNN) tail_bound = (tail_bound_items_ > 0 ? tail_bound_items_ : records_) * (long long)m;
+        if (m > 1) {
+            const int gi = (int)(cs[0] - ctx_) / tail_group_;
+            const size_t nb = (size_t)(row1_ - row0_) * W_;
+            TailMerge M;
+            memset(&M, 0, sizeof(M));
+            for (int k = 0; k < m; ++k) { M.counts[k] = cs[k]->q.counts; M.queue[k] = cs[k]->q.shade[src]; }
+            M.n = m; M.src = src; M.stride = (int)std::max(nb, (size_t)(128 * 128));
+            M.cap = tail_group_ * records_;
+            M.out = group_q_[gi].shade[src]; M.out_counts = group_q_[gi].counts;
+            HM_CUDA(cudaMemsetAsync(group_q_[gi].counts, 0, 16 * 4, s));
+            timed(3, s, [&] { launch_merge_tail(M, records_, s); });
+            P.q = group_q_[gi];
+            P.tail_merged = 1;
+        }
+        if (kind_ == HM_KIND_MSNN && tail_mega_ && m == 1) {
+            // HM_TAIL_MEGA=1: the whole tail piece in one launch (k_tail_mega) instead of a launch pair per vertex.
+            // Measured slower on B200 (profiles/r2k_steps_and_tail_mega.txt), so the launch-pair form stays the default.
+            timed(3, s, [&] { launch_tail_mega(P, src, records_, s); });
+        } else {
+            for (int vertex = c0.mp_vertex; vertex < c0.mp_max; ++vertex) {
+                timed(3, s, [&] { launch_shade(P, src, s, tail_bound); });
+                const int dst = src ^ 1;
+                HM_CUDA(cudaMemsetAsync(P.q.counts + dst, 0, 4, s));
+                timed(3, s, [&] { launch_trace(P, dst, s, tail_bound); });
+                HM_CUDA(cudaMemsetAsync(P.q.counts + 2, 0, 16, s));
+                src = dst;
+            }
+        }
+    }
+    for (int k = 0; k < m; ++k) {
+        FrameCtx& c = *cs[k];
+        if (!has_tail) s = c.main;
+        if (kind_ != HM_KIND_PT) {
+            FrameParams Pk = params_for(c);
+            timed(4, s, [&] { launch_finalize(Pk, s); });   // frame-local outputs only
+        }
+        HM_CUDA(cudaEventRecord(c.ev_traced, s));
+        HM_CUDA(cudaStreamWaitEvent(order_stream_, c.ev_traced, 0));
+        last_ctx_ = &c;
+    }
+}
+
+void Renderer::trace_frame(FrameCtx& c) {
+    trace_main(c);
+    FrameCtx* cs[1] = {&c};
+    trace_tail(cs, 1);
 }
 
 void Renderer::finish_pt(FrameCtx& c) {
@@ -498,6 +578,8 @@ void Renderer::finish_pt(FrameCtx& c) {
 
 void Renderer::end_frame(FrameCtx& c) {
     HM_CUDA(cudaEventRecord(c.ev_free, order_stream_));
+    // deferred frames (render_frames with tail groups) advanced the counters when their main piece was enqueued
+    if (c.counted) { c.counted = false; return; }
     accum_id_++;
     stats_.frames++;
 }
@@ -505,6 +587,7 @@ void Renderer::end_frame(FrameCtx& c) {
 void Renderer::msnn_trace() {
     if (kind_ != HM_KIND_MSNN) throw std::logic_error("not a HairMSNN renderer");
     if (current_) throw std::logic_error("msnn_trace: the previous frame was not finished (call msnn_finish)");
+    flush_deferred();
     FrameCtx& c = begin_frame();
     trace_frame(c);
     current_ = &c;
@@ -546,6 +629,7 @@ void Renderer::reduce_framebuffers() {
     if (!comm_) throw std::logic_error("reduce_framebuffers: no communicator attached (hm_renderer_set_comm)");
     if (current_) throw std::logic_error("reduce_framebuffers: a frame is in flight");
     HM_CUDA(cudaSetDevice(device_));
+    flush_deferred();
     const size_t n = (size_t)W_ * H_;
     const double total = comm_->all_reduce_sum((double)accum_id_) / world_;   // samples per pixel over all groups
     if (total <= 0) throw std::logic_error("reduce_framebuffers: nothing rendered yet");
@@ -564,6 +648,33 @@ void Renderer::msnn_train_apply() {
     if (kind_ != HM_KIND_MSNN) throw std::logic_error("not a HairMSNN renderer");
     all_reduce_gradients();
     timed(5, order_stream_, [&] { mlp_->optimizer_step(); });
+}
+
+// Everything of a traced HairMSNN frame that depends on the frames before it, in frame order on the order stream.
+void Renderer::msnn_order_work(FrameCtx& c) {
+    current_ = &c;
+    if (hs_.tcnn_train) {
+        msnn_train_backward();
+        msnn_train_apply();
+    }
+    msnn_finish();
+}
+
+// Enqueue what render_frames() held back: the merged tail of the deferred frames, then — in the order the calls were
+// made — each frame's order-stream work and the read-backs queued behind it.
+void Renderer::flush_deferred() {
+    if (deferred_.empty()) return;
+    std::vector<Deferred> ops;
+    ops.swap(deferred_);
+    deferred_frames_ = 0;
+    FrameCtx* cs[kTailGroupMax];
+    int m = 0;
+    for (const Deferred& d : ops) if (d.kind == 0) cs[m++] = d.c;
+    if (m > 0) trace_tail(cs, m);
+    for (const Deferred& d : ops) {
+        if (d.kind == 0) msnn_order_work(*d.c);
+        else HM_CUDA(cudaMemcpyAsync(d.dst, d.src, d.bytes, cudaMemcpyDeviceToHost, order_stream_));
+    }
 }
 
 void Renderer::msnn_finish() {
@@ -717,6 +828,18 @@ void Renderer::render_frames(int n) {
                 nrc_train_apply();
             }
             nrc_end();
+        } else if (tail_group_ > 1) {
+            if (current_) throw std::logic_error("render_frames: a split frame is in flight (call msnn_finish)");
+            // main piece now; tail, training step, inference and composite when the tail group is complete
+            FrameCtx& c = begin_frame();
+            trace_main(c);
+            c.counted = true;
+            accum_id_++;
+            stats_.frames++;
+            deferred_.push_back(Deferred{0, &c, nullptr, nullptr, 0});
+            deferred_frames_++;
+            const int ci = (int)(&c - ctx_);
+            if ((ci + 1) % tail_group_ == 0) flush_deferred();
         } else {
             msnn_trace();
             if (hs_.tcnn_train) {
@@ -745,6 +868,11 @@ Stats Renderer::stats() {
 }
 
 void* Renderer::device_buffer(int which, size_t* bytes) {
+    flush_deferred();   // per-frame buffers are those of the last frame enqueued in full
+    return buffer_ptr(which, bytes);
+}
+
+void* Renderer::buffer_ptr(int which, size_t* bytes) {
     const size_t n = (size_t)W_ * H_;
     const size_t nb = (size_t)(row1_ - row0_) * W_, first = (size_t)row0_ * W_;
     FrameCtx& c = *last_ctx_;
@@ -770,20 +898,30 @@ void* Renderer::device_buffer(int which, size_t* bytes) {
     }
 }
 
+// Image buffers do not belong to a frame context: a read-back asked for while frames are held back is queued
+// behind them (same stream order as an immediate copy would have had).
+static bool is_image_buffer(int which) { return which >= 0 && which <= 6; }
+
 void Renderer::readback_async(int which, void* host_dst, size_t bytes) {
+    const bool defer = is_image_buffer(which) && !deferred_.empty();
     size_t have = 0;
-    void* p = device_buffer(which, &have);
+    void* p = defer ? buffer_ptr(which, &have) : device_buffer(which, &have);
     if (!p) throw std::logic_error("buffer not available for this renderer kind");
     if (bytes > have) throw std::invalid_argument("requested more bytes than the buffer holds");
+    if (defer) { deferred_.push_back(Deferred{1, nullptr, p, host_dst, bytes}); return; }
     HM_CUDA(cudaMemcpyAsync(host_dst, p, bytes, cudaMemcpyDeviceToHost, order_stream_));
 }
 
 void Renderer::readback_rows_async(int which, int row0, int rows, void* host_dst) {
+    const bool defer = is_image_buffer(which) && !deferred_.empty();
     size_t have = 0;
-    char* p = (char*)device_buffer(which, &have);
+    char* p = (char*)(defer ? buffer_ptr(which, &have) : device_buffer(which, &have));
     if (!p) throw std::logic_error("buffer not available for this renderer kind");
     const size_t px = which == 6 ? 4 : 16;
-    HM_CUDA(cudaMemcpyAsync(host_dst, p + (size_t)row0 * W_ * px, (size_t)rows * W_ * px, cudaMemcpyDeviceToHost, order_stream_));
+    char* src = p + (size_t)row0 * W_ * px;
+    const size_t bytes = (size_t)rows * W_ * px;
+    if (defer) { deferred_.push_back(Deferred{1, nullptr, src, host_dst, bytes}); return; }
+    HM_CUDA(cudaMemcpyAsync(host_dst, src, bytes, cudaMemcpyDeviceToHost, order_stream_));
 }
 
 void Renderer::trace_rays_device(const float* d_org, const float* d_dir, int n, int any, float tmin, float tmax,

@@ -80,6 +80,9 @@ struct FrameCtx {
     cudaEvent_t ev_main_done = nullptr, ev_traced = nullptr, ev_free = nullptr, ev_shuffled = nullptr;
     int frame_id = 0, accum_id = 0;
     bool pretrain = false;            // this frame is a TRAIN_DATA_GEN pass
+    bool counted = false;             // accum_id / frame count already advanced for this frame (deferred frames)
+    // where the main piece stopped: shade queue holding the survivors, next vertex, vertex budget
+    int mp_src = 0, mp_vertex = 0, mp_max = 0;
 };
 
 // Frame scheduling.  The reference renders one frame at a time on the null stream.  Here a
@@ -97,12 +100,19 @@ class Renderer {
 public:
     static constexpr int kFramesInFlight = 24;   // contexts allocated lazily: frames_in_flight_ of them are used
     int frames_in_flight_ = 8;                   // HM_FRAMES_IN_FLIGHT overrides
+    // render_hair_msnn: the tail pieces of up to tail_group_ consecutive frames run as ONE launch sequence
+    // (HM_TAIL_GROUP overrides; 1 = a tail per frame).  Frames handed to render_frames() are enqueued up to the end
+    // of their main piece at once; their tail, training step, inference and composite are enqueued when the group
+    // is full or when anything that observes results is called (sync, read-backs of per-frame buffers, stats, ...).
+    // Read-backs of image buffers asked for in between are queued behind the frame they follow.
+    int tail_group_ = 1;
 
     Renderer(const HostScene& hs, int kind, int beta_cli, int device, int rank, int world);
     ~Renderer();
 
     void render_frames(int n);          // enqueue n frames (async)
     void sync();
+    void flush() { flush_deferred(); }  // enqueue everything render_frames() held back (no host wait)
     void reset_accumulation() { sync(); accum_id_ = 0; }
     // Live edits of the viewer's panels (render_hair_msnn.cu:780-1000 drawUI: hair colour / roughness / tilt /
     // lobe gains, environment scale and rotation, MIS and ENV_PDF switches).  The values travel in the kernel
@@ -137,6 +147,7 @@ public:
     int every_nth() const { return every_nth_; }
 
     void* device_buffer(int which, size_t* bytes);
+    void* buffer_ptr(int which, size_t* bytes);   // the same without enqueuing held-back frames first
     void trace_rays_device(const float* d_org, const float* d_dir, int n, int any, float tmin, float tmax,
                            float* d_out_hit, int* d_out_stats);
     // enqueue a device->host copy of an output buffer behind the last enqueued frame
@@ -179,6 +190,14 @@ public:
 private:
     FrameCtx& begin_frame(bool pretrain = false);
     void trace_frame(FrameCtx& c);        // main + tail pieces, ends with order_stream waiting on ev_traced
+    void trace_main(FrameCtx& c);         // main piece only (fills c.mp_*)
+    void trace_tail(FrameCtx* const* cs, int m);   // tail piece of m frames (m > 1: merged), finalize, ev_traced
+    void msnn_order_work(FrameCtx& c);    // training step, inference, composite of one traced frame (order stream)
+    void flush_deferred();
+    struct Deferred { int kind; FrameCtx* c; void* src; void* dst; size_t bytes; };   // kind 0: frame, 1: read-back
+    std::vector<Deferred> deferred_;
+    int deferred_frames_ = 0;
+    Queues group_q_[kFramesInFlight] = {};   // merged-tail queues, one per tail group of contexts
     void finish_pt(FrameCtx& c);
     void end_frame(FrameCtx& c);
     FrameParams params_for(const FrameCtx& c);

@@ -215,7 +215,9 @@ __device__ __forceinline__ void shade_item(const FrameParams& P, int slot, Direc
     bool training = false;
     V3 beta_short(1.f), color_short(0.f);
     if (P.mode == MODE_MSNN) {
-        training = is_training_pixel(P, slot, tr_ofs);
+        // merged tail pieces: only training paths outlive the main piece (bounces > beta ends the others), and
+        // nothing past the first vertex needs the record index
+        training = P.tail_merged ? true : is_training_pixel(P, slot, tr_ofs);
         if (training) {
             beta_short = v3(P.paths.beta_short[slot]);
             color_short = v3(P.paths.color_short[slot]);
@@ -894,6 +896,23 @@ void launch_shade(const FrameParams& P, int src, cudaStream_t stream, long long 
 void launch_trace(const FrameParams& P, int dst, cudaStream_t stream, long long max_items) {
     // a vertex pushes at most 3 rays (2 probes + 1 continuation); 2 x 32 rays per warp keeps the refill loop busy
     k_trace<<<bounded_grid(persistent_grid(kTraceCtasPerSm), 3 * max_items, 2 * kBlock), kBlock, 0, stream>>>(P, dst);
+    g_launches++;
+}
+__global__ void __launch_bounds__(256) k_merge_tail(const TailMerge M) {
+    const int k = blockIdx.y;
+    int ofs = 0;
+    for (int j = 0; j < k; ++j) ofs += M.counts[j][M.src];
+    int nk = M.counts[k][M.src];
+    if (ofs + nk > M.cap) nk = M.cap > ofs ? M.cap - ofs : 0;   // cannot happen: a frame has at most `records` training paths
+    const int* q = M.queue[k];
+    const int shift = k * M.stride;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nk; i += gridDim.x * blockDim.x) M.out[ofs + i] = q[i] + shift;
+    if (k == M.n - 1 && blockIdx.x == 0 && threadIdx.x == 0) M.out_counts[M.src] = ofs + nk;
+}
+void launch_merge_tail(const TailMerge& M, int max_items_per_frame, cudaStream_t stream) {
+    int gx = (max_items_per_frame + 255) / 256;
+    if (gx < 1) gx = 1;
+    k_merge_tail<<<dim3(gx, M.n), 256, 0, stream>>>(M);
     g_launches++;
 }
 #ifndef HM_TAIL_CTAS

@@ -80,6 +80,8 @@ struct FrameParams {
     int frame_id;        // sample index that keys the RNG streams (== accum_id unless spp-sharded)
     int collect_stats;   // accumulate nodes/prims visited into q.trav
     int tail;            // this launch belongs to the frame's tail piece (long paths only): separate counters
+    int tail_merged;     // tail piece of SEVERAL HairMSNN frames in one launch sequence (launch_merge_tail): slots run over the
+                         // frames' consecutive path-state arrays; every live path is a training path (no per-frame lookups)
     int n_primary;       // primary work items (rows * W; numTrainRecords in the TRAIN_DATA_GEN pass)
     // HairMSNN TRAIN_DATA_GEN pass (cuda/hair_msnn.cu:222-233): work item i is training record i, its
     // ray runs from the camera position to sampled_points[scene_indices[i]]
@@ -137,6 +139,18 @@ void launch_primary(const FrameParams& P, cudaStream_t stream);
 void launch_shade(const FrameParams& P, int src_queue, cudaStream_t stream, long long max_items = 0);
 // occlusion probes + continuation rays of one vertex in one launch
 void launch_trace(const FrameParams& P, int dst_queue, cudaStream_t stream, long long max_items = 0);
+// render_hair_msnn, tail pieces of n consecutive frames as one: the survivors of the frames' main pieces (shade queue
+// `src` of each) are concatenated into the group's queue `out`, frame k's slots moved up by k * stride — the frames'
+// path-state arrays lie `stride` elements apart, so the tail kernels address all of them from frame 0's pointers.
+constexpr int kTailGroupMax = 8;
+struct TailMerge {
+    const int* counts[kTailGroupMax];
+    const int* queue[kTailGroupMax];
+    int n, src, stride, cap;
+    int* out;
+    int* out_counts;
+};
+void launch_merge_tail(const TailMerge& M, int max_items_per_frame, cudaStream_t stream);
 // render_hair_msnn: all remaining vertices of the paths in shade queue `src_queue` in one launch;
 // max_paths bounds the queue length (training paths only)
 void launch_tail_mega(const FrameParams& P, int src_queue, int max_paths, cudaStream_t stream);

@@ -163,8 +163,18 @@ void hm_renderer_destroy(hm_renderer* r);
 /* n calls of RenderWindow*::render() (render_path_tracing.cu:404-423,
  * render_hair_msnn.cu:699-771): one sample per pixel each, accumId advances. */
 int hm_render_frames(hm_renderer* r, int n_frames);
-/* same, but returns after enqueueing on the renderer's stream */
+/* same, but returns after enqueueing on the renderer's stream.
+ * render_hair_msnn renderers run the tail pieces (the long training paths) of up to 4 consecutive frames as one
+ * launch sequence: a frame's main piece is enqueued by this call, its tail, training step, inference and composite
+ * when its group of frames is complete or when a call that observes results is made (hm_renderer_sync, hm_render_frames,
+ * hm_get_buffer, hm_get_device_buffer, hm_renderer_get_stats, hm_reduce_framebuffers, hm_renderer_mlp, the split-frame
+ * and live-edit calls ...).
+ * hm_readback_async / hm_readback_rows_async of the image buffers issued in between are queued behind the frame they
+ * follow, so a per-frame read-back keeps its place in the stream order without breaking the group.  Results are
+ * bit-identical to frame-at-a-time execution.  hm_render_flush enqueues whatever is held back without waiting
+ * (call it before recording an event on hm_renderer_stream that is meant to follow the frames). */
 int hm_render_frames_async(hm_renderer* r, int n_frames);
+int hm_render_flush(hm_renderer* r);
 int hm_renderer_sync(hm_renderer* r);
 /* restart accumulation (cameraChanged(): accumId = 0) */
 int hm_renderer_reset_accumulation(hm_renderer* r);
