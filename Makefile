@@ -7,6 +7,12 @@ LIB ?= hairmsnn_b200/lib/libhairmsnn.so
 ARCH := -gencode arch=compute_100a,code=sm_100a
 # -fmad=false: the traversal/intersection code must round like its host build (hit-id parity)
 NVFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC,-O3,-ffp-contract=off -fmad=false --expt-relaxed-constexpr -Xptxas -v $(EXTRA)
+# Shading kernels (their own translation unit).  `make SHADE_APPROX=1` builds them with approximate division / square
+# root: +4.2 % Mpaths/s on the bench scene, every tolerance of the north star still met, but 2-ulp quotients flip more
+# of the paths' discrete choices against the reference's host build (deep-path agreement on real hair 0.91 -> 0.88,
+# NRC training records 0.95 -> 0.92; profiles/r2x_*).  Default: IEEE.
+SHADE_APPROX ?= 0
+NVFLAGS_SHADE := $(NVFLAGS) $(if $(filter 1,$(SHADE_APPROX)),-prec-div=false -prec-sqrt=false,)
 NVFLAGS_MLP := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC,-O3 --expt-relaxed-constexpr -Xptxas -v
 CXXFLAGS := -O2 -std=c++17 -fPIC -ffp-contract=off -mfma -pthread -I/usr/local/cuda/include
 # NCCL: the copy bundled with the image's PyTorch (2.28.9) when present, so a process that also imports torch
@@ -14,8 +20,8 @@ CXXFLAGS := -O2 -std=c++17 -fPIC -ffp-contract=off -mfma -pthread -I/usr/local/c
 NCCL_HOME ?= $(firstword $(wildcard /opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/nccl) /usr)
 NCCL_INC := $(if $(filter /usr,$(NCCL_HOME)),,-I$(NCCL_HOME)/include)
 NCCL_LIB := $(if $(filter /usr,$(NCCL_HOME)),-lnccl,-L$(NCCL_HOME)/lib -l:libnccl.so.2 -Xlinker -rpath,$(NCCL_HOME)/lib)
-OBJ := $(BUILD)/hm_wavefront.o $(BUILD)/hm_renderer.o $(BUILD)/hm_mlp.o $(BUILD)/hm_capi.o $(BUILD)/hm_io.o $(BUILD)/hm_piz.o $(BUILD)/hm_scene_util.o $(BUILD)/hm_bvh_build.o $(BUILD)/hm_comm.o
-HDRS := $(wildcard $(CSRC)/*.h) include/hairmsnn.h
+OBJ := $(BUILD)/hm_wavefront.o $(BUILD)/hm_shade_kernels.o $(BUILD)/hm_renderer.o $(BUILD)/hm_mlp.o $(BUILD)/hm_capi.o $(BUILD)/hm_io.o $(BUILD)/hm_piz.o $(BUILD)/hm_scene_util.o $(BUILD)/hm_bvh_build.o $(BUILD)/hm_comm.o
+HDRS := $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh) include/hairmsnn.h
 
 all: $(LIB) bin
 lib: $(LIB)
@@ -23,6 +29,9 @@ lib: $(LIB)
 $(BUILD)/hm_wavefront.o: $(CSRC)/hm_wavefront.cu $(HDRS)
 	@mkdir -p $(BUILD)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(BUILD)/hm_wavefront.ptxas.log || (cat $(BUILD)/hm_wavefront.ptxas.log; false)
+$(BUILD)/hm_shade_kernels.o: $(CSRC)/hm_shade_kernels.cu $(HDRS)
+	@mkdir -p $(BUILD)
+	$(NVCC) $(NVFLAGS_SHADE) -c $< -o $@ 2> $(BUILD)/hm_shade_kernels.ptxas.log || (cat $(BUILD)/hm_shade_kernels.ptxas.log; false)
 $(BUILD)/hm_renderer.o: $(CSRC)/hm_renderer.cu $(HDRS)
 	@mkdir -p $(BUILD)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(BUILD)/hm_renderer.ptxas.log || (cat $(BUILD)/hm_renderer.ptxas.log; false)

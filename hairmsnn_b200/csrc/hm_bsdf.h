@@ -122,8 +122,8 @@ HM_HD float log_bessel_i0(float x) {
 static HM_HD_OUTLINE float longitudinal(const HairLobes& L, int k, float cos_i, float cos_o, float sin_i, float sin_o) {
     // a and b stay true quotients: for small v they reach several hundred and sit inside an exponential, where one ulp
     // of them is 1e-4 of the result
-    float a = cos_i * cos_o / L.v[k];
-    float b = sin_i * sin_o / L.v[k];
+    float a = div_exact(cos_i * cos_o, L.v[k]);
+    float b = div_exact(sin_i * sin_o, L.v[k]);
     if (L.v[k] <= 0.1f)
         return expf(log_bessel_i0(a) - b - L.inv_v[k] + 0.6931f + L.mp_log_term[k]);
     return (expf(-b) * bessel_i0(a)) * L.mp_inv_den[k];

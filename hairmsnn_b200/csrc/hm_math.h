@@ -74,6 +74,14 @@ HM_HD V4 operator*(V4 a, float s) { return V4(a.x * s, a.y * s, a.z * s, a.w * s
 HM_HD V4 operator/(V4 a, float s) { return V4(a.x / s, a.y / s, a.z / s, a.w / s); }
 
 HM_HD float sqr(float v) { return v * v; }
+// IEEE quotient whatever the translation unit's -prec-div setting (hm_shade_kernels.cu is built with approximate division)
+HM_HD float div_exact(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
 HM_HD float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 HM_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 HM_HD float safe_sqrt(float v) { return sqrtf(fmaxf(0.f, v)); }

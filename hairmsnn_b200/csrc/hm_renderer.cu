@@ -170,13 +170,11 @@ Renderer::Renderer(const HostScene& hs, int kind, int beta_cli, int device, int 
         if (n % 128) throw std::invalid_argument("render_nrc needs W*H to be a multiple of 128 (scene.cpp:302-306)");
         nn_frame_rows_ = nl.nn_frame_rows;
     }
-    if (const char* e = getenv("HM_TAIL_MEGA")) tail_mega_ = atoi(e) != 0;
     if (const char* e = getenv("HM_TAIL_BOUND")) tail_bound_items_ = atoi(e);
     if (const char* e = getenv("HM_FRAMES_IN_FLIGHT")) frames_in_flight_ = std::max(1, std::min((int)kFramesInFlight, atoi(e)));
     if (kind_ == HM_KIND_MSNN) {
         tail_group_ = 4;
         if (const char* e = getenv("HM_TAIL_GROUP")) tail_group_ = std::max(1, std::min((int)kTailGroupMax, atoi(e)));
-        if (tail_mega_) tail_group_ = 1;
         if (tail_group_ > 1) {
             // a group being filled + two groups' tails and order-stream work in flight, unless told otherwise
             if (!getenv("HM_FRAMES_IN_FLIGHT")) frames_in_flight_ = std::min((int)kFramesInFlight, 3 * tail_group_);
@@ -537,19 +535,13 @@ void Renderer::trace_tail(FrameCtx* const* cs, int m) {
             P.q = group_q_[gi];
             P.tail_merged = 1;
         }
-        if (kind_ == HM_KIND_MSNN && tail_mega_ && m == 1) {
-            // HM_TAIL_MEGA=1: the whole tail piece in one launch (k_tail_mega) instead of a launch pair per vertex.
-            // Measured slower on B200 (profiles/r2k_steps_and_tail_mega.txt), so the launch-pair form stays the default.
-            timed(3, s, [&] { launch_tail_mega(P, src, records_, s); });
-        } else {
-            for (int vertex = c0.mp_vertex; vertex < c0.mp_max; ++vertex) {
-                timed(3, s, [&] { launch_shade(P, src, s, tail_bound); });
-                const int dst = src ^ 1;
-                HM_CUDA(cudaMemsetAsync(P.q.counts + dst, 0, 4, s));
-                timed(3, s, [&] { launch_trace(P, dst, s, tail_bound); });
-                HM_CUDA(cudaMemsetAsync(P.q.counts + 2, 0, 16, s));
-                src = dst;
-            }
+        for (int vertex = c0.mp_vertex; vertex < c0.mp_max; ++vertex) {
+            timed(3, s, [&] { launch_shade(P, src, s, tail_bound); });
+            const int dst = src ^ 1;
+            HM_CUDA(cudaMemsetAsync(P.q.counts + dst, 0, 4, s));
+            timed(3, s, [&] { launch_trace(P, dst, s, tail_bound); });
+            HM_CUDA(cudaMemsetAsync(P.q.counts + 2, 0, 16, s));
+            src = dst;
         }
     }
     for (int k = 0; k < m; ++k) {

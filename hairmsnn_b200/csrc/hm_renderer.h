@@ -244,7 +244,7 @@ private:
     Comm* comm_ = nullptr;          // not owned
     int groups_ = 1;                // sample groups of the communicator (comm world / band world)
     void all_reduce_gradients();
-    bool profiling_ = false, collect_stats_ = false, skip_unused_queries_ = true, tail_mega_ = false;
+    bool profiling_ = false, collect_stats_ = false, skip_unused_queries_ = true;
     int frame_offset_ = 0, frame_stride_ = 1;
     unsigned profile_mask_ = 0xffffffffu;
     int profile_period_ = 1;

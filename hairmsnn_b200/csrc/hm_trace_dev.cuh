@@ -34,7 +34,18 @@ namespace hm {
 
 constexpr int kTraceBlock = 128;   // threads per CTA of every kernel that calls trace_queue
 constexpr int kLeafCap = 16;       // parked primitive references per lane (a wide node can park 8)
-constexpr int kSolveCap = 4;       // parked solver candidates per lane
+constexpr int kSolveCap = 4;       // parked solver candidates per lane (HM_TRACE_POOL == 0)
+// HM_TRACE_POOL == 1: fibre spans that survive the conservative rejects go into a WARP-level pool in shared memory
+// (their ray-space control points, 16 words each), and the solve step hands the pool out one candidate per lane:
+// the Newton iteration runs at up to 32 lanes instead of the ~7 that hold a candidate of their own, and nothing is
+// fetched or projected twice.  Hits go back to the owning lane through a shared-memory atomicMin on the bits of t.
+#ifndef HM_TRACE_POOL
+#define HM_TRACE_POOL 1
+#endif
+constexpr int kPoolCap = 64;       // pool entries per warp: a prim step adds at most 32
+#ifndef HM_POOL_SOLVE
+#define HM_POOL_SOLVE 24           // solve step once the pool holds this many candidates (<= kPoolCap - 32)
+#endif
 #ifndef HM_TRACE_REFILL
 #define HM_TRACE_REFILL 8
 #endif
@@ -88,7 +99,17 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     __shared__ int s_leaf[kLeafCap][kTraceBlock];
+#if HM_TRACE_POOL
+    __shared__ float s_pool[kTraceBlock / 32][16][kPoolCap];   // [warp][word][entry]
+    __shared__ unsigned s_bt[kTraceBlock];                     // per lane: bits of its best t, lowered by the solvers
+    __shared__ float s_bu[kTraceBlock];
+    __shared__ int s_bp[kTraceBlock];
+    float (*pool)[kPoolCap] = s_pool[threadIdx.x >> 5];
+    const int wbase = threadIdx.x & ~31;
+    int wpool = 0;           // candidates in the pool (warp-uniform)
+#else
     __shared__ int s_solve[kSolveCap][kTraceBlock];
+#endif
     const int tx = threadIdx.x;
 
     int id = -1;
@@ -144,6 +165,92 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
         const int wait_at = any ? HM_TRACE_ANY_WAIT : HM_TRACE_CLOSEST_WAIT;
         const bool waits = wait_at > 0 && nleaf >= wait_at;
         const bool can_node = id >= 0 && !waits && (next_node >= 0 || (g_bits >> 8) != 0 || sp > 0) && nleaf <= kLeafCap - 8;   // a node parks at most 8 references
+#if HM_TRACE_POOL
+        const bool can_prim = nleaf > 0;
+        const int n_node = __popc(__ballot_sync(FULL, can_node));
+        const int n_prim = __popc(__ballot_sync(FULL, can_prim));
+        const bool few_nodes = n_node < HM_TRACE_NODE_LANES;
+
+        if (wpool >= HM_POOL_SOLVE || (wpool > 0 && few_nodes && wpool >= n_prim)) {
+            // ---- solve step: the whole pool, 32 candidates per pass ----
+            s_bt[tx] = f_as_u(best.t);
+            __syncwarp();
+            for (int base = 0; base < wpool; base += 32) {
+                const int e = base + lane;
+                bool won = false;
+                int owner = 0, prim = 0;
+                SegHit sh;
+                sh.t = 0.f; sh.u = 0.f;
+                if (e < wpool) {
+                    const int tag = __float_as_int(pool[15][e]);
+                    owner = wbase + (tag & 31);
+                    const float tmax_o = u_as_f(s_bt[owner]);   // the owner's best so far (may be a pass old: conservative)
+                    if (pool[14][e] <= tmax_o) {                // depth reject again: tmax may have shrunk since the park
+                        FibreCandidate fc;
+                        fc.k0 = V3(pool[0][e], pool[1][e], pool[2][e]);
+                        fc.k1 = V3(pool[3][e], pool[4][e], pool[5][e]);
+                        fc.k2 = V3(pool[6][e], pool[7][e], pool[8][e]);
+                        fc.k3 = V3(pool[9][e], pool[10][e], pool[11][e]);
+                        fc.r = pool[12][e];
+                        fc.u_start = pool[13][e];
+                        if (fibre_solve(fc, tmin, tmax_o, sh)) {
+                            atomicMin(&s_bt[owner], f_as_u(sh.t));   // t > tmin >= 0: the bit patterns order like the values
+                            won = true;
+                            prim = tag >> 5;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (won && s_bt[owner] == f_as_u(sh.t)) { s_bu[owner] = sh.u; s_bp[owner] = prim; }
+                __syncwarp();
+            }
+            wpool = 0;
+            nsolve = 0;
+            const unsigned nt = s_bt[tx];
+            if (nt < f_as_u(best.t)) {
+                best.t = u_as_f(nt); best.u = s_bu[tx]; best.v = 0.f; best.prim = s_bp[tx];
+                if (any) { g_bits = 0; sp = 0; nleaf = 0; next_node = -1; }
+            }
+        } else if (n_prim >= HM_TRACE_PRIM_LANES || (n_prim > 0 && few_nodes)) {
+            // ---- prim step ----
+            bool park = false;
+            FibreCandidate fc;
+            float zlo = 0.f;
+            int prim_id = 0;
+            if (can_prim) {
+                const int ref = s_leaf[--nleaf][tx];
+                const F4* p = g.wleaf_data + 4 * (size_t)ref;
+                F4 a, b, c, e;
+                load_leaf64(p, a, b, c, e);
+                if (stats) stats[any ? 1 : 0].prims++;
+                if (e.w < 0.f) {
+                    float t, b1, b2;
+                    if (intersect_triangle(o, d, tmin, best.t, V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), V3(c.x, c.y, c.z), t, b1, b2)) {
+                        best.t = t; best.u = b1; best.v = b2; best.prim = f_as_i(e.x);
+                        if (any) { g_bits = 0; sp = 0; nleaf = 0; next_node = -1; }
+                    }
+                } else if (f_as_i(a.w) != best.prim) {
+                    if (fibre_candidate(rf, tmin, best.t, f4_to_v4(a), f4_to_v4(b), f4_to_v4(c), f4_to_v4(e), fc)) {
+                        park = true;
+                        prim_id = f_as_i(a.w);
+                        zlo = fminf(fminf(fc.k1.z, fmaf(fc.k2.z - fc.k0.z, 1.f / 6.f, fc.k1.z)),
+                                    fminf(fmaf(fc.k1.z - fc.k3.z, 1.f / 6.f, fc.k2.z), fc.k2.z)) - fc.r;
+                    }
+                }
+            }
+            const unsigned pm = __ballot_sync(FULL, park);
+            if (park) {
+                const int e = wpool + __popc(pm & ((1u << lane) - 1u));
+                pool[0][e] = fc.k0.x; pool[1][e] = fc.k0.y; pool[2][e] = fc.k0.z;
+                pool[3][e] = fc.k1.x; pool[4][e] = fc.k1.y; pool[5][e] = fc.k1.z;
+                pool[6][e] = fc.k2.x; pool[7][e] = fc.k2.y; pool[8][e] = fc.k2.z;
+                pool[9][e] = fc.k3.x; pool[10][e] = fc.k3.y; pool[11][e] = fc.k3.z;
+                pool[12][e] = fc.r; pool[13][e] = fc.u_start; pool[14][e] = zlo;
+                pool[15][e] = __int_as_float((prim_id << 5) | lane);
+                nsolve++;
+            }
+            wpool += __popc(pm);
+#else
         const bool can_prim = nleaf > 0 && nsolve < kSolveCap;
         const bool can_solve = nsolve > 0;
         const int n_node = __popc(__ballot_sync(FULL, can_node));
@@ -188,6 +295,7 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
                     if (fibre_candidate(rf, tmin, best.t, f4_to_v4(a), f4_to_v4(b), f4_to_v4(c), f4_to_v4(e), fc)) s_solve[nsolve++][tx] = ref;
                 }
             }
+#endif
         } else {
             // ---- node step(s) ----
             // HM_TRACE_NODE_REPEAT unit steps per vote: most iterations are node steps, and the

@@ -13,7 +13,7 @@
 //
 // shade/shadow/extend are persistent grids (148 SMs x resident CTAs) that pull their
 // item count from device memory, so the host never synchronises inside a bounce.
-#include "hm_wavefront.h"
+#include "hm_wavefront_dev.cuh"
 #include "hm_trace_dev.cuh"
 
 #include <atomic>
@@ -22,6 +22,7 @@ namespace hm {
 
 static std::atomic<uint64_t> g_launches{0};
 uint64_t wavefront_launch_count() { return g_launches.load(); }
+void wavefront_count_launch() { g_launches++; }
 
 int wavefront_sm_count() {
     static int sms = 0;
@@ -36,50 +37,16 @@ int wavefront_sm_count() {
 
 namespace {
 
-constexpr int kBlock = 128;
 #ifndef HM_TRACE_CTAS
 #define HM_TRACE_CTAS 6
 #endif
 constexpr int kTraceCtasPerSm = HM_TRACE_CTAS;   // persistent traversal grid: resident CTAs per SM (launch bounds cap the registers)
-
-__device__ __forceinline__ float4 f4(V3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
-__device__ __forceinline__ V3 v3(float4 a) { return V3(a.x, a.y, a.z); }
-
-// Warp-aggregated append: one atomicAdd per warp, returns this lane's index (or -1).
-__device__ __forceinline__ int queue_reserve(int* counter, bool want) {
-    unsigned mask = __ballot_sync(0xffffffffu, want);
-    if (mask == 0) return -1;
-    int lane = threadIdx.x & 31;
-    int leader = __ffs(mask) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(counter, __popc(mask));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    return want ? base + __popc(mask & ((1u << lane) - 1u)) : -1;
-}
-
-__device__ __forceinline__ bool is_training_pixel(const FrameParams& P, int fb_ofs, int& tr_ofs) {
-    if (P.pretrain) { tr_ofs = fb_ofs; return true; }   // TRAIN_DATA_GEN: every work item is a training record
-    tr_ofs = fb_ofs / P.every_nth;
-    // W*H need not be a multiple of numTrainRecords (everyNth = floor(W*H / 16384)): the reference reads past
-    // trainIdxs for the trailing groups (cuda/hair_msnn.cu:208); they have no training pixel here
-    if (tr_ofs >= P.train_records) return false;
-    int train_idx = __ldg(P.train_idxs + tr_ofs) % P.every_nth;
-    return fb_ofs % P.every_nth == train_idx;
-}
 
 __device__ __forceinline__ void flush_trav(unsigned long long* dst, const TraceStats& st) {
     unsigned n = (unsigned)st.nodes, p = (unsigned)st.prims;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { n += __shfl_xor_sync(0xffffffffu, n, o); p += __shfl_xor_sync(0xffffffffu, p, o); }
     if ((threadIdx.x & 31) == 0 && (n | p)) { atomicAdd(dst, (unsigned long long)n); atomicAdd(dst + 1, (unsigned long long)p); }
-}
-
-__device__ __forceinline__ void write_nn_input(float* dst, V3 p, V3 wo, V3 t, float scene_scale) {
-    V3 point = p / scene_scale;
-    float4* d4 = reinterpret_cast<float4*>(dst);
-    d4[0] = make_float4(point.x, point.y, point.z, wo.x);
-    d4[1] = make_float4(wo.y, wo.z, t.x, t.y);
-    d4[2] = make_float4(t.z, 0.f, 0.f, 0.f);
 }
 
 // ---------------------------------------------------------------------------------
@@ -171,146 +138,6 @@ __global__ void __launch_bounds__(kBlock, kTraceCtasPerSm) k_primary(const __gri
 }
 
 // ---------------------------------------------------------------------------------
-// shade
-// ---------------------------------------------------------------------------------
-__device__ __forceinline__ void push_probe(const FrameParams& P, const Probe& pr, int slot, int bit) {
-    int idx = queue_reserve(P.q.counts + 3, pr.active);
-    if (idx >= 0) {
-        P.q.shadow[2 * (size_t)idx + 0] = make_float4(pr.o.x, pr.o.y, pr.o.z, __int_as_float(slot | (bit << 30)));
-        P.q.shadow[2 * (size_t)idx + 1] = make_float4(pr.d.x, pr.d.y, pr.d.z, 0.f);
-    }
-}
-
-__device__ __forceinline__ void fold_pending(const FrameParams& P, int slot, bool training, V3& color, V3& color_short) {
-    float4 dl = P.paths.dl_light[slot];
-    if (dl.w == 0.f) return;
-    uint32_t vis = __ldcg(P.paths.vis + slot);   // cleared by whichever thread traced the probe: bypass L1
-    V3 d = resolve_direct(v3(dl), (vis & 1u) != 0, v3(P.paths.dl_bsdf[slot]), (vis & 2u) != 0);
-    color += v3(P.paths.dl_beta[slot]) * d;
-    if (training) color_short += v3(P.paths.dl_beta_short[slot]) * d;
-}
-
-#ifndef HM_SHADE_GRID
-#define HM_SHADE_GRID 8
-#endif
-// resident CTAs per SM = register cap of k_shade: 4 -> 128 regs 1.59 ms per frame, 6 -> 80 regs 1.48, 8 -> 64 regs 1.45
-// (profiles/r2d_sweep_knobs.txt: the kernel stalls on instruction fetch, more warps hide it better than fewer spills)
-#ifndef HM_SHADE_CTAS
-#define HM_SHADE_CTAS 8
-#endif
-// One path vertex of render_path_tracing / render_hair_msnn: everything k_shade does for a live queue
-// item except the queue pushes.  Reads and writes the slot's path state in HBM; the caller gets the two
-// direct-light probes and whether a continuation ray was written to paths.ray_o / ray_d.
-__device__ __forceinline__ void shade_item(const FrameParams& P, int slot, DirectSample& ds, bool& extend) {
-    Rng rng; rng.state = P.paths.rng[slot];
-    V3 ro = v3(P.paths.ray_o[slot]), rd = v3(P.paths.ray_d[slot]);
-    float4 hr = __ldcg(P.paths.hit + slot);   // written by whichever thread traced the ray: bypass L1
-    Hit hit; hit.t = hr.x; hit.prim = __float_as_int(hr.y); hit.u = hr.z; hit.v = hr.w;
-    float4 b4 = P.paths.beta[slot];
-    V3 beta = v3(b4);
-    int bounces = __float_as_int(b4.w);
-    V3 color = v3(P.paths.color[slot]);
-
-    int tr_ofs = 0;
-    bool training = false;
-    V3 beta_short(1.f), color_short(0.f);
-    if (P.mode == MODE_MSNN) {
-        // merged tail pieces: only training paths outlive the main piece (bounces > beta ends the others), and
-        // nothing past the first vertex needs the record index
-        training = P.tail_merged ? true : is_training_pixel(P, slot, tr_ofs);
-        if (training) {
-            beta_short = v3(P.paths.beta_short[slot]);
-            color_short = v3(P.paths.color_short[slot]);
-        }
-    }
-
-    fold_pending(P, slot, training, color, color_short);
-
-    Vertex v = vertex_from_hit(P.scene, hit, ro, rd);
-
-    if (P.mode == MODE_MSNN && bounces == 0) {
-        write_nn_input(P.nn_frame_in + (size_t)slot * P.in_ch, v.p, v.wo, v.t, P.scene.scene_scale);
-        P.gbuffer[slot].w = __int_as_float(1 | (v.surface ? 2 : 0));
-        if (training && tr_ofs >= P.train_slot0 && tr_ofs < P.train_slot0 + P.train_slots)
-            write_nn_input(P.nn_train_in + (size_t)tr_ofs * P.in_ch, v.p, v.wo, v.t, P.scene.scene_scale);
-    }
-
-    // direct lighting
-    const bool degenerate = P.mode == MODE_PT && P.v2_stop < P.v1_stop;   // pathTrace returns 0
-    bool do_dl = (P.mode == MODE_PT) ? (bounces >= P.v1_stop && !degenerate) : true;
-    if (do_dl) {
-        sample_direct(P.scene, v, rng, ds);
-        P.paths.dl_beta[slot] = f4(beta, 0.f);
-        if (training) P.paths.dl_beta_short[slot] = f4(beta_short, 0.f);
-        P.paths.dl_light[slot] = f4(ds.light.value, 1.f);
-        P.paths.dl_bsdf[slot] = f4(ds.bsdf.value, 0.f);
-        P.paths.vis[slot] = (ds.light.active ? 1u : 0u) | (ds.bsdf.active ? 2u : 0u);
-    } else {
-        P.paths.dl_light[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-
-    // Russian roulette (after the direct sample of every vertex but the first)
-    bool alive = !degenerate;
-    if (bounces >= 1) {
-        float q = fmaxf(0.05f, 1.f - luminance709(beta));
-        if (training) {
-            float qs = fmaxf(0.05f, 1.f - luminance709(beta_short));
-            float eps = rng_next(rng);
-            if (eps < qs || bounces > P.msnn_beta) beta_short = V3(0.f);
-            if (eps < q) alive = false;
-            else {
-                beta = beta / (1.f - q);
-                if (!(beta_short == V3(0.f))) beta_short = beta_short / (1.f - qs);
-            }
-        } else {
-            float eps = rng_next(rng);
-            if (eps < q) alive = false;
-            else if (P.mode == MODE_MSNN && bounces > P.msnn_beta) alive = false;
-            else beta = beta / (1.f - q);
-        }
-    }
-    if (alive && bounces + 1 > P.v2_stop) alive = false;
-
-    if (alive) {
-        V3 no, nd;
-        V3 mul = sample_continuation(P.scene, v, rng, no, nd);
-        beta = beta * mul;
-        if (training) beta_short = beta_short * mul;
-        P.paths.ray_o[slot] = f4(no, 0.f);
-        P.paths.ray_d[slot] = f4(nd, 0.f);
-        extend = true;
-    }
-    P.paths.rng[slot] = rng.state;
-    P.paths.beta[slot] = f4(beta, __int_as_float(bounces + 1));
-    P.paths.color[slot] = f4(color, 0.f);
-    if (training) {
-        P.paths.beta_short[slot] = f4(beta_short, 0.f);
-        P.paths.color_short[slot] = f4(color_short, 0.f);
-    }
-}
-
-__global__ void __launch_bounds__(kBlock, HM_SHADE_CTAS) k_shade(const __grid_constant__ FrameParams P, int src) {
-    const int n = P.q.counts[src];
-    const int* queue = P.q.shade[src];
-    const int rounds = (n + kBlock - 1) / kBlock;
-    for (int r = blockIdx.x; r < rounds; r += gridDim.x) {
-        int i = r * kBlock + threadIdx.x;
-        bool live = i < n;
-        int slot = live ? queue[i] : 0;
-
-        DirectSample ds;
-        ds.light.active = false; ds.bsdf.active = false;
-        bool extend = false;
-        if (live) shade_item(P, slot, ds, extend);
-        push_probe(P, ds.light, slot, 0);
-        push_probe(P, ds.bsdf, slot, 1);
-        int idx = queue_reserve(P.q.counts + 2, extend);
-        if (idx >= 0) P.q.extend[idx] = slot;
-    }
-    if (P.collect_stats && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.q.trav + 8, (unsigned long long)n);
-}
-
-// ---------------------------------------------------------------------------------
 // extend / shadow
 // ---------------------------------------------------------------------------------
 // One launch traces a vertex's occlusion probes AND its continuation rays: work items
@@ -373,123 +200,6 @@ __global__ void __launch_bounds__(kBlock, kTraceCtasPerSm) k_trace(const __grid_
 }
 
 // ---------------------------------------------------------------------------------
-// tail piece of a HairMSNN frame in ONE launch
-// ---------------------------------------------------------------------------------
-// Past vertex beta+1 only the <= 16384 training paths are alive, for up to 38 more vertices.  As
-// (shade, trace) launch pairs that is 76 tiny latency-bound launches per frame, each sweeping the GPU
-// with persistent CTAs that find almost no work while other frames' main pieces are running (measured:
-// 0.73 ms of a 5.0 ms frame).  Here a warp keeps 32 such paths and walks them to the end: shade the 32
-// vertices (shade_item, the code k_shade runs), put their <= 96 rays into a warp-private list in shared
-// memory, trace the list with the warp-cooperative traversal, repeat while any path is alive.  Path
-// state stays in the HBM arrays between steps exactly as the launch-per-vertex form leaves it, so
-// k_finalize and the parity tests see no difference.
-constexpr int kTailRaysPerWarp = 96;
-
-struct TailOps {
-    const FrameParams& P;
-    float4* rays;        // warp-private: [kTailRaysPerWarp][2]  (o.xyz, slot | bit << 30) (d.xyz, kind | lane << 8)
-    int* alive;          // warp-private [32]: set when a lane's continuation ray hit something
-    __device__ __forceinline__ bool fetch(int w, V3& o, V3& d) const {
-        const float4 a = rays[2 * w], b = rays[2 * w + 1];
-        o = V3(a.x, a.y, a.z);
-        d = V3(b.x, b.y, b.z);
-        return (__float_as_int(b.w) & 0xff) == 0;      // kind 0: occlusion probe
-    }
-    __device__ __forceinline__ void commit(int w, const Hit& h, bool finished) const {
-        if (!finished || h.prim < 0) return;
-        const int tag = __float_as_int(rays[2 * w].w), info = __float_as_int(rays[2 * w + 1].w);
-        const int slot = tag & 0x3fffffff;
-        if ((info & 0xff) == 0) {
-            atomicAnd(P.paths.vis + slot, ~(1u << (tag >> 30)));
-        } else {
-            P.paths.hit[slot] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
-            alive[info >> 8] = 1;
-        }
-    }
-};
-
-__global__ void __launch_bounds__(kBlock) k_tail_mega(const __grid_constant__ FrameParams P, int src) {
-    __shared__ float4 s_rays[kBlock / 32][kTailRaysPerWarp][2];
-    __shared__ int s_alive[kBlock / 32][32];
-    __shared__ int s_cursor[kBlock / 32];
-    const int n = P.q.counts[src];
-    const int* queue = P.q.shade[src];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    TraceStats st[2] = {{0, 0}, {0, 0}};
-    unsigned long long n_shade = 0, n_extend = 0, n_shadow = 0;
-
-    // persistent warps: a lane whose path has ended takes the next queue entry, so few warps stay resident
-    // (8 frames are in flight; idle lanes of long-lived warps would pin registers the main pieces need)
-    int* cursor = P.q.counts + 7;
-    int slot = -1;
-    bool live = false, exhausted = false;
-    while (true) {
-        const unsigned want = __ballot_sync(0xffffffffu, !live);
-        if (want && !exhausted) {
-            const int cnt = __popc(want);
-            int base = 0;
-            if (lane == 0) base = atomicAdd(cursor, cnt);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base + cnt >= n) exhausted = true;
-            if (!live) {
-                const int i = base + __popc(want & ((1u << lane) - 1u));
-                if (i < n) { slot = queue[i]; live = true; }
-            }
-        }
-        if (!__any_sync(0xffffffffu, live)) break;
-        {
-            DirectSample ds;
-            ds.light.active = false; ds.bsdf.active = false;
-            bool extend = false;
-            if (live) shade_item(P, slot, ds, extend);
-            // warp-private ray list: probes first (they end early), then continuation rays
-            const unsigned m0 = __ballot_sync(0xffffffffu, ds.light.active), m1 = __ballot_sync(0xffffffffu, ds.bsdf.active);
-            const unsigned m2 = __ballot_sync(0xffffffffu, extend);
-            const unsigned below = (1u << lane) - 1u;
-            const int n0 = __popc(m0), n1 = __popc(m1), n2 = __popc(m2);
-            if (ds.light.active) {
-                const int w = __popc(m0 & below);
-                s_rays[wib][w][0] = make_float4(ds.light.o.x, ds.light.o.y, ds.light.o.z, __int_as_float(slot));
-                s_rays[wib][w][1] = make_float4(ds.light.d.x, ds.light.d.y, ds.light.d.z, __int_as_float(lane << 8));
-            }
-            if (ds.bsdf.active) {
-                const int w = n0 + __popc(m1 & below);
-                s_rays[wib][w][0] = make_float4(ds.bsdf.o.x, ds.bsdf.o.y, ds.bsdf.o.z, __int_as_float(slot | (1 << 30)));
-                s_rays[wib][w][1] = make_float4(ds.bsdf.d.x, ds.bsdf.d.y, ds.bsdf.d.z, __int_as_float(lane << 8));
-            }
-            if (extend) {
-                const int w = n0 + n1 + __popc(m2 & below);
-                const float4 o = P.paths.ray_o[slot], d = P.paths.ray_d[slot];
-                s_rays[wib][w][0] = make_float4(o.x, o.y, o.z, __int_as_float(slot));
-                s_rays[wib][w][1] = make_float4(d.x, d.y, d.z, __int_as_float(1 | (lane << 8)));
-            }
-            s_alive[wib][lane] = 0;
-            if (lane == 0) s_cursor[wib] = 0;
-            __syncwarp();
-            n_shade += __popc(__ballot_sync(0xffffffffu, live));
-            n_shadow += n0 + n1; n_extend += n2;
-            TailOps ops{P, &s_rays[wib][0][0], s_alive[wib]};
-            trace_queue(P.scene.geom, n0 + n1 + n2, &s_cursor[wib], ops, 0.f, 1e30f, P.collect_stats ? st : nullptr);
-            __syncwarp();
-            live = s_alive[wib][lane] != 0;
-            __syncwarp();
-        }
-    }
-    if (P.collect_stats) {
-        flush_trav(P.q.trav + 0, st[0]);
-        flush_trav(P.q.trav + 2, st[1]);
-        TraceStats both{st[0].nodes + st[1].nodes, st[0].prims + st[1].prims};
-        flush_trav(P.q.trav + 10, both);
-        if (lane == 0 && (n_shade | n_extend | n_shadow)) {
-            atomicAdd(P.q.trav + 6, n_extend);
-            atomicAdd(P.q.trav + 7, n_shadow);
-            atomicAdd(P.q.trav + 8, n_shade);
-            atomicAdd(P.q.trav + 12, n_extend + n_shadow);
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------
 // finalize
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ FrameParams P) {
@@ -540,167 +250,6 @@ __global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ FrameP
     }
 }
 
-// ---------------------------------------------------------------------------------
-// render_nrc: nrcTracePaths in wavefront form (cuda/nrc.cu:135-310)
-// ---------------------------------------------------------------------------------
-// The reference loop body for bounce b is: direct light at vertex b -> sample + trace to
-// vertex b+1 -> [training pixel: record vertex b] -> spread update with the NEW vertex ->
-// terminate / query the cache / continue.  Here the shade of vertex b first finishes
-// bounce b-1 (everything that needed the new hit), then starts bounce b.  No Russian
-// roulette: paths end on the spread heuristic, on leaving the scene, or at kNrcMaxBounces.
-__device__ __forceinline__ bool nrc_training_pixel(const FrameParams& P, int fb_ofs, int& tr_ofs, bool& unbiased) {
-    tr_ofs = fb_ofs / P.every_nth;
-    unbiased = false;
-    // the reference indexes one group past the end when W*H % everyNth != 0 (trOfs == numTrainingPixels,
-    // SURVEY §8 a18): that group has no training pixel here
-    if (tr_ofs >= P.nrc_train_pixels) return false;
-    const int train_idx = __ldg(P.train_idxs + tr_ofs) % P.every_nth;
-    const bool training = fb_ofs % P.every_nth == train_idx;
-    unbiased = training && (tr_ofs % 16 == 0 || P.nrc_all_unbiased);
-    return training;
-}
-
-__device__ __forceinline__ void write3(float* dst, V3 v) { dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; }
-
-__device__ __forceinline__ void write_nrc_query(float* dst, V3 p, V3 wo, V3 n, float scene_scale) {
-    V3 point = p / scene_scale;
-    dst[0] = point.x; dst[1] = point.y; dst[2] = point.z;
-    dst[3] = wo.x; dst[4] = wo.y; dst[5] = wo.z;
-    dst[6] = n.x; dst[7] = n.y; dst[8] = n.z;
-}
-
-// pow(length(d), 2) / (4 Pi) / |cos|   (cuda/nrc.cu:153,186)
-__device__ __forceinline__ float nrc_area(V3 a, V3 b, float abscos) {
-    float l = length(a - b);
-    return l * l / (4.f * kPi) / abscos;
-}
-
-__global__ void __launch_bounds__(kBlock) k_shade_nrc(const __grid_constant__ FrameParams P, int src) {
-    const int n = P.q.counts[src];
-    const int* queue = P.q.shade[src];
-    const int rounds = (n + kBlock - 1) / kBlock;
-    const size_t frame_size = (size_t)P.W * P.H;
-    for (int r = blockIdx.x; r < rounds; r += gridDim.x) {
-        int i = r * kBlock + threadIdx.x;
-        bool live = i < n;
-        int slot = live ? queue[i] : 0;
-
-        DirectSample ds;
-        ds.light.active = false; ds.bsdf.active = false;
-        bool extend = false;
-
-        if (live) {
-            Rng rng; rng.state = P.paths.rng[slot];
-            V3 ro = v3(P.paths.ray_o[slot]), rd = v3(P.paths.ray_d[slot]);
-            float4 hr = P.paths.hit[slot];
-            Hit hit; hit.t = hr.x; hit.prim = __float_as_int(hr.y); hit.u = hr.z; hit.v = hr.w;
-            float4 b4 = P.paths.beta[slot];
-            V3 beta = v3(b4);
-            const int b = __float_as_int(b4.w);       // index of this vertex == bounce about to start
-            V3 color = v3(P.paths.color[slot]);
-
-            int tr_ofs = 0;
-            bool unbiased = false;
-            const bool training = nrc_training_pixel(P, slot, tr_ofs, unbiased);
-            NrcTrainRec* rec = P.tbuffer + tr_ofs;
-
-            // direct light of vertex b-1, now that its probes are back
-            {
-                float4 dl = P.paths.dl_light[slot];
-                if (dl.w != 0.f) {
-                    uint32_t vis = P.paths.vis[slot];
-                    V3 d = resolve_direct(v3(dl), (vis & 1u) != 0, v3(P.paths.dl_bsdf[slot]), (vis & 2u) != 0);
-                    color += v3(P.paths.dl_beta[slot]) * d;
-                    if (training) write3(rec->radiance[b - 1], d);
-                }
-            }
-
-            Vertex v = vertex_from_hit(P.scene, hit, ro, rd);
-            const float abscos = fabsf(v.wo_local.z);
-
-            float spread = 0.f, a0 = 0.f, c = P.nrc_c;
-            int flags = 0;
-            bool terminated = false;
-            if (b == 0) {
-                if (v.surface && v.wo_local.z < 0.f) {
-                    // a head triangle seen from behind counts as a miss (cuda/nrc.cu:353-360); si.Le is 0 on a hit
-                    P.gbuffer[slot] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
-                    P.gbuffer_b[slot] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
-                    terminated = true;
-                } else {
-                    a0 = nrc_area(v.p, V3(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]), abscos);
-                }
-            } else {
-                float4 st = P.paths.nrc_state[slot];
-                spread = st.x; a0 = st.y; c = st.z; flags = __float_as_int(st.w);
-                float4 pv = P.paths.nrc_prev[slot];
-                const V3 prev_point = v3(pv);
-                if (training && (flags & kNrcRecalcA0)) {
-                    a0 = nrc_area(v.p, prev_point, abscos);
-                    flags &= ~kNrcRecalcA0;
-                }
-                {   // nrcSpread (cuda_headers/utils.cuh:86-90)
-                    float l = length(v.p - prev_point);
-                    spread = spread + sqrtf(l * l / pv.w / abscos);
-                }
-                const bool cond = spread * spread > c * a0;
-                if (cond && !(flags & kNrcSuffix)) {
-                    P.gbuffer[slot] = f4(color, __int_as_float(1));
-                    P.gbuffer_b[slot] = f4(beta, __int_as_float(b - 1));
-                    write_nrc_query(P.nn_frame_in + (size_t)slot * P.in_ch, v.p, v.wo, v.n, P.scene.scene_scale);
-                    if (training) { flags |= kNrcSuffix | kNrcRecalcA0; spread = 0.f; }
-                    else terminated = true;
-                } else if (cond) {
-                    write_nrc_query(P.nn_frame_in + (frame_size + tr_ofs) * P.in_ch, v.p, v.wo, v.n, P.scene.scene_scale);
-                    rec->bounces = b - 1;
-                    rec->hit = 1;
-                    if (!unbiased) terminated = true;
-                    else c = 1e30f;
-                }
-            }
-
-            if (terminated) {
-                flags |= kNrcTerminated;
-                P.paths.dl_light[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {
-                sample_direct(P.scene, v, rng, ds);
-                P.paths.dl_beta[slot] = f4(beta, 0.f);
-                P.paths.dl_light[slot] = f4(ds.light.value, 1.f);
-                P.paths.dl_bsdf[slot] = f4(ds.bsdf.value, 0.f);
-                P.paths.vis[slot] = (ds.light.active ? 1u : 0u) | (ds.bsdf.active ? 2u : 0u);
-
-                V3 no, nd;
-                float pdf = 1.f;
-                V3 mul = sample_continuation(P.scene, v, rng, no, nd, &pdf);
-                beta = beta * mul;
-                P.paths.nrc_prev[slot] = f4(v.p, pdf);
-                if (training) {
-                    write3(rec->vert[b], v.p / P.scene.scene_scale);
-                    write3(rec->wo[b], v.wo);
-                    write3(rec->n[b], v.n);
-                    write3(rec->beta[b], mul);
-                }
-                if (b < kNrcMaxBounces - 1) {   // the last bounce's ray cannot change anything (cuda/nrc.cu:200)
-                    P.paths.ray_o[slot] = f4(no, 0.f);
-                    P.paths.ray_d[slot] = f4(nd, 0.f);
-                    extend = true;
-                }
-            }
-            P.paths.rng[slot] = rng.state;
-            P.paths.beta[slot] = f4(beta, __int_as_float(b + 1));
-            P.paths.color[slot] = f4(color, 0.f);
-            P.paths.nrc_state[slot] = make_float4(spread, a0, c, __int_as_float(flags));
-        }
-        push_probe(P, ds.light, slot, 0);
-        push_probe(P, ds.bsdf, slot, 1);
-        int idx = queue_reserve(P.q.counts + 2, extend);
-        if (idx >= 0) P.q.extend[idx] = slot;
-    }
-    if (P.collect_stats && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.q.trav + 8, (unsigned long long)n);
-}
-
-// End of the G_BUFFER pass: paths that left the scene (or reached the bounce cap) fold their last
-// direct sample and write their G-buffer entry; primary misses show the environment.
 __global__ void __launch_bounds__(256) k_finalize_nrc(const __grid_constant__ FrameParams P) {
     const int n = (P.row1 - P.row0) * P.W;
     const int first = P.row0 * P.W;
@@ -867,9 +416,9 @@ __global__ void __launch_bounds__(kBlock) k_trace_rays(const SceneView S, const 
     }
 }
 
-int persistent_grid(int ctas_per_sm) { return wavefront_sm_count() * ctas_per_sm; }
-
 }  // namespace
+
+int persistent_grid(int ctas_per_sm) { return wavefront_sm_count() * ctas_per_sm; }
 
 void launch_primary(const FrameParams& P, cudaStream_t stream) {
     int n = P.n_primary;
@@ -877,20 +426,6 @@ void launch_primary(const FrameParams& P, cudaStream_t stream) {
     int grid = blocks < persistent_grid(kTraceCtasPerSm) ? blocks : persistent_grid(kTraceCtasPerSm);
     if (grid < 1) grid = 1;
     k_primary<<<grid, kBlock, 0, stream>>>(P);
-    g_launches++;
-}
-// max_items > 0: the caller knows an upper bound of the queue length (tail pieces carry the few long paths
-// only) — the grid is sized for it instead of for the whole GPU, so these launches do not sweep every SM
-// with CTAs that find no work while other frames' main pieces are running.
-static int bounded_grid(int full, long long max_items, int items_per_cta) {
-    if (max_items <= 0) return full;
-    long long need = (max_items + items_per_cta - 1) / items_per_cta;
-    if (need < 1) need = 1;
-    return need < full ? (int)need : full;
-}
-void launch_shade(const FrameParams& P, int src, cudaStream_t stream, long long max_items) {
-    if (P.mode == MODE_NRC) k_shade_nrc<<<bounded_grid(persistent_grid(8), max_items, kBlock), kBlock, 0, stream>>>(P, src);
-    else k_shade<<<bounded_grid(persistent_grid(HM_SHADE_GRID), max_items, kBlock), kBlock, 0, stream>>>(P, src);
     g_launches++;
 }
 void launch_trace(const FrameParams& P, int dst, cudaStream_t stream, long long max_items) {
@@ -913,16 +448,6 @@ void launch_merge_tail(const TailMerge& M, int max_items_per_frame, cudaStream_t
     int gx = (max_items_per_frame + 255) / 256;
     if (gx < 1) gx = 1;
     k_merge_tail<<<dim3(gx, M.n), 256, 0, stream>>>(M);
-    g_launches++;
-}
-#ifndef HM_TAIL_CTAS
-#define HM_TAIL_CTAS 37      // x 4 warps x 32 lanes = 4736 paths in flight per frame
-#endif
-void launch_tail_mega(const FrameParams& P, int src, int max_paths, cudaStream_t stream) {
-    int grid = (max_paths + kBlock - 1) / kBlock;
-    if (grid < 1) grid = 1;
-    if (grid > HM_TAIL_CTAS) grid = HM_TAIL_CTAS;
-    k_tail_mega<<<grid, kBlock, 0, stream>>>(P, src);
     g_launches++;
 }
 void launch_finalize(const FrameParams& P, cudaStream_t stream) {
@@ -1007,35 +532,6 @@ void launch_env_tables(const float* env_rgba, const float* sin_theta, int W, int
     g_launches += 2;
 }
 
-// Test hooks: the fibre scattering model for caller-supplied local directions (device pointers).
-__global__ void __launch_bounds__(256) k_bsdf_eval(const HairLobes L, const float* wo, const float* wi, const float* h, int n,
-                                                   float* out_f, float* out_pdf) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float pdf;
-    const V3 f = hair_eval(L, V3(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]), V3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), h[i], &pdf);
-    out_f[3 * i] = f.x; out_f[3 * i + 1] = f.y; out_f[3 * i + 2] = f.z; out_pdf[i] = pdf;
-}
-__global__ void __launch_bounds__(256) k_bsdf_sample(const HairLobes L, const float* wo, const float* h, const float* u, int n,
-                                                     float* out_wi, float* out_f, float* out_pdf) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const V3 o(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]);
-    const V3 w = hair_sample_dir(L, o, h[i], u[4 * i], u[4 * i + 1], u[4 * i + 2], u[4 * i + 3]);
-    float pdf;
-    const V3 f = hair_eval(L, o, w, h[i], &pdf);
-    out_wi[3 * i] = w.x; out_wi[3 * i + 1] = w.y; out_wi[3 * i + 2] = w.z;
-    out_f[3 * i] = f.x; out_f[3 * i + 1] = f.y; out_f[3 * i + 2] = f.z; out_pdf[i] = pdf;
-}
-void launch_bsdf_eval(const HairLobes& L, const float* wo, const float* wi, const float* h, int n, float* out_f, float* out_pdf, cudaStream_t stream) {
-    k_bsdf_eval<<<(n + 255) / 256, 256, 0, stream>>>(L, wo, wi, h, n, out_f, out_pdf);
-    g_launches++;
-}
-void launch_bsdf_sample(const HairLobes& L, const float* wo, const float* h, const float* u, int n, float* out_wi, float* out_f, float* out_pdf,
-                        cudaStream_t stream) {
-    k_bsdf_sample<<<(n + 255) / 256, 256, 0, stream>>>(L, wo, h, u, n, out_wi, out_f, out_pdf);
-    g_launches++;
-}
 void launch_trace_rays(const SceneView& S, const float* org, const float* dir, int n, int any, float tmin, float tmax,
                        float4* out_hit, int* out_stats, int* cursor, cudaStream_t stream) {
     int blocks = (n + kBlock - 1) / kBlock;

@@ -151,9 +151,6 @@ struct TailMerge {
     int* out_counts;
 };
 void launch_merge_tail(const TailMerge& M, int max_items_per_frame, cudaStream_t stream);
-// render_hair_msnn: all remaining vertices of the paths in shade queue `src_queue` in one launch;
-// max_paths bounds the queue length (training paths only)
-void launch_tail_mega(const FrameParams& P, int src_queue, int max_paths, cudaStream_t stream);
 void launch_finalize(const FrameParams& P, cudaStream_t stream);
 void launch_msnn_composite(const MsnnComposite& C, cudaStream_t stream);
 void launch_nrc_render(const NrcRender& R, cudaStream_t stream);
