@@ -51,7 +51,8 @@ constexpr int kPoolCap = 64;       // pool entries per warp: a prim step adds at
 #endif
 constexpr int kRefillLanes = HM_TRACE_REFILL;    // refill when this many lanes are idle
 #ifndef HM_TRACE_PRIM_LANES
-#define HM_TRACE_PRIM_LANES 16     // prim step when this many lanes hold a parked reference
+#define HM_TRACE_PRIM_LANES 12     // prim step when this many lanes hold a parked reference (16 before the solver pool:
+                                   // profiles/r2y_*, r2z_*: 12 -> hits arrive earlier, 30.7 -> 29.8 nodes per ray)
 #endif
 #ifndef HM_TRACE_SOLVE_LANES
 #define HM_TRACE_SOLVE_LANES 10    // solve step when this many lanes hold a candidate
@@ -67,7 +68,7 @@ constexpr int kRefillLanes = HM_TRACE_REFILL;    // refill when this many lanes 
 #define HM_TRACE_CLOSEST_WAIT 0
 #endif
 #ifndef HM_TRACE_NODE_REPEAT
-#define HM_TRACE_NODE_REPEAT 2     // node steps per vote
+#define HM_TRACE_NODE_REPEAT 3     // node steps per vote
 #endif
 #ifndef HM_TRACE_PREFETCH
 #define HM_TRACE_PREFETCH 0        // 1: prefetch parked primitives and pushed far children into L2/L1
