@@ -24,6 +24,13 @@
 // the prim step instead costs more in idle lanes than it saves (HM_TRACE_*_WAIT,
 // profiles/r1m_sweep_wait_for_prim_step.txt).  Within a node the child with the smallest entry
 // distance goes first, the others in octant order.
+// Primitive work is POOLED per warp (HM_TRACE_POOL = 2, the default): a prim step collects up to two parked references
+// from every lane into a list of (ray, primitive) pairs and tests 32 pairs at once — the tester lane reads the owning
+// lane's ray from shared memory; fibre spans that survive the rejects go, as ray-space control points, into a warp-level
+// pool that the solve step hands out one candidate per lane.  Hits return to the owning lane through a shared-memory
+// atomicMin on the bits of t.  Which lane tests a pair changes nothing in the arithmetic: results stay bit-identical to
+// the host build and deterministic from run to run.  Measured on the bench scene (profiles/r2v, r2ab, r2ac): per-lane
+// prim and solve steps 183.2, pooled solver 185.2, + retuned votes 188.0, + pooled prim step 193.1 Mpaths/s.
 // Persistent warps pull rays from the queue through one atomic cursor and refill idle lanes
 // as soon as a quarter of the warp has finished; commits happen at the top of the loop with
 // the whole warp present, so queue appends stay warp-aggregated (one atomic per warp).
@@ -39,8 +46,9 @@ constexpr int kSolveCap = 4;       // parked solver candidates per lane (HM_TRAC
 // (their ray-space control points, 16 words each), and the solve step hands the pool out one candidate per lane:
 // the Newton iteration runs at up to 32 lanes instead of the ~7 that hold a candidate of their own, and nothing is
 // fetched or projected twice.  Hits go back to the owning lane through a shared-memory atomicMin on the bits of t.
+// HM_TRACE_POOL == 2: the prim step is pooled too (see the file header).  0 = per-lane prim and solve steps (round 1).
 #ifndef HM_TRACE_POOL
-#define HM_TRACE_POOL 1
+#define HM_TRACE_POOL 2
 #endif
 constexpr int kPoolCap = 64;       // pool entries per warp: a prim step adds at most 32
 #ifndef HM_POOL_SOLVE
@@ -51,8 +59,8 @@ constexpr int kPoolCap = 64;       // pool entries per warp: a prim step adds at
 #endif
 constexpr int kRefillLanes = HM_TRACE_REFILL;    // refill when this many lanes are idle
 #ifndef HM_TRACE_PRIM_LANES
-#define HM_TRACE_PRIM_LANES 12     // prim step when this many lanes hold a parked reference (16 before the solver pool:
-                                   // profiles/r2y_*, r2z_*: 12 -> hits arrive earlier, 30.7 -> 29.8 nodes per ray)
+#define HM_TRACE_PRIM_LANES 16     // prim step when the warp holds this many (ray, primitive) pairs, at most two per lane
+                                   // (HM_TRACE_POOL < 2: when this many lanes hold a parked reference; best there: 12)
 #endif
 #ifndef HM_TRACE_SOLVE_LANES
 #define HM_TRACE_SOLVE_LANES 10    // solve step when this many lanes hold a candidate
@@ -108,6 +116,16 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
     float (*pool)[kPoolCap] = s_pool[threadIdx.x >> 5];
     const int wbase = threadIdx.x & ~31;
     int wpool = 0;           // candidates in the pool (warp-uniform)
+#if HM_TRACE_POOL == 2
+    // The prim step is pooled as well: lanes hand in up to two parked references each, the warp tests 32 (ray, primitive)
+    // pairs at a time.  A tester reads the owner's ray from shared memory and rebuilds its frame (same arithmetic, same
+    // bits); triangle hits return through the same atomicMin as the solver's.
+    __shared__ float s_ray[6][kTraceBlock];
+    __shared__ int s_pair[kTraceBlock];
+    __shared__ float s_bv[kTraceBlock];
+    __shared__ int s_cur[kTraceBlock];     // the owner's current best primitive (its other references are skipped)
+    __shared__ int s_pend[kTraceBlock];    // the owner's candidates in the pool
+#endif
 #else
     __shared__ int s_solve[kSolveCap][kTraceBlock];
 #endif
@@ -116,7 +134,9 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
     int id = -1;
     V3 o, d;
     WideRay wr;
+#if HM_TRACE_POOL != 2
     RayFrame rf;
+#endif
     Hit best;
     best.t = tmax; best.prim = -1; best.u = 0.f; best.v = 0.f;
     // current group of pending inner children: base index + (imask | permuted hits << 8); older groups on the stack
@@ -130,6 +150,9 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
 
     while (true) {
         // ---- commit finished rays, refill idle lanes ----
+#if HM_TRACE_POOL == 2
+        if (id >= 0 && nleaf == 0) nsolve = s_pend[tx];
+#endif
         const bool finished = id >= 0 && next_node < 0 && (g_bits >> 8) == 0 && sp == 0 && nleaf == 0 && nsolve == 0;
         if (__any_sync(FULL, finished)) {
             ops.commit(id, best, finished);
@@ -148,7 +171,13 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
                     id = w;
                     any = ops.fetch(w, o, d);
                     wr = make_wide_ray(o, d);
+#if HM_TRACE_POOL == 2
+                    s_ray[0][tx] = o.x; s_ray[1][tx] = o.y; s_ray[2][tx] = o.z;
+                    s_ray[3][tx] = d.x; s_ray[4][tx] = d.y; s_ray[5][tx] = d.z;
+                    s_pend[tx] = 0;
+#else
                     rf = make_ray_frame(o, d);
+#endif
                     best.t = tmax; best.prim = -1; best.u = 0.f; best.v = 0.f;
                     // pseudo-group whose slot 0 is the root
                     g_base = 0;
@@ -169,7 +198,12 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
 #if HM_TRACE_POOL
         const bool can_prim = nleaf > 0;
         const int n_node = __popc(__ballot_sync(FULL, can_node));
+#if HM_TRACE_POOL == 2
+        // (ray, primitive) pairs a prim step could test: up to two per lane
+        const int n_prim = __popc(__ballot_sync(FULL, can_prim)) + __popc(__ballot_sync(FULL, nleaf >= 2));
+#else
         const int n_prim = __popc(__ballot_sync(FULL, can_prim));
+#endif
         const bool few_nodes = n_node < HM_TRACE_NODE_LANES;
 
         if (wpool >= HM_POOL_SOLVE || (wpool > 0 && few_nodes && wpool >= n_prim)) {
@@ -207,12 +241,82 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
             }
             wpool = 0;
             nsolve = 0;
+#if HM_TRACE_POOL == 2
+            s_pend[tx] = 0;
+#endif
             const unsigned nt = s_bt[tx];
             if (nt < f_as_u(best.t)) {
                 best.t = u_as_f(nt); best.u = s_bu[tx]; best.v = 0.f; best.prim = s_bp[tx];
                 if (any) { g_bits = 0; sp = 0; nleaf = 0; next_node = -1; }
             }
         } else if (n_prim >= HM_TRACE_PRIM_LANES || (n_prim > 0 && few_nodes)) {
+#if HM_TRACE_POOL == 2
+            // ---- prim step, pooled: up to two references per lane, 32 (ray, primitive) pairs per step ----
+            s_bt[tx] = f_as_u(best.t);
+            s_cur[tx] = best.prim;
+            const unsigned m1 = __ballot_sync(FULL, nleaf >= 1), m2 = __ballot_sync(FULL, nleaf >= 2);
+            const unsigned lt = (1u << lane) - 1u;
+            const int pos = __popc(m1 & lt) + __popc(m2 & lt);
+            const int npairs = min(__popc(m1) + __popc(m2), 32);
+            if (nleaf >= 1 && pos < 32) {
+                s_pair[wbase + pos] = (s_leaf[nleaf - 1][tx] << 5) | lane;
+                if (nleaf >= 2 && pos + 1 < 32) { s_pair[wbase + pos + 1] = (s_leaf[nleaf - 2][tx] << 5) | lane; nleaf--; }
+                nleaf--;
+            }
+            __syncwarp();
+            bool park = false, won = false;
+            FibreCandidate fc;
+            float zlo = 0.f, wt = 0.f, wu = 0.f, wv = 0.f;
+            int prim_id = 0, ow = wbase, olane = 0;
+            if (lane < npairs) {
+                const int pr = s_pair[wbase + lane];
+                olane = pr & 31;
+                ow = wbase + olane;
+                const F4* p = g.wleaf_data + 4 * (size_t)(pr >> 5);
+                F4 a, b, c, e;
+                load_leaf64(p, a, b, c, e);
+                if (stats) stats[any ? 1 : 0].prims++;
+                const V3 oo(s_ray[0][ow], s_ray[1][ow], s_ray[2][ow]), dd(s_ray[3][ow], s_ray[4][ow], s_ray[5][ow]);
+                const float tmax_o = u_as_f(s_bt[ow]);
+                if (e.w < 0.f) {
+                    if (intersect_triangle(oo, dd, tmin, tmax_o, V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), V3(c.x, c.y, c.z), wt, wu, wv)) {
+                        atomicMin(&s_bt[ow], f_as_u(wt));
+                        won = true;
+                        prim_id = f_as_i(e.x);
+                    }
+                } else if (f_as_i(a.w) != s_cur[ow]) {
+                    const RayFrame rf2 = make_ray_frame(oo, dd);
+                    if (fibre_candidate(rf2, tmin, tmax_o, f4_to_v4(a), f4_to_v4(b), f4_to_v4(c), f4_to_v4(e), fc)) {
+                        park = true;
+                        prim_id = f_as_i(a.w);
+                        zlo = fminf(fminf(fc.k1.z, fmaf(fc.k2.z - fc.k0.z, 1.f / 6.f, fc.k1.z)),
+                                    fminf(fmaf(fc.k1.z - fc.k3.z, 1.f / 6.f, fc.k2.z), fc.k2.z)) - fc.r;
+                    }
+                }
+            }
+            __syncwarp();
+            if (won && s_bt[ow] == f_as_u(wt)) { s_bu[ow] = wu; s_bv[ow] = wv; s_bp[ow] = prim_id; }
+            const unsigned pm = __ballot_sync(FULL, park);
+            if (park) {
+                const int e = wpool + __popc(pm & lt);
+                pool[0][e] = fc.k0.x; pool[1][e] = fc.k0.y; pool[2][e] = fc.k0.z;
+                pool[3][e] = fc.k1.x; pool[4][e] = fc.k1.y; pool[5][e] = fc.k1.z;
+                pool[6][e] = fc.k2.x; pool[7][e] = fc.k2.y; pool[8][e] = fc.k2.z;
+                pool[9][e] = fc.k3.x; pool[10][e] = fc.k3.y; pool[11][e] = fc.k3.z;
+                pool[12][e] = fc.r; pool[13][e] = fc.u_start; pool[14][e] = zlo;
+                pool[15][e] = __int_as_float((prim_id << 5) | olane);
+                atomicAdd(&s_pend[ow], 1);
+            }
+            wpool += __popc(pm);
+            __syncwarp();
+            {
+                const unsigned nt = s_bt[tx];
+                if (nt < f_as_u(best.t)) {      // a triangle of mine was hit
+                    best.t = u_as_f(nt); best.u = s_bu[tx]; best.v = s_bv[tx]; best.prim = s_bp[tx];
+                    if (any) { g_bits = 0; sp = 0; nleaf = 0; next_node = -1; }
+                }
+            }
+#else
             // ---- prim step ----
             bool park = false;
             FibreCandidate fc;
@@ -251,6 +355,7 @@ __device__ __forceinline__ void trace_queue(const GeomView& g, int n, int* curso
                 nsolve++;
             }
             wpool += __popc(pm);
+#endif
 #else
         const bool can_prim = nleaf > 0 && nsolve < kSolveCap;
         const bool can_solve = nsolve > 0;
