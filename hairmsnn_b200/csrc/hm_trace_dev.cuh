@@ -40,7 +40,12 @@
 namespace hm {
 
 constexpr int kTraceBlock = 128;   // threads per CTA of every kernel that calls trace_queue
-constexpr int kLeafCap = 16;       // parked primitive references per lane (a wide node can park 8)
+// 15, not 16: with the pools the CTA's shared memory is 26.0 KB, and 6 CTAs (+ 1 KB each of system use) stay inside the
+// 164 KB carve-out — one more reference per lane pushes the SM to the 196 KB one and costs 32 KB of L1 (194.7 vs 192.9)
+#ifndef HM_LEAF_CAP
+#define HM_LEAF_CAP 15
+#endif
+constexpr int kLeafCap = HM_LEAF_CAP;   // parked primitive references per lane (a wide node can park 8)
 constexpr int kSolveCap = 4;       // parked solver candidates per lane (HM_TRACE_POOL == 0)
 // HM_TRACE_POOL == 1: fibre spans that survive the conservative rejects go into a WARP-level pool in shared memory
 // (their ray-space control points, 16 words each), and the solve step hands the pool out one candidate per lane:
@@ -50,9 +55,12 @@ constexpr int kSolveCap = 4;       // parked solver candidates per lane (HM_TRAC
 #ifndef HM_TRACE_POOL
 #define HM_TRACE_POOL 2
 #endif
-constexpr int kPoolCap = 64;       // pool entries per warp: a prim step adds at most 32
+#ifndef HM_POOL_CAP
+#define HM_POOL_CAP 48
+#endif
+constexpr int kPoolCap = HM_POOL_CAP;   // pool entries per warp: a prim step adds at most 32 (HM_POOL_SOLVE <= cap - 32)
 #ifndef HM_POOL_SOLVE
-#define HM_POOL_SOLVE 24           // solve step once the pool holds this many candidates (<= kPoolCap - 32)
+#define HM_POOL_SOLVE 16           // solve step once the pool holds this many candidates (<= kPoolCap - 32)
 #endif
 #ifndef HM_TRACE_REFILL
 #define HM_TRACE_REFILL 8
