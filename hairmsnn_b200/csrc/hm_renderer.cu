@@ -664,8 +664,21 @@ void Renderer::flush_deferred() {
     for (const Deferred& d : ops) if (d.kind == 0) cs[m++] = d.c;
     if (m > 0) trace_tail(cs, m);
     for (const Deferred& d : ops) {
-        if (d.kind == 0) msnn_order_work(*d.c);
-        else HM_CUDA(cudaMemcpyAsync(d.dst, d.src, d.bytes, cudaMemcpyDeviceToHost, order_stream_));
+        if (d.kind == 0) {
+            // frame span on the order stream (stage 8), as render_frames() records it for frames that are not held back
+            Pending whole{8, nullptr, nullptr};
+            if (profiling_ && ((profile_mask_ >> 8) & 1u)) {
+                whole.a = take_event(); whole.b = take_event();
+                HM_CUDA(cudaEventRecord(whole.a, order_stream_));
+            }
+            msnn_order_work(*d.c);
+            if (whole.a) {
+                HM_CUDA(cudaEventRecord(whole.b, order_stream_));
+                pending_.push_back(whole);
+            }
+        } else {
+            HM_CUDA(cudaMemcpyAsync(d.dst, d.src, d.bytes, cudaMemcpyDeviceToHost, order_stream_));
+        }
     }
 }
 
@@ -802,7 +815,8 @@ void Renderer::render_frames(int n) {
     HM_CUDA(cudaSetDevice(device_));
     for (int i = 0; i < n; ++i) {
         Pending whole{8, nullptr, nullptr};
-        if (profiling_ && ((profile_mask_ >> 8) & 1u)) {
+        const bool held_back = kind_ == HM_KIND_MSNN && tail_group_ > 1;   // flush_deferred() records the span
+        if (!held_back && profiling_ && ((profile_mask_ >> 8) & 1u)) {
             // frame span on the order stream: previous frame's completion -> this frame's completion
             whole.a = take_event(); whole.b = take_event();
             HM_CUDA(cudaEventRecord(whole.a, order_stream_));

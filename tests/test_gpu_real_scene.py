@@ -145,6 +145,9 @@ def test_executables_write_png_exr_stats(curly, tmp_path, exe, args):
         assert np.isfinite(a).all() and np.isfinite(b).all()
     st = json.load(open(out.replace(".png", "_stats.json")))
     assert st and isinstance(st, dict)
+    # the frame spans cover the job: 4 frames of 256 x 256 paths, at a rate a B200 can have
+    assert st["spp"] == 4 and st["paths"] == 4 * 256 * 256
+    assert st["seconds"] > 0 and 0.1 < st["mpaths_per_s"] < 2000, (st["seconds"], st["mpaths_per_s"])
 
 
 def test_executable_reports_scene_errors(tmp_path):
