@@ -12,13 +12,13 @@
 //                inner children become the lane's current group (older groups go to its
 //                stack), hit leaf children (one primitive reference each) are PARKED in a
 //                small per-lane list in shared memory and the lane keeps descending;
-//   prim step  : pop one parked reference, fetch its 64-byte primitive; triangles are
+//   prim step  : take parked references, fetch their 64-byte primitives; triangles are
 //                intersected directly, fibre spans go through the cheap conservative
-//                rejects and survivors are parked for the solver;
-//   solve step : pop one solver candidate, run the Newton iteration.
+//                rejects and survivors are kept for the solver;
+//   solve step : run the Newton iteration of the kept candidates.
 //
-// The warp votes each iteration: a prim (solve) step runs once enough lanes hold a parked
-// reference (candidate), or when no lane can take a node step; otherwise a node step runs.
+// The warp votes each iteration: a prim (solve) step runs once enough parked references
+// (candidates) have collected, or when few lanes can take a node step; otherwise a node step runs.
 // Parking defers a leaf by a few node visits; measured against the host's test-at-once order it costs
 // 17-23 % more node visits (scripts/trav_split.py vs scripts/bvh_stats.py), but making lanes wait for
 // the prim step instead costs more in idle lanes than it saves (HM_TRACE_*_WAIT,
