@@ -39,6 +39,10 @@ DeviceScene::DeviceScene(const HostScene& hs) {
     const HostGeometry& g = hs.geo;
     const HostBvh& b = hs.bvh;
     memset(&view, 0, sizeof(view));
+    // The pooled traversal (hm_trace_dev.cuh) packs (leaf reference << 5 | lane) and (primitive id << 5 | lane) into 32-bit
+    // words: 2^26 references / primitives at most (the curly scene has 39.0 M references, 3.5 M primitives).
+    if (b.wleaf_data.size() / 4 >= ((size_t)1 << 26))
+        throw std::invalid_argument("scene too large: the traversal supports up to 67 108 863 leaf references");
     // the kernels traverse the 8-wide quantised tree only; the binary tree stays on the host (oracle hook)
     view.geom.nodes = nullptr;
     view.geom.leaf_data = nullptr;
